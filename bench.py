@@ -1,0 +1,418 @@
+#!/usr/bin/env python3
+"""bench.py — collision-checked panda configurations per second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of synthetic configurations already resident
+in HBM: `--per-gpu` panda dual-bars configurations per rank (BASELINE config 5, weak scaling),
+validity bits + valid count out; for N > 1 the step also all-gathers the packed bits and
+all-reduces the count over NCCL.  The batch (28 B/config) is far larger than the 126 MB L2, so
+no flush is needed between iterations.  `e2e` is the same metric through the host-buffer C-ABI
+entry point (pmp_check_configs_host) with pinned host inputs: H2D + kernel + D2H inside the
+timed region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "collision_checked_configs_per_sec"
+UNIT = "configs/s"
+# dense algorithmic work of one panda dual-bars configuration
+F_CFG_DENSE = 14.7e3          # flop/config (no culling, no early exit)
+BYTES_PER_CFG = 7 * 4 + 1 / 8  # q in + 1 validity bit out
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--per-gpu", type=int, default=1 << 24, help="configurations per GPU per step")
+    p.add_argument("--workload", default="panda_dual_bars", choices=["panda_dual_bars", "panda_ceiled", "fetch_table"])
+    p.add_argument("--extras", type=int, default=1, help="also measure edges/s, fetch and cloud side metrics (N=1)")
+    p.add_argument("--cpu-sample", type=int, default=1 << 22)
+    return p.parse_args()
+
+
+def make_workload(name):
+    from plainmp_b200 import workloads
+
+    if name == "panda_dual_bars":
+        return workloads.make_panda()
+    if name == "panda_ceiled":
+        return workloads.make_panda(ceiled=True)
+    return workloads.make_fetch()
+
+
+# ---- clocks ---------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "power_w_max": max((float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()), default=None),
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ---- reference arm: the restated reference CPU path (oracle) on the host cores -----------------
+def cpu_rate(cst, spec, n, threads, seed=5):
+    from oracle import bridge
+    from plainmp_b200 import workloads
+
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, n, seed).astype(np.float64)
+    o.is_valid_batch(Q[: min(n, 20000)], threads)  # warm
+    t = time.perf_counter()
+    v = o.is_valid_batch(Q, threads)
+    dt = time.perf_counter() - t
+    return n / dt, float(v.mean())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, cst = make_workload(args.workload)
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample
+    for _ in range(args.warmup):
+        cpu_rate(cst, spec, min(n, 1 << 18), cores)
+    t0 = time.perf_counter()
+    rates = [cpu_rate(cst, spec, n, cores)[0] for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = n * args.steps / sum(n / r for r in rates)
+    single = cpu_rate(cst, spec, min(n, 1 << 20), 1)[0]
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "robot": "panda", "per_step_configs": n, "note": "CPU restatement of the reference path (upstream cannot be built here: no Eigen/OMPL), all host threads, one kin+cst per thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{n} uniform random panda configs per step", "single_thread_value": single},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- B200 arm --------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from plainmp_b200 import _capi, parallel, tables, workloads
+    from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorType
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    _capi.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.load()
+
+    spec, cst = make_workload(args.workload)
+    robot, scene = cst._robot(), cst._scene()
+    n_local = args.per_gpu
+    n_global = n_local * world
+    # synthetic inputs: uniform in the joint limits, generated on the host with a fixed seed per rank
+    lb, ub = spec.angle_bounds()
+    rng = np.random.default_rng(5 + rank)
+    q_host = torch.empty((n_local, lb.shape[0]), dtype=torch.float32, pin_memory=True)
+    chunk = 1 << 20
+    for i in range(0, n_local, chunk):
+        m = min(chunk, n_local - i)
+        q_host[i : i + m] = torch.from_numpy(rng.uniform(lb, ub, size=(m, lb.shape[0])).astype(np.float32))
+    q_dev = q_host.to(dev, non_blocking=True)
+    bits = torch.empty((n_local + 31) // 32, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_words = parallel.shard_words(n_global, world)
+    gathered = torch.empty(n_words * world, dtype=torch.int32, device=dev) if world > 1 else None
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def step():
+        count.zero_()
+        tables.check_configs_device(robot, scene, q_dev, bits, count)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, bits)
+            total.copy_(count)
+            dist.all_reduce(total)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.pmp_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    ev[0].record()
+    for i in range(args.steps):
+        count.zero_()
+        kev[i][0].record()
+        tables.check_configs_device(robot, scene, q_dev, bits, count)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, bits)
+            total.copy_(count)
+            dist.all_reduce(total)
+        ev[i + 1].record()
+    sync_all()
+    launches = lib.pmp_launch_count() - launches0
+    elapsed_ms = torch.tensor([ev[0].elapsed_time(ev[-1])], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    valid_frac = float(count.item()) / n_local
+    value = n_global * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e through the host-buffer C ABI (pinned host in, bits + count out) ----
+    words_host = torch.empty((n_local + 31) // 32, dtype=torch.int32, pin_memory=True)
+    nv = C.c_uint64(0)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        _capi.check(
+            lib.pmp_check_configs_host(robot.handle, scene.handle, q_host.data_ptr(), n_local, words_host.data_ptr(), C.byref(nv))
+        )
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = n_global * e2e_steps / float(e2e_s.item())
+    assert torch.equal(words_host.to(dev), bits), "host-buffer path and device path disagree"
+    clocks = sampler.stop() if rank == 0 else None
+
+    extras = {}
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        if args.extras:
+            extras = side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorConfig, ValidatorType)
+        # CPU baseline: restated reference path, bounded sample
+        from oracle import bridge  # noqa: F401  (bench's cpu_baseline leg may use the oracle)
+
+        cores = os.cpu_count() or 1
+        n_cpu = args.cpu_sample
+        r_all, vf = cpu_rate(cst, spec, n_cpu, cores)
+        r_one, _ = cpu_rate(cst, spec, min(n_cpu, 1 << 20), 1)
+        cpu_baseline = {
+            "value": r_all, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_cpu} uniform random panda configs (valid fraction {vf:.3f}); FP64 restatement of the reference path, one kin+cst per thread",
+            "single_thread_value": r_one,
+        }
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        per_gpu_rate = n_local / (kernel_ms * 1e-3)
+        achieved_gbs = per_gpu_rate * BYTES_PER_CFG / 1e9
+        fp32_peak = extras.get("fp32_ffma_tflops_measured") or 74.4
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: uniform random 7-DOF panda configs, FK + SphereCollisionCst env (box + 2 cylinders) + 11 self pairs, validity bits + count",
+                "robot": "panda", "per_gpu_configs": n_local, "global_configs": n_global,
+                "l2": "inputs (28 B/config x per_gpu_configs) exceed the 126 MB L2; no flush needed",
+                "parallelism": f"item-sharded x{world}, tables replicated" + (", NCCL all_gather(bits)+all_reduce(count) per step" if world > 1 else ""),
+                "valid_fraction": valid_frac,
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                "traffic": None, "peak_source": hbm_src, "kernel_ms": kernel_ms,
+                "note": "algorithmic bytes = 28.125 B/config; the kernel is FP32-SIMT issue bound, see roofline_fp32",
+            },
+            "roofline_fp32": {
+                "bound": "fp32_simt", "achieved": per_gpu_rate * F_CFG_DENSE / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": per_gpu_rate * F_CFG_DENSE / 1e12 / fp32_peak,
+                "note": "dense-equivalent: 14.7 kflop/config (SURVEY 8d, no culling) x configs/s; peak = FFMA micro-benchmark on this GPU" if extras.get("fp32_ffma_tflops_measured") else "dense-equivalent; nominal peak",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * lb.shape[0] * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 16) * world, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_cuda(torch, fn, steps=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / steps
+
+
+def side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorConfig, ValidatorType):
+    """Secondary BASELINE configs at N = 1 (device-resident inputs): edges/s for both endpoint
+    distributions, fetch table configs/s, PR2-vs-cloud configs/s."""
+    out = {}
+    try:
+        spec, cst = workloads.make_panda(ceiled=True)
+        robot, scene = cst._robot(), cst._scene()
+        n_e = 1 << 20
+        valid_fn = lambda q: tables.check_configs(robot, scene, q)  # noqa: E731
+        mv = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, [0.05] * 7))
+        for tag, planner_like in (("A_random_endpoints", False), ("B_planner_like", True)):
+            q0, q1 = workloads.random_edges(spec, n_e, 3, planner_like, valid_fn if planner_like else None)
+            a, b = torch.from_numpy(q0).to(dev), torch.from_numpy(q1).to(dev)
+            bits = torch.empty((n_e + 31) // 32, dtype=torch.int32, device=dev)
+            ctr = torch.zeros(2, dtype=torch.int64, device=dev)
+
+            def run():
+                ctr.zero_()
+                _check(lib, lib.pmp_check_edges(robot.handle, scene.handle, C.byref(mv._v), a.data_ptr(), b.data_ptr(), n_e, bits.data_ptr(), ctr.data_ptr(), ctr.data_ptr() + 8, torch.cuda.current_stream().cuda_stream))
+
+            dt = time_cuda(torch, run)
+            c = ctr.cpu().numpy()
+            out[f"edges_{tag}"] = {"edges_per_s": n_e / dt, "valid_fraction": float(c[0]) / n_e, "waypoint_checks_per_edge": float(c[1]) / n_e, "waypoint_checks_per_s": float(c[1]) / dt, "n": n_e}
+        spec, cst = workloads.make_fetch()
+        robot, scene = cst._robot(), cst._scene()
+        n_f = 1 << 22
+        q = torch.from_numpy(workloads.random_configs(spec, n_f, 2)).to(dev)
+        bits = torch.empty((n_f + 31) // 32, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        dt = time_cuda(torch, lambda: tables.check_configs_device(robot, scene, q, bits, cnt))
+        out["fetch_table"] = {"configs_per_s": n_f / dt, "n": n_f}
+        spec, cst = workloads.make_pr2_cloud(1_000_000)
+        robot, scene = cst._robot(), cst._scene()
+        n_p = 1 << 20
+        q = torch.from_numpy(workloads.random_configs(spec, n_p, 4)).to(dev)
+        bits = torch.empty((n_p + 31) // 32, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        dt = time_cuda(torch, lambda: tables.check_configs_device(robot, scene, q, bits, cnt), steps=3, warmup=1)
+        out["pr2_cloud_1M_points"] = {"configs_per_s": n_p / dt, "n": n_p}
+    except Exception as e:  # side metrics must never break the headline line
+        out["error"] = repr(e)
+    return out
+
+
+def _check(lib, status):
+    if status != 0:
+        raise RuntimeError(lib.pmp_last_error().decode())
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

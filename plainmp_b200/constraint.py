@@ -1,0 +1,256 @@
+"""Host mirror of ``plainmp.constraint`` for the collision path (reference:
+cpp/plainmp/bindings/constraint.cpp:31-35,65-84,108-113).
+
+``SphereCollisionCst`` keeps the reference's constructor and methods; ``is_valid`` / ``evaluate``
+run the same device kernels as the additive batch calls (``is_valid_batch``, ``evaluate_batch``,
+``get_all_spheres_batch``), so a single configuration is just a batch of one.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import tables
+from .kinematics import BaseType, KinematicModel
+from .psdf import SDFBase, UnionSDF
+
+
+class SphereAttachmentSpec:
+    """primitive_sphere_collision.hpp:16-21; binding constraint.cpp:65-71."""
+
+    def __init__(self, parent_link_name: str, relative_positions: np.ndarray, radii: np.ndarray, only_self_collision: bool):
+        self._parent_link_name = str(parent_link_name)
+        self.relative_positions = np.array(relative_positions, dtype=np.float64).reshape(3, -1)
+        self.radii = np.array(radii, dtype=np.float64).reshape(-1)
+        if self.relative_positions.shape[1] != self.radii.shape[0]:
+            raise ValueError("relative_positions must be 3xN with N radii")
+        self.only_self_collision = bool(only_self_collision)
+
+    @property
+    def parent_link_name(self) -> str:
+        return self._parent_link_name
+
+
+def reorder_spheres_for_informative_collision_check(positions: np.ndarray) -> List[int]:
+    """primitive_sphere_collision.cpp:53-96.  The reference starts from
+    ``*unordered_set.begin()`` (implementation-defined).  With libstdc++ and consecutive integer
+    keys after ``reserve(n)`` that iterates n-1, n-2, ..., 0, so the start element is n-1 and
+    ties go to the larger index; this function reproduces that order (it only affects the order
+    in which spheres are tested, never a result — SURVEY App. C-9)."""
+    n = positions.shape[1]
+    visited = [n - 1]
+    unvisited = list(range(n - 2, -1, -1))
+    for _ in range(n - 1):
+        max_dist = 0.0
+        best = 0
+        for k, idx in enumerate(unvisited):
+            d = positions[:, [idx]] - positions[:, visited]
+            md = float(np.sqrt((d * d).sum(axis=0)).min())
+            if md > max_dist:
+                max_dist = md
+                best = k
+        visited.append(unvisited.pop(best))
+    return visited
+
+
+class IneqConstraintBase:
+    pass
+
+
+class SphereCollisionCst(IneqConstraintBase):
+    """``SphereCollisionCst(kin, control_joint_names, base_type, sphere_specs, selfcol_pairs,
+    fixed_sdf, reorder_spheres)`` — primitive_sphere_collision.cpp:117-179."""
+
+    def __init__(
+        self,
+        kin: KinematicModel,
+        control_joint_names: Sequence[str],
+        base_type: BaseType,
+        sphere_specs: Sequence[SphereAttachmentSpec],
+        selfcol_pairs: Sequence[Tuple[str, str]],
+        fixed_sdf: Optional[SDFBase],
+        reorder_spheres: bool = True,
+    ):
+        self._kin = kin
+        self._control_joint_names = list(control_joint_names)
+        self._control_joint_ids = kin.get_joint_ids(self._control_joint_names)  # ValueError on unknown names
+        self._base_type = BaseType(base_type)
+        self._group_link_names: List[str] = []
+        self._group_links: List[int] = []
+        self._group_spheres: List[np.ndarray] = []
+        self._group_only_self: List[bool] = []
+        self._group_spheres_unordered: List[np.ndarray] = []  # as given (before the reorder)
+        self._reorder_spheres = bool(reorder_spheres)
+        for spec in sphere_specs:
+            lid = kin.get_link_ids([spec.parent_link_name])[0]
+            pos = np.asarray(spec.relative_positions, dtype=np.float64).reshape(3, -1)
+            rad = np.asarray(spec.radii, dtype=np.float64).reshape(-1)
+            if pos.shape[1] == 0:
+                raise RuntimeError("a sphere group needs at least one sphere")
+            self._group_spheres_unordered.append(np.concatenate([pos.T, rad[:, None]], axis=1))
+            self._group_link_names.append(spec.parent_link_name)
+            self._group_links.append(lid)
+            self._group_spheres.append(np.concatenate([pos.T, rad[:, None]], axis=1))
+            self._group_only_self.append(bool(spec.only_self_collision))
+            if reorder_spheres:
+                # the reference re-runs the reorder for ALL groups built so far on every
+                # iteration of the spec loop (.cpp:155-159); order-only effect, kept for fidelity
+                for g in range(len(self._group_spheres)):
+                    sp = self._group_spheres[g]
+                    order = reorder_spheres_for_informative_collision_check(sp[:, :3].T)
+                    self._group_spheres[g] = sp[order]
+        self._pairs: List[Tuple[int, int]] = []
+        for a, b in selfcol_pairs:  # .cpp:162-177
+            if a not in self._group_link_names or b not in self._group_link_names:
+                raise RuntimeError("(cpp) Invalid pair of link names for self collision")
+            self._pairs.append((self._group_link_names.index(a), self._group_link_names.index(b)))
+        self._fixed_sdf = fixed_sdf
+        self._sdf: Optional[SDFBase] = None
+        self._robot_cache = None  # (kin.state_key, RobotTable)
+        self._scene_cache = None  # (state key, SceneTable)
+
+    # ---- tables ----
+    def _robot(self) -> tables.RobotTable:
+        v = self._kin.state_key(self._control_joint_ids)
+        if self._robot_cache is None or self._robot_cache[0] != v:
+            self._robot_cache = (
+                v,
+                tables.RobotTable(
+                    self._kin,
+                    self._control_joint_ids,
+                    self._base_type,
+                    self._group_links,
+                    self._group_spheres,
+                    self._group_only_self,
+                    self._pairs,
+                ),
+            )
+        return self._robot_cache[1]
+
+    def _leaves(self):
+        # set_all_sdfs: anchors first, then the user SDF, unions expanded (.cpp:426-448)
+        out = []
+        if self._fixed_sdf is not None:
+            out.extend(self._fixed_sdf._leaves())
+        if self._sdf is not None:
+            out.extend(self._sdf._leaves())
+        return out
+
+    def _scene(self) -> Optional[tables.SceneTable]:
+        leaves = self._leaves()
+        if not leaves:
+            return None
+        key = tuple(l._state_key() for l in leaves)
+        if self._scene_cache is None or self._scene_cache[0] != key:
+            self._scene_cache = (key, tables.SceneTable(leaves))
+        return self._scene_cache[1]
+
+    # ---- binding surface ----
+    def set_sdf(self, sdf: Optional[SDFBase]) -> None:
+        self._sdf = sdf
+
+    def get_sdf(self) -> Optional[SDFBase]:
+        return self._sdf
+
+    def get_kin(self) -> KinematicModel:
+        return self._kin
+
+    def get_control_joint_names(self) -> List[str]:
+        return list(self._control_joint_names)
+
+    def q_dim(self) -> int:
+        return len(self._control_joint_ids) + (6 if self._base_type == BaseType.FLOATING else 0) + (
+            3 if self._base_type == BaseType.PLANAR else 0
+        )
+
+    def cst_dim(self) -> int:  # .hpp:98-101
+        return (1 if self._leaves() else 0) + (1 if self._pairs else 0)
+
+    def update_kintree(self, q: Sequence[float], high_accuracy: bool = True) -> None:
+        """Stores q as the model's joint state (the reference also refreshes its FK cache; here
+        the cache lives on the device and is rebuilt per call)."""
+        q = np.asarray(q, dtype=np.float64).reshape(-1)
+        n = len(self._control_joint_ids)
+        accurate = True if self._base_type != BaseType.FIXED else bool(high_accuracy)
+        self._kin.set_joint_positions(self._control_joint_ids, q[:n], accurate)
+        self._last_q = q.copy()
+        self._last_accurate = accurate
+
+    def is_valid(self, q: Sequence[float]) -> bool:
+        return bool(self.is_valid_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))[0])
+
+    def evaluate(self, q: Sequence[float]):
+        """``(vals, jac)`` like the binding; the Jacobian rows are outside this repo's scope
+         and are returned as NaN."""
+        d = self.evaluate_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))[0]
+        vals = d[~np.isnan(d)]
+        return vals, np.full((vals.shape[0], self.q_dim()), np.nan)
+
+    def get_all_spheres(self) -> List[Tuple[np.ndarray, float]]:
+        """Sphere centres for the state set by the last ``update_kintree`` (.cpp:412-424)."""
+        q = getattr(self, "_last_q", None)
+        if q is None:
+            raise RuntimeError("call update_kintree(q) first")
+        s = self.get_all_spheres_batch(q.reshape(1, -1), accurate=self._last_accurate)[0]
+        return [(row[:3].astype(np.float64), float(row[3])) for row in s]
+
+    def get_group_spheres(self) -> List[Tuple[np.ndarray, float]]:
+        """Group bounding spheres for the last ``update_kintree`` state (.cpp:401-410)."""
+        q = getattr(self, "_last_q", None)
+        if q is None:
+            raise RuntimeError("call update_kintree(q) first")
+        robot = self._robot()
+        frames = tables.fk_frames(robot, q.reshape(1, -1), accurate=self._last_accurate)[0].astype(np.float64)
+        out = []
+        from .kinematics import quat_rotate
+
+        for g in range(len(self._group_links)):
+            f = frames[robot.groups[g]["op"]]
+            c = quat_rotate(f[3:7], robot.groups[g]["center"].astype(np.float64)) + f[:3]
+            out.append((c, float(robot.groups[g]["radius"])))
+        return out
+
+    # ---- additive batch surface ----
+    def is_valid_batch(self, Q) -> np.ndarray:
+        """Validity of every row of ``Q`` ([n, q_dim]); same semantics as ``is_valid`` per row."""
+        robot = self._robot()
+        scene = self._scene()
+        if scene is None and not self._pairs:
+            n = Q.shape[0]
+            return np.ones(n, dtype=bool)  # App. C-7: nothing to collide with
+        return tables.check_configs(robot, scene, Q)
+
+    def evaluate_batch(self, Q) -> np.ndarray:
+        """[n, 2] = (ext, self) min signed distances clipped at 0.1; NaN where a term is disabled."""
+        return tables.eval_configs(self._robot(), self._scene(), Q)
+
+    def get_all_spheres_batch(self, Q, accurate: bool = True) -> np.ndarray:
+        """[n, n_spheres, 4] world sphere centres + radii, groups in spec order."""
+        return tables.fk_spheres(self._robot(), Q, accurate)
+
+
+class IneqCompositeCst:
+    """composite_constraint.hpp:98-105: one FK, AND over members.  Only collision members are on
+    this repo's path; they must share the kinematic model."""
+
+    def __init__(self, constraints: Sequence[SphereCollisionCst]):
+        self.constraints = list(constraints)
+        for c in self.constraints:
+            if c.get_kin() is not self.constraints[0].get_kin():
+                raise RuntimeError("All constraints must have the same kinematic chain")
+
+    def is_valid(self, q) -> bool:
+        return all(c.is_valid(q) for c in self.constraints)
+
+    def is_valid_batch(self, Q) -> np.ndarray:
+        out = None
+        for c in self.constraints:
+            v = c.is_valid_batch(Q)
+            out = v if out is None else (out & v)
+        return out
+
+    def evaluate(self, q):
+        vals = [c.evaluate(q)[0] for c in self.constraints]
+        v = np.concatenate(vals) if vals else np.zeros(0)
+        return v, np.full((v.shape[0], self.constraints[0].q_dim()), np.nan)

@@ -1,0 +1,697 @@
+// plainmp_b200.cu — C ABI (include/plainmp_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// No torch, no CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pmp_kernels.cuh"
+
+using namespace pmp;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(PMP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+constexpr int kBlock = 128;
+constexpr int kMaxSmem = 200 * 1024;
+
+int g_num_sms = 0;
+int ensure_device() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    int n = 0;
+    err = cudaGetDeviceCount(&n);
+    if (err == cudaSuccess && n == 0) err = cudaErrorNoDevice;
+    if (err != cudaSuccess) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (err != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(err));
+  return PMP_OK;
+}
+
+template <class K>
+int grid_for(K kernel, size_t smem, long long n_tiles, int* grid) {
+  static thread_local const void* last = nullptr;
+  (void)last;
+  CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
+  if (per_sm < 1) return fail(PMP_ERR_LIMIT, "kernel does not fit on an SM with these tables");
+  long long g = (long long)g_num_sms * per_sm;
+  *grid = (int)std::max<long long>(1, std::min<long long>(g, n_tiles));
+  return PMP_OK;
+}
+
+}  // namespace
+
+struct pmp_robot {
+  RobotDev dev{};
+  float4* blob_dev = nullptr;
+  std::vector<int> group_order;  // sorted position -> caller's group index
+  size_t stash_floats_per_thread = 0;
+};
+
+struct pmp_scene {
+  SceneDev dev{};
+  float4* prims_dev = nullptr;
+  float4* cloud_pts = nullptr;
+  uint32_t* cloud_cell_start = nullptr;
+  float* cloud_dist = nullptr;
+};
+
+static SceneDev empty_scene() {
+  SceneDev s{};
+  s.prims = nullptr;
+  s.n_prims = 0;
+  s.cloud.enabled = 0;
+  return s;
+}
+
+static size_t smem_bytes(const pmp_robot* r, const SceneDev& s) {
+  return (size_t)(r->dev.blob_words + s.n_prims * 6) * 16 + r->stash_floats_per_thread * 4 * kBlock;
+}
+
+extern "C" {
+
+const char* pmp_last_error(void) { return g_err.c_str(); }
+int pmp_abi_version(void) { return PMP_ABI_VERSION; }
+uint64_t pmp_launch_count(void) { return g_launches.load(); }
+int pmp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int pmp_set_device(int device) {
+  if (int rc = ensure_device()) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  return PMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
+  if (!d || !out) return fail(PMP_ERR_INVALID, "null argument");
+  if (d->n_ops < 0 || d->n_groups < 0 || d->n_spheres < 0 || d->n_pairs < 0 || d->dof < 0)
+    return fail(PMP_ERR_INVALID, "negative table size");
+  if (d->base_type < PMP_BASE_FIXED || d->base_type > PMP_BASE_FLOATING) return fail(PMP_ERR_INVALID, "bad base_type");
+  const int q_dim = d->dof + (d->base_type == PMP_BASE_PLANAR ? 3 : 0) + (d->base_type == PMP_BASE_FLOATING ? 6 : 0);
+  for (int i = 0; i < d->n_ops; i++) {
+    const pmp_link_op_t& o = d->ops[i];
+    if (o.parent < -1 || o.parent >= i) return fail(PMP_ERR_INVALID, "ops must be in topological order (parent < index)");
+    if (o.kind < PMP_OP_FIXED || o.kind > PMP_OP_PRISMATIC) return fail(PMP_ERR_INVALID, "bad op kind");
+    if (o.kind != PMP_OP_FIXED && (o.q_index < 0 || o.q_index >= d->dof)) return fail(PMP_ERR_INVALID, "q_index out of range");
+  }
+  std::vector<char> in_pair(d->n_groups, 0);
+  for (int p = 0; p < d->n_pairs; p++) {
+    const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
+    if (a < 0 || a >= d->n_groups || b < 0 || b >= d->n_groups) return fail(PMP_ERR_INVALID, "pair refers to an unknown group");
+    in_pair[a] = in_pair[b] = 1;
+  }
+  std::vector<char> covered(d->n_spheres, 0);
+  for (int g = 0; g < d->n_groups; g++) {
+    const pmp_group_t& G = d->groups[g];
+    if (G.op < 0 || G.op >= d->n_ops) return fail(PMP_ERR_INVALID, "group refers to an unknown op");
+    if (G.sphere_begin < 0 || G.sphere_count < 0 || G.sphere_begin + G.sphere_count > d->n_spheres)
+      return fail(PMP_ERR_INVALID, "group sphere range out of bounds");
+  }
+  if (int rc = ensure_device()) return rc;
+
+  auto* r = new pmp_robot();
+  // groups sorted by op (stable), pairs remapped
+  std::vector<int> order(d->n_groups);
+  for (int g = 0; g < d->n_groups; g++) order[g] = g;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d->groups[a].op < d->groups[b].op; });
+  std::vector<int> pos(d->n_groups);
+  for (int k = 0; k < d->n_groups; k++) pos[order[k]] = k;
+  r->group_order = order;
+
+  // stash slots: a frame is kept if a later, non-adjacent op hangs off it or if one of its
+  // groups takes part in the self-collision narrow phase
+  std::vector<int> slot(d->n_ops, -1);
+  std::vector<char> need(d->n_ops, 0);
+  for (int i = 0; i < d->n_ops; i++)
+    if (d->ops[i].parent >= 0 && d->ops[i].parent != i - 1) need[d->ops[i].parent] = 1;
+  for (int g = 0; g < d->n_groups; g++)
+    if (in_pair[g]) need[d->groups[g].op] = 1;
+  int n_slots = 0;
+  for (int i = 0; i < d->n_ops; i++)
+    if (need[i]) slot[i] = n_slots++;
+
+  const int off_groups = d->n_ops * 4;
+  const int off_spheres = off_groups + d->n_groups * 2;
+  const int off_pairs = off_spheres + d->n_spheres;
+  const int words = off_pairs + (d->n_pairs + 1) / 2;
+  std::vector<float4> blob(std::max(words, 1));
+  auto fi = [](int v) {
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+  };
+  for (int i = 0; i < d->n_ops; i++) {
+    const pmp_link_op_t& o = d->ops[i];
+    blob[4 * i + 0] = make_float4(o.origin_quat[0], o.origin_quat[1], o.origin_quat[2], o.origin_quat[3]);
+    blob[4 * i + 1] = make_float4(o.origin_xyz[0], o.origin_xyz[1], o.origin_xyz[2], fi(o.kind));
+    blob[4 * i + 2] = make_float4(o.axis[0], o.axis[1], o.axis[2], fi(o.q_index));
+    const int pslot = (o.parent >= 0 && o.parent != i - 1) ? slot[o.parent] : -1;
+    blob[4 * i + 3] = make_float4(fi(o.parent), fi(o.flags), fi(slot[i]), fi(pslot));
+  }
+  for (int k = 0; k < d->n_groups; k++) {
+    const pmp_group_t& G = d->groups[order[k]];
+    blob[off_groups + 2 * k] = make_float4(G.center[0], G.center[1], G.center[2], G.radius);
+    const int sl = slot[G.op] < 0 ? 0 : slot[G.op];
+    const int fl = (G.only_self_collision ? 1 : 0) | (sl << 8);
+    blob[off_groups + 2 * k + 1] = make_float4(fi(G.op), fi(G.sphere_begin), fi(G.sphere_count), fi(fl));
+  }
+  for (int s = 0; s < d->n_spheres; s++)
+    blob[off_spheres + s] = make_float4(d->spheres[4 * s], d->spheres[4 * s + 1], d->spheres[4 * s + 2], d->spheres[4 * s + 3]);
+  {
+    int* pw = reinterpret_cast<int*>(blob.data() + off_pairs);
+    for (int p = 0; p < d->n_pairs; p++) {
+      pw[2 * p] = pos[d->pairs[2 * p]];
+      pw[2 * p + 1] = pos[d->pairs[2 * p + 1]];
+    }
+  }
+  cudaError_t e = cudaMalloc(&r->blob_dev, blob.size() * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMemcpy(r->blob_dev, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete r;
+    return fail(PMP_ERR_CUDA, std::string("robot table upload: ") + cudaGetErrorString(e));
+  }
+  RobotDev& D = r->dev;
+  D.blob = r->blob_dev;
+  D.blob_words = words;
+  D.n_ops = d->n_ops;
+  D.n_groups = d->n_groups;
+  D.n_spheres = d->n_spheres;
+  D.n_pairs = d->n_pairs;
+  D.off_groups = off_groups;
+  D.off_spheres = off_spheres;
+  D.off_pairs = off_pairs;
+  D.dof = d->dof;
+  D.q_dim = q_dim;
+  D.base_type = d->base_type;
+  D.n_slots = n_slots;
+  memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
+  r->stash_floats_per_thread = (size_t)n_slots * 7 + (d->n_pairs > 0 ? (size_t)d->n_groups * 3 : 0);
+  if (smem_bytes(r, empty_scene()) > (size_t)kMaxSmem) {
+    pmp_robot_destroy(r);
+    return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
+  }
+  *out = r;
+  return PMP_OK;
+}
+
+void pmp_robot_destroy(pmp_robot_t* r) {
+  if (!r) return;
+  if (r->blob_dev) cudaFree(r->blob_dev);
+  delete r;
+}
+int pmp_robot_q_dim(const pmp_robot_t* r) { return r ? r->dev.q_dim : -1; }
+int pmp_robot_n_spheres(const pmp_robot_t* r) { return r ? r->dev.n_spheres : -1; }
+
+// ---------------------------------------------------------------------------------------------
+int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
+  if (!d || !out) return fail(PMP_ERR_INVALID, "null argument");
+  if (d->n_prims < 0 || d->n_cloud_points < 0) return fail(PMP_ERR_INVALID, "negative table size");
+  for (int i = 0; i < d->n_prims; i++)
+    if (d->prims[i].type < PMP_PRIM_BOX || d->prims[i].type > PMP_PRIM_GROUND) return fail(PMP_ERR_INVALID, "bad primitive type");
+  if (int rc = ensure_device()) return rc;
+  auto* s = new pmp_scene();
+  s->dev = empty_scene();
+  static_assert(sizeof(pmp_prim_t) == 96, "pmp_prim_t layout");
+  if (d->n_prims > 0) {
+    cudaError_t e = cudaMalloc(&s->prims_dev, (size_t)d->n_prims * 96);
+    if (e == cudaSuccess) e = cudaMemcpy(s->prims_dev, d->prims, (size_t)d->n_prims * 96, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      pmp_scene_destroy(s);
+      return fail(PMP_ERR_CUDA, std::string("scene table upload: ") + cudaGetErrorString(e));
+    }
+    s->dev.prims = s->prims_dev;
+    s->dev.n_prims = d->n_prims;
+  }
+  if (d->n_cloud_points > 0) {
+    const int64_t n = d->n_cloud_points;
+    if (n >= (int64_t)1 << 31) {
+      pmp_scene_destroy(s);
+      return fail(PMP_ERR_LIMIT, "cloud too large");
+    }
+    CloudDev& C = s->dev.cloud;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = 0; i < n; i++)
+      for (int a = 0; a < 3; a++) {
+        const float v = d->cloud_points[3 * i + a];
+        if (!std::isfinite(v)) {
+          pmp_scene_destroy(s);
+          return fail(PMP_ERR_INVALID, "non-finite cloud point");
+        }
+        lo[a] = std::min(lo[a], v);
+        hi[a] = std::max(hi[a], v);
+      }
+    C.rho = d->cloud_radius;
+    C.lbx = lo[0] - C.rho; C.lby = lo[1] - C.rho; C.lbz = lo[2] - C.rho;
+    C.ubx = hi[0] + C.rho; C.uby = hi[1] + C.rho; C.ubz = hi[2] + C.rho;
+    const float margin = 0.35f;  // larger than any group-sphere query radius of the stock robots
+    float h = d->cloud_cell > 0.f ? d->cloud_cell : 0.02f;
+    const double ext[3] = {hi[0] - lo[0] + 2.0 * margin, hi[1] - lo[1] + 2.0 * margin, hi[2] - lo[2] + 2.0 * margin};
+    while ((ext[0] / h + 1) * (ext[1] / h + 1) * (ext[2] / h + 1) > 24.0e6) h *= 1.25f;
+    C.h = h;
+    C.inv_h = 1.f / h;
+    C.e = 0.5f * std::sqrt(3.f) * h * 1.0001f;
+    C.dist_cap = margin;
+    C.ox = lo[0] - margin; C.oy = lo[1] - margin; C.oz = lo[2] - margin;
+    C.nx = (int)std::ceil(ext[0] / h) + 1;
+    C.ny = (int)std::ceil(ext[1] / h) + 1;
+    C.nz = (int)std::ceil(ext[2] / h) + 1;
+    C.n_pts = n;
+    const int64_t n_cells = (int64_t)C.nx * C.ny * C.nz;
+    float* raw = nullptr;
+    uint32_t *counts = nullptr, *cell_of = nullptr;
+    cudaError_t e = cudaMalloc(&raw, n * 12);
+    if (e == cudaSuccess) e = cudaMemcpy(raw, d->cloud_points, n * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&counts, n_cells * 4);
+    if (e == cudaSuccess) e = cudaMemset(counts, 0, n_cells * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&cell_of, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cloud_cell_start, (n_cells + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cloud_pts, n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cloud_dist, n_cells * 4);
+    if (e == cudaSuccess) {
+      const int grid = g_num_sms * 8;
+      k_cloud_count<<<grid, 256>>>(raw, n, C, counts, cell_of);
+      k_cloud_scan<<<1, 1024>>>(counts, n_cells, s->cloud_cell_start);
+      cudaMemset(counts, 0, n_cells * 4);
+      k_cloud_scatter<<<grid, 256>>>(raw, n, cell_of, s->cloud_cell_start, counts, s->cloud_pts);
+      C.pts = s->cloud_pts;
+      C.cell_start = s->cloud_cell_start;
+      k_cloud_field<<<grid, 256>>>(C, s->cloud_dist);
+      g_launches += 4;
+      C.dist = s->cloud_dist;
+      e = cudaDeviceSynchronize();
+    }
+    if (raw) cudaFree(raw);
+    if (counts) cudaFree(counts);
+    if (cell_of) cudaFree(cell_of);
+    if (e != cudaSuccess) {
+      pmp_scene_destroy(s);
+      return fail(PMP_ERR_CUDA, std::string("cloud grid build: ") + cudaGetErrorString(e));
+    }
+    C.enabled = 1;
+  }
+  *out = s;
+  return PMP_OK;
+}
+
+void pmp_scene_destroy(pmp_scene_t* s) {
+  if (!s) return;
+  if (s->prims_dev) cudaFree(s->prims_dev);
+  if (s->cloud_pts) cudaFree(s->cloud_pts);
+  if (s->cloud_cell_start) cudaFree(s->cloud_cell_start);
+  if (s->cloud_dist) cudaFree(s->cloud_dist);
+  delete s;
+}
+
+// ---------------------------------------------------------------------------------------------
+#define CHECK_COMMON(robot, n)                                                       \
+  if (!(robot)) return fail(PMP_ERR_INVALID, "robot handle is null");               \
+  if ((n) < 0) return fail(PMP_ERR_INVALID, "negative item count");                 \
+  if (int rc_ = ensure_device()) return rc_;
+
+int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n,
+                      uint32_t* valid_bits_dev, unsigned long long* n_valid_dev, void* stream) {
+  CHECK_COMMON(robot, n);
+  if (n == 0) return PMP_OK;
+  if (!q_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const SceneDev S = scene ? scene->dev : empty_scene();
+  const size_t smem = smem_bytes(robot, S);
+  if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  const long long n_tiles = (n + kBlock - 1) / kBlock;
+  int grid = 0;
+  // is_valid uses the polynomial sin/cos only for a FIXED base (constraints/primitive.hpp:39-60)
+  if (robot->dev.base_type == PMP_BASE_FIXED) {
+    if (int rc = grid_for(k_check_configs<true>, smem, n_tiles, &grid)) return rc;
+    k_check_configs<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);
+  } else {
+    if (int rc = grid_for(k_check_configs<false>, smem, n_tiles, &grid)) return rc;
+    k_check_configs<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);
+  }
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n,
+                     float* dist_dev, void* stream) {
+  CHECK_COMMON(robot, n);
+  if (n == 0) return PMP_OK;
+  if (!q_dev || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const SceneDev S = scene ? scene->dev : empty_scene();
+  const size_t smem = smem_bytes(robot, S);
+  if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  int grid = 0;
+  if (int rc = grid_for(k_eval_configs, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+  k_eval_configs<<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, dist_dev);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* spheres_dev, void* stream) {
+  CHECK_COMMON(robot, n);
+  if (n == 0) return PMP_OK;
+  if (!q_dev || !spheres_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const SceneDev S = empty_scene();
+  const size_t smem = smem_bytes(robot, S);
+  int grid = 0;
+  // a moving base always uses exact sin/cos (constraints/primitive.hpp:42)
+  const bool approx = !accurate && robot->dev.base_type == PMP_BASE_FIXED;
+  if (approx) {
+    if (int rc = grid_for(k_fk_spheres<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+    k_fk_spheres<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, (float4*)spheres_dev);
+  } else {
+    if (int rc = grid_for(k_fk_spheres<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+    k_fk_spheres<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, (float4*)spheres_dev);
+  }
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+int pmp_fk_frames(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* frames_dev, void* stream) {
+  CHECK_COMMON(robot, n);
+  if (n == 0) return PMP_OK;
+  if (!q_dev || !frames_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const SceneDev S = empty_scene();
+  const size_t smem = smem_bytes(robot, S);
+  int grid = 0;
+  const bool approx = !accurate && robot->dev.base_type == PMP_BASE_FIXED;
+  if (approx) {
+    if (int rc = grid_for(k_fk_frames<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+    k_fk_frames<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, frames_dev);
+  } else {
+    if (int rc = grid_for(k_fk_frames<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+    k_fk_frames<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, frames_dev);
+  }
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+// ---- edges ---------------------------------------------------------------------------------------
+namespace {
+// ompl/generate_sequence.py:11-63: greedy farthest-first permutation, ties -> larger number
+std::vector<int> farthest_sequence(int N) {
+  std::vector<int> result(N, 0);
+  std::vector<char> used(N, 0);
+  used[0] = 1;
+  for (int i = 1; i < N; i++) {
+    int best_d = -1, best = -1;
+    for (int num = 0; num < N; num++) {
+      if (used[num]) continue;
+      int md = 1 << 30;
+      for (int j = 0; j < i; j++) md = std::min(md, std::abs(num - result[j]));
+      if (md > best_d || (md == best_d && num > best)) {
+        best_d = md;
+        best = num;
+      }
+    }
+    result[i] = best;
+    used[best] = 1;
+  }
+  return result;
+}
+uint8_t* g_seq_dev = nullptr;
+std::mutex g_seq_mu;
+int ensure_sequence_table() {
+  std::lock_guard<std::mutex> lk(g_seq_mu);
+  if (g_seq_dev) return PMP_OK;
+  std::vector<uint8_t> t(128 * 128, 0);
+  for (int n = 1; n <= 128; n++) {
+    auto row = farthest_sequence(n);
+    for (int i = 0; i < n; i++) t[(n - 1) * 128 + i] = (uint8_t)row[i];
+  }
+  CUDA_OK(cudaMalloc(&g_seq_dev, t.size()));
+  CUDA_OK(cudaMemcpy(g_seq_dev, t.data(), t.size(), cudaMemcpyHostToDevice));
+  return PMP_OK;
+}
+
+struct ValidatorCache {  // device copies of box widths, keyed by content
+  std::vector<double> width;
+  double* dev = nullptr;  // [2][dim]: width, inv_width
+};
+std::mutex g_val_mu;
+std::vector<ValidatorCache> g_val_cache;
+
+int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
+  if (!v) return fail(PMP_ERR_INVALID, "validator is null");
+  if (v->dim != q_dim) return fail(PMP_ERR_INVALID, "box dimension and space dimension mismatch");  // ompl_thin_wrap.hpp:84-86
+  if (int rc = ensure_sequence_table()) return rc;
+  out->seq = g_seq_dev;
+  out->type = v->type;
+  out->resolution = v->resolution;
+  out->width = out->inv_width = nullptr;
+  if (v->type == PMP_VALIDATOR_BOX) {
+    if (!v->box_width) return fail(PMP_ERR_INVALID, "box_width is null");
+    std::lock_guard<std::mutex> lk(g_val_mu);
+    std::vector<double> w(v->box_width, v->box_width + q_dim);
+    for (auto& c : g_val_cache)
+      if (c.width == w) {
+        out->width = c.dev;
+        out->inv_width = c.dev + q_dim;
+        return PMP_OK;
+      }
+    ValidatorCache c;
+    c.width = w;
+    std::vector<double> both(2 * q_dim);
+    for (int i = 0; i < q_dim; i++) {
+      if (!(w[i] > 0)) return fail(PMP_ERR_INVALID, "box width must be positive");
+      both[i] = w[i];
+      both[q_dim + i] = 1.0 / w[i];
+    }
+    CUDA_OK(cudaMalloc(&c.dev, both.size() * 8));
+    CUDA_OK(cudaMemcpy(c.dev, both.data(), both.size() * 8, cudaMemcpyHostToDevice));
+    g_val_cache.push_back(c);
+    out->width = c.dev;
+    out->inv_width = c.dev + q_dim;
+  } else if (v->type == PMP_VALIDATOR_EUCLIDEAN) {
+    if (!(v->resolution > 0)) return fail(PMP_ERR_INVALID, "resolution must be positive");
+  } else {
+    return fail(PMP_ERR_INVALID, "unknown validator type");  // ompl_thin_wrap.hpp:89-91
+  }
+  return PMP_OK;
+}
+constexpr int kLanesPerEdge = 8;
+}  // namespace
+
+int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                    const float* q0_dev, const float* q1_dev, int64_t n, uint32_t* valid_bits_dev,
+                    unsigned long long* n_valid_dev, unsigned long long* n_checked_dev, void* stream) {
+  CHECK_COMMON(robot, n);
+  ValidatorDev V;
+  if (int rc = validator_to_dev(validator, robot->dev.q_dim, &V)) return rc;
+  if (n == 0) return PMP_OK;
+  if (!q0_dev || !q1_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const SceneDev S = scene ? scene->dev : empty_scene();
+  const size_t smem = smem_bytes(robot, S);
+  if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  const long long n_words = (n + 31) / 32;
+  const long long n_tiles = (n_words + (kBlock / 32) - 1) / (kBlock / 32);
+  int grid = 0;
+  if (robot->dev.base_type == PMP_BASE_FIXED) {
+    if (int rc = grid_for(k_check_edges<true, kLanesPerEdge>, smem, n_tiles, &grid)) return rc;
+    k_check_edges<true, kLanesPerEdge><<<grid, kBlock, smem, (cudaStream_t)stream>>>(
+        robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, n_valid_dev, n_checked_dev);
+  } else {
+    if (int rc = grid_for(k_check_edges<false, kLanesPerEdge>, smem, n_tiles, &grid)) return rc;
+    k_check_edges<false, kLanesPerEdge><<<grid, kBlock, smem, (cudaStream_t)stream>>>(
+        robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, n_valid_dev, n_checked_dev);
+  }
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+// ---- host-buffer entry points ----------------------------------------------------------------------
+namespace {
+struct Workspace {  // grow-only device scratch shared by the *_host calls (serialised by mu)
+  std::mutex mu;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  void* in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  size_t in_cap[2][2] = {{0, 0}, {0, 0}};
+  void* outb[2] = {nullptr, nullptr};
+  size_t out_cap[2] = {0, 0};
+  unsigned long long* counters = nullptr;  // [2][2]
+  unsigned long long* counters_host = nullptr;
+  int init() {
+    if (stream[0]) return PMP_OK;
+    for (int i = 0; i < 2; i++) CUDA_OK(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc(&counters, 4 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMallocHost(&counters_host, 4 * sizeof(unsigned long long)));
+    return PMP_OK;
+  }
+  int reserve(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return PMP_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CUDA_OK(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return PMP_OK;
+  }
+} g_ws;
+constexpr int64_t kHostChunk = 1 << 21;  // items per pipelined chunk (multiple of 32)
+}  // namespace
+
+int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n,
+                           uint32_t* valid_bits_host, uint64_t* n_valid) {
+  CHECK_COMMON(robot, n);
+  if (n_valid) *n_valid = 0;
+  if (n == 0) return PMP_OK;
+  if (!q_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  if (int rc = g_ws.init()) return rc;
+  const int qd = robot->dev.q_dim;
+  CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
+  int k = 0;
+  for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
+    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+    if (int rc = g_ws.reserve(&g_ws.in[k][0], &g_ws.in_cap[k][0], (size_t)m * qd * 4)) return rc;
+    if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
+    cudaStream_t st = g_ws.stream[k];
+    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][0], q_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = pmp_check_configs(robot, scene, (const float*)g_ws.in[k][0], m, (uint32_t*)g_ws.outb[k], g_ws.counters + k, st)) return rc;
+    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, g_ws.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_OK(cudaMemcpyAsync(g_ws.counters_host, g_ws.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_ws.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[1]));
+  // counters copy was queued on stream 0 possibly before stream 1 finished: re-read after both drained
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
+  CUDA_OK(cudaMemcpy(g_ws.counters_host, g_ws.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (n_valid) *n_valid = g_ws.counters_host[0] + g_ws.counters_host[1];
+  return PMP_OK;
+}
+
+int pmp_eval_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n, float* dist_host) {
+  CHECK_COMMON(robot, n);
+  if (n == 0) return PMP_OK;
+  if (!q_host || !dist_host) return fail(PMP_ERR_INVALID, "null host pointer");
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  if (int rc = g_ws.init()) return rc;
+  const int qd = robot->dev.q_dim;
+  int k = 0;
+  for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
+    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+    if (int rc = g_ws.reserve(&g_ws.in[k][0], &g_ws.in_cap[k][0], (size_t)m * qd * 4)) return rc;
+    if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)m * 8)) return rc;
+    cudaStream_t st = g_ws.stream[k];
+    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][0], q_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = pmp_eval_configs(robot, scene, (const float*)g_ws.in[k][0], m, (float*)g_ws.outb[k], st)) return rc;
+    CUDA_OK(cudaMemcpyAsync(dist_host + off * 2, g_ws.outb[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[1]));
+  return PMP_OK;
+}
+
+int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                         const float* q0_host, const float* q1_host, int64_t n, uint32_t* valid_bits_host,
+                         uint64_t* n_valid, uint64_t* n_checked) {
+  CHECK_COMMON(robot, n);
+  if (n_valid) *n_valid = 0;
+  if (n_checked) *n_checked = 0;
+  if (n == 0) {
+    ValidatorDev V;
+    return validator_to_dev(validator, robot->dev.q_dim, &V);
+  }
+  if (!q0_host || !q1_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  if (int rc = g_ws.init()) return rc;
+  const int qd = robot->dev.q_dim;
+  CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
+  int k = 0;
+  for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
+    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+    for (int a = 0; a < 2; a++)
+      if (int rc = g_ws.reserve(&g_ws.in[k][a], &g_ws.in_cap[k][a], (size_t)m * qd * 4)) return rc;
+    if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
+    cudaStream_t st = g_ws.stream[k];
+    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][0], q0_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][1], q1_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = pmp_check_edges(robot, scene, validator, (const float*)g_ws.in[k][0], (const float*)g_ws.in[k][1], m,
+                                 (uint32_t*)g_ws.outb[k], g_ws.counters + k, g_ws.counters + 2 + k, st))
+      return rc;
+    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, g_ws.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(g_ws.stream[1]));
+  CUDA_OK(cudaMemcpy(g_ws.counters_host, g_ws.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (n_valid) *n_valid = g_ws.counters_host[0] + g_ws.counters_host[1];
+  if (n_checked) *n_checked = g_ws.counters_host[2] + g_ws.counters_host[3];
+  return PMP_OK;
+}
+
+// ---- psdf / kdtree ---------------------------------------------------------------------------------
+int pmp_sdf_evaluate(const pmp_scene_t* scene, const float* points_dev, int64_t n, float* out_dev, void* stream) {
+  if (!scene) return fail(PMP_ERR_INVALID, "scene handle is null");
+  if (n < 0) return fail(PMP_ERR_INVALID, "negative item count");
+  if (int rc = ensure_device()) return rc;
+  if (n == 0) return PMP_OK;
+  if (!points_dev || !out_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 8);
+  k_sdf_evaluate<<<grid, 256, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, n, out_dev);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+int pmp_sdf_is_outside(const pmp_scene_t* scene, const float* points_dev, const float* radii_dev, int64_t n,
+                       uint8_t* out_dev, void* stream) {
+  if (!scene) return fail(PMP_ERR_INVALID, "scene handle is null");
+  if (n < 0) return fail(PMP_ERR_INVALID, "negative item count");
+  if (int rc = ensure_device()) return rc;
+  if (n == 0) return PMP_OK;
+  if (!points_dev || !out_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 8);
+  k_sdf_is_outside<<<grid, 256, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, radii_dev, n, out_dev);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+int pmp_cloud_nearest(const pmp_scene_t* scene, const float* points_dev, int64_t n, float* sqdist_dev,
+                      int32_t* nearest_index_dev, void* stream) {
+  if (!scene) return fail(PMP_ERR_INVALID, "scene handle is null");
+  if (!scene->dev.cloud.enabled) return fail(PMP_ERR_INVALID, "scene has no point cloud");
+  if (n < 0) return fail(PMP_ERR_INVALID, "negative item count");
+  if (int rc = ensure_device()) return rc;
+  if (n == 0) return PMP_OK;
+  if (!points_dev || !sqdist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)g_num_sms * 16);
+  k_cloud_nearest<<<grid, 128, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, n, sqdist_dev, nearest_index_dev);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
+}  // extern "C"

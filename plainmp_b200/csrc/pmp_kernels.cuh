@@ -1,0 +1,547 @@
+// pmp_kernels.cuh — the hot-path kernels (v1: one thread per configuration / waypoint).
+//
+// Reference call stack restated per item (paths relative to cpp/plainmp/):
+//   IneqConstraintBase::is_valid            constraints/primitive.hpp:113-117
+//   ConstraintBase::update_kintree          constraints/primitive.hpp:38-62
+//   SphereCollisionCst::check_ext_collision constraints/primitive_sphere_collision.cpp:191-220
+//   SphereCollisionCst::check_self_collision                                      .cpp:222-254
+//   evaluate_ext_collision / evaluate_self_collision (values)      .cpp:256-295, .cpp:324-361
+//   CustomValidatorBase::checkMotion        ompl/motion_validator.cpp:17-79, :89-126
+//
+// Data layout.  Robot and scene tables live in HBM as 16-byte words (a few KB) and are staged
+// into shared memory once per CTA; every table read in the hot loops is a warp-uniform LDS.128
+// broadcast.  Per-thread link frames that a later op or the self-collision phase needs are
+// kept in a shared-memory stash laid out [slot][component][thread] (bank-conflict free).
+#pragma once
+#include "pmp_cloud.cuh"
+#include "pmp_device.cuh"
+
+namespace pmp {
+
+struct RobotDev {
+  const float4* blob;  // [ops: 4 words][groups: 2 words][spheres: 1 word][pairs: 1 word per 2 pairs]
+  int blob_words;
+  int n_ops, n_groups, n_spheres, n_pairs;
+  int off_groups, off_spheres, off_pairs;  // word offsets into blob
+  int dof, q_dim, base_type;
+  int n_slots;  // frames kept in the stash
+  float base_pose[7];
+};
+
+struct SceneDev {
+  const float4* prims;  // 6 words per primitive
+  int n_prims;
+  CloudDev cloud;
+};
+
+// shared-memory carve-up common to all kernels
+struct Smem {
+  const float4* ops;
+  const float4* groups;
+  const float4* spheres;
+  const int2* pairs;
+  const float4* prims;
+  float* stash;
+};
+
+__device__ __forceinline__ Smem stage_tables(const RobotDev& R, const SceneDev& S, float4* sm) {
+  for (int i = threadIdx.x; i < R.blob_words; i += blockDim.x) sm[i] = __ldg(R.blob + i);
+  float4* pr = sm + R.blob_words;
+  for (int i = threadIdx.x; i < S.n_prims * 6; i += blockDim.x) pr[i] = __ldg(S.prims + i);
+  __syncthreads();
+  Smem t;
+  t.ops = sm;
+  t.groups = sm + R.off_groups;
+  t.spheres = sm + R.off_spheres;
+  t.pairs = reinterpret_cast<const int2*>(sm + R.off_pairs);
+  t.prims = pr;
+  t.stash = reinterpret_cast<float*>(pr + S.n_prims * 6);
+  return t;
+}
+
+__device__ __forceinline__ void stash_put(float* stash, int slot, const Frame& f) {
+  float* p = stash + (slot * 7) * blockDim.x + threadIdx.x;
+  const int n = blockDim.x;
+  p[0] = f.qx; p[n] = f.qy; p[2 * n] = f.qz; p[3 * n] = f.qw;
+  p[4 * n] = f.tx; p[5 * n] = f.ty; p[6 * n] = f.tz;
+}
+__device__ __forceinline__ Frame stash_get(const float* stash, int slot) {
+  const float* p = stash + (slot * 7) * blockDim.x + threadIdx.x;
+  const int n = blockDim.x;
+  Frame f;
+  f.qx = p[0]; f.qy = p[n]; f.qz = p[2 * n]; f.qw = p[3 * n];
+  f.tx = p[4 * n]; f.ty = p[5 * n]; f.tz = p[6 * n];
+  return f;
+}
+
+// Reads of one configuration's coordinates.
+struct QDirect {  // q[item][j]
+  const float* q;
+  __device__ __forceinline__ float operator()(int j) const { return __ldg(q + j); }
+};
+struct QLerp {  // s1 + (s2 - s1) * t  (OMPL RealVectorStateSpace::interpolate)
+  const float* a;
+  const float* b;
+  float t;
+  __device__ __forceinline__ float operator()(int j) const {
+    const float x = __ldg(a + j), y = __ldg(b + j);
+    return x + (y - x) * t;
+  }
+};
+
+template <class QAcc>
+__device__ __forceinline__ Frame base_frame(const RobotDev& R, const QAcc& q) {
+  Frame f;
+  if (R.base_type == PMP_BASE_FIXED) {
+    f.tx = R.base_pose[0]; f.ty = R.base_pose[1]; f.tz = R.base_pose[2];
+    f.qx = R.base_pose[3]; f.qy = R.base_pose[4]; f.qz = R.base_pose[5]; f.qw = R.base_pose[6];
+  } else if (R.base_type == PMP_BASE_PLANAR) {  // primitive.hpp:52-57
+    f.tx = q(R.dof); f.ty = q(R.dof + 1); f.tz = 0.f;
+    quat_from_rpy(0.f, 0.f, q(R.dof + 2), f.qx, f.qy, f.qz, f.qw);
+  } else {  // primitive.hpp:44-51
+    f.tx = q(R.dof); f.ty = q(R.dof + 1); f.tz = q(R.dof + 2);
+    quat_from_rpy(q(R.dof + 3), q(R.dof + 4), q(R.dof + 5), f.qx, f.qy, f.qz, f.qw);
+  }
+  return f;
+}
+
+// Walk the link program; call visit(op_index, frame) after each frame is known.
+template <bool APPROX, class QAcc, class Visit>
+__device__ __forceinline__ void walk_links(const RobotDev& R, const Smem& T, const QAcc& q, Visit&& visit) {
+  const Frame base = base_frame(R, q);
+  Frame cur = base;
+  for (int i = 0; i < R.n_ops; i++) {
+    const float4 w0 = T.ops[4 * i], w1 = T.ops[4 * i + 1], w2 = T.ops[4 * i + 2];
+    const int4 w3 = *reinterpret_cast<const int4*>(&T.ops[4 * i + 3]);
+    const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
+    Frame parent = cur;
+    if (w3.x != i - 1) parent = (w3.x < 0) ? base : stash_get(T.stash, w3.w);
+    const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
+    cur = apply_op<APPROX>(parent, w0, w1, w2, kind, w3.y, qv);
+    if (w3.z >= 0) stash_put(T.stash, w3.z, cur);
+    if (!visit(i, cur)) return;
+  }
+}
+
+// ---- validity of one configuration -------------------------------------------------------------
+template <bool APPROX, class QAcc>
+__device__ bool config_is_valid(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q) {
+  bool valid = true;
+  int gi = 0;
+  float* gc_stash = T.stash + R.n_slots * 7 * blockDim.x;  // [group][3][thread]
+  const bool ext = (S.n_prims > 0) || S.cloud.enabled;
+  walk_links<APPROX>(R, T, q, [&](int op, const Frame& f) -> bool {
+    // groups are sorted by op
+    while (gi < R.n_groups) {
+      const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
+      if (gw.x != op) break;
+      const float4 g = T.groups[2 * gi];
+      const Rot rm = rotmat(f);
+      const float3 gc = xform(rm, f, g.x, g.y, g.z);
+      if (R.n_pairs > 0) {
+        float* p = gc_stash + (gi * 3) * blockDim.x + threadIdx.x;
+        p[0] = gc.x; p[blockDim.x] = gc.y; p[2 * blockDim.x] = gc.z;
+      }
+      const bool only_self = gw.w & 1;
+      if (ext && !only_self && valid) {
+        // check_ext_collision: broad phase per primitive, then the group's spheres
+        for (int base = 0; base < S.n_prims && valid; base += 32) {
+          unsigned mask = 0;
+          const int lim = min(32, S.n_prims - base);
+          for (int k = 0; k < lim; k++) {
+            const Prim P = load_prim(T.prims, base + k);
+            if (!prim_is_outside(P, gc, g.w)) mask |= 1u << k;
+          }
+          if (mask) {
+            for (int s = 0; s < gw.z && valid; s++) {
+              const float4 sp = T.spheres[gw.y + s];
+              const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
+              unsigned m = mask;
+              while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                const Prim P = load_prim(T.prims, base + k);
+                if (!prim_is_outside(P, c, sp.w)) {
+                  valid = false;
+                  break;
+                }
+              }
+            }
+          }
+        }
+        if (S.cloud.enabled && valid && !cloud_surely_outside(S.cloud, gc, g.w)) {
+          for (int s = 0; s < gw.z && valid; s++) {
+            const float4 sp = T.spheres[gw.y + s];
+            const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
+            if (!cloud_is_outside(S.cloud, c, sp.w)) valid = false;
+          }
+        }
+      }
+      gi++;
+    }
+    // keep walking while a later self-collision test could still matter for a valid item
+    return valid;
+  });
+  if (!valid) return false;
+
+  // check_self_collision (.cpp:222-254): strict <
+  for (int p = 0; p < R.n_pairs; p++) {
+    const int2 pr = T.pairs[p];
+    const float4 ga = T.groups[2 * pr.x], gb = T.groups[2 * pr.y];
+    const float* pa = gc_stash + (pr.x * 3) * blockDim.x + threadIdx.x;
+    const float* pb = gc_stash + (pr.y * 3) * blockDim.x + threadIdx.x;
+    const float dx = pa[0] - pb[0], dy = pa[blockDim.x] - pb[blockDim.x], dz = pa[2 * blockDim.x] - pb[2 * blockDim.x];
+    const float rs = ga.w + gb.w;
+    if (dx * dx + dy * dy + dz * dz > rs * rs) continue;
+    const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * pr.x + 1]);
+    const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * pr.y + 1]);
+    const Frame fa = stash_get(T.stash, wa.w >> 8), fb = stash_get(T.stash, wb.w >> 8);
+    const Rot ra = rotmat(fa), rb = rotmat(fb);
+    for (int i = 0; i < wa.z; i++) {
+      const float4 sa = T.spheres[wa.y + i];
+      const float3 ca = xform(ra, fa, sa.x, sa.y, sa.z);
+      for (int j = 0; j < wb.z; j++) {
+        const float4 sb = T.spheres[wb.y + j];
+        const float3 cb = xform(rb, fb, sb.x, sb.y, sb.z);
+        const float ex = ca.x - cb.x, ey = ca.y - cb.y, ez = ca.z - cb.z;
+        const float r2 = sa.w + sb.w;
+        if (ex * ex + ey * ey + ez * ez < r2 * r2) return false;
+      }
+    }
+  }
+  return true;
+}
+
+// ---- kernels ------------------------------------------------------------------------------------
+template <bool APPROX>
+__global__ void __launch_bounds__(128)
+k_check_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
+                uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  unsigned cnt = 0;
+  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (item < n) {
+      QDirect acc{q + item * R.q_dim};
+      ok = config_is_valid<APPROX>(R, S, T, acc);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && item < n) {
+      bits[item >> 5] = b;
+      cnt += __popc(b);
+    }
+  }
+  if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
+}
+
+// evaluate(): exact FK, min signed distances clipped at 0.1 (values only)
+__global__ void __launch_bounds__(128)
+k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
+               float* __restrict__ out) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  const float cutoff = 0.1f;  // primitive_sphere_collision.hpp:115
+  float* gc_stash = T.stash + R.n_slots * 7 * blockDim.x;
+  const bool ext = (S.n_prims > 0) || S.cloud.enabled;
+  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * blockDim.x + threadIdx.x;
+    if (item >= n) continue;
+    QDirect acc{q + item * R.q_dim};
+    float min_ext = cutoff, min_self = cutoff;
+    int gi = 0;
+    auto visit = [&](int op, const Frame& f) -> bool {
+      while (gi < R.n_groups) {
+        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
+        if (gw.x != op) break;
+        const float4 g = T.groups[2 * gi];
+        const Rot rm = rotmat(f);
+        const float3 gc = xform(rm, f, g.x, g.y, g.z);
+        if (R.n_pairs > 0) {
+          float* p = gc_stash + (gi * 3) * blockDim.x + threadIdx.x;
+          p[0] = gc.x; p[blockDim.x] = gc.y; p[2 * blockDim.x] = gc.z;
+        }
+        if (ext && !(gw.w & 1)) {
+          for (int k = 0; k < S.n_prims; k++) {
+            const Prim P = load_prim(T.prims, k);
+            // group-level cull with the cutoff margin (.cpp:272-275)
+            if (prim_is_outside(P, gc, g.w + cutoff)) continue;
+            for (int s = 0; s < gw.z; s++) {
+              const float4 sp = T.spheres[gw.y + s];
+              const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
+              // sphere-level AABB pre-test (.cpp:280-283): result-relevant for Ground only
+              if (P.type == PMP_PRIM_GROUND && (c.z < -(sp.w + cutoff) || c.z > sp.w + cutoff)) continue;
+              min_ext = fminf(min_ext, prim_evaluate(P, c) - sp.w);
+            }
+          }
+          if (S.cloud.enabled && !cloud_surely_outside(S.cloud, gc, g.w + cutoff)) {
+            for (int s = 0; s < gw.z; s++) {
+              const float4 sp = T.spheres[gw.y + s];
+              const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
+              const float rr = sp.w + cutoff;
+              if (c.x < S.cloud.lbx - rr || c.x > S.cloud.ubx + rr || c.y < S.cloud.lby - rr ||
+                  c.y > S.cloud.uby + rr || c.z < S.cloud.lbz - rr || c.z > S.cloud.ubz + rr)
+                continue;
+              float lo, hi;
+              cloud_bounds(S.cloud, c, lo, hi);
+              const float need = min_ext + sp.w + S.cloud.rho;  // only NN below this can lower the min
+              if (lo >= need) continue;
+              const float b = fminf(hi * (1.f + 1e-6f) + 1e-6f, need);
+              const float d2 = cloud_nn_within(S.cloud, c, b * b, nullptr);
+              if (d2 <= b * b) min_ext = fminf(min_ext, sqrtf(d2) - S.cloud.rho - sp.w);
+            }
+          }
+        }
+        gi++;
+      }
+      return true;
+    };
+    walk_links<false>(R, T, acc, visit);
+    for (int p = 0; p < R.n_pairs; p++) {
+      const int2 pr = T.pairs[p];
+      const float4 ga = T.groups[2 * pr.x], gb = T.groups[2 * pr.y];
+      const float* pa = gc_stash + (pr.x * 3) * blockDim.x + threadIdx.x;
+      const float* pb = gc_stash + (pr.y * 3) * blockDim.x + threadIdx.x;
+      const float dx = pa[0] - pb[0], dy = pa[blockDim.x] - pb[blockDim.x], dz = pa[2 * blockDim.x] - pb[2 * blockDim.x];
+      const float rs = ga.w + gb.w + cutoff;
+      if (dx * dx + dy * dy + dz * dz > rs * rs) continue;
+      const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * pr.x + 1]);
+      const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * pr.y + 1]);
+      const Frame fa = stash_get(T.stash, wa.w >> 8), fb = stash_get(T.stash, wb.w >> 8);
+      const Rot ra = rotmat(fa), rb = rotmat(fb);
+      for (int i = 0; i < wa.z; i++) {
+        const float4 sa = T.spheres[wa.y + i];
+        const float3 ca = xform(ra, fa, sa.x, sa.y, sa.z);
+        for (int j = 0; j < wb.z; j++) {
+          const float4 sb = T.spheres[wb.y + j];
+          const float3 cb = xform(rb, fb, sb.x, sb.y, sb.z);
+          const float ex = ca.x - cb.x, ey = ca.y - cb.y, ez = ca.z - cb.z;
+          min_self = fminf(min_self, sqrtf(ex * ex + ey * ey + ez * ez) - (sa.w + sb.w));
+        }
+      }
+    }
+    const float nanv = __int_as_float(0x7fc00000);
+    out[2 * item] = ext ? min_ext : nanv;
+    out[2 * item + 1] = (R.n_pairs > 0) ? min_self : nanv;
+  }
+}
+
+// get_all_spheres for a batch: out[item][sphere][4], caller's sphere order
+template <bool APPROX>
+__global__ void __launch_bounds__(128)
+k_fk_spheres(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
+             float4* __restrict__ out) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * blockDim.x + threadIdx.x;
+    if (item >= n) continue;
+    QDirect acc{q + item * R.q_dim};
+    int gi = 0;
+    walk_links<APPROX>(R, T, acc, [&](int op, const Frame& f) -> bool {
+      while (gi < R.n_groups) {
+        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
+        if (gw.x != op) break;
+        const Rot rm = rotmat(f);
+        for (int s = 0; s < gw.z; s++) {
+          const float4 sp = T.spheres[gw.y + s];
+          const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
+          out[item * R.n_spheres + gw.y + s] = make_float4(c.x, c.y, c.z, sp.w);
+        }
+        gi++;
+      }
+      return true;
+    });
+  }
+}
+
+// link frames for a batch: out[item][op][7] = x,y,z,qx,qy,qz,qw
+template <bool APPROX>
+__global__ void __launch_bounds__(128)
+k_fk_frames(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
+            float* __restrict__ out) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * blockDim.x + threadIdx.x;
+    if (item >= n) continue;
+    QDirect acc{q + item * R.q_dim};
+    walk_links<APPROX>(R, T, acc, [&](int op, const Frame& f) -> bool {
+      float* o = out + (item * R.n_ops + op) * 7;
+      o[0] = f.tx; o[1] = f.ty; o[2] = f.tz; o[3] = f.qx; o[4] = f.qy; o[5] = f.qz; o[6] = f.qw;
+      return true;
+    });
+  }
+}
+
+// ---- motion edges ---------------------------------------------------------------------------------
+struct ValidatorDev {
+  int type;           // PMP_VALIDATOR_*
+  double resolution;  // euclidean
+  const double* width;      // [q_dim] device
+  const double* inv_width;  // [q_dim] device (1.0 / width, motion_validator.cpp:81-87)
+  const uint8_t* seq;       // [128][128] SEQUENCE_TABLE (generate_sequence.py), device
+};
+
+// determine_step_ratio in FP64 (the waypoint count must not depend on FP32 rounding)
+__device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const float* a, const float* b, int dim) {
+  if (V.type == PMP_VALIDATOR_BOX) {  // motion_validator.cpp:89-111
+    double diff_longest = 0.0, max_diff = -INFINITY;
+    int longest = 0;
+    for (int i = 0; i < dim; i++) {
+      const double diff = (double)__ldg(b + i) - (double)__ldg(a + i);
+      const double sc = fabs(diff) * V.inv_width[i];
+      if (sc > max_diff) {
+        max_diff = sc;
+        longest = i;
+        diff_longest = diff;
+      }
+    }
+    if (fabs(diff_longest) < 1e-6) return INFINITY;
+    return V.width[longest] / fabs(diff_longest);
+  }
+  double d2 = 0.0;  // motion_validator.cpp:113-126
+  for (int i = 0; i < dim; i++) {
+    const double d = (double)__ldg(a + i) - (double)__ldg(b + i);
+    d2 += d * d;
+  }
+  return V.resolution / sqrt(d2);
+}
+
+// LPE lanes cooperate on one edge; each round they test LPE waypoints in the reference's
+// visiting order (coarse to fine) and the edge retires as soon as one is invalid.
+template <bool APPROX, int LPE>
+__global__ void __launch_bounds__(128)
+k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const float* __restrict__ q0,
+              const float* __restrict__ q1, const long long n, uint32_t* __restrict__ bits,
+              unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ n_checked) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  constexpr int EPW = 32 / LPE;  // edges per warp
+  const int lane = threadIdx.x & 31, sub = lane % LPE, slot = lane / LPE;
+  const unsigned sub_mask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (slot * LPE));
+  const int warps_per_block = blockDim.x >> 5;
+  const long long n_groups32 = (n + 31) / 32;  // one output word per 32 edges
+  unsigned cnt_valid = 0;
+  unsigned long long cnt_checked = 0;
+  for (long long wg = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wg < n_groups32;
+       wg += (long long)gridDim.x * warps_per_block) {
+    unsigned word = 0;
+    for (int pass = 0; pass < LPE; pass++) {  // 32 edges per word, EPW at a time
+      const long long e = wg * 32 + pass * EPW + slot;
+      const bool have = e < n;
+      const float* a = q0 + e * R.q_dim;
+      const float* b = q1 + e * R.q_dim;
+      double ratio = INFINITY;
+      long long n_test = 0;
+      if (have) {
+        ratio = edge_step_ratio(V, a, b, R.q_dim);
+        if (ratio != INFINITY) n_test = (long long)floor(1.0 / ratio) + 2;  // motion_validator.cpp:45
+      }
+      // waypoint w = 0 is s2; w = 1 .. n_test-2 are the interior points
+      const long long n_way = have ? (n_test >= 2 ? n_test - 1 : 0) : 0;
+      bool edge_ok = true;
+      long long w0 = 0;
+      while (true) {
+        const bool more = have && edge_ok && (w0 < n_way);
+        if (!__any_sync(0xffffffffu, more)) break;
+        bool bad = false;
+        const long long w = w0 + sub;
+        if (more && w < n_way) {
+          float t;
+          if (w == 0) {
+            t = 1.f;
+          } else if (n_test < 129) {
+            t = (float)((double)V.seq[(n_test - 1) * 128 + (w + 1)] * ratio);  // sequence[i], i = w+1
+          } else {
+            t = (float)((double)w * ratio);
+          }
+          bool ok;
+          if (w == 0) {
+            QDirect acc{b};
+            ok = config_is_valid<APPROX>(R, S, T, acc);
+          } else {
+            QLerp acc{a, b, t};
+            ok = config_is_valid<APPROX>(R, S, T, acc);
+          }
+          bad = !ok;
+          cnt_checked++;
+        }
+        const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+        if (badmask & sub_mask) edge_ok = false;
+        w0 += LPE;
+      }
+      const unsigned okmask = __ballot_sync(0xffffffffu, have && edge_ok && sub == 0);
+      // lanes with sub == 0 sit at bit positions slot*LPE; compact them to pass*EPW + slot
+      for (int s2 = 0; s2 < EPW; s2++)
+        if (okmask & (1u << (s2 * LPE))) word |= 1u << (pass * EPW + s2);
+    }
+    if (lane == 0) {
+      bits[wg] = word;
+      cnt_valid += __popc(word);
+    }
+  }
+  if (n_valid && cnt_valid) atomicAdd(n_valid, (unsigned long long)cnt_valid);
+  if (n_checked) {
+    for (int off = 16; off; off >>= 1) cnt_checked += __shfl_down_sync(0xffffffffu, cnt_checked, off);
+    if (lane == 0 && cnt_checked) atomicAdd(n_checked, cnt_checked);
+  }
+}
+
+// ---- psdf / kdtree surface ------------------------------------------------------------------------
+__global__ void k_sdf_evaluate(const SceneDev S, const float* __restrict__ pts, const long long n,
+                               float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float3 p = make3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    float v = 3.402823466e+38f;  // UnionSDF::evaluate starts from numeric_limits::max()
+    for (int k = 0; k < S.n_prims; k++) v = fminf(v, prim_evaluate(load_prim(S.prims, k), p));
+    if (S.cloud.enabled) v = fminf(v, sqrtf(cloud_nn_exact(S.cloud, p, nullptr)) - S.cloud.rho);
+    out[i] = v;
+  }
+}
+
+// UnionSDF::is_outside / PrimitiveSDF::is_outside — NO AABB pre-test here (the binding calls
+// is_outside directly, bindings/primitive.cpp:52), so Ground uses the plain plane test.
+__global__ void k_sdf_is_outside(const SceneDev S, const float* __restrict__ pts, const float* __restrict__ radii,
+                                 const long long n, uint8_t* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float3 p = make3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    const float r = radii ? radii[i] : 0.f;
+    bool outside = true;
+    for (int k = 0; k < S.n_prims && outside; k++) {
+      const Prim P = load_prim(S.prims, k);
+      if (P.type == PMP_PRIM_GROUND)
+        outside = (p.z + P.p1.w > r);
+      else
+        outside = prim_is_outside(P, p, r);
+    }
+    if (outside && S.cloud.enabled) {
+      // CloudSDF::is_outside(p, r) = evaluate(p) > r, no AABB
+      const float d = r + S.cloud.rho;
+      float lo, hi;
+      cloud_bounds(S.cloud, p, lo, hi);
+      if (lo > d + 1e-5f) outside = true;
+      else if (hi < d - 1e-5f) outside = false;
+      else if (d < 0.f) outside = true;
+      else outside = !cloud_any_within(S.cloud, p, d * d);
+    }
+    out[i] = outside ? 1 : 0;
+  }
+}
+
+__global__ void k_cloud_nearest(const SceneDev S, const float* __restrict__ pts, const long long n,
+                                float* __restrict__ sqd, int* __restrict__ idx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float3 p = make3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    int bi;
+    sqd[i] = cloud_nn_exact(S.cloud, p, &bi);
+    if (idx) idx[i] = bi;
+  }
+}
+
+}  // namespace pmp

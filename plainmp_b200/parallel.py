@@ -1,0 +1,71 @@
+"""Item sharding over the GPUs of one node.
+
+The reference has no data parallelism at all (its ``ParallelSolver`` forks N processes that race
+on the same problem, src/plainmp/parallel.py:31-49).  Validity checking shards trivially:
+configurations / edges are independent, robot and scene tables are replicated (KBs; a cloud grid
+is tens of MB), and there is no exchange step inside the computation.  One process per GPU; NCCL
+is used only to gather the bit-packed validity words and to reduce counts / minimum distances.
+
+Every collective here takes the compute step as a callable so that the plumbing is testable on
+CPU with the gloo backend (tests/test_parallel_gloo.py); the product compute is
+``tables.check_configs_device``.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of ceil(n / world) items rounded up to a multiple of 32, so that packed
+    validity words never straddle ranks."""
+    per = -(-n // world)
+    per = -(-per // 32) * 32
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def shard_words(n: int, world: int) -> int:
+    per = -(-n // world)
+    return -(-per // 32)
+
+
+def gather_validity(
+    local_words: torch.Tensor, n: int, local_count: torch.Tensor, group: Optional[dist.ProcessGroup] = None
+) -> Tuple[torch.Tensor, int]:
+    """All-gather the per-rank packed words (padded to equal length) and sum the valid counts.
+    Returns (words for all n items, total valid count) on every rank."""
+    world = dist.get_world_size(group)
+    w = shard_words(n, world)
+    padded = torch.zeros(w, dtype=local_words.dtype, device=local_words.device)
+    padded[: local_words.numel()] = local_words
+    out = torch.empty(w * world, dtype=local_words.dtype, device=local_words.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    total = local_count.clone().to(torch.int64)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return out[: (n + 31) // 32], int(total.item())
+
+
+def reduce_min(local_min: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    out = local_min.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.MIN, group=group)
+    return out
+
+
+def check_configs_sharded(
+    compute: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
+    q_local: torch.Tensor,
+    n_global: int,
+    group: Optional[dist.ProcessGroup] = None,
+) -> Tuple[torch.Tensor, int]:
+    """``q_local`` is this rank's shard (rows shard_bounds(n_global, rank, world)).  ``compute``
+    maps it to (packed words, valid count) — on a GPU box
+    ``lambda q: tables.check_configs_device(robot, scene, q)``."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_bounds(n_global, rank, world)
+    if q_local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} expects {hi - lo} rows, got {q_local.shape[0]}")
+    words, count = compute(q_local)
+    return gather_validity(words, n_global, count, group)

@@ -1,0 +1,189 @@
+"""Robot specs for the collision path (reference: src/plainmp/robot_spec.py:93-162,263-325,
+345-492 — only the parts that build the kinematic model and the collision constraint).
+
+The sphere / pair / anchor tables are the reference's own data, imported into
+``data/conf/*.json`` by ``tools/import_reference_conf.py``.  The panda / fetch / pr2 URDFs are
+not in the reference tree (scikit-robot downloads them at run time); ``data/urdf/*.urdf`` are
+kinematic skeletons authored by this repo from the public robot descriptions.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .constraint import SphereAttachmentSpec, SphereCollisionCst
+from .kinematics import BaseType, KinematicModel
+from .psdf import BoxSDF, CylinderSDF, Pose, SDFBase, SphereSDF, UnionSDF
+
+DATA_DIR = Path(__file__).resolve().parent / "data"
+
+
+def rpy_matrix(yaw: float, pitch: float, roll: float) -> np.ndarray:
+    """Rz(yaw) @ Ry(pitch) @ Rx(roll) — the convention of skrobot.coordinates.math.rpy_matrix,
+    which robot_spec.py:287 calls as rpy_matrix(yaw, pitch, roll)."""
+    cz, sz = np.cos(yaw), np.sin(yaw)
+    cy, sy = np.cos(pitch), np.sin(pitch)
+    cx, sx = np.cos(roll), np.sin(roll)
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]])
+    ry = np.array([[cy, 0, sy], [0, 1.0, 0], [-sy, 0, cy]])
+    rx = np.array([[1.0, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    return rz @ ry @ rx
+
+
+class RobotSpec:
+    conf_name: str = ""
+    urdf_name: str = ""
+
+    def __init__(self, base_type: BaseType = BaseType.FIXED):
+        with open(DATA_DIR / "conf" / f"{self.conf_name}.json") as f:
+            self.conf_dict = json.load(f)
+        self.base_type = BaseType(base_type)
+        self._kin: Optional[KinematicModel] = None
+        self._csts: Dict[bool, SphereCollisionCst] = {}
+
+    @property
+    def urdf_path(self) -> Path:
+        return DATA_DIR / "urdf" / f"{self.urdf_name}.urdf"
+
+    def get_kin(self) -> KinematicModel:
+        # one shared kinematic model per spec (robot_spec.py:132-162)
+        if self._kin is None:
+            self._kin = KinematicModel(self.urdf_path.read_text())
+            for name, d in self.conf_dict.get("custom_links", {}).items():
+                try:
+                    self._kin.get_link_ids([name])
+                except ValueError:
+                    self._kin.add_new_link(name, d["parent_link"], np.array(d["position"]), np.array(d["rpy"]), True)
+        return self._kin
+
+    @property
+    def control_joint_names(self) -> List[str]:
+        return self.conf_dict["control_joint_names"]
+
+    def reflect_joint_positions(self, table: Dict[str, float]) -> None:
+        """robot_spec.py:164-175: set non-controlled joints on the shared model."""
+        kin = self.get_kin()
+        kin.set_joint_positions(kin.get_joint_ids(list(table.keys())), list(table.values()))
+
+    def angle_bounds(self) -> Tuple[np.ndarray, np.ndarray]:
+        """URDF limits with +-inf clipped to +-2 pi (robot_spec.py:301-325)."""
+        kin = self.get_kin()
+        limits = kin.get_joint_position_limits(kin.get_joint_ids(self.control_joint_names))
+        lb = np.array([l[0] for l in limits])
+        ub = np.array([l[1] for l in limits])
+        lb[lb == -np.inf] = -np.pi * 2
+        ub[ub == np.inf] = np.pi * 2
+        return lb, ub
+
+    def self_body_collision_primitives(self) -> List[SDFBase]:
+        """Anchor primitives as psdf objects (robot_spec.py:263-299 + utils.py:25-57)."""
+        out: List[SDFBase] = []
+        for d in self.conf_dict.get("self_body_collision_primitives", []):
+            roll, pitch, yaw = d["rotation"]
+            pose = Pose(np.array(d["position"], dtype=np.float64), rpy_matrix(yaw, pitch, roll))
+            if d["type"] == "box":
+                out.append(BoxSDF(d["extents"], pose))
+            elif d["type"] == "sphere":
+                out.append(SphereSDF(d["radius"], pose))
+            elif d["type"] == "cylinder":
+                out.append(CylinderSDF(d["radius"], d["height"], pose))
+            else:
+                raise ValueError("Invalid primitive type")
+        if self.base_type != BaseType.FIXED and out:
+            raise ValueError("self_body_collision_primitives are only used for the fixed base robot.")
+        return out
+
+    def parse_sphere_specs(self) -> List[SphereAttachmentSpec]:
+        """robot_spec.py:345-382."""
+        only_self = set(self.conf_dict.get("only_self_collision_links", []))
+        specs = []
+        for link, spheres in self.conf_dict["collision_spheres"].items():
+            arr = np.array(spheres, dtype=np.float64)
+            flag = (link in only_self) if self.base_type == BaseType.FIXED else False
+            specs.append(SphereAttachmentSpec(link, arr[:, :3].T, arr[:, 3], flag))
+        return specs
+
+    def get_self_collision_pairs(self) -> List[List[str]]:
+        return [list(p) for p in self.conf_dict.get("self_collision_pairs", [])]
+
+    def create_collision_const(
+        self,
+        self_collision: bool = True,
+        attachments: Sequence[SphereAttachmentSpec] = tuple(),
+        use_cache: bool = True,
+        reorder_spheres: bool = True,
+    ) -> SphereCollisionCst:
+        """robot_spec.py:413-492."""
+        if not attachments and use_cache and self_collision in self._csts:
+            return self._csts[self_collision]
+        specs = self.parse_sphere_specs()
+        for att in attachments:
+            for spec in specs:
+                if spec.parent_link_name == att.parent_link_name:
+                    spec.relative_positions = np.hstack([spec.relative_positions, att.relative_positions])
+                    spec.radii = np.hstack([spec.radii, att.radii])
+                    break
+            else:
+                specs.append(att)
+        pairs: List[List[str]] = []
+        anchor = None
+        if self_collision:
+            pairs = self.get_self_collision_pairs()
+            prims = self.self_body_collision_primitives()
+            if prims:
+                anchor = UnionSDF(prims)
+        cst = SphereCollisionCst(
+            self.get_kin(), self.control_joint_names, self.base_type, specs, [tuple(p) for p in pairs], anchor, reorder_spheres
+        )
+        if use_cache and not attachments:
+            self._csts[self_collision] = cst
+        return cst
+
+
+class PandaSpec(RobotSpec):
+    conf_name = "panda"
+    urdf_name = "panda"
+
+
+class FetchSpec(RobotSpec):
+    conf_name = "fetch"
+    urdf_name = "fetch"
+
+    def q_default(self) -> np.ndarray:
+        d = self.conf_dict["default_joint_positions"]
+        return np.array([d[n] for n in self.control_joint_names])
+
+
+class PR2DualarmSpec(RobotSpec):
+    conf_name = "pr2_dualarm"
+    urdf_name = "pr2"
+
+    def reflect_default_joint_positions(self) -> None:
+        """example/pr2_dualarm_ik_and_plan.py:27-29: non-controlled joints at the aux.yaml values."""
+        self.reflect_joint_positions(self.conf_dict["default_joint_positions"])
+
+
+class PR2RarmSpec(PR2DualarmSpec):
+    conf_name = "pr2_rarm"
+
+
+class PR2LarmSpec(PR2DualarmSpec):
+    conf_name = "pr2_larm"
+
+
+class OpenArmV10DualSpec(RobotSpec):
+    conf_name = "openarm_v10_dual"
+    urdf_name = "openarm_v10"
+
+
+class OpenArmV10RarmSpec(RobotSpec):
+    conf_name = "openarm_v10_rarm"
+    urdf_name = "openarm_v10"
+
+
+class OpenArmV10LarmSpec(RobotSpec):
+    conf_name = "openarm_v10_larm"
+    urdf_name = "openarm_v10"

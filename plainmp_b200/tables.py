@@ -1,0 +1,454 @@
+"""Flattening of the host objects into the packed tables the C ABI takes, and the thin device
+plumbing (torch tensors as device buffers, ``data_ptr`` into ctypes).
+
+Reference counterparts of what is flattened here (setup-time code, runs once per robot/scene):
+  SphereCollisionCst ctor            cpp/plainmp/constraints/primitive_sphere_collision.cpp:117-179
+  set_all_sdfs / set_all_sdfs_inner  .cpp:426-448
+  KinematicModel tables              cpp/plainmp/kinematics/kinematics.cpp:29-181
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from .kinematics import J_CONTINUOUS, J_FIXED, J_NONE, J_PRISMATIC, J_REVOLUTE, BaseType, KinematicModel
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _device():
+    _capi.require_cuda()
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _capi.PmpError("torch reports no CUDA device; plainmp_b200 has no CPU fallback")
+    idx = torch.cuda.current_device()
+    _capi.check(_capi.load().pmp_set_device(idx))
+    return torch.device("cuda", idx)
+
+
+def _stream_ptr() -> int:
+    return _torch().cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------
+# robot
+# ---------------------------------------------------------------------------------------------
+class LinkProgram:
+    """The ancestor-closed, topologically ordered list of link ops for a set of needed links."""
+
+    def __init__(
+        self,
+        kin: KinematicModel,
+        control_joint_ids: Sequence[int],
+        needed_links: Sequence[int],
+    ):
+        links = kin.links
+        needed = set()
+        for lid in needed_links:
+            while lid >= 0 and lid not in needed:
+                needed.add(lid)
+                lid = links[lid].parent
+        root = next(i for i, L in enumerate(links) if L.parent < 0)
+        needed.add(root)
+        children: Dict[int, List[int]] = {i: [] for i in needed}
+        for i in sorted(needed):
+            if links[i].parent >= 0:
+                children[links[i].parent].append(i)
+        # depth-first so that chains stay adjacent (parent == index - 1)
+        order: List[int] = []
+        stack = [root]
+        while stack:
+            i = stack.pop()
+            order.append(i)
+            stack.extend(reversed(children[i]))
+        self.link_of_op = order
+        self.op_of_link = {lid: k for k, lid in enumerate(order)}
+        q_index_of_joint = {jid: k for k, jid in enumerate(control_joint_ids)}
+        all_ident = kin.all_joint_orientation_identity
+        ops = np.zeros(len(order), dtype=_capi.LINK_OP_DTYPE)
+        for k, lid in enumerate(order):
+            L = links[lid]
+            if not L.consider_rotation:
+                raise NotImplementedError(
+                    f"link {L.name}: consider_rotation=False links cannot carry spheres or children on the CUDA path"
+                )
+            op = ops[k]
+            op["parent"] = -1 if L.parent < 0 else self.op_of_link[L.parent]
+            op["q_index"] = -1
+            if L.kind == J_NONE:
+                # the root: frame = base pose (identity-flagged product is skipped, exact)
+                op["origin_quat"] = (0, 0, 0, 1)
+                op["kind"] = _capi.OP_FIXED
+                op["flags"] = _capi.OPFLAG_ORIGIN_IDENTITY
+            elif L.joint_id >= 0 and L.joint_id in q_index_of_joint:
+                op["origin_quat"] = L.origin_quat
+                op["origin_xyz"] = L.origin_xyz
+                op["axis"] = L.axis
+                op["q_index"] = q_index_of_joint[L.joint_id]
+                if L.kind == J_PRISMATIC:
+                    op["kind"] = _capi.OP_PRISMATIC
+                else:
+                    op["kind"] = _capi.OP_REVOLUTE
+                    # algorithm.cpp:140-147
+                    if all_ident or abs(L.origin_quat[3] - 1.0) < 1e-6:
+                        op["flags"] = _capi.OPFLAG_ORIGIN_IDENTITY
+            else:
+                # fixed joint, or a movable joint that is not controlled: bake its current
+                # local transform
+                quat, trans, ident = kin.local_transform(lid)
+                op["origin_quat"] = quat
+                op["origin_xyz"] = trans
+                op["kind"] = _capi.OP_FIXED
+                op["flags"] = _capi.OPFLAG_ORIGIN_IDENTITY if ident else 0
+        self.ops = ops
+
+
+class RobotTable:
+    """Device-resident robot tables (``pmp_robot_t``)."""
+
+    def __init__(
+        self,
+        kin: KinematicModel,
+        control_joint_ids: Sequence[int],
+        base_type: BaseType,
+        group_links: Sequence[int],
+        group_spheres: Sequence[np.ndarray],  # each (n_i, 4): x, y, z, r in the link frame
+        group_only_self: Sequence[bool],
+        pairs: Sequence[Tuple[int, int]],
+        extra_links: Sequence[int] = (),
+    ):
+        self.program = LinkProgram(kin, control_joint_ids, list(group_links) + list(extra_links))
+        n_groups = len(group_links)
+        groups = np.zeros(n_groups, dtype=_capi.GROUP_DTYPE)
+        flat: List[np.ndarray] = []
+        begin = 0
+        for g in range(n_groups):
+            sp = np.asarray(group_spheres[g], dtype=np.float64).reshape(-1, 4)
+            centre, radius = group_bounding_sphere(sp)
+            groups[g]["center"] = centre
+            groups[g]["radius"] = radius
+            groups[g]["op"] = self.program.op_of_link[group_links[g]]
+            groups[g]["sphere_begin"] = begin
+            groups[g]["sphere_count"] = sp.shape[0]
+            groups[g]["only_self_collision"] = 1 if group_only_self[g] else 0
+            begin += sp.shape[0]
+            flat.append(sp)
+        self.groups = groups
+        self.spheres = (
+            np.ascontiguousarray(np.concatenate(flat, axis=0), dtype=np.float32)
+            if flat
+            else np.zeros((0, 4), dtype=np.float32)
+        )
+        self.pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        self.dof = len(control_joint_ids)
+        self.base_type = BaseType(base_type)
+        self.q_dim = self.dof + (3 if base_type == BaseType.PLANAR else 0) + (6 if base_type == BaseType.FLOATING else 0)
+        self.n_spheres = int(self.spheres.shape[0])
+        self.n_ops = int(self.program.ops.shape[0])
+        self.base_pose = np.asarray(kin.get_base_pose(), dtype=np.float32)
+
+        lib = _capi.load()
+        desc = _capi.RobotDesc()
+        desc.dof = self.dof
+        desc.base_type = int(self.base_type)
+        for i in range(7):
+            desc.base_pose[i] = float(self.base_pose[i])
+        desc.n_ops = self.n_ops
+        desc.ops = self.program.ops.ctypes.data
+        desc.n_groups = n_groups
+        desc.groups = self.groups.ctypes.data
+        desc.n_spheres = self.n_spheres
+        desc.spheres = self.spheres.ctypes.data
+        desc.n_pairs = int(self.pairs.shape[0])
+        desc.pairs = self.pairs.ctypes.data
+        h = C.c_void_p()
+        _device()  # tables are uploaded to torch's current device
+        _capi.check(lib.pmp_robot_create(C.byref(desc), C.byref(h)))
+        self._h = h
+        self._lib = lib
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.pmp_robot_destroy(h)
+
+
+def group_bounding_sphere(sp: np.ndarray) -> Tuple[np.ndarray, float]:
+    """Group centre = mean of member centres, radius = max(|p_j - centre| + r_j)
+    (primitive_sphere_collision.cpp:130-144), float64."""
+    centre = np.zeros(3)
+    for p in sp[:, :3]:
+        centre = centre + p
+    centre = centre / sp.shape[0]
+    radius = 0.0
+    for p, r in zip(sp[:, :3], sp[:, 3]):
+        d = float(np.sqrt(((p - centre) ** 2).sum())) + float(r)
+        if d > radius:
+            radius = d
+    return centre, radius
+
+
+def link_pose_via_cuda(kin: KinematicModel, link_name: str) -> np.ndarray:
+    """debug_get_link_pose: every joint baked at its stored angle, one FK on the device."""
+    lid = kin.get_link_ids([link_name])[0]
+    table = RobotTable(kin, [], BaseType.FIXED, [], [], [], [], extra_links=[lid])
+    frames = fk_frames(table, np.zeros((1, 0), dtype=np.float32), accurate=True)
+    return frames[0, table.program.op_of_link[lid]].astype(np.float64)
+
+
+# ---------------------------------------------------------------------------------------------
+# scene
+# ---------------------------------------------------------------------------------------------
+def flatten_primitives(leaves) -> Tuple[np.ndarray, Optional[object]]:
+    """[anchor primitives..., user primitives...] -> pmp_prim_t array (+ the CloudSDF if any)."""
+    from . import psdf
+
+    prims = []
+    cloud = None
+    for leaf in leaves:
+        t = leaf.get_type()
+        if t == psdf.T_CLOUD:
+            if cloud is not None:
+                raise NotImplementedError("at most one CloudSDF per scene is supported on the CUDA path")
+            cloud = leaf
+            continue
+        rec = np.zeros((), dtype=_capi.PRIM_DTYPE)
+        rec["lb"] = np.maximum(leaf._lb, -3.0e38)
+        rec["ub"] = np.minimum(leaf._ub, 3.0e38)
+        if t == psdf.T_GROUND:
+            rec["type"] = _capi.PRIM_GROUND
+            rec["param0"] = leaf.height
+            rec["rot_col0"], rec["rot_col1"], rec["rot_col2"] = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+            rec["flags"] = _capi.PRIMFLAG_AXIS_ALIGNED | _capi.PRIMFLAG_Z_ALIGNED
+        else:
+            pose = leaf._pose
+            rot = pose._rot
+            if not np.allclose(pose._rot_inv, rot.T, atol=1e-6):
+                raise ValueError("the CUDA path requires an orthonormal primitive rotation")
+            flags = (_capi.PRIMFLAG_AXIS_ALIGNED if pose.axis_aligned else 0) | (
+                _capi.PRIMFLAG_Z_ALIGNED if pose.z_axis_aligned else 0
+            )
+            cols = rot.copy()
+            if pose.axis_aligned:
+                cols = np.eye(3)  # the reference skips the rotation entirely (primitive_sdf.hpp:328-340)
+            rec["position"] = pose._position
+            rec["flags"] = flags
+            if t == psdf.T_BOX:
+                rec["type"] = _capi.PRIM_BOX
+                hw = 0.5 * leaf._width
+                rec["param0"], rec["param1"], rec["param2"] = hw
+            elif t == psdf.T_CYLINDER:
+                rec["type"] = _capi.PRIM_CYLINDER
+                rec["param0"] = leaf.radius
+                rec["param1"] = 0.5 * leaf.height
+                if pose.z_axis_aligned:
+                    cols = np.eye(3)  # world axes for all three coordinates (primitive_sdf.hpp:446-449,466-472)
+            elif t == psdf.T_SPHERE:
+                rec["type"] = _capi.PRIM_SPHERE
+                rec["param0"] = leaf.radius
+            else:
+                raise ValueError(f"unsupported SDF type {t}")
+            rec["rot_col0"], rec["rot_col1"], rec["rot_col2"] = cols[:, 0], cols[:, 1], cols[:, 2]
+        prims.append(rec)
+    arr = np.array(prims, dtype=_capi.PRIM_DTYPE) if prims else np.zeros(0, dtype=_capi.PRIM_DTYPE)
+    return arr, cloud
+
+
+class SceneTable:
+    """Device-resident scene (``pmp_scene_t``): flattened primitive list + optional cloud grid."""
+
+    def __init__(self, leaves, cloud_cell: float = 0.0):
+        self.prims, cloud = flatten_primitives(leaves)
+        self.n_prims = int(self.prims.shape[0])
+        self.has_cloud = cloud is not None
+        lib = _capi.load()
+        desc = _capi.SceneDesc()
+        desc.n_prims = self.n_prims
+        desc.prims = self.prims.ctypes.data if self.n_prims else None
+        self._cloud_pts = None
+        if cloud is not None:
+            self._cloud_pts = np.ascontiguousarray(cloud.points, dtype=np.float32)
+            desc.n_cloud_points = self._cloud_pts.shape[0]
+            desc.cloud_points = self._cloud_pts.ctypes.data
+            desc.cloud_radius = cloud.radius
+            desc.cloud_cell = cloud_cell
+        h = C.c_void_p()
+        _device()
+        _capi.check(lib.pmp_scene_create(C.byref(desc), C.byref(h)))
+        self._h = h
+        self._lib = lib
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.pmp_scene_destroy(h)
+
+    # -- psdf surface --
+    def evaluate(self, points_nx3: np.ndarray) -> np.ndarray:
+        torch = _torch()
+        dev = _device()
+        p = torch.from_numpy(np.ascontiguousarray(points_nx3, dtype=np.float32)).to(dev)
+        out = torch.empty(p.shape[0], dtype=torch.float32, device=dev)
+        _capi.check(self._lib.pmp_sdf_evaluate(self._h, p.data_ptr(), p.shape[0], out.data_ptr(), _stream_ptr()))
+        return out.cpu().numpy().astype(np.float64)
+
+    def is_outside(self, points_nx3: np.ndarray, radii: np.ndarray) -> np.ndarray:
+        torch = _torch()
+        dev = _device()
+        p = torch.from_numpy(np.ascontiguousarray(points_nx3, dtype=np.float32)).to(dev)
+        r = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(radii, (p.shape[0],)), dtype=np.float32)).to(dev)
+        out = torch.empty(p.shape[0], dtype=torch.uint8, device=dev)
+        _capi.check(
+            self._lib.pmp_sdf_is_outside(self._h, p.data_ptr(), r.data_ptr(), p.shape[0], out.data_ptr(), _stream_ptr())
+        )
+        return out.cpu().numpy().astype(bool)
+
+    def cloud_nearest(self, points_nx3: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        torch = _torch()
+        dev = _device()
+        p = torch.from_numpy(np.ascontiguousarray(points_nx3, dtype=np.float32)).to(dev)
+        sq = torch.empty(p.shape[0], dtype=torch.float32, device=dev)
+        idx = torch.empty(p.shape[0], dtype=torch.int32, device=dev)
+        _capi.check(
+            self._lib.pmp_cloud_nearest(self._h, p.data_ptr(), p.shape[0], sq.data_ptr(), idx.data_ptr(), _stream_ptr())
+        )
+        return sq.cpu().numpy().astype(np.float64), idx.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# device calls on resident buffers
+# ---------------------------------------------------------------------------------------------
+def _as_q(table: RobotTable, q) -> "object":
+    """q as a contiguous float32 CUDA tensor [n, q_dim] (numpy or torch in)."""
+    torch = _torch()
+    dev = _device()
+    if isinstance(q, torch.Tensor):
+        t = q
+        if t.device.type != "cuda":
+            t = t.to(dev)
+        t = t.to(torch.float32).contiguous()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(dev)
+    if t.ndim != 2 or t.shape[1] != table.q_dim:
+        raise ValueError(f"q must have shape [n, {table.q_dim}], got {tuple(t.shape)}")
+    return t
+
+
+def check_configs_device(table: RobotTable, scene: Optional[SceneTable], q_dev, bits_dev=None, count_dev=None):
+    """Stream-ordered launch on caller-resident tensors; returns (bits tensor, count tensor)."""
+    torch = _torch()
+    n = q_dev.shape[0]
+    if bits_dev is None:
+        bits_dev = torch.empty((n + 31) // 32, dtype=torch.int32, device=q_dev.device)
+    if count_dev is None:
+        count_dev = torch.zeros(1, dtype=torch.int64, device=q_dev.device)
+    _capi.check(
+        table._lib.pmp_check_configs(
+            table.handle,
+            scene.handle if scene is not None else None,
+            q_dev.data_ptr(),
+            n,
+            bits_dev.data_ptr(),
+            count_dev.data_ptr(),
+            _stream_ptr(),
+        )
+    )
+    return bits_dev, count_dev
+
+
+def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
+    w = np.ascontiguousarray(words).view(np.uint32)
+    return np.unpackbits(w.view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+def check_configs(table: RobotTable, scene: Optional[SceneTable], q) -> np.ndarray:
+    qd = _as_q(table, q)
+    bits, _ = check_configs_device(table, scene, qd)
+    return unpack_bits(bits.cpu().numpy(), qd.shape[0])
+
+
+def eval_configs(table: RobotTable, scene: Optional[SceneTable], q) -> np.ndarray:
+    torch = _torch()
+    qd = _as_q(table, q)
+    out = torch.empty((qd.shape[0], 2), dtype=torch.float32, device=qd.device)
+    _capi.check(
+        table._lib.pmp_eval_configs(
+            table.handle, scene.handle if scene is not None else None, qd.data_ptr(), qd.shape[0], out.data_ptr(), _stream_ptr()
+        )
+    )
+    return out.cpu().numpy().astype(np.float64)
+
+
+def fk_spheres(table: RobotTable, q, accurate: bool) -> np.ndarray:
+    torch = _torch()
+    qd = _as_q(table, q)
+    out = torch.empty((qd.shape[0], table.n_spheres, 4), dtype=torch.float32, device=qd.device)
+    _capi.check(
+        table._lib.pmp_fk_spheres(table.handle, qd.data_ptr(), qd.shape[0], 1 if accurate else 0, out.data_ptr(), _stream_ptr())
+    )
+    return out.cpu().numpy()
+
+
+def fk_frames(table: RobotTable, q, accurate: bool) -> np.ndarray:
+    torch = _torch()
+    qd = _as_q(table, q)
+    out = torch.empty((qd.shape[0], table.n_ops, 7), dtype=torch.float32, device=qd.device)
+    _capi.check(
+        table._lib.pmp_fk_frames(table.handle, qd.data_ptr(), qd.shape[0], 1 if accurate else 0, out.data_ptr(), _stream_ptr())
+    )
+    return out.cpu().numpy()
+
+
+def make_validator(vtype: int, dim: int, box_width: Optional[Sequence[float]], resolution: float):
+    v = _capi.Validator()
+    v.type = vtype
+    v.dim = dim
+    keep = None
+    if box_width is not None:
+        keep = np.ascontiguousarray(box_width, dtype=np.float64)
+        v.box_width = keep.ctypes.data
+    v.resolution = float(resolution)
+    return v, keep
+
+
+def check_edges(table: RobotTable, scene: Optional[SceneTable], validator, q0, q1):
+    """Returns (valid bool[n], n_waypoint_checks)."""
+    torch = _torch()
+    a = _as_q(table, q0)
+    b = _as_q(table, q1)
+    if a.shape != b.shape:
+        raise ValueError("q0 and q1 must have the same shape")
+    n = a.shape[0]
+    bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=a.device)
+    counters = torch.zeros(2, dtype=torch.int64, device=a.device)
+    _capi.check(
+        table._lib.pmp_check_edges(
+            table.handle,
+            scene.handle if scene is not None else None,
+            C.byref(validator),
+            a.data_ptr(),
+            b.data_ptr(),
+            n,
+            bits.data_ptr(),
+            counters.data_ptr(),
+            counters.data_ptr() + 8,
+            _stream_ptr(),
+        )
+    )
+    c = counters.cpu().numpy()
+    return unpack_bits(bits.cpu().numpy(), n), int(c[1])

@@ -1,0 +1,109 @@
+"""The BASELINE.json workloads: robots, scenes and seeded inputs shared by the
+tests, bench.py and smoke().  Scene definitions follow the reference's bench scripts:
+example/bench/panda_plan.py:19-34, example/bench/fetch_plan.py:14-19, example/fetch_plan.py:24-30.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import psdf
+from .kinematics import BaseType
+from .robot_spec import FetchSpec, OpenArmV10DualSpec, PandaSpec, PR2DualarmSpec, PR2RarmSpec
+
+
+def panda_dual_bars_sdf(ceiled: bool = False) -> psdf.UnionSDF:
+    height = 1.0
+    prims = [
+        psdf.BoxSDF([2.0, 2.0, 0.05], psdf.Pose([0.0, 0.0, -0.05])),
+        psdf.CylinderSDF(0.05, height, psdf.Pose([0.3, 0.3, 0.5 * height])),
+        psdf.CylinderSDF(0.05, height, psdf.Pose([-0.3, -0.3, 0.5 * height])),
+    ]
+    if ceiled:
+        prims.append(psdf.BoxSDF([2.0, 2.0, 0.05], psdf.Pose([0.0, 0.0, height])))
+    return psdf.UnionSDF(prims)
+
+
+def fetch_table_sdf() -> psdf.UnionSDF:
+    table = psdf.BoxSDF([1.0, 2.0, 0.05], psdf.Pose([0.95, 0.0, 0.8]))
+    return psdf.UnionSDF([table, psdf.GroundSDF(0.0)])
+
+
+def table_cloud(n_points: int, seed: int = 4) -> np.ndarray:
+    """Synthetic depth-camera-like cloud for config 4: half of the points sample the top slab of
+    a 1 x 2 x 0.05 table centred at (0.8, 0, 0.8) (as example/fetch_plan.py:24-30 samples its
+    table), the other half sample a dozen box-shaped objects standing on it.  (The SURVEY's
+    'uniform clutter in the whole workspace' variant makes every configuration collide at these
+    densities, which would turn the workload into pure early-exit.)"""
+    rng = np.random.default_rng(seed)
+    n_slab = n_points // 2
+    slab = rng.uniform([0.3, -1.0, 0.775], [1.3, 1.0, 0.825], size=(n_slab, 3))
+    n_obj = 12
+    centres = rng.uniform([0.45, -0.85, 0.0], [1.15, 0.85, 0.0], size=(n_obj, 3))
+    sizes = rng.uniform([0.06, 0.06, 0.08], [0.2, 0.2, 0.35], size=(n_obj, 3))
+    which = rng.integers(0, n_obj, size=n_points - n_slab)
+    u = rng.uniform(-0.5, 0.5, size=(n_points - n_slab, 3))
+    obj = centres[which] + u * sizes[which]
+    obj[:, 2] = 0.825 + (u[:, 2] + 0.5) * sizes[which, 2]
+    return np.concatenate([slab, obj], axis=0).astype(np.float32).astype(np.float64)
+
+
+def make_panda(ceiled: bool = False, self_collision: bool = True):
+    spec = PandaSpec()
+    cst = spec.create_collision_const(self_collision=self_collision, use_cache=False)
+    cst.set_sdf(panda_dual_bars_sdf(ceiled))
+    return spec, cst
+
+
+def make_fetch():
+    spec = FetchSpec()
+    cst = spec.create_collision_const(use_cache=False)
+    cst.set_sdf(fetch_table_sdf())
+    return spec, cst
+
+
+def make_pr2_cloud(n_points: int, seed: int = 4):
+    spec = PR2DualarmSpec()
+    spec.reflect_default_joint_positions()
+    cst = spec.create_collision_const(use_cache=False)
+    cst.set_sdf(psdf.CloudSDF(table_cloud(n_points, seed), 0.002))
+    return spec, cst
+
+
+def make_openarm():
+    spec = OpenArmV10DualSpec()
+    cst = spec.create_collision_const(use_cache=False)
+    cst.set_sdf(psdf.UnionSDF([psdf.BoxSDF([0.6, 1.2, 0.05], psdf.Pose([0.45, 0.0, 0.55])), psdf.GroundSDF(0.0)]))
+    return spec, cst
+
+
+def random_configs(spec, n: int, seed: int) -> np.ndarray:
+    """Uniform in the joint limits (angle_bounds: +-inf -> +-2 pi), rounded to float32 so that
+    the FP64 oracle and the FP32 kernels consume bit-identical inputs."""
+    lb, ub = spec.angle_bounds()
+    rng = np.random.default_rng(seed)
+    return rng.uniform(lb, ub, size=(n, lb.shape[0])).astype(np.float32)
+
+
+def random_edges(spec, n: int, seed: int, planner_like: bool, valid_fn=None):
+    """Distribution A: both endpoints uniform in the joint limits (long edges, almost all
+    invalid: the early-exit regime).  Distribution B: q1 = q0 + U(-0.5, 0.5)^dof clipped
+    (planner-like short edges); when ``valid_fn`` (q[n, dof] float32 -> bool[n]) is given, q0 is
+    rejection-sampled to be collision-free as SURVEY §8d-3 asks (checkMotion assumes s1 valid)."""
+    lb, ub = spec.angle_bounds()
+    rng = np.random.default_rng(seed)
+    dof = lb.shape[0]
+    if valid_fn is None:
+        q0 = rng.uniform(lb, ub, size=(n, dof)).astype(np.float32)
+    else:
+        chunks, have = [], 0
+        while have < n:
+            cand = rng.uniform(lb, ub, size=(max(1024, 2 * (n - have)), dof)).astype(np.float32)
+            keep = cand[np.asarray(valid_fn(cand), dtype=bool)]
+            chunks.append(keep)
+            have += keep.shape[0]
+        q0 = np.concatenate(chunks, axis=0)[:n]
+    if planner_like:
+        q1 = np.clip(q0.astype(np.float64) + rng.uniform(-0.5, 0.5, size=q0.shape), lb, ub).astype(np.float32)
+    else:
+        q1 = rng.uniform(lb, ub, size=q0.shape).astype(np.float32)
+    return q0, q1

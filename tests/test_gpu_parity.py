@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the FP64 oracle and the committed
+golden vectors, on the BASELINE.json configurations.
+
+Parity rule (BASELINE.json north_star): validity bit-exact except items whose signed distance
+lies within EPS of the contact threshold; signed distances and sphere centres within TOL.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import bridge
+from plainmp_b200 import _capi, psdf, tables, workloads
+from plainmp_b200.constraint import SphereAttachmentSpec, SphereCollisionCst
+from plainmp_b200.kdtree import KDTree
+from plainmp_b200.kinematics import BaseType
+from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorType
+from plainmp_b200.robot_spec import PandaSpec, PR2RarmSpec, rpy_matrix
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).parent / "golden"
+EPS_BAND = 1e-5  # metres: |signed distance - threshold| below which FP32 may disagree
+TOL = 1e-5       # metres: distances and sphere centres, FP32 vs FP64
+
+
+def assert_validity_parity(got, want, margin, what):
+    bad = np.where(got != want)[0]
+    out_of_band = [int(i) for i in bad if margin[i] > EPS_BAND]
+    assert not out_of_band, f"{what}: {len(out_of_band)} validity mismatches outside the {EPS_BAND} band, e.g. {out_of_band[:5]} margins {margin[out_of_band[:5]]}"
+    return len(bad)
+
+
+MAKERS = {
+    "panda_dualbars_seed1": lambda: workloads.make_panda(),
+    "fetch_table_seed2": lambda: workloads.make_fetch(),
+    "pr2_cloud20k_seed4": lambda: workloads.make_pr2_cloud(20000),
+    "openarm_dual_seed6": lambda: workloads.make_openarm(),
+}
+
+
+@pytest.mark.parametrize("name", list(MAKERS))
+def test_configs_against_golden_and_oracle(cuda_lib, name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    spec, cst = MAKERS[name]()
+    n = int(g["n"])
+    Q = workloads.random_configs(spec, n, int(g["seed"]))
+    np.testing.assert_array_equal(Q[:64], g["q_head"])
+    want = np.unpackbits(g["valid_bits"], bitorder="little")[:n].astype(bool)
+    got = cst.is_valid_batch(Q)
+    n_bad = assert_validity_parity(got, want, g["margin"], name)
+    assert n_bad <= (g["margin"] < EPS_BAND).sum()
+    # distances (exact FK), cutoff 0.1
+    dist = cst.evaluate_batch(Q)
+    np.testing.assert_allclose(dist, g["dist"], atol=TOL, rtol=0)
+    # sphere centres, both FK flavours; the device keeps the reference's re-ordered sphere order
+    k = g["spheres_exact"].shape[0]
+    np.testing.assert_allclose(cst.get_all_spheres_batch(Q[:k], accurate=True), g["spheres_exact"], atol=TOL, rtol=0)
+    np.testing.assert_allclose(cst.get_all_spheres_batch(Q[:k], accurate=False), g["spheres_approx"], atol=TOL, rtol=0)
+    # live oracle on a fresh seed as well
+    o = bridge.OracleCst(cst, n_threads=4)
+    Q2 = workloads.random_configs(spec, 4000, 1234)
+    Qd = Q2.astype(np.float64)
+    assert_validity_parity(cst.is_valid_batch(Q2), o.is_valid_batch(Qd), o.margin_batch(Qd), name + "/live")
+    np.testing.assert_allclose(cst.evaluate_batch(Q2), o.evaluate_batch(Qd), atol=TOL, rtol=0)
+
+
+def test_single_item_api_equals_batch(cuda_lib):
+    spec, cst = workloads.make_panda()
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, 40, 5)
+    m = o.margin_batch(Q.astype(np.float64))
+    for q, mi in zip(Q, m):
+        if mi < EPS_BAND:
+            continue
+        assert cst.is_valid(q) == o.is_valid(q.astype(np.float64))
+        vals, jac = cst.evaluate(q)
+        np.testing.assert_allclose(vals, o.evaluate(q.astype(np.float64)), atol=TOL)
+        assert jac.shape == (2, 7)
+    cst.update_kintree(Q[0], True)
+    sph = cst.get_all_spheres()
+    want = o.spheres_batch(Q[:1].astype(np.float64), True)[0]
+    assert len(sph) == 72
+    np.testing.assert_allclose(np.array([np.append(c, r) for c, r in sph]), want, atol=TOL)
+    grp = cst.get_group_spheres()
+    np.testing.assert_allclose(np.array([np.append(c, r) for c, r in grp]), o.group_spheres(Q[0].astype(np.float64), True), atol=TOL)
+
+
+@pytest.mark.parametrize("base_type", [BaseType.PLANAR, BaseType.FLOATING])
+@pytest.mark.parametrize("with_self", [False, True])
+def test_moving_base(cuda_lib, base_type, with_self):
+    # tests/test_constraints.py:47-53,148-162 set-up: PR2 right arm + unit box
+    spec = PR2RarmSpec(base_type=base_type)
+    cst = spec.create_collision_const(self_collision=with_self, use_cache=False)
+    cst.set_sdf(psdf.BoxSDF([1, 1, 1], psdf.Pose([0.5, 0.5, 0.5])))
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(11)
+    Q = rng.standard_normal((3000, o.q_dim))
+    Q[:, 7:] *= 0.3
+    Q = Q.astype(np.float32)
+    Qd = Q.astype(np.float64)
+    assert_validity_parity(cst.is_valid_batch(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), f"pr2 {base_type}")
+    got, want = cst.evaluate_batch(Q), o.evaluate_batch(Qd)
+    np.testing.assert_allclose(got, want, atol=TOL, rtol=0, equal_nan=True)
+    # is_valid == all(evaluate > 0) away from contact (exact FK on both sides for a moving base)
+    v = cst.is_valid_batch(Q)
+    clear = np.nanmin(np.abs(got), axis=1) > 1e-4
+    assert (v[clear] == (np.nan_to_num(got[clear], nan=1.0) > 0).all(axis=1)).all()
+
+
+def test_no_sdf_no_pairs_always_valid(cuda_lib):
+    spec = PR2RarmSpec()
+    cst = spec.create_collision_const(self_collision=False, use_cache=False)
+    Q = np.random.default_rng(0).standard_normal((100, 7)).astype(np.float32)
+    assert cst.is_valid_batch(Q).all()
+    assert np.isnan(cst.evaluate_batch(Q)).all()
+    vals, jac = cst.evaluate(Q[0])
+    assert vals.shape == (0,)
+
+
+def test_self_collision_only_and_env_only(cuda_lib):
+    spec = PandaSpec()
+    a = spec.create_collision_const(self_collision=True, use_cache=False)  # pairs, no sdf
+    b = spec.create_collision_const(self_collision=False, use_cache=False)
+    b.set_sdf(workloads.panda_dual_bars_sdf())
+    Q = workloads.random_configs(spec, 5000, 21)
+    Qd = Q.astype(np.float64)
+    for cst in (a, b):
+        o = bridge.OracleCst(cst)
+        assert_validity_parity(cst.is_valid_batch(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), "panda partial")
+        np.testing.assert_allclose(cst.evaluate_batch(Q), o.evaluate_batch(Qd), atol=TOL, rtol=0, equal_nan=True)
+
+
+def test_zero_radius_attachment_and_rotated_primitives(cuda_lib):
+    # App. B: example/attach_box_ik_and_plan.py attaches a grid of zero-radius spheres; exercises
+    # the r < 1e-6 branches and a group far larger than a warp
+    spec = PandaSpec()
+    g = np.linspace(-0.05, 0.05, 5)
+    pts = np.array([[x, y, z + 0.2] for x in g for y in g for z in g]).T
+    att = SphereAttachmentSpec("panda_link8", pts, np.zeros(pts.shape[1]), False)
+    cst = spec.create_collision_const(attachments=[att], use_cache=False, reorder_spheres=False)
+    sdf = psdf.UnionSDF(
+        [
+            psdf.BoxSDF([0.4, 0.3, 0.5], psdf.Pose([0.5, 0.1, 0.4], rpy_matrix(0.4, 0.3, -0.2))),
+            psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([-0.4, 0.3, 0.5], rpy_matrix(0.7, 0.0, 0.0))),
+            psdf.CylinderSDF(0.1, 0.6, psdf.Pose([0.1, -0.5, 0.5], rpy_matrix(0.1, 1.2, 0.5))),
+            psdf.SphereSDF(0.15, psdf.Pose([0.3, 0.4, 0.9])),
+            psdf.GroundSDF(0.02),
+        ]
+    )
+    cst.set_sdf(sdf)
+    o = bridge.OracleCst(cst, n_threads=4)
+    Q = workloads.random_configs(spec, 6000, 31)
+    Qd = Q.astype(np.float64)
+    assert_validity_parity(cst.is_valid_batch(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), "attachment")
+    np.testing.assert_allclose(cst.evaluate_batch(Q), o.evaluate_batch(Qd), atol=TOL, rtol=0)
+
+
+def test_empty_and_ragged_batches(cuda_lib):
+    spec, cst = workloads.make_panda()
+    assert cst.is_valid_batch(np.zeros((0, 7), dtype=np.float32)).shape == (0,)
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, 1000, 77)
+    ref = cst.is_valid_batch(Q)
+    for n in (1, 31, 32, 33, 127, 129, 999):
+        assert (cst.is_valid_batch(Q[:n]) == ref[:n]).all()
+    with pytest.raises(ValueError):
+        cst.is_valid_batch(np.zeros((4, 6), dtype=np.float32))
+
+
+@pytest.mark.parametrize("dist", ["A", "B"])
+def test_edges_against_golden_and_oracle(cuda_lib, dist):
+    g = np.load(GOLDEN / f"panda_ceiled_edges_{dist}_seed3.npz")
+    spec, cst = workloads.make_panda(ceiled=True)
+    o = bridge.OracleCst(cst, n_threads=4)
+    n = int(g["n"])
+    valid_fn = (lambda q: o.is_valid_batch(q.astype(np.float64))) if dist == "B" else None
+    q0, q1 = workloads.random_edges(spec, n, int(g["seed"]), dist == "B", valid_fn)
+    mv = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, list(g["widths"])))
+    got, n_checked = mv.check_motion_batch(q0, q1)
+    want = np.unpackbits(g["valid_bits"], bitorder="little")[:n].astype(bool)
+    bad = np.where(got != want)[0]
+    # an edge may differ only if one of its waypoints sits in the epsilon band
+    ov = bridge.OracleValidator(0, 7, g["widths"])
+    for e in bad:
+        a, b = q0[e].astype(np.float64), q1[e].astype(np.float64)
+        ratio = ov.step_ratio(a, b)
+        n_test = int(np.floor(1 / ratio)) + 2
+        ts = [1.0] + [m * ratio for m in range(1, n_test - 1)]
+        W = np.array([a + (b - a) * t for t in ts])
+        assert o.margin_batch(W).min() < 5 * EPS_BAND, f"edge {e} differs outside the band"
+    assert len(bad) <= 8
+    assert n_checked >= int(g["n_calls"])  # lane-parallel expansion never checks fewer than the serial early exit
+    assert mv.check_motion(q0[0], q1[0]) == bool(got[0])
+
+
+def test_edge_validator_variants(cuda_lib):
+    spec, cst = workloads.make_fetch()
+    o = bridge.OracleCst(cst, n_threads=4)
+    q0, q1 = workloads.random_edges(spec, 1500, 9, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    w = np.array([0.05, 0.05, 0.05, 0.1, 0.1, 0.1, 0.2, 0.2])  # tests/test_ompl_solver.py box widths
+    for cfg, ov in [
+        (ValidatorConfig(ValidatorType.BOX, 0.0, list(w)), bridge.OracleValidator(0, 8, w)),
+        (ValidatorConfig(ValidatorType.EUCLIDEAN, 0.03, []), bridge.OracleValidator(1, 8, None, 0.03)),
+        (ValidatorConfig(ValidatorType.BOX, 0.0, [0.002] * 8), bridge.OracleValidator(0, 8, np.full(8, 0.002))),  # n_test >= 129: naive order
+    ]:
+        mv = MotionValidator(cst, cfg)
+        got, _ = mv.check_motion_batch(q0, q1)
+        want, _ = ov.check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64), n_threads=4)
+        assert (got != want).sum() <= 6
+    # zero-length edges are valid without any check (step_ratio == inf), even from an invalid state
+    mv = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, list(w)))
+    bad_state = np.tile(np.array([[0.0, 0.0, 1.5, 0.0, 0.0, 0.0, 0.0, 0.0]], dtype=np.float32), (5, 1))
+    got, n_checked = mv.check_motion_batch(bad_state, bad_state)
+    assert got.all() and n_checked == 0
+    with pytest.raises(RuntimeError):
+        MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, [0.05] * 7))
+
+
+@pytest.mark.parametrize("kind", ["box", "cylinder", "sphere", "ground", "union"])
+def test_psdf_surface_matches_oracle(cuda_lib, kind):
+    rng = np.random.default_rng(2)
+    for i in range(6):
+        rot = np.eye(3) if i == 0 else (rpy_matrix(rng.uniform(-3, 3), 0, 0) if i == 1 else rpy_matrix(*rng.uniform(-3, 3, 3)))
+        pose = psdf.Pose(rng.standard_normal(3) * 0.5, rot)
+        host = {
+            "box": lambda: psdf.BoxSDF([0.5, 0.3, 0.6], pose),
+            "cylinder": lambda: psdf.CylinderSDF(0.7, 0.2, pose),
+            "sphere": lambda: psdf.SphereSDF(0.5, pose),
+            "ground": lambda: psdf.GroundSDF(0.37),
+            "union": lambda: psdf.UnionSDF([psdf.BoxSDF([0.5, 0.3, 0.6], pose), psdf.SphereSDF(0.2, psdf.Pose([0.5, 0, 0])), psdf.GroundSDF(1.0)]),
+        }[kind]()
+        o = bridge.OracleSDF.from_psdf(host)
+        pts = rng.standard_normal((1000, 3))
+        want = o.evaluate_batch(pts)
+        np.testing.assert_allclose(host.evaluate_batch(pts.T), want, atol=TOL, rtol=0)
+        assert abs(host.evaluate(pts[0]) - want[0]) < TOL
+        radii = np.where(rng.random(1000) < 0.5, 0.0, rng.uniform(0, 0.3, 1000))
+        got = host.is_outside_batch(pts.T, radii)
+        clear = np.abs(want - radii) > EPS_BAND
+        assert (got == o.is_outside_batch(pts, radii))[clear].all()
+        assert host.is_outside(pts[1], 0.1) == o.is_outside(pts[1], 0.1) or abs(want[1] - 0.1) < EPS_BAND
+        if kind not in ("ground", "union"):
+            host.translate([0.1, -0.2, 0.3])
+            host.rotate_z(0.4)
+            o.translate([0.1, -0.2, 0.3])
+            o.rotate_z(0.4)
+            np.testing.assert_allclose(host.evaluate_batch(pts.T), o.evaluate_batch(pts), atol=TOL, rtol=0)
+
+
+def test_cloud_sdf_and_kdtree_match_oracle(cuda_lib):
+    rng = np.random.default_rng(3)
+    # tests/test_psdf.py:205-215: 100 points in the unit cube, radius 0.1
+    small = rng.uniform(0, 1, (100, 3)).astype(np.float32).astype(np.float64)
+    for pts_cloud, rho in ((small, 0.1), (workloads.table_cloud(50000), 0.002)):
+        host = psdf.CloudSDF(pts_cloud, rho)
+        o = bridge.OracleSDF.from_psdf(host)
+        q = np.concatenate([rng.standard_normal((1500, 3)) * 1.5, pts_cloud[:500] + rng.standard_normal((500, 3)) * 0.02])
+        q = q.astype(np.float32).astype(np.float64)
+        want = o.evaluate_batch(q)
+        np.testing.assert_allclose(host.evaluate_batch(q.T), want, atol=TOL, rtol=0)
+        for r in (0.0, 0.05, 0.3):
+            clear = np.abs(want - r) > EPS_BAND
+            assert (host.is_outside_batch(q.T, np.full(len(q), r)) == o.is_outside_batch(q, r))[clear].all()
+    # tests/test_kdtree.py:6-20
+    pts = rng.standard_normal((1000, 3)).astype(np.float32).astype(np.float64)
+    tree, otree = KDTree(pts), bridge.OracleKDTree(pts)
+    qs = rng.standard_normal((1000, 3)).astype(np.float32).astype(np.float64)
+    want = otree.sqdist_batch(qs)
+    np.testing.assert_allclose(tree.sqdist_batch(qs), want, rtol=1e-5, atol=1e-7)
+    nn = tree.query_batch(qs)
+    np.testing.assert_allclose(((nn - qs) ** 2).sum(axis=1), want, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(tree.query(qs[0]), otree.query(qs[0]), atol=1e-6)
+    assert abs(tree.sqdist(qs[0]) - want[0]) < 1e-6
+
+
+def test_link_poses_match_oracle(cuda_lib):
+    # tests/test_kinematics.py:37-67 (vs skrobot, atol 1e-3) -> here vs the FP64 oracle, 1e-5
+    for maker in (workloads.make_panda, workloads.make_fetch, lambda: workloads.make_pr2_cloud(100)):
+        spec, _ = maker()
+        kin = spec.get_kin()
+        ids = kin.get_joint_ids(spec.control_joint_names)
+        lb, ub = spec.angle_bounds()
+        rng = np.random.default_rng(4)
+        for _ in range(3):
+            q = rng.uniform(lb, ub)
+            kin.set_joint_positions(ids, q)
+            ok = bridge.OracleKin(kin)
+            for L in kin.links[:: max(1, len(kin.links) // 8)]:
+                got = kin.debug_get_link_pose(L.name)
+                want = ok.link_pose(kin.get_link_ids([L.name])[0])
+                np.testing.assert_allclose(got[:3], want[:3], atol=TOL)
+                np.testing.assert_allclose(got[3:], want[3:], atol=1e-5)
+
+
+def test_full_size_properties(cuda_lib):
+    # BASELINE config 5 shape (1M panda configs): size-independent properties
+    import torch
+
+    spec, cst = workloads.make_panda()
+    n = 1 << 20
+    Q = workloads.random_configs(spec, n, 5)
+    robot, scene = cst._robot(), cst._scene()
+    qd = torch.from_numpy(Q).cuda()
+    bits, cnt = tables.check_configs_device(robot, scene, qd)
+    v = tables.unpack_bits(bits.cpu().numpy(), n)
+    assert int(cnt.item()) == int(v.sum())                       # counter == popcount of the bits
+    assert 0.67 < v.mean() < 0.70                                # SURVEY finding 8: ~69 % valid
+    bits2, _ = tables.check_configs_device(robot, scene, qd)
+    assert torch.equal(bits, bits2)                              # idempotent / deterministic
+    # shard invariance: any 32-aligned split gives the same words
+    k = (n // 3) // 32 * 32
+    b_lo, _ = tables.check_configs_device(robot, scene, qd[:k])
+    b_hi, _ = tables.check_configs_device(robot, scene, qd[k:])
+    assert torch.equal(torch.cat([b_lo, b_hi]), bits)
+    # permutation equivariance
+    perm = torch.randperm(n, device="cuda")
+    vp = tables.unpack_bits(tables.check_configs_device(robot, scene, qd[perm].contiguous())[0].cpu().numpy(), n)
+    assert (vp == v[perm.cpu().numpy()]).all()
+    # the host-buffer C entry point agrees with the device one
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    import ctypes as C
+
+    nv = C.c_uint64(0)
+    _capi.check(cuda_lib.pmp_check_configs_host(robot.handle, scene.handle, Q.ctypes.data, n, words.ctypes.data, C.byref(nv)))
+    assert (words.view(np.int32) == bits.cpu().numpy()).all() and nv.value == int(v.sum())
+    # is_valid == (ext > 0 and self > 0) away from contact: approximate vs exact FK agree on sign
+    d = cst.evaluate_batch(Q[:200000])
+    clear = np.abs(d).min(axis=1) > 2e-4
+    assert (v[:200000][clear] == (d[clear] > 0).all(axis=1)).all()

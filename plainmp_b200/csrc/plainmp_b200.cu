@@ -340,7 +340,7 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
                       uint32_t* valid_bits_dev, unsigned long long* n_valid_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if (!q_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->dev.q_dim > 0) || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
   const size_t smem = smem_bytes(robot, S);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
@@ -363,7 +363,7 @@ int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const f
                      float* dist_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if (!q_dev || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
   const size_t smem = smem_bytes(robot, S);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
@@ -378,7 +378,7 @@ int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const f
 int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* spheres_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if (!q_dev || !spheres_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->dev.q_dim > 0) || !spheres_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = empty_scene();
   const size_t smem = smem_bytes(robot, S);
   int grid = 0;
@@ -399,7 +399,7 @@ int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int 
 int pmp_fk_frames(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* frames_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if (!q_dev || !frames_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->dev.q_dim > 0) || !frames_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = empty_scene();
   const size_t smem = smem_bytes(robot, S);
   int grid = 0;

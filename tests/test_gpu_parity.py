@@ -255,7 +255,8 @@ def test_cloud_sdf_and_kdtree_match_oracle(cuda_lib):
     for pts_cloud, rho in ((small, 0.1), (workloads.table_cloud(50000), 0.002)):
         host = psdf.CloudSDF(pts_cloud, rho)
         o = bridge.OracleSDF.from_psdf(host)
-        q = np.concatenate([rng.standard_normal((1500, 3)) * 1.5, pts_cloud[:500] + rng.standard_normal((500, 3)) * 0.02])
+        near = pts_cloud[rng.integers(0, len(pts_cloud), 500)] + rng.standard_normal((500, 3)) * 0.02
+        q = np.concatenate([rng.standard_normal((1500, 3)) * 1.5, near])
         q = q.astype(np.float32).astype(np.float64)
         want = o.evaluate_batch(q)
         np.testing.assert_allclose(host.evaluate_batch(q.T), want, atol=TOL, rtol=0)

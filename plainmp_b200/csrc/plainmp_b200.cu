@@ -51,12 +51,10 @@ int ensure_device() {
 }
 
 template <class K>
-int grid_for(K kernel, size_t smem, long long n_tiles, int* grid) {
-  static thread_local const void* last = nullptr;
-  (void)last;
+int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kBlock) {
   CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
   if (per_sm < 1) return fail(PMP_ERR_LIMIT, "kernel does not fit on an SM with these tables");
   long long g = (long long)g_num_sms * per_sm;
   *grid = (int)std::max<long long>(1, std::min<long long>(g, n_tiles));
@@ -88,8 +86,19 @@ static SceneDev empty_scene() {
   return s;
 }
 
-static size_t smem_bytes(const pmp_robot* r, const SceneDev& s) {
-  return (size_t)(r->dev.blob_words + s.n_prims * 6) * 16 + r->stash_floats_per_thread * 4 * kBlock;
+static size_t smem_bytes(const pmp_robot* r, const SceneDev& s, int block = kBlock) {
+  return (size_t)(r->dev.blob_words + s.n_prims * 6) * 16 + r->stash_floats_per_thread * 4 * block;
+}
+// 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
+static int pick_block(const pmp_robot* r, const SceneDev& s) {
+  return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
+}
+static bool use_v1() {
+  static const bool v = [] {
+    const char* e = getenv("PMP_KERNEL");
+    return e && std::string(e) == "v1";
+  }();
+  return v;
 }
 
 extern "C" {
@@ -152,8 +161,8 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   std::vector<char> need(d->n_ops, 0);
   for (int i = 0; i < d->n_ops; i++)
     if (d->ops[i].parent >= 0 && d->ops[i].parent != i - 1) need[d->ops[i].parent] = 1;
-  for (int g = 0; g < d->n_groups; g++)
-    if (in_pair[g]) need[d->groups[g].op] = 1;
+  // (v2) every op that carries a group keeps its frame: the cooperative narrow phases read it
+  for (int g = 0; g < d->n_groups; g++) need[d->groups[g].op] = 1;
   int n_slots = 0;
   for (int i = 0; i < d->n_ops; i++)
     if (need[i]) slot[i] = n_slots++;
@@ -213,7 +222,8 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   D.base_type = d->base_type;
   D.n_slots = n_slots;
   memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
-  r->stash_floats_per_thread = (size_t)n_slots * 7 + (d->n_pairs > 0 ? (size_t)d->n_groups * 3 : 0);
+  // per thread: frames [slot][7], group centres [group][3], primitive masks [group], 1 scratch word
+  r->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)d->n_groups * 4 + 1;
   if (smem_bytes(r, empty_scene()) > (size_t)kMaxSmem) {
     pmp_robot_destroy(r);
     return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
@@ -342,18 +352,25 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
   if (n == 0) return PMP_OK;
   if ((!q_dev && robot->dev.q_dim > 0) || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const size_t smem = smem_bytes(robot, S);
+  const int block = pick_block(robot, S);
+  const size_t smem = smem_bytes(robot, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
-  const long long n_tiles = (n + kBlock - 1) / kBlock;
+  const long long n_tiles = (n + block - 1) / block;
   int grid = 0;
+  cudaStream_t st = (cudaStream_t)stream;
   // is_valid uses the polynomial sin/cos only for a FIXED base (constraints/primitive.hpp:39-60)
-  if (robot->dev.base_type == PMP_BASE_FIXED) {
-    if (int rc = grid_for(k_check_configs<true>, smem, n_tiles, &grid)) return rc;
-    k_check_configs<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);
+  const bool approx = robot->dev.base_type == PMP_BASE_FIXED;
+#define PMP_LAUNCH_CHECK(KERNEL)                                                                  \
+  do {                                                                                            \
+    if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                        \
+    KERNEL<<<grid, block, smem, st>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);      \
+  } while (0)
+  if (use_v1()) {
+    if (approx) PMP_LAUNCH_CHECK(k_check_configs_v1<true>); else PMP_LAUNCH_CHECK(k_check_configs_v1<false>);
   } else {
-    if (int rc = grid_for(k_check_configs<false>, smem, n_tiles, &grid)) return rc;
-    k_check_configs<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);
+    if (approx) PMP_LAUNCH_CHECK(k_check_configs<true>); else PMP_LAUNCH_CHECK(k_check_configs<false>);
   }
+#undef PMP_LAUNCH_CHECK
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return PMP_OK;
@@ -511,18 +528,19 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
   if (n == 0) return PMP_OK;
   if (!q0_dev || !q1_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const size_t smem = smem_bytes(robot, S);
+  const int block = pick_block(robot, S);
+  const size_t smem = smem_bytes(robot, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const long long n_words = (n + 31) / 32;
-  const long long n_tiles = (n_words + (kBlock / 32) - 1) / (kBlock / 32);
+  const long long n_tiles = (n_words + (block / 32) - 1) / (block / 32);
   int grid = 0;
   if (robot->dev.base_type == PMP_BASE_FIXED) {
-    if (int rc = grid_for(k_check_edges<true, kLanesPerEdge>, smem, n_tiles, &grid)) return rc;
-    k_check_edges<true, kLanesPerEdge><<<grid, kBlock, smem, (cudaStream_t)stream>>>(
+    if (int rc = grid_for(k_check_edges<true, kLanesPerEdge>, smem, n_tiles, &grid, block)) return rc;
+    k_check_edges<true, kLanesPerEdge><<<grid, block, smem, (cudaStream_t)stream>>>(
         robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, n_valid_dev, n_checked_dev);
   } else {
-    if (int rc = grid_for(k_check_edges<false, kLanesPerEdge>, smem, n_tiles, &grid)) return rc;
-    k_check_edges<false, kLanesPerEdge><<<grid, kBlock, smem, (cudaStream_t)stream>>>(
+    if (int rc = grid_for(k_check_edges<false, kLanesPerEdge>, smem, n_tiles, &grid, block)) return rc;
+    k_check_edges<false, kLanesPerEdge><<<grid, block, smem, (cudaStream_t)stream>>>(
         robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, n_valid_dev, n_checked_dev);
   }
   g_launches++;

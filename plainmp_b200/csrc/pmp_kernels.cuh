@@ -123,7 +123,25 @@ __device__ __forceinline__ void walk_links(const RobotDev& R, const Smem& T, con
   }
 }
 
-// ---- validity of one configuration -------------------------------------------------------------
+}  // namespace pmp
+#include "pmp_warp.cuh"
+namespace pmp {
+
+// waypoint of an edge: s2 itself (use_b) or s1 + (s2 - s1) * t
+struct QEdge {
+  const float* a;
+  const float* b;
+  float t;
+  bool use_b;
+  __device__ __forceinline__ float operator()(int j) const {
+    const float y = __ldg(b + j);
+    if (use_b) return y;
+    const float x = __ldg(a + j);
+    return x + (y - x) * t;
+  }
+};
+
+// ---- v1: validity of one configuration, everything per thread (kept for A/B measurements) ------
 template <bool APPROX, class QAcc>
 __device__ bool config_is_valid(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q) {
   bool valid = true;
@@ -216,6 +234,29 @@ __device__ bool config_is_valid(const RobotDev& R, const SceneDev& S, const Smem
 template <bool APPROX>
 __global__ void __launch_bounds__(128)
 k_check_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
+                uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  unsigned cnt = 0;
+  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * blockDim.x + threadIdx.x;
+    const bool active = item < n;
+    QDirect acc{q + (active ? item : 0) * R.q_dim};
+    const bool ok = warp_check<APPROX>(R, S, T, acc, active);
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && active) {
+      bits[item >> 5] = b;
+      cnt += __popc(b);
+    }
+    __syncwarp();
+  }
+  if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
+}
+
+template <bool APPROX>
+__global__ void __launch_bounds__(128)
+k_check_configs_v1(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
                 uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
   extern __shared__ float4 sm[];
   const Smem T = stage_tables(R, S, sm);
@@ -450,10 +491,10 @@ k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const fl
       while (true) {
         const bool more = have && edge_ok && (w0 < n_way);
         if (!__any_sync(0xffffffffu, more)) break;
-        bool bad = false;
         const long long w = w0 + sub;
-        if (more && w < n_way) {
-          float t;
+        const bool work = more && w < n_way;
+        float t = 1.f;
+        if (work) {
           if (w == 0) {
             t = 1.f;
           } else if (n_test < 129) {
@@ -461,17 +502,12 @@ k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const fl
           } else {
             t = (float)((double)w * ratio);
           }
-          bool ok;
-          if (w == 0) {
-            QDirect acc{b};
-            ok = config_is_valid<APPROX>(R, S, T, acc);
-          } else {
-            QLerp acc{a, b, t};
-            ok = config_is_valid<APPROX>(R, S, T, acc);
-          }
-          bad = !ok;
           cnt_checked++;
         }
+        // all 32 lanes enter the cooperative check; lanes without a waypoint are inactive
+        QEdge acc{have ? a : q0, have ? b : q1, t, w == 0};
+        const bool ok = warp_check<APPROX>(R, S, T, acc, work);
+        const bool bad = work && !ok;
         const unsigned badmask = __ballot_sync(0xffffffffu, bad);
         if (badmask & sub_mask) edge_ok = false;
         w0 += LPE;

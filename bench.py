@@ -34,6 +34,7 @@ UNIT = "configs/s"
 # dense algorithmic work of one panda dual-bars configuration
 F_CFG_DENSE = 14.7e3          # flop/config (no culling, no early exit)
 BYTES_PER_CFG = 7 * 4 + 1 / 8  # q in + 1 validity bit out
+DRAM_BYTES_PER_CFG_NCU = 29.0   # measured once with ncu --set full (profiles/), per configuration
 
 
 def parse_args():
@@ -276,8 +277,11 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        tf = C.c_double(0.0)
+        if lib.pmp_measure_fp32_peak(C.byref(tf)) == 0:
+            extras["fp32_ffma_tflops_measured"] = tf.value
         if args.extras:
-            extras = side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorConfig, ValidatorType)
+            extras.update(side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorConfig, ValidatorType))
         # CPU baseline: restated reference path, bounded sample
         from oracle import bridge  # noqa: F401  (bench's cpu_baseline leg may use the oracle)
 
@@ -322,7 +326,10 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "traffic": None, "peak_source": hbm_src, "kernel_ms": kernel_ms,
+                "traffic": DRAM_BYTES_PER_CFG_NCU * n_local / 1e9, "traffic_unit": "GB per launch",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 29.0 B/config (profiles/r01_v2b_check_configs_ncu.md), scaled to this launch",
+                "algorithmic_gb_per_launch": BYTES_PER_CFG * n_local / 1e9,
+                "peak_source": hbm_src, "kernel_ms": kernel_ms,
                 "note": "algorithmic bytes = 28.125 B/config; the kernel is FP32-SIMT issue bound, see roofline_fp32",
             },
             "roofline_fp32": {

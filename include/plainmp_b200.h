@@ -214,6 +214,9 @@ int pmp_device_count(void);
 /* Select the CUDA device for the calling host thread (the library carries its own copy of the
  * CUDA runtime, so a host framework's current-device setting is not visible to it). */
 int pmp_set_device(int device);
+/* FFMA micro-benchmark on the current device: best-of-5 dense FP32 FMA throughput in TFLOP/s
+ * (the FP32-SIMT roofline denominator; MEASURED_PEAKS.json has no FP32 figure). */
+int pmp_measure_fp32_peak(double* tflops);
 /* Number of kernel launches issued by this library since load (all threads). */
 uint64_t pmp_launch_count(void);
 

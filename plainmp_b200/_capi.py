@@ -120,6 +120,7 @@ SYMBOLS = {
     "pmp_device_count": (_i32, []),
     "pmp_launch_count": (C.c_uint64, []),
     "pmp_set_device": (_i32, [_i32]),
+    "pmp_measure_fp32_peak": (_i32, [C.POINTER(C.c_double)]),
     "pmp_robot_create": (_i32, [C.POINTER(RobotDesc), C.POINTER(_p)]),
     "pmp_robot_destroy": (None, [_p]),
     "pmp_robot_q_dim": (_i32, [_p]),

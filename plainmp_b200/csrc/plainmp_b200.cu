@@ -713,3 +713,48 @@ int pmp_cloud_nearest(const pmp_scene_t* scene, const float* points_dev, int64_t
 }
 
 }  // extern "C"
+
+// ---- FP32 roofline denominator ---------------------------------------------------------------------
+namespace {
+__global__ void k_ffma_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f,
+        x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" int pmp_measure_fp32_peak(double* tflops) {
+  if (!tflops) return fail(PMP_ERR_INVALID, "null argument");
+  if (int rc = ensure_device()) return rc;
+  const int block = 256, grid = g_num_sms * 8, iters = 4096;
+  float* out = nullptr;
+  CUDA_OK(cudaMalloc(&out, (size_t)grid * block * 4));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CUDA_OK(cudaEventRecord(e0));
+    k_ffma_peak<<<grid, block>>>(out, iters, 0.999f, 1e-3f);
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 8 * 16 * (double)iters * grid * block;
+    best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  g_launches += 5;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return PMP_OK;
+}

@@ -87,16 +87,23 @@ static SceneDev empty_scene() {
 }
 
 static size_t smem_bytes(const pmp_robot* r, const SceneDev& s, int block = kBlock) {
-  return (size_t)(r->dev.blob_words + s.n_prims * 6) * 16 + r->stash_floats_per_thread * 4 * block;
+  return (size_t)(r->dev.blob_words + s.n_prims * kPrimWords) * 16 + r->stash_floats_per_thread * 4 * block;
 }
 // 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
 static int pick_block(const pmp_robot* r, const SceneDev& s) {
   return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
 }
-static bool use_v1() {
-  static const bool v = [] {
+// kernel generation: 3 = v3 with the AABB group cull (default), 4 = v3 with the exact group
+// predicate, 2 / 1 = the earlier kernels kept for A/B measurements (PMP_KERNEL=v1|v2|v3|v3x)
+static int kernel_version() {
+  static const int v = [] {
     const char* e = getenv("PMP_KERNEL");
-    return e && std::string(e) == "v1";
+    if (!e) return 3;
+    const std::string s(e);
+    if (s == "v1") return 1;
+    if (s == "v2") return 2;
+    if (s == "v3x") return 4;
+    return 3;
   }();
   return v;
 }
@@ -123,6 +130,7 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   if (!d || !out) return fail(PMP_ERR_INVALID, "null argument");
   if (d->n_ops < 0 || d->n_groups < 0 || d->n_spheres < 0 || d->n_pairs < 0 || d->dof < 0)
     return fail(PMP_ERR_INVALID, "negative table size");
+  if (d->n_groups > kMaxGroupsV3) return fail(PMP_ERR_LIMIT, "too many sphere groups (limit 2048)");
   if (d->base_type < PMP_BASE_FIXED || d->base_type > PMP_BASE_FLOATING) return fail(PMP_ERR_INVALID, "bad base_type");
   const int q_dim = d->dof + (d->base_type == PMP_BASE_PLANAR ? 3 : 0) + (d->base_type == PMP_BASE_FLOATING ? 6 : 0);
   for (int i = 0; i < d->n_ops; i++) {
@@ -167,10 +175,11 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   for (int i = 0; i < d->n_ops; i++)
     if (need[i]) slot[i] = n_slots++;
 
-  const int off_groups = d->n_ops * 4;
+  const int off_groups = d->n_ops * kOpWords;
   const int off_spheres = off_groups + d->n_groups * 2;
   const int off_pairs = off_spheres + d->n_spheres;
-  const int words = off_pairs + (d->n_pairs + 1) / 2;
+  const int off_pairs4 = off_pairs + (d->n_pairs + 1) / 2;
+  const int words = off_pairs4 + d->n_pairs;
   std::vector<float4> blob(std::max(words, 1));
   auto fi = [](int v) {
     float f;
@@ -179,11 +188,21 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   };
   for (int i = 0; i < d->n_ops; i++) {
     const pmp_link_op_t& o = d->ops[i];
-    blob[4 * i + 0] = make_float4(o.origin_quat[0], o.origin_quat[1], o.origin_quat[2], o.origin_quat[3]);
-    blob[4 * i + 1] = make_float4(o.origin_xyz[0], o.origin_xyz[1], o.origin_xyz[2], fi(o.kind));
-    blob[4 * i + 2] = make_float4(o.axis[0], o.axis[1], o.axis[2], fi(o.q_index));
+    const bool ident = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
+    // identity-flagged origins are never multiplied in (kinematics/transform.hpp:64-74): store the exact identity
+    const double oq[4] = {ident ? 0.0 : o.origin_quat[0], ident ? 0.0 : o.origin_quat[1], ident ? 0.0 : o.origin_quat[2],
+                          ident ? 1.0 : o.origin_quat[3]};
+    blob[kOpWords * i + 0] = make_float4((float)oq[0], (float)oq[1], (float)oq[2], (float)oq[3]);
+    blob[kOpWords * i + 1] = make_float4(o.origin_xyz[0], o.origin_xyz[1], o.origin_xyz[2], fi(o.kind));
+    blob[kOpWords * i + 2] = make_float4(o.axis[0], o.axis[1], o.axis[2], fi(o.q_index));
     const int pslot = (o.parent >= 0 && o.parent != i - 1) ? slot[o.parent] : -1;
-    blob[4 * i + 3] = make_float4(fi(o.parent), fi(o.flags), fi(slot[i]), fi(pslot));
+    int flags = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
+    if (o.origin_xyz[0] == 0.f && o.origin_xyz[1] == 0.f && o.origin_xyz[2] == 0.f) flags |= PMP_OPFLAG_ZERO_XYZ;
+    blob[kOpWords * i + 3] = make_float4(fi(o.parent), fi(flags), fi(slot[i]), fi(pslot));
+    // v3 sine basis: origin (x) (axis, 0) in FP64 (Eigen product, w = -o.a, vec = ow a + o x a)
+    const double ax = o.axis[0], ay = o.axis[1], az = o.axis[2];
+    blob[kOpWords * i + 4] = make_float4((float)(oq[3] * ax + oq[1] * az - oq[2] * ay), (float)(oq[3] * ay + oq[2] * ax - oq[0] * az),
+                                         (float)(oq[3] * az + oq[0] * ay - oq[1] * ax), (float)(-oq[0] * ax - oq[1] * ay - oq[2] * az));
   }
   for (int k = 0; k < d->n_groups; k++) {
     const pmp_group_t& G = d->groups[order[k]];
@@ -199,6 +218,8 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
     for (int p = 0; p < d->n_pairs; p++) {
       pw[2 * p] = pos[d->pairs[2 * p]];
       pw[2 * p + 1] = pos[d->pairs[2 * p + 1]];
+      const float rs = d->groups[d->pairs[2 * p]].radius + d->groups[d->pairs[2 * p + 1]].radius;
+      blob[off_pairs4 + p] = make_float4(fi(pw[2 * p]), fi(pw[2 * p + 1]), rs * rs, 0.f);
     }
   }
   cudaError_t e = cudaMalloc(&r->blob_dev, blob.size() * sizeof(float4));
@@ -217,13 +238,15 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   D.off_groups = off_groups;
   D.off_spheres = off_spheres;
   D.off_pairs = off_pairs;
+  D.off_pairs4 = off_pairs4;
   D.dof = d->dof;
   D.q_dim = q_dim;
   D.base_type = d->base_type;
   D.n_slots = n_slots;
   memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
   // per thread: frames [slot][7], group centres [group][3], primitive masks [group], 1 scratch word
-  r->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)d->n_groups * 4 + 1;
+  // (v3: frames, group centres, + the per-warp scratch row and queues)
+  r->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)d->n_groups * 3 + std::max<size_t>((size_t)d->n_groups + 1, kV3WordsPerThread);
   if (smem_bytes(r, empty_scene()) > (size_t)kMaxSmem) {
     pmp_robot_destroy(r);
     return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
@@ -251,8 +274,41 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
   s->dev = empty_scene();
   static_assert(sizeof(pmp_prim_t) == 96, "pmp_prim_t layout");
   if (d->n_prims > 0) {
-    cudaError_t e = cudaMalloc(&s->prims_dev, (size_t)d->n_prims * 96);
-    if (e == cudaSuccess) e = cudaMemcpy(s->prims_dev, d->prims, (size_t)d->n_prims * 96, cudaMemcpyHostToDevice);
+    // repack pmp_prim_t into the device record (pmp_device.cuh): type | flags in p0.w, AABB as centre / half extent
+    std::vector<float4> rec((size_t)d->n_prims * kPrimWords, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < d->n_prims; i++) {
+      const pmp_prim_t& P = d->prims[i];
+      int flags = P.flags;
+      // a z-aligned cylinder is evaluated in world axes for all three coordinates (primitive_sdf.hpp:446-449,466-472)
+      if (P.type == PMP_PRIM_CYLINDER && (flags & PMP_PRIMFLAG_Z_ALIGNED)) flags |= PMP_PRIMFLAG_AXIS_ALIGNED;
+      int kind = P.type;
+      if (P.type == PMP_PRIM_BOX && (flags & PMP_PRIMFLAG_AXIS_ALIGNED)) kind = PMP_KIND_BOX_AA;
+      if (P.type == PMP_PRIM_CYLINDER && (flags & PMP_PRIMFLAG_AXIS_ALIGNED)) kind = PMP_KIND_CYL_AA;
+      const int tf = P.type | (flags << 8) | (kind << 16);
+      float tfw;
+      memcpy(&tfw, &tf, 4);
+      float4* w = rec.data() + (size_t)kPrimWords * i;
+      w[0] = make_float4(P.position[0], P.position[1], P.position[2], tfw);
+      w[1] = make_float4(P.param0, P.param1, P.param2, 0.f);
+      w[2] = make_float4(P.rot_col0[0], P.rot_col0[1], P.rot_col0[2], 0.f);
+      w[3] = make_float4(P.rot_col1[0], P.rot_col1[1], P.rot_col1[2], 0.f);
+      w[4] = make_float4(P.rot_col2[0], P.rot_col2[1], P.rot_col2[2], 0.f);
+      float ctr[3], half[3];
+      for (int a = 0; a < 3; a++) {
+        const double lo = P.lb[a], hi = P.ub[a];
+        if (!(lo > -1e37) || !(hi < 1e37)) {  // unbounded axis (Ground x, y)
+          ctr[a] = 0.f;
+          half[a] = INFINITY;
+        } else {
+          ctr[a] = (float)(0.5 * (lo + hi));
+          half[a] = (float)(0.5 * (hi - lo) + 1e-6 + 1e-6 * std::max(std::fabs(lo), std::fabs(hi)));
+        }
+      }
+      w[5] = make_float4(ctr[0], ctr[1], ctr[2], 0.f);
+      w[6] = make_float4(half[0], half[1], half[2], 0.f);
+    }
+    cudaError_t e = cudaMalloc(&s->prims_dev, rec.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpy(s->prims_dev, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       pmp_scene_destroy(s);
       return fail(PMP_ERR_CUDA, std::string("scene table upload: ") + cudaGetErrorString(e));
@@ -365,10 +421,26 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
     if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                        \
     KERNEL<<<grid, block, smem, st>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);      \
   } while (0)
-  if (use_v1()) {
-    if (approx) PMP_LAUNCH_CHECK(k_check_configs_v1<true>); else PMP_LAUNCH_CHECK(k_check_configs_v1<false>);
-  } else {
-    if (approx) PMP_LAUNCH_CHECK(k_check_configs<true>); else PMP_LAUNCH_CHECK(k_check_configs<false>);
+  switch (kernel_version()) {
+    case 1:
+      if (approx) PMP_LAUNCH_CHECK(k_check_configs_v1<true>); else PMP_LAUNCH_CHECK(k_check_configs_v1<false>);
+      break;
+    case 2:
+      if (approx) PMP_LAUNCH_CHECK(k_check_configs<true>); else PMP_LAUNCH_CHECK(k_check_configs<false>);
+      break;
+    case 4:
+      if (block == 128) {
+        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<128, true, false>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<128, false, false>));
+      } else {
+        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<64, true, false>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<64, false, false>));
+      }
+      break;
+    default:
+      if (block == 128) {
+        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<128, true, true>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<128, false, true>));
+      } else {
+        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<64, true, true>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<64, false, true>));
+      }
   }
 #undef PMP_LAUNCH_CHECK
   g_launches++;
@@ -534,15 +606,31 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
   const long long n_words = (n + 31) / 32;
   const long long n_tiles = (n_words + (block / 32) - 1) / (block / 32);
   int grid = 0;
-  if (robot->dev.base_type == PMP_BASE_FIXED) {
-    if (int rc = grid_for(k_check_edges<true, kLanesPerEdge>, smem, n_tiles, &grid, block)) return rc;
-    k_check_edges<true, kLanesPerEdge><<<grid, block, smem, (cudaStream_t)stream>>>(
-        robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, n_valid_dev, n_checked_dev);
-  } else {
-    if (int rc = grid_for(k_check_edges<false, kLanesPerEdge>, smem, n_tiles, &grid, block)) return rc;
-    k_check_edges<false, kLanesPerEdge><<<grid, block, smem, (cudaStream_t)stream>>>(
-        robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, n_valid_dev, n_checked_dev);
+#define PMP_LAUNCH_EDGES(KERNEL)                                                                         \
+  do {                                                                                                  \
+    if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                              \
+    KERNEL<<<grid, block, smem, (cudaStream_t)stream>>>(robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
+                                                        n_valid_dev, n_checked_dev);                    \
+  } while (0)
+  const bool approx = robot->dev.base_type == PMP_BASE_FIXED;
+#define PMP_EDGES_VER(VER)                                                                                    \
+  do {                                                                                                       \
+    if (block == 128) {                                                                                      \
+      if (approx) PMP_LAUNCH_EDGES((k_check_edges<true, kLanesPerEdge, VER, 128>));                          \
+      else PMP_LAUNCH_EDGES((k_check_edges<false, kLanesPerEdge, VER, 128>));                                \
+    } else {                                                                                                 \
+      if (approx) PMP_LAUNCH_EDGES((k_check_edges<true, kLanesPerEdge, VER, 64>));                           \
+      else PMP_LAUNCH_EDGES((k_check_edges<false, kLanesPerEdge, VER, 64>));                                 \
+    }                                                                                                        \
+  } while (0)
+  switch (kernel_version()) {
+    case 1:
+    case 2: PMP_EDGES_VER(2); break;
+    case 4: PMP_EDGES_VER(4); break;
+    default: PMP_EDGES_VER(3);
   }
+#undef PMP_EDGES_VER
+#undef PMP_LAUNCH_EDGES
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return PMP_OK;

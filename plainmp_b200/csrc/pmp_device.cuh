@@ -108,11 +108,13 @@ __device__ __forceinline__ void half_sincos(float theta, float& s, float& c) {
   }
 }
 
-// Device copy of one link op: 4 x 16 bytes.
-//   w0 = origin quat (x,y,z,w)
+// Device copy of one link op: 5 x 16 bytes.
+//   w0 = origin quat (x,y,z,w); exactly (0,0,0,1) when flagged identity
 //   w1 = origin xyz, kind
 //   w2 = axis xyz, q_index
 //   w3 = parent, flags, slot (stash slot of this op's frame or -1), parent_slot
+//   w4 = revolute: origin (x) (axis, 0), the sine basis of the local quaternion (v3)
+#define PMP_OPFLAG_ZERO_XYZ 256 /* device-internal: origin_xyz == 0, the translation term is skipped */
 struct OpWords {
   float4 w0, w1, w2;
   int4 w3;
@@ -177,102 +179,136 @@ __device__ __forceinline__ void quat_from_rpy(float roll, float pitch, float yaw
 }
 
 // ---------------------------------------------------------------------------------------------
-// primitives: 6 x float4 per primitive (same layout as pmp_prim_t)
-//   p0 = position, type      p1 = col0, param0     p2 = col1, param1
-//   p3 = col2, param2        p4 = lb, flags        p5 = ub, -
+// primitives: kPrimWords x float4 per primitive, repacked from pmp_prim_t by pmp_scene_create
+//   [0] position, type | flags << 8 | kind << 16   (kind: the test variant resolved at scene build)
+//   [1] params: box half widths x,y,z | cylinder radius, half height | sphere radius | ground height
+//   [2..4] rotation columns (read only when the pose is not axis- / z-aligned)
+//   [5] AABB centre      [6] AABB half extent (+inf = unbounded)      [7] unused
+// The AABB words are the reference's lb/ub (primitive_sdf.hpp:218-219; Ground pinned at z = 0,
+// :250-255) in centre/half form, inflated by a few ulps so that the FP32 cull stays conservative.
 // ---------------------------------------------------------------------------------------------
+constexpr int kPrimWords = 8;
+// test variants: the aligned ones need no rotation columns at all
+enum { PMP_KIND_BOX = 1, PMP_KIND_CYL = 2, PMP_KIND_SPHERE = 3, PMP_KIND_GROUND = 4, PMP_KIND_BOX_AA = 5, PMP_KIND_CYL_AA = 6 };
+
 struct Prim {
-  float4 p0, p1, p2, p3;
-  int type, flags;
+  const float4* w;  // the primitive's record (rotation columns are fetched on demand)
+  float4 p0, pr;
+  int type, flags, kind;
 };
 
 __device__ __forceinline__ Prim load_prim(const float4* __restrict__ prims, int i) {
   Prim P;
-  P.p0 = prims[6 * i + 0];
-  P.p1 = prims[6 * i + 1];
-  P.p2 = prims[6 * i + 2];
-  P.p3 = prims[6 * i + 3];
-  P.type = __float_as_int(P.p0.w);
-  P.flags = __float_as_int(prims[6 * i + 4].w);
+  P.w = prims + kPrimWords * i;
+  P.p0 = P.w[0];
+  P.pr = P.w[1];
+  const int tf = __float_as_int(P.p0.w);
+  P.type = tf & 0xff;
+  P.flags = (tf >> 8) & 0xff;
+  P.kind = tf >> 16;
   return P;
+}
+
+// |R^T d| per axis, following the reference's alignment shortcuts: axis-aligned poses skip the
+// rotation (primitive_sdf.hpp:328-340), z-aligned ones use world z for the third coordinate
+// (:341-345, :466-472).  `box` selects the Box rule (world x, y only when fully axis-aligned); for
+// cylinders the host stores identity columns whenever the pose is z-aligned, so the same rule holds.
+__device__ __forceinline__ void prim_local_abs(const Prim& P, const float dx, const float dy, const float dz,
+                                               float& ax, float& ay, float& az) {
+  if (P.flags & PMP_PRIMFLAG_AXIS_ALIGNED) {
+    ax = fabsf(dx); ay = fabsf(dy); az = fabsf(dz);
+    return;
+  }
+  const float4 c0 = P.w[2], c1 = P.w[3];
+  ax = fabsf(dx * c0.x + dy * c0.y + dz * c0.z);
+  ay = fabsf(dx * c1.x + dy * c1.y + dz * c1.z);
+  if (P.flags & PMP_PRIMFLAG_Z_ALIGNED) {
+    az = fabsf(dz);
+  } else {
+    const float4 c2 = P.w[4];
+    az = fabsf(dx * c2.x + dy * c2.y + dz * c2.z);
+  }
 }
 
 // !is_outside_aabb && !is_outside of the reference collapsed into one predicate: for Box /
 // Cylinder / Sphere the AABB is conservative and therefore implied; for Ground it is
 // semantically active (AABB pinned at z = 0).  Contact (sdf == r) is NOT
-// outside (strict >).
-__device__ __forceinline__ bool prim_is_outside(const Prim& P, const float3 c, const float r) {
-  if (P.type == PMP_PRIM_GROUND) {
-    const bool aabb_out = (c.z < -r) || (c.z > r);
-    return aabb_out || (c.z + P.p1.w > r);
-  }
-  const float dx = c.x - P.p0.x, dy = c.y - P.p0.y, dz = c.z - P.p0.z;
-  if (P.type == PMP_PRIM_SPHERE) {
-    const float d2 = dx * dx + dy * dy + dz * dz;
-    const float R = P.p1.w;
-    if (r < 1e-6f) return d2 > R * R;
-    return d2 > (R + r) * (R + r);
-  }
-  const float ax = fabsf(dx * P.p1.x + dy * P.p1.y + dz * P.p1.z);
-  const float ay = fabsf(dx * P.p2.x + dy * P.p2.y + dz * P.p2.z);
-  // z test in world axes when the pose is z-aligned (primitive_sdf.hpp:341-345, :466-472)
-  const float az = (P.flags & PMP_PRIMFLAG_Z_ALIGNED) ? fabsf(dz)
-                                                      : fabsf(dx * P.p3.x + dy * P.p3.y + dz * P.p3.z);
-  if (P.type == PMP_PRIM_BOX) {
-    const float sx = ax - P.p1.w, sy = ay - P.p2.w, sz = az - P.p3.w;
-    if (sx > r || sy > r || sz > r) return true;
-    if (r < 1e-6f) return false;
-    // edge / corner case: with fewer than two positive axis distances the sum below cannot
-    // exceed r^2 (each is <= r), so the reference's out_count branches reduce to this.
-    const float px = fmaxf(sx, 0.f), py = fmaxf(sy, 0.f), pz = fmaxf(sz, 0.f);
-    const int cnt = (sx > 0.f) + (sy > 0.f) + (sz > 0.f);
-    if (cnt < 2) return false;
-    return px * px + py * py + pz * pz > r * r;
-  }
-  // cylinder: p1.w = radius, p2.w = half height
-  const float sz = az - P.p2.w;
-  if (sz > r) return true;
-  const float R = P.p1.w;
-  const float d2 = ax * ax + ay * ay;
-  if (r < 1e-6f) return d2 > R * R;
-  if (d2 > (R + r) * (R + r)) return true;
-  if (sz > 0.f && d2 > R * R) {
+// outside (strict >).  One straight-line case per test variant, no early returns inside a case.
+__device__ __forceinline__ bool box_outside(const float sx, const float sy, const float sz, const float r) {
+  const float px = fmaxf(sx, 0.f), py = fmaxf(sy, 0.f), pz = fmaxf(sz, 0.f);
+  // edge / corner case (primitive_sdf.hpp:374-397): with fewer than two positive axis distances, each
+  // <= r, the sum below cannot exceed r^2, so the reference's out_count branches reduce to this;
+  // r < 1e-6 skips it (:371-373).
+  return (fmaxf(fmaxf(sx, sy), sz) > r) | ((r >= 1e-6f) & (px * px + py * py + pz * pz > r * r));
+}
+__device__ __forceinline__ bool cyl_outside(const float d2, const float sz, const float R, const float r) {
+  const bool tiny = r < 1e-6f;  // :483-485
+  const float rr = tiny ? R : R + r;
+  bool out = (sz > r) | (d2 > rr * rr);
+  if (!out & !tiny & (sz > 0.f) & (d2 > R * R)) {  // rim case (rare): the only place that needs a square root
     const float sr = sqrtf(d2) - R;
-    return sz * sz + sr * sr > r * r;
+    out = sz * sz + sr * sr > r * r;
   }
-  return false;
+  return out;
+}
+__device__ __forceinline__ bool prim_is_outside(const Prim& P, const float3 c, const float r) {
+  if (P.kind == PMP_KIND_GROUND) return (fabsf(c.z) > r) | (c.z + P.pr.x > r);
+  const float dx = c.x - P.p0.x, dy = c.y - P.p0.y, dz = c.z - P.p0.z;
+  switch (P.kind) {
+    case PMP_KIND_CYL_AA:
+      return cyl_outside(dx * dx + dy * dy, fabsf(dz) - P.pr.y, P.pr.x, r);
+    case PMP_KIND_BOX_AA:
+      return box_outside(fabsf(dx) - P.pr.x, fabsf(dy) - P.pr.y, fabsf(dz) - P.pr.z, r);
+    case PMP_KIND_SPHERE: {
+      const float rr = (r < 1e-6f) ? P.pr.x : P.pr.x + r;  // :547-549
+      return dx * dx + dy * dy + dz * dz > rr * rr;
+    }
+    default: {
+      float ax, ay, az;
+      prim_local_abs(P, dx, dy, dz, ax, ay, az);
+      if (P.kind == PMP_KIND_BOX) return box_outside(ax - P.pr.x, ay - P.pr.y, az - P.pr.z, r);
+      return cyl_outside(ax * ax + ay * ay, az - P.pr.y, P.pr.x, r);
+    }
+  }
 }
 
 // SDF value.  Ground has no AABB here; callers apply the reference's AABB pre-test where the
 // reference does (evaluate_ext_collision, primitive_sphere_collision.cpp:272-283).
 __device__ __forceinline__ float prim_evaluate(const Prim& P, const float3 c) {
-  if (P.type == PMP_PRIM_GROUND) return c.z + P.p1.w;
+  if (P.type == PMP_PRIM_GROUND) return c.z + P.pr.x;
   const float dx = c.x - P.p0.x, dy = c.y - P.p0.y, dz = c.z - P.p0.z;
-  if (P.type == PMP_PRIM_SPHERE) return sqrtf(dx * dx + dy * dy + dz * dz) - P.p1.w;
-  const float ax = fabsf(dx * P.p1.x + dy * P.p1.y + dz * P.p1.z);
-  const float ay = fabsf(dx * P.p2.x + dy * P.p2.y + dz * P.p2.z);
+  if (P.type == PMP_PRIM_SPHERE) return sqrtf(dx * dx + dy * dy + dz * dz) - P.pr.x;
   if (P.type == PMP_PRIM_BOX) {
     // BoxSDF::evaluate uses rot_inv for every non-axis-aligned pose (no z-aligned shortcut)
-    const float az = fabsf(dx * P.p3.x + dy * P.p3.y + dz * P.p3.z);
-    const float sx = ax - P.p1.w, sy = ay - P.p2.w, sz = az - P.p3.w;
+    float ax, ay, az;
+    if (P.flags & PMP_PRIMFLAG_AXIS_ALIGNED) {
+      ax = fabsf(dx); ay = fabsf(dy); az = fabsf(dz);
+    } else {
+      const float4 c0 = P.w[2], c1 = P.w[3], c2 = P.w[4];
+      ax = fabsf(dx * c0.x + dy * c0.y + dz * c0.z);
+      ay = fabsf(dx * c1.x + dy * c1.y + dz * c1.z);
+      az = fabsf(dx * c2.x + dy * c2.y + dz * c2.z);
+    }
+    const float sx = ax - P.pr.x, sy = ay - P.pr.y, sz = az - P.pr.z;
     const float px = fmaxf(sx, 0.f), py = fmaxf(sy, 0.f), pz = fmaxf(sz, 0.f);
     const float outside = sqrtf(px * px + py * py + pz * pz);
     const float inside = fmaxf(fmaxf(fminf(sx, 0.f), fminf(sy, 0.f)), fminf(sz, 0.f));
     return outside + inside;
   }
-  const float az = (P.flags & PMP_PRIMFLAG_Z_ALIGNED) ? fabsf(dz)
-                                                      : fabsf(dx * P.p3.x + dy * P.p3.y + dz * P.p3.z);
-  const float sz = az - P.p2.w;
-  const float sr = sqrtf(ax * ax + ay * ay) - P.p1.w;
+  float ax, ay, az;
+  prim_local_abs(P, dx, dy, dz, ax, ay, az);
+  const float sz = az - P.pr.y;
+  const float sr = sqrtf(ax * ax + ay * ay) - P.pr.x;
   const float pr = fmaxf(sr, 0.f), pz = fmaxf(sz, 0.f);
   return sqrtf(pr * pr + pz * pz) + fmaxf(fminf(sr, 0.f), fminf(sz, 0.f));
 }
 
-// is_outside_aabb(c, r) against the stored AABB (primitive_sdf.hpp:180-184).
-__device__ __forceinline__ bool prim_aabb_outside(const float4 lb, const float4 ub, const float3 c,
+// is_outside_aabb(c, r) (primitive_sdf.hpp:180-184) against the AABB in centre / half-extent form,
+// branch-free: outside <=> max_k(|c_k - ctr_k| - half_k) > r.
+__device__ __forceinline__ bool prim_aabb_outside(const float4 ctr, const float4 half, const float3 c,
                                                   const float r) {
-  return c.x < lb.x - r || c.x > ub.x + r || c.y < lb.y - r || c.y > ub.y + r || c.z < lb.z - r ||
-         c.z > ub.z + r;
+  const float ex = fabsf(c.x - ctr.x) - half.x, ey = fabsf(c.y - ctr.y) - half.y, ez = fabsf(c.z - ctr.z) - half.z;
+  return fmaxf(fmaxf(ex, ey), ez) > r;
 }
 
 }  // namespace pmp

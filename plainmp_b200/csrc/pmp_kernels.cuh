@@ -19,10 +19,10 @@
 namespace pmp {
 
 struct RobotDev {
-  const float4* blob;  // [ops: 4 words][groups: 2 words][spheres: 1 word][pairs: 1 word per 2 pairs]
+  const float4* blob;  // [ops: 5 words][groups: 2 words][spheres: 1 word][pairs: 1 word per 2 pairs][pairs4: 1 word per pair]
   int blob_words;
   int n_ops, n_groups, n_spheres, n_pairs;
-  int off_groups, off_spheres, off_pairs;  // word offsets into blob
+  int off_groups, off_spheres, off_pairs, off_pairs4;  // word offsets into blob
   int dof, q_dim, base_type;
   int n_slots;  // frames kept in the stash
   float base_pose[7];
@@ -40,22 +40,26 @@ struct Smem {
   const float4* groups;
   const float4* spheres;
   const int2* pairs;
+  const float4* pairs4;  // per pair: group a, group b (int bits), (Ra + Rb)^2, -
   const float4* prims;
   float* stash;
 };
 
+constexpr int kOpWords = 5;  // 16-byte words per link op (see OpWords in pmp_device.cuh + the v3 basis word)
+
 __device__ __forceinline__ Smem stage_tables(const RobotDev& R, const SceneDev& S, float4* sm) {
   for (int i = threadIdx.x; i < R.blob_words; i += blockDim.x) sm[i] = __ldg(R.blob + i);
   float4* pr = sm + R.blob_words;
-  for (int i = threadIdx.x; i < S.n_prims * 6; i += blockDim.x) pr[i] = __ldg(S.prims + i);
+  for (int i = threadIdx.x; i < S.n_prims * kPrimWords; i += blockDim.x) pr[i] = __ldg(S.prims + i);
   __syncthreads();
   Smem t;
   t.ops = sm;
   t.groups = sm + R.off_groups;
   t.spheres = sm + R.off_spheres;
   t.pairs = reinterpret_cast<const int2*>(sm + R.off_pairs);
+  t.pairs4 = sm + R.off_pairs4;
   t.prims = pr;
-  t.stash = reinterpret_cast<float*>(pr + S.n_prims * 6);
+  t.stash = reinterpret_cast<float*>(pr + S.n_prims * kPrimWords);
   return t;
 }
 
@@ -111,8 +115,8 @@ __device__ __forceinline__ void walk_links(const RobotDev& R, const Smem& T, con
   const Frame base = base_frame(R, q);
   Frame cur = base;
   for (int i = 0; i < R.n_ops; i++) {
-    const float4 w0 = T.ops[4 * i], w1 = T.ops[4 * i + 1], w2 = T.ops[4 * i + 2];
-    const int4 w3 = *reinterpret_cast<const int4*>(&T.ops[4 * i + 3]);
+    const float4 w0 = T.ops[kOpWords * i], w1 = T.ops[kOpWords * i + 1], w2 = T.ops[kOpWords * i + 2];
+    const int4 w3 = *reinterpret_cast<const int4*>(&T.ops[kOpWords * i + 3]);
     const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
     Frame parent = cur;
     if (w3.x != i - 1) parent = (w3.x < 0) ? base : stash_get(T.stash, w3.w);
@@ -125,6 +129,7 @@ __device__ __forceinline__ void walk_links(const RobotDev& R, const Smem& T, con
 
 }  // namespace pmp
 #include "pmp_warp.cuh"
+#include "pmp_v3.cuh"
 namespace pmp {
 
 // waypoint of an edge: s2 itself (use_b) or s1 + (s2 - s1) * t
@@ -244,6 +249,31 @@ k_check_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q,
     const bool active = item < n;
     QDirect acc{q + (active ? item : 0) * R.q_dim};
     const bool ok = warp_check<APPROX>(R, S, T, acc, active);
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && active) {
+      bits[item >> 5] = b;
+      cnt += __popc(b);
+    }
+    __syncwarp();
+  }
+  if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
+}
+
+// v3: lean phase 1 + warp-local work queue (pmp_v3.cuh).  AABB_BROAD selects the group-level cull.
+// B = blockDim.x (compile-time so that the stash offsets fold into immediates).
+template <int B, bool APPROX, bool AABB_BROAD>
+__global__ void __launch_bounds__(B, 512 / B)
+k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
+                   uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  unsigned cnt = 0;
+  const long long n_tiles = (n + B - 1) / B;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * B + threadIdx.x;
+    const bool active = item < n;
+    QDirect acc{q + (active ? item : 0) * R.q_dim};
+    const bool ok = warp_check_v3<B, APPROX, AABB_BROAD>(R, S, T, acc, active);
     const unsigned b = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && active) {
       bits[item >> 5] = b;
@@ -456,8 +486,8 @@ __device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const f
 
 // LPE lanes cooperate on one edge; each round they test LPE waypoints in the reference's
 // visiting order (coarse to fine) and the edge retires as soon as one is invalid.
-template <bool APPROX, int LPE>
-__global__ void __launch_bounds__(128)
+template <bool APPROX, int LPE, int VER, int B>
+__global__ void __launch_bounds__(B)
 k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const float* __restrict__ q0,
               const float* __restrict__ q1, const long long n, uint32_t* __restrict__ bits,
               unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ n_checked) {
@@ -506,7 +536,9 @@ k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const fl
         }
         // all 32 lanes enter the cooperative check; lanes without a waypoint are inactive
         QEdge acc{have ? a : q0, have ? b : q1, t, w == 0};
-        const bool ok = warp_check<APPROX>(R, S, T, acc, work);
+        const bool ok = (VER == 3)   ? warp_check_v3<B, APPROX, true>(R, S, T, acc, work)
+                        : (VER == 4) ? warp_check_v3<B, APPROX, false>(R, S, T, acc, work)
+                                     : warp_check<APPROX>(R, S, T, acc, work);
         const bool bad = work && !ok;
         const unsigned badmask = __ballot_sync(0xffffffffu, bad);
         if (badmask & sub_mask) edge_ok = false;
@@ -552,7 +584,7 @@ __global__ void k_sdf_is_outside(const SceneDev S, const float* __restrict__ pts
     for (int k = 0; k < S.n_prims && outside; k++) {
       const Prim P = load_prim(S.prims, k);
       if (P.type == PMP_PRIM_GROUND)
-        outside = (p.z + P.p1.w > r);
+        outside = (p.z + P.pr.x > r);
       else
         outside = prim_is_outside(P, p, r);
     }

@@ -1,0 +1,339 @@
+// pmp_v3.cuh — v3 validity check: lean per-lane phase 1 + flat, warp-local work queues for the
+// narrow phases.
+//
+// ncu on v2 (profiles/r01_v2b_check_configs_ncu.md): 259 warp-instructions per configuration, of
+// which ~60 % sit in the narrow phases although only ~1.7 (configuration, group | pair) items per
+// configuration survive the broad phase.  v2 walks every group and every listed pair with a
+// ballot + publish + partially filled rounds; v3 instead
+//
+//   phase 1  (lane = configuration, uniform): FK with the joint quaternion taken from a
+//            host-precomputed basis (local = s * A + c * B, A = origin (x) (axis, 0), B = origin:
+//            8 instructions instead of 19), points placed with q * v directly (no rotation
+//            matrices), group bounding spheres against the primitives' AABBs (or the exact
+//            predicate, template switch) -> every surviving (configuration, group, primitive)
+//            triple is PUSHED into a warp-local queue in shared memory (the warp is converged, so
+//            the queue tail is a warp-uniform register: ballot + popc + one STS, no atomics);
+//   drain    one flat loop over the queue, four independent 8-lane sub-warps per round: an env
+//            item is one group against ONE primitive (one sphere per lane, the primitive's test
+//            variant resolved at scene build), a self item is one listed group pair.  A
+//            warp-uniform `bad` mask retires configurations (REDUX.OR); later items of a retired
+//            configuration are skipped.  If a queue would overflow it is drained early and phase 1
+//            resumes where it stopped, so any table size works with fixed 512 + 128 byte queues.
+//
+// The result is unchanged: validity depends neither on the broad-phase hierarchy nor on the order
+// of the tests (SURVEY finding 7, App. A.4; reference: check_ext_collision / check_self_collision,
+// constraints/primitive_sphere_collision.cpp:191-254).
+#pragma once
+
+namespace pmp {
+
+constexpr int kQE = 128;  // env items per warp:  lane | group << 5 | primitive << 16
+constexpr int kQS = 32;   // self items per warp: lane | pair << 5
+constexpr int kV3WordsPerThread = (32 * 4 + kQE + kQS) / 32;  // scratch float4[32] + queues, per warp
+constexpr unsigned kItemCloud = 0xffffu;     // primitive field: the scene's point cloud
+constexpr unsigned kItemOverflow = 0xfffeu;  // primitive field: every primitive with index >= 30
+constexpr int kMaxGroupsV3 = 2048;           // the group field of an env item has 11 bits
+
+// shared-memory views with the CTA size B known at compile time (offsets fold into immediates)
+template <int B>
+struct V3View {
+  float* frames;    // [slot][7][B]
+  float* gc;        // [group][3][B]
+  float4* scratch;  // [warp][32]
+  unsigned* qenv;   // [warp][kQE]
+  unsigned* qself;  // [warp][kQS]
+};
+
+template <int B>
+__device__ __forceinline__ V3View<B> v3_view(const RobotDev& R, const Smem& T) {
+  V3View<B> v;
+  v.frames = T.stash;
+  v.gc = T.stash + R.n_slots * 7 * B;
+  v.scratch = reinterpret_cast<float4*>(v.gc + R.n_groups * 3 * B);
+  v.qenv = reinterpret_cast<unsigned*>(v.scratch + B);
+  v.qself = v.qenv + kQE * (B / 32);
+  return v;
+}
+
+template <int B>
+__device__ __forceinline__ Frame v3_frame_at(const V3View<B>& v, int slot, int tid) {
+  const float* p = v.frames + slot * (7 * B) + tid;
+  Frame f;
+  f.qx = p[0]; f.qy = p[B]; f.qz = p[2 * B]; f.qw = p[3 * B];
+  f.tx = p[4 * B]; f.ty = p[5 * B]; f.tz = p[6 * B];
+  return f;
+}
+
+// t + q * v  (Eigen's q * v, algebraically equal to toRotationMatrix() * v for any q)
+__device__ __forceinline__ float3 place(const Frame& f, const float vx, const float vy, const float vz) {
+  const float3 r = quat_rot(f.qx, f.qy, f.qz, f.qw, make3(vx, vy, vz));
+  return make3(f.tx + r.x, f.ty + r.y, f.tz + r.z);
+}
+
+// frame = parent (x) local(q).  Revolute: local quaternion = s * A + c * B with
+// A = origin (x) (axis, 0) and B = origin (the product origin (x) (axis s, c) of
+// kinematics/algorithm.cpp:140-147 is linear in (s, c)); for identity-flagged origins A = (axis, 0),
+// B = (0, 0, 0, 1), which reproduces the reference's skipped product exactly.
+template <bool APPROX>
+__device__ __forceinline__ Frame apply_op_v3(const Frame& p, const float4 wB, const float4 w1, const float4 w2,
+                                             const float4 wA, const int kind, const int flags, const float qv) {
+  Frame f;
+  float ltx = w1.x, lty = w1.y, ltz = w1.z;
+  if (kind == PMP_OP_REVOLUTE) {
+    float s, c;
+    half_sincos<APPROX>(qv, s, c);
+    const float lx = fmaf(s, wA.x, c * wB.x), ly = fmaf(s, wA.y, c * wB.y), lz = fmaf(s, wA.z, c * wB.z),
+                lw = fmaf(s, wA.w, c * wB.w);
+    quat_mul(p.qx, p.qy, p.qz, p.qw, lx, ly, lz, lw, f.qx, f.qy, f.qz, f.qw);
+  } else {
+    if (kind == PMP_OP_PRISMATIC) {
+      ltx = fmaf(w2.x, qv, ltx);
+      lty = fmaf(w2.y, qv, lty);
+      ltz = fmaf(w2.z, qv, ltz);
+    }
+    if (flags & PMP_OPFLAG_ORIGIN_IDENTITY) {
+      f.qx = p.qx; f.qy = p.qy; f.qz = p.qz; f.qw = p.qw;
+    } else {
+      quat_mul(p.qx, p.qy, p.qz, p.qw, wB.x, wB.y, wB.z, wB.w, f.qx, f.qy, f.qz, f.qw);
+    }
+  }
+  if ((flags & PMP_OPFLAG_ZERO_XYZ) && kind != PMP_OP_PRISMATIC) {
+    f.tx = p.tx; f.ty = p.ty; f.tz = p.tz;
+  } else {
+    const float3 r = quat_rot(p.qx, p.qy, p.qz, p.qw, make3(ltx, lty, ltz));
+    f.tx = p.tx + r.x; f.ty = p.ty + r.y; f.tz = p.tz + r.z;
+  }
+  return f;
+}
+
+// ---- drains ---------------------------------------------------------------------------------------
+// env items: 8 lanes per (configuration, group, primitive) item, one sphere per lane per round.
+// Sub-warps are independent; they meet again at the REDUX that retires configurations.
+template <int B>
+__device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const unsigned* qenv,
+                                              const int n_env, unsigned bad, const int lane, const int wbase) {
+  constexpr unsigned full = 0xffffffffu;
+  const int sub = lane & 7, k = lane >> 3;
+  for (int b0 = 0; b0 < n_env; b0 += 4) {
+    const int it = b0 + k;
+    unsigned hitbit = 0;
+    if (it < n_env) {
+      const unsigned h = qenv[it];
+      const int src = h & 31;
+      if (!((bad >> src) & 1u)) {
+        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * ((h >> 5) & (kMaxGroupsV3 - 1)) + 1]);
+        const Frame f = v3_frame_at(V, gw.w >> 8, wbase + src);
+        const unsigned kp = h >> 16;
+        bool hit = false;
+        if (kp < 30u) {
+          const Prim P = load_prim(T.prims, kp);
+          for (int s = sub; s < gw.z; s += 8) {
+            const float4 sp = T.spheres[gw.y + s];
+            hit |= !prim_is_outside(P, place(f, sp.x, sp.y, sp.z), sp.w);
+          }
+        } else if (kp == kItemCloud) {
+          for (int s = sub; s < gw.z && !hit; s += 8) {
+            const float4 sp = T.spheres[gw.y + s];
+            hit = !cloud_is_outside(S.cloud, place(f, sp.x, sp.y, sp.z), sp.w);
+          }
+        } else {
+          for (int s = sub; s < gw.z; s += 8) {
+            const float4 sp = T.spheres[gw.y + s];
+            const float3 c = place(f, sp.x, sp.y, sp.z);
+            for (int kk = 30; kk < S.n_prims; kk++) hit |= !prim_is_outside(load_prim(T.prims, kk), c, sp.w);
+          }
+        }
+        hitbit = hit ? (1u << src) : 0u;
+      }
+    }
+    bad |= __reduce_or_sync(full, hitbit);
+  }
+  return bad;
+}
+
+// self items: 8 lanes per (configuration, pair) item, four independent sub-warps per round (their
+// ballots / barriers use the sub-warp's own lane mask).  The lanes place 8 spheres of A at a time,
+// cull them against B's bounding sphere and compact the survivors into the sub-warp's scratch row;
+// then every lane owns one sphere of B (culled against A's bounding sphere) and tests it against the
+// compacted A spheres (strict <, .cpp:240-248).
+template <int B>
+__device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V, const unsigned* qself, float4* scratch,
+                                               const int n_self, unsigned bad, const int lane, const int wbase) {
+  constexpr unsigned full = 0xffffffffu;
+  const int sub = lane & 7, k = lane >> 3;
+  const unsigned smask = 0xffu << (k * 8);
+  float4* my = scratch + k * 8;
+  for (int b0 = 0; b0 < n_self; b0 += 4) {
+    const int it = b0 + k;
+    unsigned hitbit = 0;
+    if (it < n_self) {
+      const unsigned h = qself[it];
+      const int src = h & 31;
+      if (!((bad >> src) & 1u)) {
+        const float4 pw = T.pairs4[h >> 5];
+        const int ga = __float_as_int(pw.x), gb = __float_as_int(pw.y);
+        const float Ra = T.groups[2 * ga].w, Rb = T.groups[2 * gb].w;
+        const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * ga + 1]);
+        const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * gb + 1]);
+        const int stid = wbase + src;
+        const Frame fa = v3_frame_at(V, wa.w >> 8, stid), fb = v3_frame_at(V, wb.w >> 8, stid);
+        const float* pa = V.gc + ga * (3 * B) + stid;
+        const float* pb = V.gc + gb * (3 * B) + stid;
+        const float3 gca = make3(pa[0], pa[B], pa[2 * B]);
+        const float3 gcb = make3(pb[0], pb[B], pb[2 * B]);
+        bool hit = false;
+        for (int i0 = 0; i0 < wa.z; i0 += 8) {
+          const int i = i0 + sub;
+          const float4 sa = T.spheres[wa.y + i];  // reads past the group stay inside the CTA's tables and are masked
+          const float3 ca = place(fa, sa.x, sa.y, sa.z);
+          const float ex = ca.x - gcb.x, ey = ca.y - gcb.y, ez = ca.z - gcb.z, er = sa.w + Rb;
+          const bool keep_a = (i < wa.z) & !(ex * ex + ey * ey + ez * ez > er * er);
+          const unsigned MA = (__ballot_sync(smask, keep_a) >> (k * 8)) & 0xffu;
+          if (!MA) continue;
+          __syncwarp(smask);  // readers of the previous chunk are done
+          if (keep_a) my[__popc(MA & ((1u << sub) - 1u))] = make_float4(ca.x, ca.y, ca.z, sa.w);
+          __syncwarp(smask);
+          const int ka = __popc(MA);
+          for (int j0 = 0; j0 < wb.z; j0 += 8) {
+            const int j = j0 + sub;
+            const float4 sb = T.spheres[wb.y + j];
+            const float3 cb = place(fb, sb.x, sb.y, sb.z);
+            const float fx = cb.x - gca.x, fy = cb.y - gca.y, fz = cb.z - gca.z, fr = sb.w + Ra;
+            if ((j < wb.z) & !(fx * fx + fy * fy + fz * fz > fr * fr)) {
+              for (int t = 0; t < ka; t++) {
+                const float4 a = my[t];
+                const float hx = a.x - cb.x, hy = a.y - cb.y, hz = a.z - cb.z, hr = a.w + sb.w;
+                hit |= hx * hx + hy * hy + hz * hz < hr * hr;
+              }
+            }
+          }
+        }
+        hitbit = hit ? (1u << src) : 0u;
+      }
+    }
+    bad |= __reduce_or_sync(full, hitbit);
+  }
+  return bad;
+}
+
+// All 32 lanes of the warp must call this (lanes without a configuration pass active = false).
+// B = blockDim.x.
+template <int B, bool APPROX, bool AABB_BROAD, class QAcc>
+__device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q, const bool active) {
+  constexpr unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid & ~31;
+  const unsigned lt = (1u << lane) - 1u;
+  const V3View<B> V = v3_view<B>(R, T);
+  unsigned* qenv = V.qenv + warp * kQE;
+  unsigned* qself = V.qself + warp * kQS;
+  float4* scratch = V.scratch + warp * 32;
+  const bool ext = (S.n_prims > 0) || S.cloud.enabled;
+  unsigned bad = 0;  // warp-uniform: bit l set = lane l's configuration is known to be invalid
+
+  // ---- phase 1 (resumable: the env queue is drained early if a push would overflow it) ----
+  const Frame base = base_frame(R, q);
+  Frame cur = base;
+  int i = 0, gi = 0, n_env = 0;
+  bool ready = false;
+  for (;;) {
+    bool stalled = false;
+    for (; i < R.n_ops; i++) {
+      if (!ready) {
+        const float4* ow = T.ops + kOpWords * i;
+        const float4 wB = ow[0], w1 = ow[1], w2 = ow[2];
+        const int4 w3 = *reinterpret_cast<const int4*>(ow + 3);
+        const float4 wA = ow[4];
+        const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
+        Frame parent = cur;
+        if (w3.x != i - 1) parent = (w3.x < 0) ? base : v3_frame_at(V, w3.w, tid);
+        const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
+        cur = apply_op_v3<APPROX>(parent, wB, w1, w2, wA, kind, w3.y, qv);
+        if (w3.z >= 0) {
+          float* p = V.frames + w3.z * (7 * B) + tid;
+          p[0] = cur.qx; p[B] = cur.qy; p[2 * B] = cur.qz; p[3 * B] = cur.qw;
+          p[4 * B] = cur.tx; p[5 * B] = cur.ty; p[6 * B] = cur.tz;
+        }
+        ready = true;
+      }
+      while (gi < R.n_groups) {
+        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
+        if (gw.x != i) break;
+        const float4 g = T.groups[2 * gi];
+        const float3 gc = place(cur, g.x, g.y, g.z);
+        float* p = V.gc + gi * (3 * B) + tid;
+        p[0] = gc.x; p[B] = gc.y; p[2 * B] = gc.z;
+        if (ext && !(gw.w & 1)) {
+          // bits 0..29: primitive k passes the group-level cull, 30: cloud, 31: some primitive >= 30
+          unsigned pm = 0;
+          const int n30 = min(S.n_prims, 30);
+          for (int kp = 0; kp < n30; kp++) {
+            const float4* pw = T.prims + kPrimWords * kp;
+            const bool out = AABB_BROAD ? prim_aabb_outside(pw[5], pw[6], gc, g.w) : prim_is_outside(load_prim(T.prims, kp), gc, g.w);
+            pm |= out ? 0u : (1u << kp);
+          }
+          for (int kp = 30; kp < S.n_prims; kp++) {
+            const float4* pw = T.prims + kPrimWords * kp;
+            const bool out = AABB_BROAD ? prim_aabb_outside(pw[5], pw[6], gc, g.w) : prim_is_outside(load_prim(T.prims, kp), gc, g.w);
+            pm |= out ? 0u : kMaskOverflow;
+          }
+          if (S.cloud.enabled && !cloud_surely_outside(S.cloud, gc, g.w)) pm |= kMaskCloud;
+          // one queue item per set bit
+          unsigned rem = active ? pm : 0u;
+          unsigned ball = __ballot_sync(full, rem != 0u);
+          while (ball) {
+            const int cnt = __popc(ball);
+            if (n_env + cnt > kQE) {
+              stalled = true;  // drain, then redo this group (already queued items are only re-tested)
+              break;
+            }
+            if (rem) {
+              const unsigned b = __ffs(rem) - 1;
+              rem &= rem - 1u;
+              const unsigned kp = (b < 30u) ? b : (b == 30u ? kItemCloud : kItemOverflow);
+              qenv[n_env + __popc(ball & lt)] = (unsigned)lane | ((unsigned)gi << 5) | (kp << 16);
+            }
+            n_env += cnt;
+            ball = __ballot_sync(full, rem != 0u);
+          }
+          if (stalled) break;
+        }
+        gi++;
+      }
+      if (stalled) break;
+      ready = false;
+    }
+    __syncwarp();
+    bad = drain_env<B>(S, T, V, qenv, n_env, bad, lane, wbase);
+    n_env = 0;
+    if (!stalled) break;
+    __syncwarp();
+  }
+
+  // ---- listed group pairs: bounding-sphere test per lane, survivors queued ----
+  int n_self = 0;
+  for (int p = 0; R.n_pairs > 0;) {
+    const bool alive = active && !((bad >> lane) & 1u);
+    for (; p < R.n_pairs; p++) {
+      const float4 pw = T.pairs4[p];
+      const float* pa = V.gc + __float_as_int(pw.x) * (3 * B) + tid;
+      const float* pb = V.gc + __float_as_int(pw.y) * (3 * B) + tid;
+      const float dx = pa[0] - pb[0], dy = pa[B] - pb[B], dz = pa[2 * B] - pb[2 * B];
+      const bool near = alive & !(dx * dx + dy * dy + dz * dz > pw.z);
+      const unsigned ball = __ballot_sync(full, near);
+      if (ball) {
+        const int cnt = __popc(ball);
+        if (n_self + cnt > kQS) break;
+        if (near) qself[n_self + __popc(ball & lt)] = (unsigned)lane | ((unsigned)p << 5);
+        n_self += cnt;
+      }
+    }
+    __syncwarp();
+    bad = drain_self<B>(T, V, qself, scratch, n_self, bad, lane, wbase);
+    n_self = 0;
+    if (p >= R.n_pairs) break;
+    __syncwarp();
+  }
+  return active && !((bad >> lane) & 1u);
+}
+
+}  // namespace pmp

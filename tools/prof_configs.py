@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Small driver for ncu: a few launches of the validity kernel on a resident batch.
+  python tools/prof_configs.py [workload] [n] [launches]      (workload: panda | panda_ceiled | fetch | edgesA | edgesB)
+"""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from plainmp_b200 import _capi, tables, workloads  # noqa: E402
+from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorType  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "panda"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 22
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+lib = _capi.load()
+if wl.startswith("edges"):
+    spec, cst = workloads.make_panda(ceiled=True)
+    robot, scene = cst._robot(), cst._scene()
+    planner_like = wl.endswith("B")
+    q0, q1 = workloads.random_edges(spec, n, 3, planner_like, (lambda q: tables.check_configs(robot, scene, q)) if planner_like else None)
+    a, b = torch.from_numpy(q0).to(dev), torch.from_numpy(q1).to(dev)
+    mv = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, [0.05] * 7))
+    bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
+    ctr = torch.zeros(2, dtype=torch.int64, device=dev)
+    for _ in range(reps):
+        _capi.check(lib.pmp_check_edges(robot.handle, scene.handle, C.byref(mv._v), a.data_ptr(), b.data_ptr(), n, bits.data_ptr(), ctr.data_ptr(), ctr.data_ptr() + 8, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    print(wl, n, "valid", ctr[0].item() / reps / n, "checks/edge", ctr[1].item() / reps / n)
+else:
+    spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch}[wl]()
+    robot, scene = cst._robot(), cst._scene()
+    q = torch.from_numpy(workloads.random_configs(spec, n, 5)).to(dev)
+    bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    for _ in range(reps):
+        tables.check_configs_device(robot, scene, q, bits, cnt)
+    torch.cuda.synchronize()
+    print(wl, n, "valid fraction", cnt.item() / reps / n)

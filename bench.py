@@ -34,7 +34,7 @@ UNIT = "configs/s"
 # dense algorithmic work of one panda dual-bars configuration
 F_CFG_DENSE = 14.7e3          # flop/config (no culling, no early exit)
 BYTES_PER_CFG = 7 * 4 + 1 / 8  # q in + 1 validity bit out
-DRAM_BYTES_PER_CFG_NCU = 29.0   # measured once with ncu --set full (profiles/), per configuration
+DRAM_BYTES_PER_CFG_NCU = 28.9   # measured once with ncu --set full (profiles/r01_v3_check_configs_ncu.md), per configuration
 
 
 def parse_args():
@@ -178,6 +178,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.load()
 
@@ -327,7 +329,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": DRAM_BYTES_PER_CFG_NCU * n_local / 1e9, "traffic_unit": "GB per launch",
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 29.0 B/config (profiles/r01_v2b_check_configs_ncu.md), scaled to this launch",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 28.9 B/config (profiles/r01_v3_check_configs_ncu.md), scaled to this launch",
                 "algorithmic_gb_per_launch": BYTES_PER_CFG * n_local / 1e9,
                 "peak_source": hbm_src, "kernel_ms": kernel_ms,
                 "note": "algorithmic bytes = 28.125 B/config; the kernel is FP32-SIMT issue bound, see roofline_fp32",

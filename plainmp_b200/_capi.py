@@ -154,7 +154,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(SRC_DIR / "plainmp_b200.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, "--threads", "2", "-o", str(LIB_PATH), str(SRC_DIR / "plainmp_b200.cu"), str(SRC_DIR / "pmp_cloud_build.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

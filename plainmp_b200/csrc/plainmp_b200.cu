@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "pmp_cloud_build.h"
 #include "pmp_kernels.cuh"
 
 using namespace pmp;
@@ -73,9 +74,7 @@ struct pmp_robot {
 struct pmp_scene {
   SceneDev dev{};
   float4* prims_dev = nullptr;
-  float4* cloud_pts = nullptr;
-  uint32_t* cloud_cell_start = nullptr;
-  float* cloud_dist = nullptr;
+  CloudBuffers cloud;
 };
 
 static SceneDev empty_scene() {
@@ -93,8 +92,8 @@ static size_t smem_bytes(const pmp_robot* r, const SceneDev& s, int block = kBlo
 static int pick_block(const pmp_robot* r, const SceneDev& s) {
   return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
 }
-// kernel generation: 3 = v3 with the AABB group cull (default), 4 = v3 with the exact group
-// predicate, 2 / 1 = the earlier kernels kept for A/B measurements (PMP_KERNEL=v1|v2|v3|v3x)
+// kernel generation: 3 = v3 (default); 2 / 1 = the earlier kernels kept for A/B measurements
+// (PMP_KERNEL=v1|v2|v3)
 static int kernel_version() {
   static const int v = [] {
     const char* e = getenv("PMP_KERNEL");
@@ -102,7 +101,6 @@ static int kernel_version() {
     const std::string s(e);
     if (s == "v1") return 1;
     if (s == "v2") return 2;
-    if (s == "v3x") return 4;
     return 3;
   }();
   return v;
@@ -317,71 +315,22 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
     s->dev.n_prims = d->n_prims;
   }
   if (d->n_cloud_points > 0) {
-    const int64_t n = d->n_cloud_points;
-    if (n >= (int64_t)1 << 31) {
+    if (d->n_cloud_points >= (int64_t)1 << 31) {
       pmp_scene_destroy(s);
       return fail(PMP_ERR_LIMIT, "cloud too large");
     }
-    CloudDev& C = s->dev.cloud;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int64_t i = 0; i < n; i++)
-      for (int a = 0; a < 3; a++) {
-        const float v = d->cloud_points[3 * i + a];
-        if (!std::isfinite(v)) {
-          pmp_scene_destroy(s);
-          return fail(PMP_ERR_INVALID, "non-finite cloud point");
-        }
-        lo[a] = std::min(lo[a], v);
-        hi[a] = std::max(hi[a], v);
-      }
-    C.rho = d->cloud_radius;
-    C.lbx = lo[0] - C.rho; C.lby = lo[1] - C.rho; C.lbz = lo[2] - C.rho;
-    C.ubx = hi[0] + C.rho; C.uby = hi[1] + C.rho; C.ubz = hi[2] + C.rho;
-    const float margin = 0.35f;  // larger than any group-sphere query radius of the stock robots
-    float h = d->cloud_cell > 0.f ? d->cloud_cell : 0.02f;
-    const double ext[3] = {hi[0] - lo[0] + 2.0 * margin, hi[1] - lo[1] + 2.0 * margin, hi[2] - lo[2] + 2.0 * margin};
-    while ((ext[0] / h + 1) * (ext[1] / h + 1) * (ext[2] / h + 1) > 24.0e6) h *= 1.25f;
-    C.h = h;
-    C.inv_h = 1.f / h;
-    C.e = 0.5f * std::sqrt(3.f) * h * 1.0001f;
-    C.dist_cap = margin;
-    C.ox = lo[0] - margin; C.oy = lo[1] - margin; C.oz = lo[2] - margin;
-    C.nx = (int)std::ceil(ext[0] / h) + 1;
-    C.ny = (int)std::ceil(ext[1] / h) + 1;
-    C.nz = (int)std::ceil(ext[2] / h) + 1;
-    C.n_pts = n;
-    const int64_t n_cells = (int64_t)C.nx * C.ny * C.nz;
-    float* raw = nullptr;
-    uint32_t *counts = nullptr, *cell_of = nullptr;
-    cudaError_t e = cudaMalloc(&raw, n * 12);
-    if (e == cudaSuccess) e = cudaMemcpy(raw, d->cloud_points, n * 12, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&counts, n_cells * 4);
-    if (e == cudaSuccess) e = cudaMemset(counts, 0, n_cells * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&cell_of, n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->cloud_cell_start, (n_cells + 1) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&s->cloud_pts, n * 16);
-    if (e == cudaSuccess) e = cudaMalloc(&s->cloud_dist, n_cells * 4);
-    if (e == cudaSuccess) {
-      const int grid = g_num_sms * 8;
-      k_cloud_count<<<grid, 256>>>(raw, n, C, counts, cell_of);
-      k_cloud_scan<<<1, 1024>>>(counts, n_cells, s->cloud_cell_start);
-      cudaMemset(counts, 0, n_cells * 4);
-      k_cloud_scatter<<<grid, 256>>>(raw, n, cell_of, s->cloud_cell_start, counts, s->cloud_pts);
-      C.pts = s->cloud_pts;
-      C.cell_start = s->cloud_cell_start;
-      k_cloud_field<<<grid, 256>>>(C, s->cloud_dist);
-      g_launches += 4;
-      C.dist = s->cloud_dist;
-      e = cudaDeviceSynchronize();
-    }
-    if (raw) cudaFree(raw);
-    if (counts) cudaFree(counts);
-    if (cell_of) cudaFree(cell_of);
-    if (e != cudaSuccess) {
+    if (!d->cloud_points) {
       pmp_scene_destroy(s);
-      return fail(PMP_ERR_CUDA, std::string("cloud grid build: ") + cudaGetErrorString(e));
+      return fail(PMP_ERR_INVALID, "cloud_points is null");
     }
-    C.enabled = 1;
+    std::string err;
+    int launches = 0;
+    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_cell, g_num_sms, &s->dev.cloud, &s->cloud,
+                    &launches, &err)) {
+      pmp_scene_destroy(s);
+      return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
+    }
+    g_launches += launches;
   }
   *out = s;
   return PMP_OK;
@@ -390,9 +339,7 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
 void pmp_scene_destroy(pmp_scene_t* s) {
   if (!s) return;
   if (s->prims_dev) cudaFree(s->prims_dev);
-  if (s->cloud_pts) cudaFree(s->cloud_pts);
-  if (s->cloud_cell_start) cudaFree(s->cloud_cell_start);
-  if (s->cloud_dist) cudaFree(s->cloud_dist);
+  cloud_free(&s->cloud);
   delete s;
 }
 
@@ -428,19 +375,18 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
     case 2:
       if (approx) PMP_LAUNCH_CHECK(k_check_configs<true>); else PMP_LAUNCH_CHECK(k_check_configs<false>);
       break;
-    case 4:
-      if (block == 128) {
-        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<128, true, false>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<128, false, false>));
-      } else {
-        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<64, true, false>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<64, false, false>));
-      }
-      break;
-    default:
-      if (block == 128) {
-        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<128, true, true>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<128, false, true>));
-      } else {
-        if (approx) PMP_LAUNCH_CHECK((k_check_configs_v3<64, true, true>)); else PMP_LAUNCH_CHECK((k_check_configs_v3<64, false, true>));
-      }
+    default: {
+      const bool cloud = S.cloud.enabled != 0;
+#define PMP_V3(BB, AP, CL) PMP_LAUNCH_CHECK((k_check_configs_v3<BB, AP, CL>))
+#define PMP_V3_B(BB)                                                         \
+  do {                                                                       \
+    if (approx) { if (cloud) PMP_V3(BB, true, true); else PMP_V3(BB, true, false); }   \
+    else { if (cloud) PMP_V3(BB, false, true); else PMP_V3(BB, false, false); }        \
+  } while (0)
+      if (block == 128) PMP_V3_B(128); else PMP_V3_B(64);
+#undef PMP_V3_B
+#undef PMP_V3
+    }
   }
 #undef PMP_LAUNCH_CHECK
   g_launches++;
@@ -626,8 +572,8 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
   switch (kernel_version()) {
     case 1:
     case 2: PMP_EDGES_VER(2); break;
-    case 4: PMP_EDGES_VER(4); break;
-    default: PMP_EDGES_VER(3);
+    default:
+      if (S.cloud.enabled) PMP_EDGES_VER(4); else PMP_EDGES_VER(3);  // 4 = v3 with the cloud traversal compiled in
   }
 #undef PMP_EDGES_VER
 #undef PMP_LAUNCH_EDGES

@@ -259,9 +259,10 @@ k_check_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q,
   if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
 }
 
-// v3: lean phase 1 + warp-local work queue (pmp_v3.cuh).  AABB_BROAD selects the group-level cull.
-// B = blockDim.x (compile-time so that the stash offsets fold into immediates).
-template <int B, bool APPROX, bool AABB_BROAD>
+// v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  B = blockDim.x (compile-time so that the
+// stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
+// out of the primitives-only kernel).
+template <int B, bool APPROX, bool CLOUD>
 __global__ void __launch_bounds__(B, 512 / B)
 k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
                    uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
@@ -273,7 +274,7 @@ k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__
     const long long item = tile * B + threadIdx.x;
     const bool active = item < n;
     QDirect acc{q + (active ? item : 0) * R.q_dim};
-    const bool ok = warp_check_v3<B, APPROX, AABB_BROAD>(R, S, T, acc, active);
+    const bool ok = warp_check_v3<B, APPROX, CLOUD>(R, S, T, acc, active);
     const unsigned b = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && active) {
       bits[item >> 5] = b;
@@ -536,8 +537,8 @@ k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const fl
         }
         // all 32 lanes enter the cooperative check; lanes without a waypoint are inactive
         QEdge acc{have ? a : q0, have ? b : q1, t, w == 0};
-        const bool ok = (VER == 3)   ? warp_check_v3<B, APPROX, true>(R, S, T, acc, work)
-                        : (VER == 4) ? warp_check_v3<B, APPROX, false>(R, S, T, acc, work)
+        const bool ok = (VER == 3)   ? warp_check_v3<B, APPROX, false>(R, S, T, acc, work)
+                        : (VER == 4) ? warp_check_v3<B, APPROX, true>(R, S, T, acc, work)
                                      : warp_check<APPROX>(R, S, T, acc, work);
         const bool bad = work && !ok;
         const unsigned badmask = __ballot_sync(0xffffffffu, bad);

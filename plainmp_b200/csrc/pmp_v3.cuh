@@ -9,8 +9,8 @@
 //   phase 1  (lane = configuration, uniform): FK with the joint quaternion taken from a
 //            host-precomputed basis (local = s * A + c * B, A = origin (x) (axis, 0), B = origin:
 //            8 instructions instead of 19), points placed with q * v directly (no rotation
-//            matrices), group bounding spheres against the primitives' AABBs (or the exact
-//            predicate, template switch) -> every surviving (configuration, group, primitive)
+//            matrices), group bounding spheres against the primitives' AABBs (branch-free
+//            centre / half-extent form) -> every surviving (configuration, group, primitive)
 //            triple is PUSHED into a warp-local queue in shared memory (the warp is converged, so
 //            the queue tail is a warp-uniform register: ballot + popc + one STS, no atomics);
 //   drain    one flat loop over the queue, four independent 8-lane sub-warps per round: an env
@@ -109,7 +109,7 @@ __device__ __forceinline__ Frame apply_op_v3(const Frame& p, const float4 wB, co
 // ---- drains ---------------------------------------------------------------------------------------
 // env items: 8 lanes per (configuration, group, primitive) item, one sphere per lane per round.
 // Sub-warps are independent; they meet again at the REDUX that retires configurations.
-template <int B>
+template <int B, bool CLOUD>
 __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const unsigned* qenv,
                                               const int n_env, unsigned bad, const int lane, const int wbase) {
   constexpr unsigned full = 0xffffffffu;
@@ -131,7 +131,7 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
             const float4 sp = T.spheres[gw.y + s];
             hit |= !prim_is_outside(P, place(f, sp.x, sp.y, sp.z), sp.w);
           }
-        } else if (kp == kItemCloud) {
+        } else if (CLOUD && kp == kItemCloud) {
           for (int s = sub; s < gw.z && !hit; s += 8) {
             const float4 sp = T.spheres[gw.y + s];
             hit = !cloud_is_outside(S.cloud, place(f, sp.x, sp.y, sp.z), sp.w);
@@ -218,7 +218,7 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
 
 // All 32 lanes of the warp must call this (lanes without a configuration pass active = false).
 // B = blockDim.x.
-template <int B, bool APPROX, bool AABB_BROAD, class QAcc>
+template <int B, bool APPROX, bool CLOUD, class QAcc>
 __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q, const bool active) {
   constexpr unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid & ~31;
@@ -227,7 +227,7 @@ __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& 
   unsigned* qenv = V.qenv + warp * kQE;
   unsigned* qself = V.qself + warp * kQS;
   float4* scratch = V.scratch + warp * 32;
-  const bool ext = (S.n_prims > 0) || S.cloud.enabled;
+  const bool ext = (S.n_prims > 0) || CLOUD;
   unsigned bad = 0;  // warp-uniform: bit l set = lane l's configuration is known to be invalid
 
   // ---- phase 1 (resumable: the env queue is drained early if a push would overflow it) ----
@@ -268,15 +268,13 @@ __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& 
           const int n30 = min(S.n_prims, 30);
           for (int kp = 0; kp < n30; kp++) {
             const float4* pw = T.prims + kPrimWords * kp;
-            const bool out = AABB_BROAD ? prim_aabb_outside(pw[5], pw[6], gc, g.w) : prim_is_outside(load_prim(T.prims, kp), gc, g.w);
-            pm |= out ? 0u : (1u << kp);
+            pm |= prim_aabb_outside(pw[5], pw[6], gc, g.w) ? 0u : (1u << kp);
           }
           for (int kp = 30; kp < S.n_prims; kp++) {
             const float4* pw = T.prims + kPrimWords * kp;
-            const bool out = AABB_BROAD ? prim_aabb_outside(pw[5], pw[6], gc, g.w) : prim_is_outside(load_prim(T.prims, kp), gc, g.w);
-            pm |= out ? 0u : kMaskOverflow;
+            pm |= prim_aabb_outside(pw[5], pw[6], gc, g.w) ? 0u : kMaskOverflow;
           }
-          if (S.cloud.enabled && !cloud_surely_outside(S.cloud, gc, g.w)) pm |= kMaskCloud;
+          if (CLOUD && !cloud_surely_outside(S.cloud, gc, g.w)) pm |= kMaskCloud;
           // one queue item per set bit
           unsigned rem = active ? pm : 0u;
           unsigned ball = __ballot_sync(full, rem != 0u);
@@ -303,7 +301,7 @@ __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& 
       ready = false;
     }
     __syncwarp();
-    bad = drain_env<B>(S, T, V, qenv, n_env, bad, lane, wbase);
+    bad = drain_env<B, CLOUD>(S, T, V, qenv, n_env, bad, lane, wbase);
     n_env = 0;
     if (!stalled) break;
     __syncwarp();

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for ncu: a few launches of the validity kernel on a resident batch.
-  python tools/prof_configs.py [workload] [n] [launches]      (workload: panda | panda_ceiled | fetch | edgesA | edgesB)
+  python tools/prof_configs.py [workload] [n] [launches]      (workload: panda | panda_ceiled | fetch | pr2cloud | pr2cloud100k | edgesA | edgesB)
 """
 import ctypes as C
 import sys
@@ -33,7 +33,8 @@ if wl.startswith("edges"):
     torch.cuda.synchronize()
     print(wl, n, "valid", ctr[0].item() / reps / n, "checks/edge", ctr[1].item() / reps / n)
 else:
-    spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch}[wl]()
+    spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch,
+                 "pr2cloud": lambda: workloads.make_pr2_cloud(1_000_000), "pr2cloud100k": lambda: workloads.make_pr2_cloud(100_000)}[wl]()
     robot, scene = cst._robot(), cst._scene()
     q = torch.from_numpy(workloads.random_configs(spec, n, 5)).to(dev)
     bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=dev)

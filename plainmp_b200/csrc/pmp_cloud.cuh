@@ -71,7 +71,7 @@ __device__ inline bool cloud_any_within(const CloudDev& C, const float3 p, const
   int l = top, n = 0;
   unsigned long long masks = 0;
   if (top == 0) {
-    masks = 1ull;  // the root is a leaf: treat it as the only child of a virtual level-1 node
+    masks = 1ull << 8;  // the root is a leaf: treat it as the only child of a virtual level-1 node
     l = 1;
   } else {
     masks = (unsigned long long)cloud_children_mask<false>(C, l - 1, 0, p, bound2) << (8 * l);
@@ -116,7 +116,7 @@ __device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const
   int l = top, n = 0;
   unsigned long long masks = 0;
   if (top == 0) {
-    masks = 1ull;
+    masks = 1ull << 8;
     l = 1;
   } else {
     masks = (unsigned long long)cloud_children_mask<true>(C, l - 1, 0, p, best) << (8 * l);

@@ -329,3 +329,86 @@ def test_full_size_properties(cuda_lib):
     d = cst.evaluate_batch(Q[:200000])
     clear = np.abs(d).min(axis=1) > 2e-4
     assert (v[:200000][clear] == (d[clear] > 0).all(axis=1)).all()
+
+
+def test_many_primitives_queue_overflow(cuda_lib):
+    # 44 primitives wrapped around the arm: every group passes the cull against many of them, so the
+    # per-warp env queue (128 items) overflows and phase 1 is drained and resumed several times per
+    # tile; primitives 30.. go through the overflow item of the queue.
+    spec = PandaSpec()
+    cst = spec.create_collision_const(use_cache=False)
+    rng = np.random.default_rng(41)
+    prims = []
+    for i in range(44):
+        pos = rng.uniform([-0.6, -0.6, 0.0], [0.6, 0.6, 1.1])
+        rot = np.eye(3) if i % 3 == 0 else rpy_matrix(*rng.uniform(-1, 1, 3))
+        pose = psdf.Pose(pos, rot)
+        kind = i % 4
+        if kind == 0:
+            prims.append(psdf.BoxSDF(rng.uniform(0.02, 0.12, 3), pose))
+        elif kind == 1:
+            prims.append(psdf.CylinderSDF(rng.uniform(0.01, 0.05), rng.uniform(0.05, 0.4), pose))
+        elif kind == 2:
+            prims.append(psdf.SphereSDF(rng.uniform(0.01, 0.06), pose))
+        else:
+            prims.append(psdf.BoxSDF([0.6, 0.6, 0.01], psdf.Pose([pos[0], pos[1], 1.25 + 0.01 * i])))
+    cst.set_sdf(psdf.UnionSDF(prims))
+    o = bridge.OracleCst(cst, n_threads=4)
+    Q = workloads.random_configs(spec, 6000, 43)
+    Qd = Q.astype(np.float64)
+    got = cst.is_valid_batch(Q)
+    assert 0.02 < got.mean() < 0.98
+    assert_validity_parity(got, o.is_valid_batch(Qd), o.margin_batch(Qd), "many primitives")
+    np.testing.assert_allclose(cst.evaluate_batch(Q), o.evaluate_batch(Qd), atol=TOL, rtol=0)
+
+
+def test_dense_self_pairs_queue_overflow(cuda_lib):
+    # PR2 dual arm, self collision only, arms folded in front of the body: most lanes keep several of
+    # the 45 listed pairs, so the 32-entry self queue is drained early again and again
+    from plainmp_b200.robot_spec import PR2DualarmSpec
+
+    spec = PR2DualarmSpec()
+    spec.reflect_default_joint_positions()
+    cst = spec.create_collision_const(use_cache=False)
+    o = bridge.OracleCst(cst, n_threads=4)
+    lb, ub = spec.angle_bounds()
+    rng = np.random.default_rng(47)
+    centre = np.array([-0.3, 0.4, -0.8, -1.6, 0.0, -0.8, 0.0, 0.3, 0.4, 0.8, -1.6, 0.0, -0.8, 0.0])
+    Q = np.clip(centre + rng.standard_normal((6000, 14)) * 0.35, lb, ub).astype(np.float32)
+    Qd = Q.astype(np.float64)
+    got = cst.is_valid_batch(Q)
+    assert 0.02 < got.mean() < 0.98
+    assert_validity_parity(got, o.is_valid_batch(Qd), o.margin_batch(Qd), "pr2 self")
+    np.testing.assert_allclose(cst.evaluate_batch(Q), o.evaluate_batch(Qd), atol=TOL, rtol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("n_points", [1, 5, 8, 9, 64, 65, 513, 4097])
+def test_cloud_tree_shapes(cuda_lib, n_points):
+    # the implicit 8-ary box tree at its edge shapes: a single leaf, exactly full levels, one point over
+    rng = np.random.default_rng(100 + n_points)
+    pts = rng.uniform(-0.5, 0.5, (n_points, 3)).astype(np.float32).astype(np.float64)
+    host = psdf.CloudSDF(pts, 0.01)
+    q = np.concatenate([rng.uniform(-1.5, 1.5, (400, 3)), pts[rng.integers(0, n_points, 100)] + rng.standard_normal((100, 3)) * 0.01])
+    q = q.astype(np.float32).astype(np.float64)
+    want = np.sqrt(((q[:, None, :] - pts[None, :, :]) ** 2).sum(-1).min(axis=1)) - 0.01
+    np.testing.assert_allclose(host.evaluate_batch(q.T), want, atol=TOL, rtol=0)
+    for r in (0.0, 0.05, 0.4):
+        clear = np.abs(want - r) > EPS_BAND
+        assert (host.is_outside_batch(q.T, np.full(len(q), r)) == (want > r))[clear].all()
+    tree = KDTree(pts)
+    d2 = ((q[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(tree.sqdist_batch(q), d2.min(axis=1), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(((tree.query_batch(q) - q) ** 2).sum(axis=1), d2.min(axis=1), rtol=1e-5, atol=1e-7)
+
+
+def test_edges_against_cloud_scene(cuda_lib):
+    # the edge kernel with the cloud traversal compiled in (PR2 dual arm vs the table cloud)
+    spec, cst = workloads.make_pr2_cloud(20000)
+    o = bridge.OracleCst(cst, n_threads=4)
+    q0, q1 = workloads.random_edges(spec, 600, 13, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    w = np.full(14, 0.1)
+    mv = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, list(w)))
+    got, n_checked = mv.check_motion_batch(q0, q1)
+    want, _ = bridge.OracleValidator(0, 14, w).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64), n_threads=4)
+    assert 0.05 < want.mean() < 0.95
+    assert (got != want).sum() <= 4 and n_checked > 0

@@ -101,6 +101,7 @@ static int kernel_version() {
     const std::string s(e);
     if (s == "v1") return 1;
     if (s == "v2") return 2;
+    if (s == "v3e") return 4;  // v3 check, but the earlier 8-lanes-per-edge expansion
     return 3;
   }();
   return v;
@@ -535,6 +536,20 @@ int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
   return PMP_OK;
 }
 constexpr int kLanesPerEdge = 8;
+
+// A ring of device counters for the edge kernel's chunk dispenser: one per launch in flight.
+constexpr int kEdgeCounters = 256;
+unsigned long long* g_edge_counters = nullptr;
+std::atomic<unsigned> g_edge_counter_next{0};
+std::mutex g_edge_counter_mu;
+int next_edge_counter(unsigned long long** out) {
+  {
+    std::lock_guard<std::mutex> lk(g_edge_counter_mu);
+    if (!g_edge_counters) CUDA_OK(cudaMalloc(&g_edge_counters, kEdgeCounters * sizeof(unsigned long long)));
+  }
+  *out = g_edge_counters + (g_edge_counter_next++ % kEdgeCounters);
+  return PMP_OK;
+}
 }  // namespace
 
 int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
@@ -572,8 +587,34 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
   switch (kernel_version()) {
     case 1:
     case 2: PMP_EDGES_VER(2); break;
-    default:
-      if (S.cloud.enabled) PMP_EDGES_VER(4); else PMP_EDGES_VER(3);  // 4 = v3 with the cloud traversal compiled in
+    case 4:  // PMP_KERNEL=v3e: the 8-lanes-per-edge expansion on top of the v3 check (A/B only)
+      if (S.cloud.enabled) PMP_EDGES_VER(4); else PMP_EDGES_VER(3);
+      break;
+    default: {
+      // lane = edge with dynamic refill; valid edges atomicOr their bit into zeroed words
+      cudaStream_t st = (cudaStream_t)stream;
+      unsigned long long* counter = nullptr;
+      if (int rc = next_edge_counter(&counter)) return rc;
+      CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+      CUDA_OK(cudaMemsetAsync(valid_bits_dev, 0, (size_t)n_words * 4, st));
+      const long long n_warp_tiles = (n + 31) / 32;
+      const long long tiles = (n_warp_tiles + (block / 32) - 1) / (block / 32);
+      const bool cloud = S.cloud.enabled != 0;
+#define PMP_E3(BB, AP, CL)                                                                                   \
+  do {                                                                                                       \
+    if (int rc = grid_for(k_check_edges_v3<BB, AP, CL>, smem, tiles, &grid, block)) return rc;              \
+    k_check_edges_v3<BB, AP, CL><<<grid, block, smem, st>>>(robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
+                                                            n_valid_dev, n_checked_dev, counter);           \
+  } while (0)
+#define PMP_E3_B(BB)                                                                       \
+  do {                                                                                     \
+    if (approx) { if (cloud) PMP_E3(BB, true, true); else PMP_E3(BB, true, false); }       \
+    else { if (cloud) PMP_E3(BB, false, true); else PMP_E3(BB, false, false); }            \
+  } while (0)
+      if (block == 128) PMP_E3_B(128); else PMP_E3_B(64);
+#undef PMP_E3_B
+#undef PMP_E3
+    }
   }
 #undef PMP_EDGES_VER
 #undef PMP_LAUNCH_EDGES

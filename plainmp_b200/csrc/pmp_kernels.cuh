@@ -562,6 +562,103 @@ k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const fl
   }
 }
 
+// ---- motion edges, v3: lane = edge with dynamic refill ----------------------------------------------
+// Every lane walks ITS OWN edge through the reference's visiting order (s2 first, then the
+// farthest-first table order, motion_validator.cpp:45-78) one waypoint per round, exactly like the
+// serial reference; the 32 waypoints of a round (from 32 different edges) go through one
+// warp_check_v3.  A lane whose edge is decided (first invalid waypoint, or all waypoints valid)
+// immediately takes the next edge of the warp's chunk, and the warp takes a new chunk of
+// kEdgeChunk edges from a global counter when its chunk runs dry, so no check is ever spent on a
+// waypoint the reference would not have tested and the lanes stay full until the batch ends.
+// Valid edges set their bit with one atomicOr (the host wrapper zeroes the words first).
+constexpr int kEdgeChunk = 256;
+
+template <int B, bool APPROX, bool CLOUD>
+__global__ void __launch_bounds__(B, 512 / B)
+k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const float* __restrict__ q0,
+                 const float* __restrict__ q1, const long long n, uint32_t* __restrict__ bits,
+                 unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ n_checked,
+                 unsigned long long* __restrict__ next_chunk) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  constexpr unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  long long next = 0, chunk_end = 0;  // warp-uniform: the unassigned part of the warp's chunk
+  bool more_chunks = true;            // warp-uniform
+  // per-lane edge state
+  long long e = -1;
+  long long w = 0, n_way = 0, n_test = 0;
+  double ratio = 0.0;
+  unsigned cnt_valid = 0;
+  unsigned long long cnt_checked = 0;
+  for (;;) {
+    // ---- refill: every lane without an edge takes the next one ----
+    for (;;) {
+      const unsigned need = __ballot_sync(full, e < 0);
+      if (!need) break;
+      if (next >= chunk_end) {
+        if (!more_chunks) break;
+        long long c = 0;
+        if (lane == 0) c = (long long)atomicAdd(next_chunk, (unsigned long long)kEdgeChunk);
+        c = __shfl_sync(full, c, 0);
+        if (c >= n) {
+          more_chunks = false;
+          break;
+        }
+        next = c;
+        chunk_end = min(c + (long long)kEdgeChunk, n);
+      }
+      const long long cand = next + __popc(need & lt);
+      next = min(next + (long long)__popc(need), chunk_end);
+      if (e < 0 && cand < chunk_end) {
+        e = cand;
+        ratio = edge_step_ratio(V, q0 + e * R.q_dim, q1 + e * R.q_dim, R.q_dim);
+        if (ratio == INFINITY) {  // zero-length edge: valid without any check (motion_validator.cpp:41-43)
+          atomicOr(bits + (e >> 5), 1u << (e & 31));
+          cnt_valid++;
+          e = -1;
+        } else {
+          n_test = (long long)floor(1.0 / ratio) + 2;  // :45
+          n_way = n_test - 1;                           // s2, then the interior points 1 .. n_test-2
+          w = 0;
+        }
+      }
+    }
+    const bool work = e >= 0;
+    if (!__any_sync(full, work)) break;
+    // ---- one waypoint per lane ----
+    float t = 1.f;
+    if (work && w > 0) {
+      if (n_test < 129)
+        t = (float)((double)V.seq[(n_test - 1) * 128 + (w + 1)] * ratio);  // sequence[i], i = w + 1
+      else
+        t = (float)((double)w * ratio);
+    }
+    const long long ee = work ? e : 0;
+    QEdge acc{q0 + ee * R.q_dim, q1 + ee * R.q_dim, t, w == 0};
+    const bool ok = warp_check_v3<B, APPROX, CLOUD>(R, S, T, acc, work);
+    if (work) {
+      cnt_checked++;
+      if (!ok) {
+        e = -1;  // first invalid waypoint decides the edge
+      } else if (++w >= n_way) {
+        atomicOr(bits + (e >> 5), 1u << (e & 31));
+        cnt_valid++;
+        e = -1;
+      }
+    }
+  }
+  for (int off = 16; off; off >>= 1) {
+    cnt_valid += __shfl_down_sync(full, cnt_valid, off);
+    cnt_checked += __shfl_down_sync(full, cnt_checked, off);
+  }
+  if (lane == 0) {
+    if (n_valid && cnt_valid) atomicAdd(n_valid, (unsigned long long)cnt_valid);
+    if (n_checked && cnt_checked) atomicAdd(n_checked, cnt_checked);
+  }
+}
+
 // ---- psdf / kdtree surface ------------------------------------------------------------------------
 __global__ void k_sdf_evaluate(const SceneDev S, const float* __restrict__ pts, const long long n,
                                float* __restrict__ out) {

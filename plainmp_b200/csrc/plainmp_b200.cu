@@ -85,28 +85,20 @@ static SceneDev empty_scene() {
   return s;
 }
 
+static size_t extra_smem() {  // PMP_EXTRA_SMEM=<bytes>: occupancy experiments only
+  static const size_t v = [] {
+    const char* e = getenv("PMP_EXTRA_SMEM");
+    return e ? (size_t)atol(e) : (size_t)0;
+  }();
+  return v;
+}
 static size_t smem_bytes(const pmp_robot* r, const SceneDev& s, int block = kBlock) {
-  return (size_t)(r->dev.blob_words + s.n_prims * kPrimWords) * 16 + r->stash_floats_per_thread * 4 * block;
+  return (size_t)(r->dev.blob_words + s.n_prims * kPrimWords) * 16 + r->stash_floats_per_thread * 4 * block + extra_smem();
 }
 // 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
 static int pick_block(const pmp_robot* r, const SceneDev& s) {
   return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
 }
-// kernel generation: 3 = v3 (default); 2 / 1 = the earlier kernels kept for A/B measurements
-// (PMP_KERNEL=v1|v2|v3)
-static int kernel_version() {
-  static const int v = [] {
-    const char* e = getenv("PMP_KERNEL");
-    if (!e) return 3;
-    const std::string s(e);
-    if (s == "v1") return 1;
-    if (s == "v2") return 2;
-    if (s == "v3e") return 4;  // v3 check, but the earlier 8-lanes-per-edge expansion
-    return 3;
-  }();
-  return v;
-}
-
 extern "C" {
 
 const char* pmp_last_error(void) { return g_err.c_str(); }
@@ -369,14 +361,7 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
     if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                        \
     KERNEL<<<grid, block, smem, st>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);      \
   } while (0)
-  switch (kernel_version()) {
-    case 1:
-      if (approx) PMP_LAUNCH_CHECK(k_check_configs_v1<true>); else PMP_LAUNCH_CHECK(k_check_configs_v1<false>);
-      break;
-    case 2:
-      if (approx) PMP_LAUNCH_CHECK(k_check_configs<true>); else PMP_LAUNCH_CHECK(k_check_configs<false>);
-      break;
-    default: {
+  {
       const bool cloud = S.cloud.enabled != 0;
 #define PMP_V3(BB, AP, CL) PMP_LAUNCH_CHECK((k_check_configs_v3<BB, AP, CL>))
 #define PMP_V3_B(BB)                                                         \
@@ -387,7 +372,6 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
       if (block == 128) PMP_V3_B(128); else PMP_V3_B(64);
 #undef PMP_V3_B
 #undef PMP_V3
-    }
   }
 #undef PMP_LAUNCH_CHECK
   g_launches++;
@@ -535,7 +519,6 @@ int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
   }
   return PMP_OK;
 }
-constexpr int kLanesPerEdge = 8;
 
 // A ring of device counters for the edge kernel's chunk dispenser: one per launch in flight.
 constexpr int kEdgeCounters = 256;
@@ -565,41 +548,17 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
   const size_t smem = smem_bytes(robot, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const long long n_words = (n + 31) / 32;
-  const long long n_tiles = (n_words + (block / 32) - 1) / (block / 32);
+  const long long tiles = (n_words + (block / 32) - 1) / (block / 32);  // one warp per 32 edges at most
   int grid = 0;
-#define PMP_LAUNCH_EDGES(KERNEL)                                                                         \
-  do {                                                                                                  \
-    if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                              \
-    KERNEL<<<grid, block, smem, (cudaStream_t)stream>>>(robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
-                                                        n_valid_dev, n_checked_dev);                    \
-  } while (0)
   const bool approx = robot->dev.base_type == PMP_BASE_FIXED;
-#define PMP_EDGES_VER(VER)                                                                                    \
-  do {                                                                                                       \
-    if (block == 128) {                                                                                      \
-      if (approx) PMP_LAUNCH_EDGES((k_check_edges<true, kLanesPerEdge, VER, 128>));                          \
-      else PMP_LAUNCH_EDGES((k_check_edges<false, kLanesPerEdge, VER, 128>));                                \
-    } else {                                                                                                 \
-      if (approx) PMP_LAUNCH_EDGES((k_check_edges<true, kLanesPerEdge, VER, 64>));                           \
-      else PMP_LAUNCH_EDGES((k_check_edges<false, kLanesPerEdge, VER, 64>));                                 \
-    }                                                                                                        \
-  } while (0)
-  switch (kernel_version()) {
-    case 1:
-    case 2: PMP_EDGES_VER(2); break;
-    case 4:  // PMP_KERNEL=v3e: the 8-lanes-per-edge expansion on top of the v3 check (A/B only)
-      if (S.cloud.enabled) PMP_EDGES_VER(4); else PMP_EDGES_VER(3);
-      break;
-    default: {
-      // lane = edge with dynamic refill; valid edges atomicOr their bit into zeroed words
-      cudaStream_t st = (cudaStream_t)stream;
-      unsigned long long* counter = nullptr;
-      if (int rc = next_edge_counter(&counter)) return rc;
-      CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-      CUDA_OK(cudaMemsetAsync(valid_bits_dev, 0, (size_t)n_words * 4, st));
-      const long long n_warp_tiles = (n + 31) / 32;
-      const long long tiles = (n_warp_tiles + (block / 32) - 1) / (block / 32);
-      const bool cloud = S.cloud.enabled != 0;
+  const bool cloud = S.cloud.enabled != 0;
+  // lane = edge with dynamic refill (k_check_edges_v3); valid edges atomicOr their bit into zeroed words
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* counter = nullptr;
+  if (int rc = next_edge_counter(&counter)) return rc;
+  CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  CUDA_OK(cudaMemsetAsync(valid_bits_dev, 0, (size_t)n_words * 4, st));
+  {
 #define PMP_E3(BB, AP, CL)                                                                                   \
   do {                                                                                                       \
     if (int rc = grid_for(k_check_edges_v3<BB, AP, CL>, smem, tiles, &grid, block)) return rc;              \
@@ -614,10 +573,7 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
       if (block == 128) PMP_E3_B(128); else PMP_E3_B(64);
 #undef PMP_E3_B
 #undef PMP_E3
-    }
   }
-#undef PMP_EDGES_VER
-#undef PMP_LAUNCH_EDGES
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return PMP_OK;

@@ -1,4 +1,4 @@
-// pmp_kernels.cuh — the hot-path kernels (v1: one thread per configuration / waypoint).
+// pmp_kernels.cuh — the hot-path kernels.
 //
 // Reference call stack restated per item (paths relative to cpp/plainmp/):
 //   IneqConstraintBase::is_valid            constraints/primitive.hpp:113-117
@@ -128,7 +128,6 @@ __device__ __forceinline__ void walk_links(const RobotDev& R, const Smem& T, con
 }
 
 }  // namespace pmp
-#include "pmp_warp.cuh"
 #include "pmp_v3.cuh"
 namespace pmp {
 
@@ -146,119 +145,7 @@ struct QEdge {
   }
 };
 
-// ---- v1: validity of one configuration, everything per thread (kept for A/B measurements) ------
-template <bool APPROX, class QAcc>
-__device__ bool config_is_valid(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q) {
-  bool valid = true;
-  int gi = 0;
-  float* gc_stash = T.stash + R.n_slots * 7 * blockDim.x;  // [group][3][thread]
-  const bool ext = (S.n_prims > 0) || S.cloud.enabled;
-  walk_links<APPROX>(R, T, q, [&](int op, const Frame& f) -> bool {
-    // groups are sorted by op
-    while (gi < R.n_groups) {
-      const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
-      if (gw.x != op) break;
-      const float4 g = T.groups[2 * gi];
-      const Rot rm = rotmat(f);
-      const float3 gc = xform(rm, f, g.x, g.y, g.z);
-      if (R.n_pairs > 0) {
-        float* p = gc_stash + (gi * 3) * blockDim.x + threadIdx.x;
-        p[0] = gc.x; p[blockDim.x] = gc.y; p[2 * blockDim.x] = gc.z;
-      }
-      const bool only_self = gw.w & 1;
-      if (ext && !only_self && valid) {
-        // check_ext_collision: broad phase per primitive, then the group's spheres
-        for (int base = 0; base < S.n_prims && valid; base += 32) {
-          unsigned mask = 0;
-          const int lim = min(32, S.n_prims - base);
-          for (int k = 0; k < lim; k++) {
-            const Prim P = load_prim(T.prims, base + k);
-            if (!prim_is_outside(P, gc, g.w)) mask |= 1u << k;
-          }
-          if (mask) {
-            for (int s = 0; s < gw.z && valid; s++) {
-              const float4 sp = T.spheres[gw.y + s];
-              const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
-              unsigned m = mask;
-              while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                const Prim P = load_prim(T.prims, base + k);
-                if (!prim_is_outside(P, c, sp.w)) {
-                  valid = false;
-                  break;
-                }
-              }
-            }
-          }
-        }
-        if (S.cloud.enabled && valid && !cloud_surely_outside(S.cloud, gc, g.w)) {
-          for (int s = 0; s < gw.z && valid; s++) {
-            const float4 sp = T.spheres[gw.y + s];
-            const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
-            if (!cloud_is_outside(S.cloud, c, sp.w)) valid = false;
-          }
-        }
-      }
-      gi++;
-    }
-    // keep walking while a later self-collision test could still matter for a valid item
-    return valid;
-  });
-  if (!valid) return false;
-
-  // check_self_collision (.cpp:222-254): strict <
-  for (int p = 0; p < R.n_pairs; p++) {
-    const int2 pr = T.pairs[p];
-    const float4 ga = T.groups[2 * pr.x], gb = T.groups[2 * pr.y];
-    const float* pa = gc_stash + (pr.x * 3) * blockDim.x + threadIdx.x;
-    const float* pb = gc_stash + (pr.y * 3) * blockDim.x + threadIdx.x;
-    const float dx = pa[0] - pb[0], dy = pa[blockDim.x] - pb[blockDim.x], dz = pa[2 * blockDim.x] - pb[2 * blockDim.x];
-    const float rs = ga.w + gb.w;
-    if (dx * dx + dy * dy + dz * dz > rs * rs) continue;
-    const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * pr.x + 1]);
-    const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * pr.y + 1]);
-    const Frame fa = stash_get(T.stash, wa.w >> 8), fb = stash_get(T.stash, wb.w >> 8);
-    const Rot ra = rotmat(fa), rb = rotmat(fb);
-    for (int i = 0; i < wa.z; i++) {
-      const float4 sa = T.spheres[wa.y + i];
-      const float3 ca = xform(ra, fa, sa.x, sa.y, sa.z);
-      for (int j = 0; j < wb.z; j++) {
-        const float4 sb = T.spheres[wb.y + j];
-        const float3 cb = xform(rb, fb, sb.x, sb.y, sb.z);
-        const float ex = ca.x - cb.x, ey = ca.y - cb.y, ez = ca.z - cb.z;
-        const float r2 = sa.w + sb.w;
-        if (ex * ex + ey * ey + ez * ez < r2 * r2) return false;
-      }
-    }
-  }
-  return true;
-}
-
 // ---- kernels ------------------------------------------------------------------------------------
-template <bool APPROX>
-__global__ void __launch_bounds__(128)
-k_check_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
-                uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
-  extern __shared__ float4 sm[];
-  const Smem T = stage_tables(R, S, sm);
-  unsigned cnt = 0;
-  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long item = tile * blockDim.x + threadIdx.x;
-    const bool active = item < n;
-    QDirect acc{q + (active ? item : 0) * R.q_dim};
-    const bool ok = warp_check<APPROX>(R, S, T, acc, active);
-    const unsigned b = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0 && active) {
-      bits[item >> 5] = b;
-      cnt += __popc(b);
-    }
-    __syncwarp();
-  }
-  if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
-}
-
 // v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  B = blockDim.x (compile-time so that the
 // stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
 // out of the primitives-only kernel).
@@ -281,30 +168,6 @@ k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__
       cnt += __popc(b);
     }
     __syncwarp();
-  }
-  if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
-}
-
-template <bool APPROX>
-__global__ void __launch_bounds__(128)
-k_check_configs_v1(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
-                uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
-  extern __shared__ float4 sm[];
-  const Smem T = stage_tables(R, S, sm);
-  unsigned cnt = 0;
-  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long item = tile * blockDim.x + threadIdx.x;
-    bool ok = false;
-    if (item < n) {
-      QDirect acc{q + item * R.q_dim};
-      ok = config_is_valid<APPROX>(R, S, T, acc);
-    }
-    const unsigned b = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0 && item < n) {
-      bits[item >> 5] = b;
-      cnt += __popc(b);
-    }
   }
   if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
 }
@@ -485,84 +348,7 @@ __device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const f
   return V.resolution / sqrt(d2);
 }
 
-// LPE lanes cooperate on one edge; each round they test LPE waypoints in the reference's
-// visiting order (coarse to fine) and the edge retires as soon as one is invalid.
-template <bool APPROX, int LPE, int VER, int B>
-__global__ void __launch_bounds__(B)
-k_check_edges(const RobotDev R, const SceneDev S, const ValidatorDev V, const float* __restrict__ q0,
-              const float* __restrict__ q1, const long long n, uint32_t* __restrict__ bits,
-              unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ n_checked) {
-  extern __shared__ float4 sm[];
-  const Smem T = stage_tables(R, S, sm);
-  constexpr int EPW = 32 / LPE;  // edges per warp
-  const int lane = threadIdx.x & 31, sub = lane % LPE, slot = lane / LPE;
-  const unsigned sub_mask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << (slot * LPE));
-  const int warps_per_block = blockDim.x >> 5;
-  const long long n_groups32 = (n + 31) / 32;  // one output word per 32 edges
-  unsigned cnt_valid = 0;
-  unsigned long long cnt_checked = 0;
-  for (long long wg = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wg < n_groups32;
-       wg += (long long)gridDim.x * warps_per_block) {
-    unsigned word = 0;
-    for (int pass = 0; pass < LPE; pass++) {  // 32 edges per word, EPW at a time
-      const long long e = wg * 32 + pass * EPW + slot;
-      const bool have = e < n;
-      const float* a = q0 + e * R.q_dim;
-      const float* b = q1 + e * R.q_dim;
-      double ratio = INFINITY;
-      long long n_test = 0;
-      if (have) {
-        ratio = edge_step_ratio(V, a, b, R.q_dim);
-        if (ratio != INFINITY) n_test = (long long)floor(1.0 / ratio) + 2;  // motion_validator.cpp:45
-      }
-      // waypoint w = 0 is s2; w = 1 .. n_test-2 are the interior points
-      const long long n_way = have ? (n_test >= 2 ? n_test - 1 : 0) : 0;
-      bool edge_ok = true;
-      long long w0 = 0;
-      while (true) {
-        const bool more = have && edge_ok && (w0 < n_way);
-        if (!__any_sync(0xffffffffu, more)) break;
-        const long long w = w0 + sub;
-        const bool work = more && w < n_way;
-        float t = 1.f;
-        if (work) {
-          if (w == 0) {
-            t = 1.f;
-          } else if (n_test < 129) {
-            t = (float)((double)V.seq[(n_test - 1) * 128 + (w + 1)] * ratio);  // sequence[i], i = w+1
-          } else {
-            t = (float)((double)w * ratio);
-          }
-          cnt_checked++;
-        }
-        // all 32 lanes enter the cooperative check; lanes without a waypoint are inactive
-        QEdge acc{have ? a : q0, have ? b : q1, t, w == 0};
-        const bool ok = (VER == 3)   ? warp_check_v3<B, APPROX, false>(R, S, T, acc, work)
-                        : (VER == 4) ? warp_check_v3<B, APPROX, true>(R, S, T, acc, work)
-                                     : warp_check<APPROX>(R, S, T, acc, work);
-        const bool bad = work && !ok;
-        const unsigned badmask = __ballot_sync(0xffffffffu, bad);
-        if (badmask & sub_mask) edge_ok = false;
-        w0 += LPE;
-      }
-      const unsigned okmask = __ballot_sync(0xffffffffu, have && edge_ok && sub == 0);
-      // lanes with sub == 0 sit at bit positions slot*LPE; compact them to pass*EPW + slot
-      for (int s2 = 0; s2 < EPW; s2++)
-        if (okmask & (1u << (s2 * LPE))) word |= 1u << (pass * EPW + s2);
-    }
-    if (lane == 0) {
-      bits[wg] = word;
-      cnt_valid += __popc(word);
-    }
-  }
-  if (n_valid && cnt_valid) atomicAdd(n_valid, (unsigned long long)cnt_valid);
-  if (n_checked) {
-    for (int off = 16; off; off >>= 1) cnt_checked += __shfl_down_sync(0xffffffffu, cnt_checked, off);
-    if (lane == 0 && cnt_checked) atomicAdd(n_checked, cnt_checked);
-  }
-}
-
-// ---- motion edges, v3: lane = edge with dynamic refill ----------------------------------------------
+// ---- motion edges: lane = edge with dynamic refill ------------------------------------------------
 // Every lane walks ITS OWN edge through the reference's visiting order (s2 first, then the
 // farthest-first table order, motion_validator.cpp:45-78) one waypoint per round, exactly like the
 // serial reference; the 32 waypoints of a round (from 32 different edges) go through one

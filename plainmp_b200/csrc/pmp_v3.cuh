@@ -17,8 +17,9 @@
 //            item is one group against ONE primitive (one sphere per lane, the primitive's test
 //            variant resolved at scene build), a self item is one listed group pair.  A
 //            warp-uniform `bad` mask retires configurations (REDUX.OR); later items of a retired
-//            configuration are skipped.  If a queue would overflow it is drained early and phase 1
-//            resumes where it stopped, so any table size works with fixed 512 + 128 byte queues.
+//            configuration are skipped.  If a push would overflow a queue, phase 1 stops, the
+//            queue is drained and phase 1 resumes where it stopped, so any table size works with
+//            fixed 512 + 128 byte queues.
 //
 // The result is unchanged: validity depends neither on the broad-phase hierarchy nor on the order
 // of the tests (SURVEY finding 7, App. A.4; reference: check_ext_collision / check_self_collision,
@@ -33,6 +34,9 @@ constexpr int kV3WordsPerThread = (32 * 4 + kQE + kQS) / 32;  // scratch float4[
 constexpr unsigned kItemCloud = 0xffffu;     // primitive field: the scene's point cloud
 constexpr unsigned kItemOverflow = 0xfffeu;  // primitive field: every primitive with index >= 30
 constexpr int kMaxGroupsV3 = 2048;           // the group field of an env item has 11 bits
+// bits of the per-(lane, group) cull mask: 0..29 primitive k, 30 cloud, 31 some primitive >= 30
+constexpr unsigned kMaskCloud = 1u << 30;
+constexpr unsigned kMaskOverflow = 1u << 31;
 
 // shared-memory views with the CTA size B known at compile time (offsets fold into immediates)
 template <int B>
@@ -216,24 +220,122 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
   return bad;
 }
 
-// All 32 lanes of the warp must call this (lanes without a configuration pass active = false).
-// B = blockDim.x.
-template <int B, bool APPROX, bool CLOUD, class QAcc>
-__device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q, const bool active) {
-  constexpr unsigned full = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid & ~31;
-  const unsigned lt = (1u << lane) - 1u;
-  const V3View<B> V = v3_view<B>(R, T);
-  unsigned* qenv = V.qenv + warp * kQE;
-  unsigned* qself = V.qself + warp * kQS;
-  float4* scratch = V.scratch + warp * 32;
-  const bool ext = (S.n_prims > 0) || CLOUD;
-  unsigned bad = 0;  // warp-uniform: bit l set = lane l's configuration is known to be invalid
+// ---- per-warp context and the building blocks of phase 1 -------------------------------------------
+// Used by the table interpreter below and by the per-robot code that pmp_jit.cu generates
+// (straight-line FK with the robot's constants folded in, calling the same helpers).
+template <int B>
+struct V3Ctx {
+  V3View<B> V;
+  unsigned* qenv;
+  unsigned* qself;
+  float4* scratch;
+  int tid, lane, wbase;
+  unsigned lt;        // lanes below this one
+  unsigned bad;       // warp-uniform: bit l set = lane l's configuration is known to be invalid
+  int n_env, n_self;  // warp-uniform queue fills
+  bool active;
+  bool redo;          // generated code only: an item of this lane did not fit into a queue
+};
 
-  // ---- phase 1 (resumable: the env queue is drained early if a push would overflow it) ----
+template <int B>
+__device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, const bool active) {
+  V3Ctx<B> X;
+  X.tid = threadIdx.x;
+  X.lane = X.tid & 31;
+  X.wbase = X.tid & ~31;
+  X.lt = (1u << X.lane) - 1u;
+  X.V = v3_view<B>(R, T);
+  const int warp = X.tid >> 5;
+  X.qenv = X.V.qenv + warp * kQE;
+  X.qself = X.V.qself + warp * kQS;
+  X.scratch = X.V.scratch + warp * 32;
+  X.bad = 0;
+  X.n_env = 0;
+  X.n_self = 0;
+  X.active = active;
+  X.redo = false;
+  return X;
+}
+
+template <int B>
+__device__ __forceinline__ void v3_stash_frame(const V3Ctx<B>& X, const int slot, const Frame& f) {
+  float* p = X.V.frames + slot * (7 * B) + X.tid;
+  p[0] = f.qx; p[B] = f.qy; p[2 * B] = f.qz; p[3 * B] = f.qw;
+  p[4 * B] = f.tx; p[5 * B] = f.ty; p[6 * B] = f.tz;
+}
+
+template <int B>
+__device__ __forceinline__ void v3_store_gc(const V3Ctx<B>& X, const int gi, const float3 gc) {
+  float* p = X.V.gc + gi * (3 * B) + X.tid;
+  p[0] = gc.x; p[B] = gc.y; p[2 * B] = gc.z;
+}
+
+// Group-level cull of a bounding sphere against every primitive's AABB and the cloud's distance
+// field.  Bits 0..29: primitive k passes, 30: cloud, 31: some primitive >= 30.
+template <bool CLOUD>
+__device__ __forceinline__ unsigned v3_cull_mask(const SceneDev& S, const Smem& T, const float3 gc, const float radius) {
+  unsigned pm = 0;
+  const int n30 = min(S.n_prims, 30);
+  for (int kp = 0; kp < n30; kp++) {
+    const float4* pw = T.prims + kPrimWords * kp;
+    pm |= prim_aabb_outside(pw[5], pw[6], gc, radius) ? 0u : (1u << kp);
+  }
+  for (int kp = 30; kp < S.n_prims; kp++) {
+    const float4* pw = T.prims + kPrimWords * kp;
+    pm |= prim_aabb_outside(pw[5], pw[6], gc, radius) ? 0u : kMaskOverflow;
+  }
+  if (CLOUD && !cloud_surely_outside(S.cloud, gc, radius)) pm |= kMaskCloud;
+  return pm;
+}
+
+// Push one queue item per set bit of this lane's cull mask for group gi.  Returns false (without
+// pushing the rest) when the items of the next round do not fit: the caller drains and calls again
+// with the same mask (items already queued are then only re-tested).
+template <int B>
+__device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, const unsigned pm) {
+  constexpr unsigned full = 0xffffffffu;
+  unsigned rem = (X.active && !((X.bad >> X.lane) & 1u)) ? pm : 0u;
+  unsigned ball = __ballot_sync(full, rem != 0u);
+  while (ball) {
+    const int cnt = __popc(ball);
+    if (X.n_env + cnt > kQE) return false;
+    if (rem) {
+      const unsigned b = __ffs(rem) - 1;
+      rem &= rem - 1u;
+      const unsigned kp = (b < 30u) ? b : (b == 30u ? kItemCloud : kItemOverflow);
+      X.qenv[X.n_env + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)gi << 5) | (kp << 16);
+    }
+    X.n_env += cnt;
+    ball = __ballot_sync(full, rem != 0u);
+  }
+  return true;
+}
+
+// One listed group pair p; `near` = this lane's bounding spheres are within reach and the
+// configuration is still alive.  Returns false when the items do not fit (drain, call again).
+template <int B>
+__device__ __forceinline__ bool v3_push_self(V3Ctx<B>& X, const int p, const bool near) {
+  const unsigned ball = __ballot_sync(0xffffffffu, near);
+  if (ball) {
+    const int cnt = __popc(ball);
+    if (X.n_self + cnt > kQS) return false;
+    if (near) X.qself[X.n_self + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)p << 5);
+    X.n_self += cnt;
+  }
+  return true;
+}
+
+// Table interpreter: FK over the link program, groups in op order, single drain site per queue
+// (phase 1 is resumable: when a push does not fit, the queue is drained and the group redone).
+// All 32 lanes of the warp must call this (lanes without a configuration pass active = false).
+template <int B, bool APPROX, bool CLOUD, class QAcc>
+__device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
+                                                  const bool active) {
+  V3Ctx<B> X = v3_begin<B>(R, T, active);
+  const bool ext = (S.n_prims > 0) || CLOUD;
   const Frame base = base_frame(R, q);
   Frame cur = base;
-  int i = 0, gi = 0, n_env = 0;
+  int i = 0, gi = 0;
   bool ready = false;
   for (;;) {
     bool stalled = false;
@@ -244,15 +346,10 @@ __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& 
         const int4 w3 = *reinterpret_cast<const int4*>(ow + 3);
         const float4 wA = ow[4];
         const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
-        Frame parent = cur;
-        if (w3.x != i - 1) parent = (w3.x < 0) ? base : v3_frame_at(V, w3.w, tid);
+        if (w3.x != i - 1) cur = (w3.x < 0) ? base : v3_frame_at(X.V, w3.w, X.tid);
         const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
-        cur = apply_op_v3<APPROX>(parent, wB, w1, w2, wA, kind, w3.y, qv);
-        if (w3.z >= 0) {
-          float* p = V.frames + w3.z * (7 * B) + tid;
-          p[0] = cur.qx; p[B] = cur.qy; p[2 * B] = cur.qz; p[3 * B] = cur.qw;
-          p[4 * B] = cur.tx; p[5 * B] = cur.ty; p[6 * B] = cur.tz;
-        }
+        cur = apply_op_v3<APPROX>(cur, wB, w1, w2, wA, kind, w3.y, qv);
+        if (w3.z >= 0) v3_stash_frame(X, w3.z, cur);
         ready = true;
       }
       while (gi < R.n_groups) {
@@ -260,40 +357,12 @@ __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& 
         if (gw.x != i) break;
         const float4 g = T.groups[2 * gi];
         const float3 gc = place(cur, g.x, g.y, g.z);
-        float* p = V.gc + gi * (3 * B) + tid;
-        p[0] = gc.x; p[B] = gc.y; p[2 * B] = gc.z;
+        v3_store_gc(X, gi, gc);
         if (ext && !(gw.w & 1)) {
-          // bits 0..29: primitive k passes the group-level cull, 30: cloud, 31: some primitive >= 30
-          unsigned pm = 0;
-          const int n30 = min(S.n_prims, 30);
-          for (int kp = 0; kp < n30; kp++) {
-            const float4* pw = T.prims + kPrimWords * kp;
-            pm |= prim_aabb_outside(pw[5], pw[6], gc, g.w) ? 0u : (1u << kp);
+          if (!v3_push_env(X, gi, v3_cull_mask<CLOUD>(S, T, gc, g.w))) {
+            stalled = true;
+            break;
           }
-          for (int kp = 30; kp < S.n_prims; kp++) {
-            const float4* pw = T.prims + kPrimWords * kp;
-            pm |= prim_aabb_outside(pw[5], pw[6], gc, g.w) ? 0u : kMaskOverflow;
-          }
-          if (CLOUD && !cloud_surely_outside(S.cloud, gc, g.w)) pm |= kMaskCloud;
-          // one queue item per set bit
-          unsigned rem = active ? pm : 0u;
-          unsigned ball = __ballot_sync(full, rem != 0u);
-          while (ball) {
-            const int cnt = __popc(ball);
-            if (n_env + cnt > kQE) {
-              stalled = true;  // drain, then redo this group (already queued items are only re-tested)
-              break;
-            }
-            if (rem) {
-              const unsigned b = __ffs(rem) - 1;
-              rem &= rem - 1u;
-              const unsigned kp = (b < 30u) ? b : (b == 30u ? kItemCloud : kItemOverflow);
-              qenv[n_env + __popc(ball & lt)] = (unsigned)lane | ((unsigned)gi << 5) | (kp << 16);
-            }
-            n_env += cnt;
-            ball = __ballot_sync(full, rem != 0u);
-          }
-          if (stalled) break;
         }
         gi++;
       }
@@ -301,37 +370,55 @@ __device__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& 
       ready = false;
     }
     __syncwarp();
-    bad = drain_env<B, CLOUD>(S, T, V, qenv, n_env, bad, lane, wbase);
-    n_env = 0;
+    X.bad = drain_env<B, CLOUD>(S, T, X.V, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
+    X.n_env = 0;
     if (!stalled) break;
     __syncwarp();
   }
-
-  // ---- listed group pairs: bounding-sphere test per lane, survivors queued ----
-  int n_self = 0;
+  // listed group pairs: bounding-sphere test per lane, survivors queued
   for (int p = 0; R.n_pairs > 0;) {
-    const bool alive = active && !((bad >> lane) & 1u);
+    const bool alive = active && !((X.bad >> X.lane) & 1u);
     for (; p < R.n_pairs; p++) {
       const float4 pw = T.pairs4[p];
-      const float* pa = V.gc + __float_as_int(pw.x) * (3 * B) + tid;
-      const float* pb = V.gc + __float_as_int(pw.y) * (3 * B) + tid;
+      const float* pa = X.V.gc + __float_as_int(pw.x) * (3 * B) + X.tid;
+      const float* pb = X.V.gc + __float_as_int(pw.y) * (3 * B) + X.tid;
       const float dx = pa[0] - pb[0], dy = pa[B] - pb[B], dz = pa[2 * B] - pb[2 * B];
-      const bool near = alive & !(dx * dx + dy * dy + dz * dz > pw.z);
-      const unsigned ball = __ballot_sync(full, near);
-      if (ball) {
-        const int cnt = __popc(ball);
-        if (n_self + cnt > kQS) break;
-        if (near) qself[n_self + __popc(ball & lt)] = (unsigned)lane | ((unsigned)p << 5);
-        n_self += cnt;
-      }
+      if (!v3_push_self(X, p, alive & !(dx * dx + dy * dy + dz * dz > pw.z))) break;
     }
     __syncwarp();
-    bad = drain_self<B>(T, V, qself, scratch, n_self, bad, lane, wbase);
-    n_self = 0;
+    X.bad = drain_self<B>(T, X.V, X.qself, X.scratch, X.n_self, X.bad, X.lane, X.wbase);
+    X.n_self = 0;
     if (p >= R.n_pairs) break;
     __syncwarp();
   }
-  return active && !((bad >> lane) & 1u);
+  return active && !((X.bad >> X.lane) & 1u);
 }
+
+#ifdef PMP_JIT
+}  // namespace pmp
+#include "pmp_jit_robot.cuh"  // generated: pmp::jit_phase1<B, APPROX, CLOUD>(X, R, S, T, q)
+namespace pmp {
+
+// Generated straight-line phase 1 + the same drains.  A lane whose item did not fit into a queue
+// (X.redo) is simply run again through the interpreter, which can drain in the middle of phase 1.
+template <int B, bool APPROX, bool CLOUD, class QAcc>
+__device__ __forceinline__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
+                                              const bool active) {
+  V3Ctx<B> X = v3_begin<B>(R, T, active);
+  jit_phase1<B, APPROX, CLOUD>(X, R, S, T, q);
+  bool ok = active && !((X.bad >> X.lane) & 1u);
+  if (__any_sync(0xffffffffu, X.redo)) {
+    const bool again = warp_check_interp<B, APPROX, CLOUD>(R, S, T, q, X.redo && ok);
+    if (X.redo) ok = ok && again;
+  }
+  return ok;
+}
+#else
+template <int B, bool APPROX, bool CLOUD, class QAcc>
+__device__ __forceinline__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
+                                              const bool active) {
+  return warp_check_interp<B, APPROX, CLOUD>(R, S, T, q, active);
+}
+#endif
 
 }  // namespace pmp

@@ -64,11 +64,19 @@ int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kB
 
 }  // namespace
 
-struct pmp_robot {
+// One flattened program on the device: the table blob + what the kernels need to carve it up.
+struct RobotTables {
   RobotDev dev{};
   float4* blob_dev = nullptr;
-  std::vector<int> group_order;  // sorted position -> caller's group index
   size_t stash_floats_per_thread = 0;
+};
+
+struct pmp_robot {
+  // `full` is the program exactly as the caller described it (one op per link): it serves the
+  // calls that report per-link or per-sphere quantities (evaluate, get_all_spheres, link poses).
+  // `fast` is the same kinematics with every fixed op folded away on the host in FP64 (see
+  // fold_fixed_ops): the validity kernels walk only the controlled joints.
+  RobotTables full, fast;
 };
 
 struct pmp_scene {
@@ -92,13 +100,213 @@ static size_t extra_smem() {  // PMP_EXTRA_SMEM=<bytes>: occupancy experiments o
   }();
   return v;
 }
-static size_t smem_bytes(const pmp_robot* r, const SceneDev& s, int block = kBlock) {
-  return (size_t)(r->dev.blob_words + s.n_prims * kPrimWords) * 16 + r->stash_floats_per_thread * 4 * block + extra_smem();
+static size_t smem_bytes(const RobotTables& r, const SceneDev& s, int block = kBlock) {
+  return (size_t)(r.dev.blob_words + s.n_prims * kPrimWords) * 16 + r.stash_floats_per_thread * 4 * block + extra_smem();
 }
 // 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
-static int pick_block(const pmp_robot* r, const SceneDev& s) {
+static int pick_block(const RobotTables& r, const SceneDev& s) {
   return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
 }
+
+namespace {
+// Host-side (FP64) description of a program, the common input of build_tables.
+struct OpD {
+  double oq[4], oxyz[3], axis[3];
+  int kind, q_index, parent, flags;
+};
+struct GroupD {
+  double center[3], radius;
+  int op, sphere_begin, sphere_count, only_self;
+};
+struct ProgramD {
+  std::vector<OpD> ops;
+  std::vector<GroupD> groups;
+  std::vector<double> spheres;  // [n][4]
+  std::vector<int> pairs;       // [n][2]
+};
+
+inline void qmul(const double* a, const double* b, double* r) {  // Eigen product, (x, y, z, w)
+  const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  const double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z; r[3] = w;
+}
+inline void qrot(const double* q, const double* v, double* r) {  // Eigen q * v
+  double u[3] = {2 * (q[1] * v[2] - q[2] * v[1]), 2 * (q[2] * v[0] - q[0] * v[2]), 2 * (q[0] * v[1] - q[1] * v[0])};
+  const double x = v[0] + q[3] * u[0] + (q[1] * u[2] - q[2] * u[1]);
+  const double y = v[1] + q[3] * u[1] + (q[2] * u[0] - q[0] * u[2]);
+  const double z = v[2] + q[3] * u[2] + (q[0] * u[1] - q[1] * u[0]);
+  r[0] = x; r[1] = y; r[2] = z;
+}
+
+// Fold every fixed op into what hangs off it.  For op i let anchor(i) be the nearest movable
+// ancestor-or-self (or the base) and F_i the constant transform with frame_i = frame_anchor (x) F_i
+// (kinematics/algorithm.cpp:181-210 composes exactly these products, in FP64, at run time; the
+// identity-flag shortcut of transform.hpp:64-74 is kept by treating flagged origins as the exact
+// identity).  Then
+//   * a movable op keeps its joint and takes origin' = F_parent (x) origin,
+//   * a sphere group on op i moves to anchor(i) with centre and members mapped through F_i,
+// and the folded program has one op per controlled joint plus a root op that stands for the base.
+// World-frame results are the same up to FP64 rounding of the constant products.
+ProgramD fold_fixed_ops(const ProgramD& in) {
+  const int n = (int)in.ops.size();
+  struct Fix { double q[4], t[3]; int anchor; };  // anchor = folded op index
+  std::vector<Fix> F(n);
+  ProgramD out;
+  OpD root{};
+  root.oq[3] = 1.0;
+  root.kind = PMP_OP_FIXED;
+  root.q_index = -1;
+  root.parent = -1;
+  root.flags = PMP_OPFLAG_ORIGIN_IDENTITY;
+  out.ops.push_back(root);
+  for (int i = 0; i < n; i++) {
+    const OpD& o = in.ops[i];
+    Fix P;  // the parent's (anchor, F)
+    if (o.parent < 0) {
+      P.q[0] = P.q[1] = P.q[2] = 0.0; P.q[3] = 1.0;
+      P.t[0] = P.t[1] = P.t[2] = 0.0;
+      P.anchor = 0;
+    } else {
+      P = F[o.parent];
+    }
+    const bool ident = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
+    const double oq[4] = {ident ? 0.0 : o.oq[0], ident ? 0.0 : o.oq[1], ident ? 0.0 : o.oq[2], ident ? 1.0 : o.oq[3]};
+    Fix L;  // P (x) (oq, oxyz)
+    qmul(P.q, oq, L.q);
+    double rt[3];
+    qrot(P.q, o.oxyz, rt);
+    for (int a = 0; a < 3; a++) L.t[a] = P.t[a] + rt[a];
+    if (o.kind == PMP_OP_FIXED) {
+      L.anchor = P.anchor;
+      F[i] = L;
+      continue;
+    }
+    OpD c = o;
+    for (int a = 0; a < 4; a++) c.oq[a] = L.q[a];
+    for (int a = 0; a < 3; a++) c.oxyz[a] = L.t[a];
+    if (o.kind == PMP_OP_PRISMATIC) qrot(P.q, o.axis, c.axis);  // the axis lives in the parent link's frame
+    c.parent = P.anchor;
+    c.flags = (L.q[0] == 0.0 && L.q[1] == 0.0 && L.q[2] == 0.0 && L.q[3] == 1.0) ? PMP_OPFLAG_ORIGIN_IDENTITY : 0;
+    out.ops.push_back(c);
+    F[i].q[0] = F[i].q[1] = F[i].q[2] = 0.0; F[i].q[3] = 1.0;
+    F[i].t[0] = F[i].t[1] = F[i].t[2] = 0.0;
+    F[i].anchor = (int)out.ops.size() - 1;
+  }
+  out.spheres = in.spheres;
+  out.pairs = in.pairs;
+  for (const GroupD& g : in.groups) {
+    GroupD c = g;
+    const Fix& f = F[g.op];
+    c.op = f.anchor;
+    double r[3];
+    qrot(f.q, g.center, r);
+    for (int a = 0; a < 3; a++) c.center[a] = f.t[a] + r[a];
+    for (int s = g.sphere_begin; s < g.sphere_begin + g.sphere_count; s++) {
+      qrot(f.q, &in.spheres[4 * s], r);
+      for (int a = 0; a < 3; a++) out.spheres[4 * s + a] = f.t[a] + r[a];
+    }
+    out.groups.push_back(c);
+  }
+  return out;
+}
+
+int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, RobotTables* out) {
+  const int n_ops = (int)P.ops.size(), n_groups = (int)P.groups.size(), n_spheres = (int)P.spheres.size() / 4,
+            n_pairs = (int)P.pairs.size() / 2;
+  // groups sorted by op (stable), pairs remapped
+  std::vector<int> order(n_groups);
+  for (int g = 0; g < n_groups; g++) order[g] = g;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return P.groups[a].op < P.groups[b].op; });
+  std::vector<int> pos(n_groups);
+  for (int k = 0; k < n_groups; k++) pos[order[k]] = k;
+
+  // stash slots: a frame is kept if a later, non-adjacent op hangs off it or if it carries a group
+  // (the cooperative narrow phases read the frames of the groups they work on)
+  std::vector<int> slot(n_ops, -1);
+  std::vector<char> need(n_ops, 0);
+  for (int i = 0; i < n_ops; i++)
+    if (P.ops[i].parent >= 0 && P.ops[i].parent != i - 1) need[P.ops[i].parent] = 1;
+  for (int g = 0; g < n_groups; g++) need[P.groups[g].op] = 1;
+  int n_slots = 0;
+  for (int i = 0; i < n_ops; i++)
+    if (need[i]) slot[i] = n_slots++;
+
+  const int off_groups = n_ops * kOpWords;
+  const int off_spheres = off_groups + n_groups * 2;
+  const int off_pairs = off_spheres + n_spheres;
+  const int off_pairs4 = off_pairs + (n_pairs + 1) / 2;
+  const int words = off_pairs4 + n_pairs;
+  std::vector<float4> blob(std::max(words, 1));
+  auto fi = [](int v) {
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+  };
+  for (int i = 0; i < n_ops; i++) {
+    const OpD& o = P.ops[i];
+    const bool ident = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
+    // identity-flagged origins are never multiplied in (kinematics/transform.hpp:64-74): store the exact identity
+    const double oq[4] = {ident ? 0.0 : o.oq[0], ident ? 0.0 : o.oq[1], ident ? 0.0 : o.oq[2], ident ? 1.0 : o.oq[3]};
+    blob[kOpWords * i + 0] = make_float4((float)oq[0], (float)oq[1], (float)oq[2], (float)oq[3]);
+    blob[kOpWords * i + 1] = make_float4((float)o.oxyz[0], (float)o.oxyz[1], (float)o.oxyz[2], fi(o.kind));
+    blob[kOpWords * i + 2] = make_float4((float)o.axis[0], (float)o.axis[1], (float)o.axis[2], fi(o.q_index));
+    const int pslot = (o.parent >= 0 && o.parent != i - 1) ? slot[o.parent] : -1;
+    int flags = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
+    if ((float)o.oxyz[0] == 0.f && (float)o.oxyz[1] == 0.f && (float)o.oxyz[2] == 0.f) flags |= PMP_OPFLAG_ZERO_XYZ;
+    blob[kOpWords * i + 3] = make_float4(fi(o.parent), fi(flags), fi(slot[i]), fi(pslot));
+    // v3 sine basis: origin (x) (axis, 0) in FP64 (Eigen product, w = -o.a, vec = ow a + o x a)
+    const double ax = o.axis[0], ay = o.axis[1], az = o.axis[2];
+    blob[kOpWords * i + 4] = make_float4((float)(oq[3] * ax + oq[1] * az - oq[2] * ay), (float)(oq[3] * ay + oq[2] * ax - oq[0] * az),
+                                         (float)(oq[3] * az + oq[0] * ay - oq[1] * ax), (float)(-oq[0] * ax - oq[1] * ay - oq[2] * az));
+  }
+  for (int k = 0; k < n_groups; k++) {
+    const GroupD& G = P.groups[order[k]];
+    blob[off_groups + 2 * k] = make_float4((float)G.center[0], (float)G.center[1], (float)G.center[2], (float)G.radius);
+    const int sl = slot[G.op] < 0 ? 0 : slot[G.op];
+    const int fl = (G.only_self ? 1 : 0) | (sl << 8);
+    blob[off_groups + 2 * k + 1] = make_float4(fi(G.op), fi(G.sphere_begin), fi(G.sphere_count), fi(fl));
+  }
+  for (int s = 0; s < n_spheres; s++)
+    blob[off_spheres + s] = make_float4((float)P.spheres[4 * s], (float)P.spheres[4 * s + 1], (float)P.spheres[4 * s + 2], (float)P.spheres[4 * s + 3]);
+  {
+    int* pw = reinterpret_cast<int*>(blob.data() + off_pairs);
+    for (int p = 0; p < n_pairs; p++) {
+      pw[2 * p] = pos[P.pairs[2 * p]];
+      pw[2 * p + 1] = pos[P.pairs[2 * p + 1]];
+      const float rs = (float)P.groups[P.pairs[2 * p]].radius + (float)P.groups[P.pairs[2 * p + 1]].radius;
+      blob[off_pairs4 + p] = make_float4(fi(pw[2 * p]), fi(pw[2 * p + 1]), rs * rs, 0.f);
+    }
+  }
+  cudaError_t e = cudaMalloc(&out->blob_dev, blob.size() * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMemcpy(out->blob_dev, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("robot table upload: ") + cudaGetErrorString(e));
+  RobotDev& D = out->dev;
+  D.blob = out->blob_dev;
+  D.blob_words = words;
+  D.n_ops = n_ops;
+  D.n_groups = n_groups;
+  D.n_spheres = n_spheres;
+  D.n_pairs = n_pairs;
+  D.off_groups = off_groups;
+  D.off_spheres = off_spheres;
+  D.off_pairs = off_pairs;
+  D.off_pairs4 = off_pairs4;
+  D.dof = d->dof;
+  D.q_dim = q_dim;
+  D.base_type = d->base_type;
+  D.n_slots = n_slots;
+  memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
+  // per thread: frames [slot][7], group centres [group][3], + the per-warp scratch row and queues
+  // (the evaluate kernel keeps one word per group instead)
+  out->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)n_groups * 3 + std::max<size_t>((size_t)n_groups + 1, kV3WordsPerThread);
+  if (smem_bytes(*out, empty_scene()) > (size_t)kMaxSmem)
+    return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
+  return PMP_OK;
+}
+}  // namespace
+
 extern "C" {
 
 const char* pmp_last_error(void) { return g_err.c_str(); }
@@ -130,13 +338,10 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
     if (o.kind < PMP_OP_FIXED || o.kind > PMP_OP_PRISMATIC) return fail(PMP_ERR_INVALID, "bad op kind");
     if (o.kind != PMP_OP_FIXED && (o.q_index < 0 || o.q_index >= d->dof)) return fail(PMP_ERR_INVALID, "q_index out of range");
   }
-  std::vector<char> in_pair(d->n_groups, 0);
   for (int p = 0; p < d->n_pairs; p++) {
     const int a = d->pairs[2 * p], b = d->pairs[2 * p + 1];
     if (a < 0 || a >= d->n_groups || b < 0 || b >= d->n_groups) return fail(PMP_ERR_INVALID, "pair refers to an unknown group");
-    in_pair[a] = in_pair[b] = 1;
   }
-  std::vector<char> covered(d->n_spheres, 0);
   for (int g = 0; g < d->n_groups; g++) {
     const pmp_group_t& G = d->groups[g];
     if (G.op < 0 || G.op >= d->n_ops) return fail(PMP_ERR_INVALID, "group refers to an unknown op");
@@ -145,102 +350,39 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   }
   if (int rc = ensure_device()) return rc;
 
-  auto* r = new pmp_robot();
-  // groups sorted by op (stable), pairs remapped
-  std::vector<int> order(d->n_groups);
-  for (int g = 0; g < d->n_groups; g++) order[g] = g;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d->groups[a].op < d->groups[b].op; });
-  std::vector<int> pos(d->n_groups);
-  for (int k = 0; k < d->n_groups; k++) pos[order[k]] = k;
-  r->group_order = order;
-
-  // stash slots: a frame is kept if a later, non-adjacent op hangs off it or if one of its
-  // groups takes part in the self-collision narrow phase
-  std::vector<int> slot(d->n_ops, -1);
-  std::vector<char> need(d->n_ops, 0);
-  for (int i = 0; i < d->n_ops; i++)
-    if (d->ops[i].parent >= 0 && d->ops[i].parent != i - 1) need[d->ops[i].parent] = 1;
-  // (v2) every op that carries a group keeps its frame: the cooperative narrow phases read it
-  for (int g = 0; g < d->n_groups; g++) need[d->groups[g].op] = 1;
-  int n_slots = 0;
-  for (int i = 0; i < d->n_ops; i++)
-    if (need[i]) slot[i] = n_slots++;
-
-  const int off_groups = d->n_ops * kOpWords;
-  const int off_spheres = off_groups + d->n_groups * 2;
-  const int off_pairs = off_spheres + d->n_spheres;
-  const int off_pairs4 = off_pairs + (d->n_pairs + 1) / 2;
-  const int words = off_pairs4 + d->n_pairs;
-  std::vector<float4> blob(std::max(words, 1));
-  auto fi = [](int v) {
-    float f;
-    memcpy(&f, &v, 4);
-    return f;
-  };
+  ProgramD P;
+  P.ops.resize(d->n_ops);
   for (int i = 0; i < d->n_ops; i++) {
     const pmp_link_op_t& o = d->ops[i];
-    const bool ident = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
-    // identity-flagged origins are never multiplied in (kinematics/transform.hpp:64-74): store the exact identity
-    const double oq[4] = {ident ? 0.0 : o.origin_quat[0], ident ? 0.0 : o.origin_quat[1], ident ? 0.0 : o.origin_quat[2],
-                          ident ? 1.0 : o.origin_quat[3]};
-    blob[kOpWords * i + 0] = make_float4((float)oq[0], (float)oq[1], (float)oq[2], (float)oq[3]);
-    blob[kOpWords * i + 1] = make_float4(o.origin_xyz[0], o.origin_xyz[1], o.origin_xyz[2], fi(o.kind));
-    blob[kOpWords * i + 2] = make_float4(o.axis[0], o.axis[1], o.axis[2], fi(o.q_index));
-    const int pslot = (o.parent >= 0 && o.parent != i - 1) ? slot[o.parent] : -1;
-    int flags = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
-    if (o.origin_xyz[0] == 0.f && o.origin_xyz[1] == 0.f && o.origin_xyz[2] == 0.f) flags |= PMP_OPFLAG_ZERO_XYZ;
-    blob[kOpWords * i + 3] = make_float4(fi(o.parent), fi(flags), fi(slot[i]), fi(pslot));
-    // v3 sine basis: origin (x) (axis, 0) in FP64 (Eigen product, w = -o.a, vec = ow a + o x a)
-    const double ax = o.axis[0], ay = o.axis[1], az = o.axis[2];
-    blob[kOpWords * i + 4] = make_float4((float)(oq[3] * ax + oq[1] * az - oq[2] * ay), (float)(oq[3] * ay + oq[2] * ax - oq[0] * az),
-                                         (float)(oq[3] * az + oq[0] * ay - oq[1] * ax), (float)(-oq[0] * ax - oq[1] * ay - oq[2] * az));
+    OpD& c = P.ops[i];
+    for (int a = 0; a < 4; a++) c.oq[a] = o.origin_quat[a];
+    for (int a = 0; a < 3; a++) c.oxyz[a] = o.origin_xyz[a];
+    for (int a = 0; a < 3; a++) c.axis[a] = o.axis[a];
+    c.kind = o.kind;
+    c.q_index = o.q_index;
+    c.parent = o.parent;
+    c.flags = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
   }
-  for (int k = 0; k < d->n_groups; k++) {
-    const pmp_group_t& G = d->groups[order[k]];
-    blob[off_groups + 2 * k] = make_float4(G.center[0], G.center[1], G.center[2], G.radius);
-    const int sl = slot[G.op] < 0 ? 0 : slot[G.op];
-    const int fl = (G.only_self_collision ? 1 : 0) | (sl << 8);
-    blob[off_groups + 2 * k + 1] = make_float4(fi(G.op), fi(G.sphere_begin), fi(G.sphere_count), fi(fl));
+  P.groups.resize(d->n_groups);
+  for (int g = 0; g < d->n_groups; g++) {
+    const pmp_group_t& G = d->groups[g];
+    GroupD& c = P.groups[g];
+    for (int a = 0; a < 3; a++) c.center[a] = G.center[a];
+    c.radius = G.radius;
+    c.op = G.op;
+    c.sphere_begin = G.sphere_begin;
+    c.sphere_count = G.sphere_count;
+    c.only_self = G.only_self_collision ? 1 : 0;
   }
-  for (int s = 0; s < d->n_spheres; s++)
-    blob[off_spheres + s] = make_float4(d->spheres[4 * s], d->spheres[4 * s + 1], d->spheres[4 * s + 2], d->spheres[4 * s + 3]);
-  {
-    int* pw = reinterpret_cast<int*>(blob.data() + off_pairs);
-    for (int p = 0; p < d->n_pairs; p++) {
-      pw[2 * p] = pos[d->pairs[2 * p]];
-      pw[2 * p + 1] = pos[d->pairs[2 * p + 1]];
-      const float rs = d->groups[d->pairs[2 * p]].radius + d->groups[d->pairs[2 * p + 1]].radius;
-      blob[off_pairs4 + p] = make_float4(fi(pw[2 * p]), fi(pw[2 * p + 1]), rs * rs, 0.f);
-    }
-  }
-  cudaError_t e = cudaMalloc(&r->blob_dev, blob.size() * sizeof(float4));
-  if (e == cudaSuccess) e = cudaMemcpy(r->blob_dev, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    delete r;
-    return fail(PMP_ERR_CUDA, std::string("robot table upload: ") + cudaGetErrorString(e));
-  }
-  RobotDev& D = r->dev;
-  D.blob = r->blob_dev;
-  D.blob_words = words;
-  D.n_ops = d->n_ops;
-  D.n_groups = d->n_groups;
-  D.n_spheres = d->n_spheres;
-  D.n_pairs = d->n_pairs;
-  D.off_groups = off_groups;
-  D.off_spheres = off_spheres;
-  D.off_pairs = off_pairs;
-  D.off_pairs4 = off_pairs4;
-  D.dof = d->dof;
-  D.q_dim = q_dim;
-  D.base_type = d->base_type;
-  D.n_slots = n_slots;
-  memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
-  // per thread: frames [slot][7], group centres [group][3], primitive masks [group], 1 scratch word
-  // (v3: frames, group centres, + the per-warp scratch row and queues)
-  r->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)d->n_groups * 3 + std::max<size_t>((size_t)d->n_groups + 1, kV3WordsPerThread);
-  if (smem_bytes(r, empty_scene()) > (size_t)kMaxSmem) {
+  P.spheres.assign(d->spheres, d->spheres + (size_t)4 * d->n_spheres);
+  P.pairs.assign(d->pairs, d->pairs + (size_t)2 * d->n_pairs);
+
+  auto* r = new pmp_robot();
+  int rc = build_tables(P, d, q_dim, &r->full);
+  if (rc == PMP_OK) rc = build_tables(fold_fixed_ops(P), d, q_dim, &r->fast);
+  if (rc != PMP_OK) {
     pmp_robot_destroy(r);
-    return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
+    return rc;
   }
   *out = r;
   return PMP_OK;
@@ -248,11 +390,12 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
 
 void pmp_robot_destroy(pmp_robot_t* r) {
   if (!r) return;
-  if (r->blob_dev) cudaFree(r->blob_dev);
+  if (r->full.blob_dev) cudaFree(r->full.blob_dev);
+  if (r->fast.blob_dev) cudaFree(r->fast.blob_dev);
   delete r;
 }
-int pmp_robot_q_dim(const pmp_robot_t* r) { return r ? r->dev.q_dim : -1; }
-int pmp_robot_n_spheres(const pmp_robot_t* r) { return r ? r->dev.n_spheres : -1; }
+int pmp_robot_q_dim(const pmp_robot_t* r) { return r ? r->full.dev.q_dim : -1; }
+int pmp_robot_n_spheres(const pmp_robot_t* r) { return r ? r->full.dev.n_spheres : -1; }
 
 // ---------------------------------------------------------------------------------------------
 int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
@@ -346,20 +489,20 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
                       uint32_t* valid_bits_dev, unsigned long long* n_valid_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if ((!q_dev && robot->dev.q_dim > 0) || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->fast.dev.q_dim > 0) || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const int block = pick_block(robot, S);
-  const size_t smem = smem_bytes(robot, S, block);
+  const int block = pick_block(robot->fast, S);
+  const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const long long n_tiles = (n + block - 1) / block;
   int grid = 0;
   cudaStream_t st = (cudaStream_t)stream;
   // is_valid uses the polynomial sin/cos only for a FIXED base (constraints/primitive.hpp:39-60)
-  const bool approx = robot->dev.base_type == PMP_BASE_FIXED;
+  const bool approx = robot->fast.dev.base_type == PMP_BASE_FIXED;
 #define PMP_LAUNCH_CHECK(KERNEL)                                                                  \
   do {                                                                                            \
     if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                        \
-    KERNEL<<<grid, block, smem, st>>>(robot->dev, S, q_dev, n, valid_bits_dev, n_valid_dev);      \
+    KERNEL<<<grid, block, smem, st>>>(robot->fast.dev, S, q_dev, n, valid_bits_dev, n_valid_dev);      \
   } while (0)
   {
       const bool cloud = S.cloud.enabled != 0;
@@ -383,13 +526,13 @@ int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const f
                      float* dist_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if ((!q_dev && robot->dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->full.dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const size_t smem = smem_bytes(robot, S);
+  const size_t smem = smem_bytes(robot->full, S);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   int grid = 0;
   if (int rc = grid_for(k_eval_configs, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-  k_eval_configs<<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, dist_dev);
+  k_eval_configs<<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, dist_dev);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return PMP_OK;
@@ -398,18 +541,18 @@ int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const f
 int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* spheres_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if ((!q_dev && robot->dev.q_dim > 0) || !spheres_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->full.dev.q_dim > 0) || !spheres_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = empty_scene();
-  const size_t smem = smem_bytes(robot, S);
+  const size_t smem = smem_bytes(robot->full, S);
   int grid = 0;
   // a moving base always uses exact sin/cos (constraints/primitive.hpp:42)
-  const bool approx = !accurate && robot->dev.base_type == PMP_BASE_FIXED;
+  const bool approx = !accurate && robot->full.dev.base_type == PMP_BASE_FIXED;
   if (approx) {
     if (int rc = grid_for(k_fk_spheres<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_spheres<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, (float4*)spheres_dev);
+    k_fk_spheres<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, (float4*)spheres_dev);
   } else {
     if (int rc = grid_for(k_fk_spheres<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_spheres<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, (float4*)spheres_dev);
+    k_fk_spheres<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, (float4*)spheres_dev);
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -419,17 +562,17 @@ int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int 
 int pmp_fk_frames(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* frames_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if ((!q_dev && robot->dev.q_dim > 0) || !frames_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->full.dev.q_dim > 0) || !frames_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = empty_scene();
-  const size_t smem = smem_bytes(robot, S);
+  const size_t smem = smem_bytes(robot->full, S);
   int grid = 0;
-  const bool approx = !accurate && robot->dev.base_type == PMP_BASE_FIXED;
+  const bool approx = !accurate && robot->full.dev.base_type == PMP_BASE_FIXED;
   if (approx) {
     if (int rc = grid_for(k_fk_frames<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_frames<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, frames_dev);
+    k_fk_frames<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, frames_dev);
   } else {
     if (int rc = grid_for(k_fk_frames<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_frames<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->dev, S, q_dev, n, frames_dev);
+    k_fk_frames<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, frames_dev);
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -540,17 +683,17 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
                     unsigned long long* n_valid_dev, unsigned long long* n_checked_dev, void* stream) {
   CHECK_COMMON(robot, n);
   ValidatorDev V;
-  if (int rc = validator_to_dev(validator, robot->dev.q_dim, &V)) return rc;
+  if (int rc = validator_to_dev(validator, robot->fast.dev.q_dim, &V)) return rc;
   if (n == 0) return PMP_OK;
   if (!q0_dev || !q1_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const int block = pick_block(robot, S);
-  const size_t smem = smem_bytes(robot, S, block);
+  const int block = pick_block(robot->fast, S);
+  const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const long long n_words = (n + 31) / 32;
   const long long tiles = (n_words + (block / 32) - 1) / (block / 32);  // one warp per 32 edges at most
   int grid = 0;
-  const bool approx = robot->dev.base_type == PMP_BASE_FIXED;
+  const bool approx = robot->fast.dev.base_type == PMP_BASE_FIXED;
   const bool cloud = S.cloud.enabled != 0;
   // lane = edge with dynamic refill (k_check_edges_v3); valid edges atomicOr their bit into zeroed words
   cudaStream_t st = (cudaStream_t)stream;
@@ -562,7 +705,7 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
 #define PMP_E3(BB, AP, CL)                                                                                   \
   do {                                                                                                       \
     if (int rc = grid_for(k_check_edges_v3<BB, AP, CL>, smem, tiles, &grid, block)) return rc;              \
-    k_check_edges_v3<BB, AP, CL><<<grid, block, smem, st>>>(robot->dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
+    k_check_edges_v3<BB, AP, CL><<<grid, block, smem, st>>>(robot->fast.dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
                                                             n_valid_dev, n_checked_dev, counter);           \
   } while (0)
 #define PMP_E3_B(BB)                                                                       \
@@ -618,7 +761,7 @@ int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, c
   if (!q_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
   std::lock_guard<std::mutex> lk(g_ws.mu);
   if (int rc = g_ws.init()) return rc;
-  const int qd = robot->dev.q_dim;
+  const int qd = robot->full.dev.q_dim;
   CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
   CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
   int k = 0;
@@ -646,7 +789,7 @@ int pmp_eval_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, co
   if (!q_host || !dist_host) return fail(PMP_ERR_INVALID, "null host pointer");
   std::lock_guard<std::mutex> lk(g_ws.mu);
   if (int rc = g_ws.init()) return rc;
-  const int qd = robot->dev.q_dim;
+  const int qd = robot->full.dev.q_dim;
   int k = 0;
   for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
     const int64_t m = std::min<int64_t>(kHostChunk, n - off);
@@ -670,12 +813,12 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, con
   if (n_checked) *n_checked = 0;
   if (n == 0) {
     ValidatorDev V;
-    return validator_to_dev(validator, robot->dev.q_dim, &V);
+    return validator_to_dev(validator, robot->full.dev.q_dim, &V);
   }
   if (!q0_host || !q1_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
   std::lock_guard<std::mutex> lk(g_ws.mu);
   if (int rc = g_ws.init()) return rc;
-  const int qd = robot->dev.q_dim;
+  const int qd = robot->full.dev.q_dim;
   CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
   CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
   int k = 0;

@@ -169,10 +169,15 @@ __device__ __forceinline__ void cloud_bounds(const CloudDev& C, const float3 p, 
     hi = INFINITY;
     return;
   }
-  const int64_t cell = ((int64_t)(int)fz * C.ny + (int)fy) * C.nx + (int)fx;
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const int64_t cell = ((int64_t)iz * C.ny + iy) * C.nx + ix;
   const float d = __ldg(C.dist + cell);
-  lo = d - C.e;
-  hi = (d >= C.dist_cap) ? INFINITY : d + C.e;
+  // NN is 1-Lipschitz: |NN(p) - NN(centre)| <= |p - centre| (<= e, the half diagonal); the guard
+  // covers the FP32 rounding of the offset
+  const float ux = (fx - (float)ix - 0.5f), uy = (fy - (float)iy - 0.5f), uz = (fz - (float)iz - 0.5f);
+  const float off = fminf(C.h * sqrtf(ux * ux + uy * uy + uz * uz) + 2e-6f, C.e);
+  lo = d - off;
+  hi = (d >= C.dist_cap) ? INFINITY : d + off;
 }
 
 // CloudSDF::is_outside(p, r) preceded by is_outside_aabb(p, r), exact:
@@ -188,6 +193,70 @@ __device__ inline bool cloud_is_outside(const CloudDev& C, const float3 p, const
   if (lo > d + 1e-5f) return true;
   if (hi < d - 1e-5f) return false;
   return !cloud_any_within(C, p, d * d);
+}
+
+// ---- 8-lane cooperative traversal ------------------------------------------------------------------
+// The tree is 8-ary and a narrow-phase item is worked by 8 lanes, so one sub-warp visits one node per
+// step: lane j tests child j (two LDG.128 + ~12 instructions per lane instead of 8 x that in one
+// lane), the ballot over the sub-warp is the child mask, and a leaf is one point per lane.  All
+// 8 lanes of `smask` (lanes 8k .. 8k+7) must call with identical p / bound2; the traversal state
+// (level, node, pending masks) is sub-warp uniform, so there is no divergence inside a sub-warp.
+__device__ __forceinline__ unsigned cloud_children_mask8(const CloudDev& C, const int level, const int first, const float3 p,
+                                                         const float bound2, const unsigned smask, const int sub, const int kshift) {
+  const float4* b = C.nodes + 2 * (size_t)(C.level_off[level] + first + sub);
+  const float d2 = box_dist2(__ldg(b), __ldg(b + 1), p);
+  return (__ballot_sync(smask, d2 <= bound2) >> kshift) & 0xffu;
+}
+
+__device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, const float bound2, const unsigned smask,
+                                         const int sub, const int kshift) {
+  const int top = C.n_levels - 1;
+  int l = top, n = 0;
+  unsigned long long masks = 0;
+  if (top == 0) {
+    masks = 1ull << 8;
+    l = 1;
+  } else {
+    masks = (unsigned long long)cloud_children_mask8(C, l - 1, 0, p, bound2, smask, sub, kshift) << (8 * l);
+  }
+  const int vtop = l;
+  for (;;) {
+    const unsigned m = (unsigned)(masks >> (8 * l)) & 0xffu;
+    if (!m) {
+      if (l == vtop) return false;
+      n >>= 3;
+      l++;
+      continue;
+    }
+    const int j = __ffs(m) - 1;
+    masks &= ~(1ull << (8 * l + j));
+    const int child = n * 8 + j;
+    if (l == 1) {  // leaf box: one point per lane
+      const float4 x = __ldg(C.pts + 8 * (size_t)child + sub);
+      const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+      if (__ballot_sync(smask, dx * dx + dy * dy + dz * dz <= bound2) & smask) return true;
+    } else {
+      l--;
+      n = child;
+      masks = (masks & ~(0xffull << (8 * l))) |
+              ((unsigned long long)cloud_children_mask8(C, l - 1, n * 8, p, bound2, smask, sub, kshift) << (8 * l));
+    }
+  }
+}
+
+// The O(1) part of cloud_is_outside: 0 = certainly outside, 1 = certainly not outside, 2 = the
+// distance field cannot decide (p lies within +-e of the r + rho iso-surface): ask the tree with
+// bound (r + rho)^2.
+__device__ __forceinline__ int cloud_classify(const CloudDev& C, const float3 p, const float r) {
+  if (p.x < C.lbx - r || p.x > C.ubx + r || p.y < C.lby - r || p.y > C.uby + r || p.z < C.lbz - r ||
+      p.z > C.ubz + r)
+    return 0;
+  const float d = r + C.rho;
+  float lo, hi;
+  cloud_bounds(C, p, lo, hi);
+  if (lo > d + 1e-5f) return 0;
+  if (hi < d - 1e-5f) return 1;
+  return 2;
 }
 
 // Conservative group-level cull: true only if certainly no point within r + rho.

@@ -136,9 +136,32 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
             hit |= !prim_is_outside(P, place(f, sp.x, sp.y, sp.z), sp.w);
           }
         } else if (CLOUD && kp == kItemCloud) {
-          for (int s = sub; s < gw.z && !hit; s += 8) {
-            const float4 sp = T.spheres[gw.y + s];
-            hit = !cloud_is_outside(S.cloud, place(f, sp.x, sp.y, sp.z), sp.w);
+          // one sphere per lane through the O(1) distance-field test; the few spheres the field
+          // cannot decide go to the tree one at a time, the sub-warp's 8 lanes on one node per step
+          const unsigned smask = 0xffu << (k * 8);
+          for (int s0 = 0; s0 < gw.z && !hit; s0 += 8) {
+            const int s = s0 + sub;
+            int st = 0;
+            float3 c = make3(0.f, 0.f, 0.f);
+            float d = 0.f;
+            if (s < gw.z) {
+              const float4 sp = T.spheres[gw.y + s];
+              c = place(f, sp.x, sp.y, sp.z);
+              d = sp.w + S.cloud.rho;
+              st = cloud_classify(S.cloud, c, sp.w);
+            }
+            if (__ballot_sync(smask, st == 1)) {
+              hit = true;
+              break;
+            }
+            unsigned mb = (__ballot_sync(smask, st == 2) >> (k * 8)) & 0xffu;
+            while (mb && !hit) {
+              const int owner = k * 8 + __ffs(mb) - 1;
+              mb &= mb - 1u;
+              const float3 pq = make3(__shfl_sync(smask, c.x, owner), __shfl_sync(smask, c.y, owner), __shfl_sync(smask, c.z, owner));
+              const float dq = __shfl_sync(smask, d, owner);
+              hit = cloud_any_within8(S.cloud, pq, dq * dq, smask, sub, k * 8);
+            }
           }
         } else {
           for (int s = sub; s < gw.z; s += 8) {

@@ -93,7 +93,11 @@ class LinkProgram:
                 op["axis"] = L.axis
                 op["q_index"] = q_index_of_joint[L.joint_id]
                 if L.kind == J_PRISMATIC:
+                    # algorithm.cpp:149-155: quat = identity (the joint origin's rotation is
+                    # dropped and the product skipped), trans = origin + axis * q
                     op["kind"] = _capi.OP_PRISMATIC
+                    op["origin_quat"] = (0, 0, 0, 1)
+                    op["flags"] = _capi.OPFLAG_ORIGIN_IDENTITY
                 else:
                     op["kind"] = _capi.OP_REVOLUTE
                     # algorithm.cpp:140-147

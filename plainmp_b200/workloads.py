@@ -69,6 +69,15 @@ def make_pr2_cloud(n_points: int, seed: int = 4):
     return spec, cst
 
 
+def make_pr2_table():
+    """PR2 dual arm against the table as primitives (the slab the cloud of config 4 samples)."""
+    spec = PR2DualarmSpec()
+    spec.reflect_default_joint_positions()
+    cst = spec.create_collision_const(use_cache=False)
+    cst.set_sdf(psdf.UnionSDF([psdf.BoxSDF([1.0, 2.0, 0.05], psdf.Pose([0.8, 0.0, 0.8])), psdf.GroundSDF(0.0)]))
+    return spec, cst
+
+
 def make_openarm():
     spec = OpenArmV10DualSpec()
     cst = spec.create_collision_const(use_cache=False)

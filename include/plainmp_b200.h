@@ -157,6 +157,15 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
 int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev,
                      int64_t n, float* dist_dev, void* stream);
 
+/* Batched ConstraintBase::evaluate WITH its Jacobian rows (bindings/constraint.cpp:33;
+ * primitive_sphere_collision.cpp:297-322, 363-399; point Jacobian kinematics/algorithm.cpp:346-433):
+ * dist_dev as above, jac_dev [n][2][q_dim] row-major = d(ext)/dq, d(self)/dq at the arg-min sphere /
+ * sphere pair; a row is all zero when the term sits at the 0.1 cutoff and NaN when it is disabled.
+ * The SDF gradient and the base-rotation columns are analytic where the reference uses forward
+ * differences (steps 1e-6 / 1e-7); the two agree to the reference's own test tolerance (1e-4). */
+int pmp_eval_grad_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev,
+                          int64_t n, float* dist_dev, float* jac_dev, void* stream);
+
 /* Batched get_all_spheres after update_kintree(q, accurate): out [n][n_spheres][4]. */
 int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate,
                    float* spheres_dev, void* stream);

@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
             "orc_cst_get_sphere_order": (None, [vp, vp]),
             "orc_cst_is_valid_batch": (None, [vp, vp, i64, i, vp]),
             "orc_cst_evaluate_batch": (None, [vp, vp, i64, i, vp]),
+            "orc_cst_evaluate_grad_batch": (None, [vp, vp, i64, i, vp, vp]),
             "orc_cst_margin_batch": (None, [vp, vp, i64, i, vp]),
             "orc_cst_spheres_batch": (None, [vp, vp, i64, i, vp]),
             "orc_validator_create": (vp, [i, i, vp, d]),
@@ -320,6 +321,14 @@ class OracleCst:
         out = np.zeros((Q.shape[0], 2))
         lib().orc_cst_evaluate_batch(self.h, _p(Q), Q.shape[0], n_threads or self.n_threads, _p(out))
         return out
+
+    def evaluate_grad_batch(self, Q, n_threads: Optional[int] = None):
+        """(vals [n, 2], jac [n, 2, q_dim]) — evaluate() with its Jacobian rows, NaN where disabled."""
+        Q = _f64(Q)
+        vals = np.zeros((Q.shape[0], 2))
+        jac = np.zeros((Q.shape[0], 2, Q.shape[1]))
+        lib().orc_cst_evaluate_grad_batch(self.h, _p(Q), Q.shape[0], n_threads or self.n_threads, _p(vals), _p(jac))
+        return vals, jac
 
     def margin_batch(self, Q, n_threads: Optional[int] = None) -> np.ndarray:
         Q = _f64(Q)

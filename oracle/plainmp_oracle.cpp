@@ -161,6 +161,42 @@ struct QuatTrans {
       result.trans = trans + quat * other.trans;
     }
   }
+  // transform.hpp:56-62 operator*
+  QuatTrans mul(const QuatTrans& other) const {
+    QuatTrans r;
+    r.quat = other.is_quat_identity ? quat : quat * other.quat;
+    r.trans = trans + quat * other.trans;
+    return r;
+  }
+  // transform.hpp:87-90 getInverse (Eigen Quaternion::inverse = conjugate / squaredNorm)
+  QuatTrans get_inverse() const {
+    const double n2 = quat.x * quat.x + quat.y * quat.y + quat.z * quat.z + quat.w * quat.w;
+    QuatTrans r;
+    r.quat = {-quat.x / n2, -quat.y / n2, -quat.z / n2, quat.w / n2};
+    r.trans = r.quat * (trans * -1.0);
+    return r;
+  }
+  // transform.hpp:92-120 getRPY
+  V3 get_rpy() const {
+    const double sqx = quat.x * quat.x, sqy = quat.y * quat.y, sqz = quat.z * quat.z, sqw = quat.w * quat.w;
+    const double sarg = -2 * (quat.x * quat.z - quat.w * quat.y);
+    const double pi_2 = 1.57079632679489661923;
+    double roll, pitch, yaw;
+    if (sarg <= -0.99999) {
+      pitch = -pi_2;
+      roll = 0;
+      yaw = -2 * atan2(quat.x, quat.y);
+    } else if (sarg >= 0.99999) {
+      pitch = pi_2;
+      roll = 0;
+      yaw = 2 * atan2(quat.x, quat.y);
+    } else {
+      pitch = asin(sarg);
+      roll = atan2(2 * (quat.y * quat.z + quat.w * quat.x), sqw - sqx - sqy + sqz);
+      yaw = atan2(2 * (quat.x * quat.y + quat.w * quat.z), sqw + sqx - sqy - sqz);
+    }
+    return {roll, pitch, yaw};
+  }
   // transform.hpp:122-130
   void set_quaternion_from_rpy(double roll, double pitch, double yaw) {
     const double phi = roll / 2.0, the = pitch / 2.0, psi = yaw / 2.0;
@@ -357,6 +393,69 @@ struct KinModel {
       transform_cache[hid_prev].quat_identity_sensitive_mult_and_assign(
           tf_plink_to_hlink_cache[hid], transform_cache[hid]);
       cache_pred[hid] = 1;
+    }
+  }
+  // kinematics.hpp:31-46 + kinematics.cpp:340-363: rptable_[link][joint] is true iff the link lies
+  // in the subtree under the joint's child link (restated as a climb to the root)
+  bool is_relevant(size_t link_id, size_t joint_id) const {
+    const size_t clink = (size_t)joint_child_link_ids[joint_id];
+    for (size_t l = link_id; l != std::numeric_limits<size_t>::max(); l = link_parent_link_ids[l])
+      if (l == clink) return true;
+    return false;
+  }
+  // algorithm.cpp:346-433 get_attached_point_jacobian: 3 x dim_dof, row-major into jac
+  void get_attached_point_jacobian(size_t plink_id, const V3& apoint_global_pos, const std::vector<size_t>& joint_ids,
+                                   int base_type, std::vector<double>& jac) const {
+    const size_t dim_dof = joint_ids.size() + (base_type == BASE_FLOATING) * 6 + (base_type == BASE_PLANAR) * 3;
+    jac.assign(3 * dim_dof, 0.0);
+    auto set_col = [&](size_t c, const V3& v) {
+      jac[c] = v.x;
+      jac[dim_dof + c] = v.y;
+      jac[2 * dim_dof + c] = v.z;
+    };
+    for (size_t i = 0; i < joint_ids.size(); i++) {
+      const size_t jid = joint_ids[i];
+      if (!is_relevant(plink_id, jid)) continue;
+      const QuatTrans& tf_rlink_to_clink = get_link_pose((size_t)joint_child_link_ids[jid]);
+      const V3 world_axis = tf_rlink_to_clink.quat * joint_axes[jid];
+      V3 dpos;
+      if (joint_types[jid] == J_PRISMATIC) {
+        dpos = world_axis;
+      } else {
+        dpos = eig::cross(world_axis, apoint_global_pos - tf_rlink_to_clink.trans);
+      }
+      set_col(i, dpos);
+    }
+    QuatTrans tf_rlink_to_elink;  // Identity with trans = the point
+    tf_rlink_to_elink.trans = apoint_global_pos;
+    QuatTrans tf_rlink_to_blink, tf_blink_to_elink;
+    V3 rpy_rlink_to_blink{0, 0, 0};
+    if (base_type != BASE_FIXED) {
+      tf_rlink_to_blink = get_link_pose(root_link_id);
+      tf_blink_to_elink = tf_rlink_to_blink.get_inverse().mul(tf_rlink_to_elink);
+      rpy_rlink_to_blink = tf_rlink_to_blink.get_rpy();
+    }
+    constexpr double eps = 1e-7;
+    const size_t n_joint = joint_ids.size();
+    auto tweak_col = [&](int rpy_idx, size_t idx_col) {
+      double rpy[3] = {rpy_rlink_to_blink.x, rpy_rlink_to_blink.y, rpy_rlink_to_blink.z};
+      rpy[rpy_idx] += eps;
+      QuatTrans tweaked;
+      tweaked.assign(tf_rlink_to_blink);
+      tweaked.set_quaternion_from_rpy(rpy[0], rpy[1], rpy[2]);
+      const QuatTrans pose_out = tweaked.mul(tf_blink_to_elink);
+      const V3 d = pose_out.trans - tf_rlink_to_elink.trans;
+      set_col(idx_col, {d.x / eps, d.y / eps, d.z / eps});
+    };
+    if (base_type == BASE_FLOATING) {
+      jac[n_joint + 0] = 1.0;
+      jac[dim_dof + n_joint + 1] = 1.0;
+      jac[2 * dim_dof + n_joint + 2] = 1.0;
+      for (int k = 0; k < 3; k++) tweak_col(k, n_joint + 3 + k);
+    } else if (base_type == BASE_PLANAR) {
+      jac[n_joint + 0] = 1.0;
+      jac[dim_dof + n_joint + 1] = 1.0;
+      tweak_col(2, n_joint + 2);
     }
   }
   // kinematics.cpp:300-337 add_new_link(parent, pose, consider_rotation)
@@ -1013,6 +1112,117 @@ struct SphereCollisionCst {
     return dist_min;
   }
 
+  // primitive.hpp:74-79 + .cpp:385-399 WITH the Jacobian rows: jac is [cst_dim][q_dim] row-major
+  int evaluate_with_grad(const double* q, double* vals, double* jac) {
+    update_kintree(q, true);
+    post_update_kintree();
+    const size_t dim = q_dim();
+    int head = 0;
+    if (ext_collision_enabled()) {
+      vals[head] = evaluate_ext_collision_grad(jac + head * dim);
+      head++;
+    }
+    if (self_collision_enabled()) {
+      vals[head] = evaluate_self_collision_grad(jac + head * dim);
+      head++;
+    }
+    return head;
+  }
+  // .cpp:256-322
+  double evaluate_ext_collision_grad(double* grad_out) {
+    const size_t dim = q_dim();
+    double min_val_other = cutoff_dist;
+    long min_sphere_idx = -1, min_group_idx = -1, min_sdf_idx = -1;
+    for (size_t i = 0; i < sphere_groups.size(); i++) {
+      auto& group = sphere_groups[i];
+      if (group.only_self_collision) continue;
+      group.create_group_sphere_position_cache(*kin);
+      for (size_t j = 0; j < all_sdfs_cache.size(); j++) {
+        auto& s = all_sdfs_cache[j];
+        if (!s->is_outside_aabb(group.group_sphere_position_cache, group.group_radius + cutoff_dist)) {
+          if (!s->is_outside(group.group_sphere_position_cache, group.group_radius + cutoff_dist)) {
+            group.create_sphere_position_cache(*kin);
+            for (size_t k = 0; k < group.radii.size(); k++) {
+              const V3& c = group.sphere_positions_cache[k];
+              if (s->is_outside_aabb(c, group.radii[k] + cutoff_dist)) continue;
+              double val = s->evaluate(c) - group.radii[k];
+              if (val < min_val_other) {
+                min_val_other = val;
+                min_group_idx = (long)i;
+                min_sdf_idx = (long)j;
+                min_sphere_idx = (long)k;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (min_sphere_idx < 0) {  // cutoff case
+      for (size_t c = 0; c < dim; c++) grad_out[c] = 0.0;
+      return min_val_other;
+    }
+    const V3 min_sphere_trans = sphere_groups[min_group_idx].sphere_positions_cache[min_sphere_idx];
+    const double r = sphere_groups[min_group_idx].radii[min_sphere_idx];
+    double grad[3];
+    for (int i = 0; i < 3; i++) {
+      V3 perturbed = min_sphere_trans;
+      (i == 0 ? perturbed.x : i == 1 ? perturbed.y : perturbed.z) += 1e-6;
+      const double val = all_sdfs_cache[min_sdf_idx]->evaluate(perturbed) - r;
+      grad[i] = (val - min_val_other) / 1e-6;
+    }
+    std::vector<double> J;
+    kin->get_attached_point_jacobian(sphere_groups[min_group_idx].parent_link_id, min_sphere_trans, control_joint_ids,
+                                     base_type, J);
+    for (size_t c = 0; c < dim; c++) grad_out[c] = J[c] * grad[0] + J[dim + c] * grad[1] + J[2 * dim + c] * grad[2];
+    return min_val_other;
+  }
+  // .cpp:324-383
+  double evaluate_self_collision_grad(double* grad) {
+    const size_t dim = q_dim();
+    bool found = false;
+    size_t mp[4] = {0, 0, 0, 0};
+    double dist_min = cutoff_dist;
+    for (auto& pr : selcol_group_id_pairs) {
+      auto& group1 = sphere_groups[pr.first];
+      auto& group2 = sphere_groups[pr.second];
+      group1.create_group_sphere_position_cache(*kin);
+      group2.create_group_sphere_position_cache(*kin);
+      double outer_sqdist =
+          eig::sqnorm(group1.group_sphere_position_cache - group2.group_sphere_position_cache);
+      double m = group1.group_radius + group2.group_radius + cutoff_dist;
+      if (outer_sqdist > m * m) continue;
+      group1.create_sphere_position_cache(*kin);
+      group2.create_sphere_position_cache(*kin);
+      for (size_t i = 0; i < group1.radii.size(); i++)
+        for (size_t j = 0; j < group2.radii.size(); j++) {
+          double dist = eig::norm(group1.sphere_positions_cache[i] - group2.sphere_positions_cache[j]) -
+                        (group1.radii[i] + group2.radii[j]);
+          if (dist < dist_min) {
+            dist_min = dist;
+            found = true;
+            mp[0] = pr.first; mp[1] = i; mp[2] = pr.second; mp[3] = j;
+          }
+        }
+    }
+    if (!found) {
+      for (size_t c = 0; c < dim; c++) grad[c] = 0.0;
+      return dist_min;
+    }
+    auto& group1 = sphere_groups[mp[0]];
+    const V3 center1 = group1.sphere_positions_cache[mp[1]];
+    auto& group2 = sphere_groups[mp[2]];
+    const V3 center2 = group2.sphere_positions_cache[mp[3]];
+    const V3 center_diff = center1 - center2;
+    std::vector<double> J1, J2;
+    kin->get_attached_point_jacobian(group1.parent_link_id, center1, control_joint_ids, base_type, J1);
+    kin->get_attached_point_jacobian(group2.parent_link_id, center2, control_joint_ids, base_type, J2);
+    const double norminv = 1.0 / eig::norm(center_diff);
+    for (size_t c = 0; c < dim; c++)
+      grad[c] = norminv * (center_diff.x * (J1[c] - J2[c]) + center_diff.y * (J1[dim + c] - J2[dim + c]) +
+                           center_diff.z * (J1[2 * dim + c] - J2[2 * dim + c]));
+    return dist_min;
+  }
+
   // .cpp:412-424 get_all_spheres (after an update_kintree)
   size_t n_spheres() const {
     size_t n = 0;
@@ -1444,6 +1654,27 @@ void orc_cst_evaluate_batch(void* h, const double* q, int64_t n, int n_threads, 
     }
   });
 }
+// vals [n][2] (NaN for a disabled term), jac [n][2][q_dim] (NaN rows for a disabled term)
+void orc_cst_evaluate_grad_batch(void* h, const double* q, int64_t n, int n_threads, double* vals, double* jac) {
+  auto* base = (SphereCollisionCst*)h;
+  const size_t dim = base->q_dim();
+  const bool ext = base->ext_collision_enabled(), slf = base->self_collision_enabled();
+  parallel_for(n, n_threads, [&](int, int64_t lo, int64_t hi) {
+    auto c = base->clone_for_thread();
+    std::vector<double> v(2), J(2 * dim);
+    for (int64_t i = lo; i < hi; i++) {
+      c->evaluate_with_grad(q + i * dim, v.data(), J.data());
+      int head = 0;
+      for (int t = 0; t < 2; t++) {
+        const bool on = t == 0 ? ext : slf;
+        vals[2 * i + t] = on ? v[head] : std::nan("");
+        for (size_t k = 0; k < dim; k++) jac[(2 * i + t) * dim + k] = on ? J[head * dim + k] : std::nan("");
+        if (on) head++;
+      }
+    }
+  });
+}
+
 void orc_cst_margin_batch(void* h, const double* q, int64_t n, int n_threads, double* out) {
   auto* base = (SphereCollisionCst*)h;
   const size_t d = base->q_dim();

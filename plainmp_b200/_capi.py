@@ -129,6 +129,7 @@ SYMBOLS = {
     "pmp_scene_destroy": (None, [_p]),
     "pmp_check_configs": (_i32, [_p, _p, _p, _i64, _p, _p, _p]),
     "pmp_eval_configs": (_i32, [_p, _p, _p, _i64, _p, _p]),
+    "pmp_eval_grad_configs": (_i32, [_p, _p, _p, _i64, _p, _p, _p]),
     "pmp_fk_spheres": (_i32, [_p, _p, _i64, _i32, _p, _p]),
     "pmp_fk_frames": (_i32, [_p, _p, _i64, _i32, _p, _p]),
     "pmp_check_edges": (_i32, [_p, _p, C.POINTER(Validator), _p, _p, _i64, _p, _p, _p, _p]),

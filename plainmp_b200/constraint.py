@@ -181,11 +181,11 @@ class SphereCollisionCst(IneqConstraintBase):
         return bool(self.is_valid_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))[0])
 
     def evaluate(self, q: Sequence[float]):
-        """``(vals, jac)`` like the binding; the Jacobian rows are outside this repo's scope
-         and are returned as NaN."""
-        d = self.evaluate_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))[0]
-        vals = d[~np.isnan(d)]
-        return vals, np.full((vals.shape[0], self.q_dim()), np.nan)
+        """``(vals, jac)`` like the binding (constraint.cpp:33): one row per enabled term
+        (ext, then self), jac = d vals / d q at the arg-min sphere / sphere pair."""
+        d, j = self.evaluate_grad_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))
+        on = ~np.isnan(d[0])
+        return d[0][on], j[0][on]
 
     def get_all_spheres(self) -> List[Tuple[np.ndarray, float]]:
         """Sphere centres for the state set by the last ``update_kintree`` (.cpp:412-424)."""
@@ -225,6 +225,11 @@ class SphereCollisionCst(IneqConstraintBase):
         """[n, 2] = (ext, self) min signed distances clipped at 0.1; NaN where a term is disabled."""
         return tables.eval_configs(self._robot(), self._scene(), Q)
 
+    def evaluate_grad_batch(self, Q):
+        """``evaluate_batch`` plus the Jacobian rows: ([n, 2], [n, 2, q_dim]); a row is zero when the
+        term sits at the 0.1 cutoff (primitive_sphere_collision.cpp:297-300, 363-365), NaN when disabled."""
+        return tables.eval_grad_configs(self._robot(), self._scene(), Q)
+
     def get_all_spheres_batch(self, Q, accurate: bool = True) -> np.ndarray:
         """[n, n_spheres, 4] world sphere centres + radii, groups in spec order."""
         return tables.fk_spheres(self._robot(), Q, accurate)
@@ -251,6 +256,9 @@ class IneqCompositeCst:
         return out
 
     def evaluate(self, q):
-        vals = [c.evaluate(q)[0] for c in self.constraints]
-        v = np.concatenate(vals) if vals else np.zeros(0)
-        return v, np.full((v.shape[0], self.constraints[0].q_dim()), np.nan)
+        # composite_constraint.hpp:63-79: member values and Jacobian rows stacked in order
+        parts = [c.evaluate(q) for c in self.constraints]
+        dim = self.constraints[0].q_dim()
+        v = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0)
+        j = np.concatenate([p[1].reshape(-1, dim) for p in parts], axis=0) if parts else np.zeros((0, dim))
+        return v, j

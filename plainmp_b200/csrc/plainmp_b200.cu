@@ -522,20 +522,36 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
   return PMP_OK;
 }
 
-int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n,
-                     float* dist_dev, void* stream) {
+static int eval_launch(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n, float* dist_dev,
+                       float* jac_dev, void* stream) {
   CHECK_COMMON(robot, n);
   if (n == 0) return PMP_OK;
-  if ((!q_dev && robot->full.dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  if ((!q_dev && robot->fast.dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const size_t smem = smem_bytes(robot->full, S);
+  const size_t smem = smem_bytes(robot->fast, S);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   int grid = 0;
-  if (int rc = grid_for(k_eval_configs, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-  k_eval_configs<<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, dist_dev);
+  if (jac_dev) {
+    if (int rc = grid_for(k_eval_configs<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+    k_eval_configs<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, jac_dev);
+  } else {
+    if (int rc = grid_for(k_eval_configs<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
+    k_eval_configs<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, nullptr);
+  }
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return PMP_OK;
+}
+
+int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n,
+                     float* dist_dev, void* stream) {
+  return eval_launch(robot, scene, q_dev, n, dist_dev, nullptr, stream);
+}
+
+int pmp_eval_grad_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n,
+                          float* dist_dev, float* jac_dev, void* stream) {
+  if (!jac_dev && n > 0) return fail(PMP_ERR_INVALID, "null device pointer");
+  return eval_launch(robot, scene, q_dev, n, dist_dev, jac_dev, stream);
 }
 
 int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int accurate, float* spheres_dev, void* stream) {

@@ -107,12 +107,14 @@ __device__ inline bool cloud_any_within(const CloudDev& C, const float3 p, const
 
 // exact: squared distance to the nearest cloud point if it is <= bound2, else a value > bound2
 // (+inf).  `idx` receives the original index of the best point (or -1).
-__device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const float bound2, int* idx) {
+__device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const float bound2, int* idx,
+                                        float3* nearest = nullptr) {
   const int top = C.n_levels - 1;
   // accept d2 <= bound2: search with a strict test against a bound nudged up by one ulp
   float best = __uint_as_float(__float_as_uint(fminf(fmaxf(bound2, 0.f), 3.0e38f)) + 1u);
   const float limit = best;
   int best_i = -1;
+  float3 best_p = make_float3(0.f, 0.f, 0.f);
   int l = top, n = 0;
   unsigned long long masks = 0;
   if (top == 0) {
@@ -143,6 +145,7 @@ __device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const
         if (d2 < best) {
           best = d2;
           best_i = __float_as_int(x.w);
+          best_p = make_float3(x.x, x.y, x.z);
         }
       }
     } else {
@@ -153,6 +156,7 @@ __device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const
     }
   }
   if (idx) *idx = best_i;
+  if (nearest) *nearest = best_p;
   return (best < limit) ? best : INFINITY;
 }
 

@@ -303,6 +303,54 @@ __device__ __forceinline__ float prim_evaluate(const Prim& P, const float3 c) {
   return sqrtf(pr * pr + pz * pz) + fmaxf(fminf(sr, 0.f), fminf(sz, 0.f));
 }
 
+// Analytic gradient of prim_evaluate w.r.t. the query point (world frame, unit length away from the
+// medial axis).  The reference differentiates evaluate() numerically (forward difference, step 1e-6,
+// constraints/primitive_sphere_collision.cpp:307-314); the closed forms below are the limits of
+// that quotient wherever the SDF is differentiable.
+__device__ __forceinline__ float3 prim_gradient(const Prim& P, const float3 c) {
+  if (P.type == PMP_PRIM_GROUND) return make3(0.f, 0.f, 1.f);
+  const float dx = c.x - P.p0.x, dy = c.y - P.p0.y, dz = c.z - P.p0.z;
+  if (P.type == PMP_PRIM_SPHERE) {
+    const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
+    return make3(dx * inv, dy * inv, dz * inv);
+  }
+  const bool aligned = P.flags & PMP_PRIMFLAG_AXIS_ALIGNED;
+  float4 c0 = make_float4(1.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 1.f, 0.f, 0.f), c2 = make_float4(0.f, 0.f, 1.f, 0.f);
+  if (!aligned) {
+    c0 = P.w[2]; c1 = P.w[3]; c2 = P.w[4];
+  }
+  const float lx = dx * c0.x + dy * c0.y + dz * c0.z, ly = dx * c1.x + dy * c1.y + dz * c1.z,
+              lz = dx * c2.x + dy * c2.y + dz * c2.z;
+  float gx, gy, gz;  // gradient in the primitive's frame
+  if (P.type == PMP_PRIM_BOX) {
+    const float sx = fabsf(lx) - P.pr.x, sy = fabsf(ly) - P.pr.y, sz = fabsf(lz) - P.pr.z;
+    if (fmaxf(fmaxf(sx, sy), sz) > 0.f) {
+      const float px = fmaxf(sx, 0.f), py = fmaxf(sy, 0.f), pz = fmaxf(sz, 0.f);
+      const float inv = rsqrtf(px * px + py * py + pz * pz);
+      gx = copysignf(px * inv, lx); gy = copysignf(py * inv, ly); gz = copysignf(pz * inv, lz);
+    } else {  // inside: the face with the largest (least negative) distance
+      gx = (sx >= sy && sx >= sz) ? copysignf(1.f, lx) : 0.f;
+      gy = (gx == 0.f && sy >= sz) ? copysignf(1.f, ly) : 0.f;
+      gz = (gx == 0.f && gy == 0.f) ? copysignf(1.f, lz) : 0.f;
+    }
+  } else {  // cylinder: axis = local z
+    const float rho = sqrtf(lx * lx + ly * ly);
+    const float irho = rho > 0.f ? 1.f / rho : 0.f;
+    const float sr = rho - P.pr.x, sz = fabsf(lz) - P.pr.y;
+    float wr, wz;  // weights of the radial and axial directions
+    if (fmaxf(sr, sz) > 0.f) {
+      const float pr = fmaxf(sr, 0.f), pz = fmaxf(sz, 0.f);
+      const float inv = rsqrtf(pr * pr + pz * pz);
+      wr = pr * inv; wz = pz * inv;
+    } else {
+      wr = (sr > sz) ? 1.f : 0.f;
+      wz = 1.f - wr;
+    }
+    gx = wr * lx * irho; gy = wr * ly * irho; gz = copysignf(wz, lz);
+  }
+  return make3(c0.x * gx + c1.x * gy + c2.x * gz, c0.y * gx + c1.y * gy + c2.y * gz, c0.z * gx + c1.z * gy + c2.z * gz);
+}
+
 // is_outside_aabb(c, r) (primitive_sdf.hpp:180-184) against the AABB in centre / half-extent form,
 // branch-free: outside <=> max_k(|c_k - ctr_k| - half_k) > r.
 __device__ __forceinline__ bool prim_aabb_outside(const float4 ctr, const float4 half, const float3 c,

@@ -172,10 +172,34 @@ k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__
   if (n_valid && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
 }
 
-// evaluate(): exact FK, min signed distances clipped at 0.1 (values only)
+// evaluate(): exact FK, min signed distances clipped at 0.1, optionally with the Jacobian rows
+// (primitive_sphere_collision.cpp:256-383).  GRAD: the arg-min sphere (ext) and sphere pair (self)
+// are remembered in pass 1; pass 2 walks the links once more and, for every controlled joint that is
+// an ancestor of the arg-min sphere's link, adds the column of get_attached_point_jacobian
+// (kinematics/algorithm.cpp:346-375: world_axis x (c - joint position), or world_axis for a
+// prismatic joint) contracted with the distance gradient.  Two deliberate differences from the
+// reference, both below its own test tolerance (tests/test_constraints.py:36-44, 4 decimals):
+// the SDF gradient is the analytic one (the reference takes a forward difference with a 1e-6 step
+// in FP64, .cpp:307-314, which FP32 cannot resolve), and the base-rotation columns are the analytic
+// derivatives w.r.t. the roll/pitch/yaw entries of q (reference: forward difference, eps 1e-7,
+// algorithm.cpp:388-430).
+struct EvalArgmin {
+  int ext_op, ext_prim;  // op carrying the arg-min sphere (-1 = cutoff case), primitive (-1 = cloud)
+  float3 ext_c, ext_nn;  // its world centre; nearest cloud point when ext_prim < 0
+  int self_op_a, self_op_b;
+  float3 self_ca, self_cb;
+};
+
+// ancestor-or-self test on the topologically ordered op table (parent < index)
+__device__ __forceinline__ bool op_is_ancestor(const Smem& T, const int anc, int x) {
+  while (x > anc) x = __float_as_int(T.ops[kOpWords * x + 3].x);
+  return x == anc;
+}
+
+template <bool GRAD>
 __global__ void __launch_bounds__(128)
 k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
-               float* __restrict__ out) {
+               float* __restrict__ out, float* __restrict__ jac) {
   extern __shared__ float4 sm[];
   const Smem T = stage_tables(R, S, sm);
   const float cutoff = 0.1f;  // primitive_sphere_collision.hpp:115
@@ -187,6 +211,9 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
     if (item >= n) continue;
     QDirect acc{q + item * R.q_dim};
     float min_ext = cutoff, min_self = cutoff;
+    EvalArgmin A;
+    A.ext_op = -1; A.ext_prim = -1; A.self_op_a = -1; A.self_op_b = -1;
+    A.ext_c = A.ext_nn = A.self_ca = A.self_cb = make3(0.f, 0.f, 0.f);
     int gi = 0;
     auto visit = [&](int op, const Frame& f) -> bool {
       while (gi < R.n_groups) {
@@ -209,7 +236,13 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
               const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
               // sphere-level AABB pre-test (.cpp:280-283): result-relevant for Ground only
               if (P.type == PMP_PRIM_GROUND && (c.z < -(sp.w + cutoff) || c.z > sp.w + cutoff)) continue;
-              min_ext = fminf(min_ext, prim_evaluate(P, c) - sp.w);
+              const float val = prim_evaluate(P, c) - sp.w;
+              if (val < min_ext) {
+                min_ext = val;
+                if (GRAD) {
+                  A.ext_op = op; A.ext_prim = k; A.ext_c = c;
+                }
+              }
             }
           }
           if (S.cloud.enabled && !cloud_surely_outside(S.cloud, gc, g.w + cutoff)) {
@@ -225,8 +258,17 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
               const float need = min_ext + sp.w + S.cloud.rho;  // only NN below this can lower the min
               if (lo >= need) continue;
               const float b = fminf(hi * (1.f + 1e-6f) + 1e-6f, need);
-              const float d2 = cloud_nn_within(S.cloud, c, b * b, nullptr);
-              if (d2 <= b * b) min_ext = fminf(min_ext, sqrtf(d2) - S.cloud.rho - sp.w);
+              float3 nn;
+              const float d2 = cloud_nn_within(S.cloud, c, b * b, nullptr, GRAD ? &nn : nullptr);
+              if (d2 <= b * b) {
+                const float val = sqrtf(d2) - S.cloud.rho - sp.w;
+                if (val < min_ext) {
+                  min_ext = val;
+                  if (GRAD) {
+                    A.ext_op = op; A.ext_prim = -1; A.ext_c = c; A.ext_nn = nn;
+                  }
+                }
+              }
             }
           }
         }
@@ -254,13 +296,97 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
           const float4 sb = T.spheres[wb.y + j];
           const float3 cb = xform(rb, fb, sb.x, sb.y, sb.z);
           const float ex = ca.x - cb.x, ey = ca.y - cb.y, ez = ca.z - cb.z;
-          min_self = fminf(min_self, sqrtf(ex * ex + ey * ey + ez * ez) - (sa.w + sb.w));
+          const float val = sqrtf(ex * ex + ey * ey + ez * ez) - (sa.w + sb.w);
+          if (val < min_self) {
+            min_self = val;
+            if (GRAD) {
+              A.self_op_a = wa.x; A.self_op_b = wb.x; A.self_ca = ca; A.self_cb = cb;
+            }
+          }
         }
       }
     }
     const float nanv = __int_as_float(0x7fc00000);
     out[2 * item] = ext ? min_ext : nanv;
     out[2 * item + 1] = (R.n_pairs > 0) ? min_self : nanv;
+    if (!GRAD) continue;
+
+    // ---- pass 2: Jacobian rows ----
+    float* je = jac + (2 * item) * R.q_dim;
+    float* js = je + R.q_dim;
+    for (int c = 0; c < R.q_dim; c++) {
+      je[c] = ext ? 0.f : nanv;
+      js[c] = (R.n_pairs > 0) ? 0.f : nanv;
+    }
+    float3 ge = make3(0.f, 0.f, 0.f);  // d(sdf)/d(centre) at the arg-min sphere
+    if (A.ext_op >= 0) {
+      if (A.ext_prim >= 0) {
+        ge = prim_gradient(load_prim(T.prims, A.ext_prim), A.ext_c);
+      } else {
+        const float dx = A.ext_c.x - A.ext_nn.x, dy = A.ext_c.y - A.ext_nn.y, dz = A.ext_c.z - A.ext_nn.z;
+        const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
+        ge = make3(dx * inv, dy * inv, dz * inv);
+      }
+    }
+    float3 ns = make3(0.f, 0.f, 0.f);  // (c1 - c2) / |c1 - c2|
+    if (A.self_op_a >= 0) {
+      const float dx = A.self_ca.x - A.self_cb.x, dy = A.self_ca.y - A.self_cb.y, dz = A.self_ca.z - A.self_cb.z;
+      const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
+      ns = make3(dx * inv, dy * inv, dz * inv);
+    }
+    if (A.ext_op < 0 && A.self_op_a < 0) continue;
+    walk_links<false>(R, T, acc, [&](int op, const Frame& f) -> bool {
+      const int kind = __float_as_int(T.ops[kOpWords * op + 1].w);
+      if (kind == PMP_OP_FIXED) return true;
+      const float4 w2 = T.ops[kOpWords * op + 2];
+      const int qi = __float_as_int(w2.w);
+      const float3 wa = quat_rot(f.qx, f.qy, f.qz, f.qw, make3(w2.x, w2.y, w2.z));  // axis w.r.t. the root
+      auto column = [&](const float3 c) -> float3 {
+        if (kind == PMP_OP_PRISMATIC) return wa;
+        const float rx = c.x - f.tx, ry = c.y - f.ty, rz = c.z - f.tz;
+        return make3(wa.y * rz - wa.z * ry, wa.z * rx - wa.x * rz, wa.x * ry - wa.y * rx);
+      };
+      if (A.ext_op >= 0 && op_is_ancestor(T, op, A.ext_op)) {
+        const float3 col = column(A.ext_c);
+        je[qi] = col.x * ge.x + col.y * ge.y + col.z * ge.z;
+      }
+      if (A.self_op_a >= 0) {
+        float v = 0.f;
+        if (op_is_ancestor(T, op, A.self_op_a)) {
+          const float3 col = column(A.self_ca);
+          v += col.x * ns.x + col.y * ns.y + col.z * ns.z;
+        }
+        if (op_is_ancestor(T, op, A.self_op_b)) {
+          const float3 col = column(A.self_cb);
+          v -= col.x * ns.x + col.y * ns.y + col.z * ns.z;
+        }
+        js[qi] = v;
+      }
+      return true;
+    });
+    // moving base (algorithm.cpp:378-430): translation columns are unit vectors, rotation columns
+    // axis_k x (c - t_base) with the roll / pitch / yaw axes of R = Rz(yaw) Ry(pitch) Rx(roll).
+    // For the self row every base column cancels (both points move rigidly with the base).
+    if (R.base_type != PMP_BASE_FIXED && A.ext_op >= 0) {
+      const Frame b = base_frame(R, acc);
+      const float rx = A.ext_c.x - b.tx, ry = A.ext_c.y - b.ty, rz = A.ext_c.z - b.tz;
+      auto rot_col = [&](const float ax, const float ay, const float az) -> float {
+        return (ay * rz - az * ry) * ge.x + (az * rx - ax * rz) * ge.y + (ax * ry - ay * rx) * ge.z;
+      };
+      je[R.dof] = ge.x;
+      je[R.dof + 1] = ge.y;
+      if (R.base_type == PMP_BASE_PLANAR) {
+        je[R.dof + 2] = rot_col(0.f, 0.f, 1.f);
+      } else {
+        je[R.dof + 2] = ge.z;
+        float sy, cy, sp, cp;
+        sincosf(acc(R.dof + 5), &sy, &cy);
+        sincosf(acc(R.dof + 4), &sp, &cp);
+        je[R.dof + 3] = rot_col(cy * cp, sy * cp, -sp);
+        je[R.dof + 4] = rot_col(-sy, cy, 0.f);
+        je[R.dof + 5] = rot_col(0.f, 0.f, 1.f);
+      }
+    }
   }
 }
 

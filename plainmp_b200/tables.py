@@ -398,6 +398,20 @@ def eval_configs(table: RobotTable, scene: Optional[SceneTable], q) -> np.ndarra
     return out.cpu().numpy().astype(np.float64)
 
 
+def eval_grad_configs(table: RobotTable, scene: Optional[SceneTable], q):
+    """(values [n, 2], jacobian rows [n, 2, q_dim]) of evaluate(); NaN where a term is disabled."""
+    torch = _torch()
+    qd = _as_q(table, q)
+    out = torch.empty((qd.shape[0], 2), dtype=torch.float32, device=qd.device)
+    jac = torch.empty((qd.shape[0], 2, table.q_dim), dtype=torch.float32, device=qd.device)
+    _capi.check(
+        table._lib.pmp_eval_grad_configs(
+            table.handle, scene.handle if scene is not None else None, qd.data_ptr(), qd.shape[0], out.data_ptr(), jac.data_ptr(), _stream_ptr()
+        )
+    )
+    return out.cpu().numpy().astype(np.float64), jac.cpu().numpy().astype(np.float64)
+
+
 def fk_spheres(table: RobotTable, q, accurate: bool) -> np.ndarray:
     torch = _torch()
     qd = _as_q(table, q)

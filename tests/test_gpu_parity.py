@@ -76,7 +76,7 @@ def test_single_item_api_equals_batch(cuda_lib):
         assert cst.is_valid(q) == o.is_valid(q.astype(np.float64))
         vals, jac = cst.evaluate(q)
         np.testing.assert_allclose(vals, o.evaluate(q.astype(np.float64)), atol=TOL)
-        assert jac.shape == (2, 7)
+        assert jac.shape == (2, 7) and not np.isnan(jac).any()
     cst.update_kintree(Q[0], True)
     sph = cst.get_all_spheres()
     want = o.spheres_batch(Q[:1].astype(np.float64), True)[0]
@@ -412,3 +412,64 @@ def test_edges_against_cloud_scene(cuda_lib):
     want, _ = bridge.OracleValidator(0, 14, w).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64), n_threads=4)
     assert 0.05 < want.mean() < 0.95
     assert (got != want).sum() <= 4 and n_checked > 0
+
+
+# ---- evaluate() with Jacobian rows -------------------------------------------------
+JAC_TOL = 5e-4  # the reference's own Jacobian test passes at 4 decimals (tests/test_constraints.py:36-44)
+
+
+def _jacobian_parity(cst, o, Q, what):
+    Qd = Q.astype(np.float64)
+    vals, jac = cst.evaluate_grad_batch(Q)
+    want_v, want_j = o.evaluate_grad_batch(Qd)
+    np.testing.assert_allclose(vals, want_v, atol=TOL, rtol=0, equal_nan=True)
+    assert jac.shape == want_j.shape
+    assert (np.isnan(jac) == np.isnan(want_j)).all()
+    err = np.abs(np.nan_to_num(jac) - np.nan_to_num(want_j)).max(axis=2)  # [n, 2]
+    # rows may legitimately differ where the arg-min is (nearly) tied between two spheres / primitive
+    # faces, or where the reference's forward difference straddles a kink of the SDF: allow 1 %
+    frac_bad = (err > JAC_TOL).mean()
+    assert frac_bad < 0.01, f"{what}: {frac_bad:.3%} Jacobian rows differ by more than {JAC_TOL} (max {err.max():.3e})"
+    live = np.abs(np.nan_to_num(want_j)).max(axis=2) > 0
+    assert live.mean() > 0.2, f"{what}: too few non-trivial rows to mean anything"
+    return err
+
+
+@pytest.mark.parametrize("name", ["panda_dualbars_seed1", "fetch_table_seed2", "pr2_cloud20k_seed4", "openarm_dual_seed6"])
+def test_evaluate_jacobian_against_oracle(cuda_lib, name):
+    spec, cst = MAKERS[name]()
+    o = bridge.OracleCst(cst, n_threads=4)
+    Q = workloads.random_configs(spec, 3000, 77)
+    _jacobian_parity(cst, o, Q, name)
+    # single-item surface: rows only for enabled terms
+    vals, jac = cst.evaluate(Q[0])
+    assert vals.shape == (2,) and jac.shape == (2, Q.shape[1])
+
+
+@pytest.mark.parametrize("base_type", [BaseType.FIXED, BaseType.PLANAR, BaseType.FLOATING])
+@pytest.mark.parametrize("with_self", [False, True])
+def test_evaluate_jacobian_moving_base_and_numerical(cuda_lib, base_type, with_self):
+    # tests/test_constraints.py:148-160: PR2 right arm + unit box, std 1.0 (fixed) / 0.1 (moving base)
+    spec = PR2RarmSpec(base_type=base_type)
+    cst = spec.create_collision_const(self_collision=with_self, use_cache=False)
+    cst.set_sdf(psdf.BoxSDF([1, 1, 1], psdf.Pose([0.5, 0.5, 0.5])))
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(12)
+    std = 1.0 if base_type == BaseType.FIXED else 0.1
+    Q = (rng.standard_normal((2000, o.q_dim)) * std).astype(np.float32)
+    _jacobian_parity(cst, o, Q, f"pr2 rarm {base_type} self={with_self}")
+    vals, jac = cst.evaluate(Q[0])
+    assert vals.shape == ((2,) if with_self else (1,)) and jac.shape == (len(vals), o.q_dim)
+    # the reference's check_jacobian, with the FP64 oracle supplying the finite differences of the values
+    _, jac_gpu = cst.evaluate_grad_batch(Q[:50])
+    eps = 1e-7
+    n_bad = 0
+    for i in range(50):
+        qd = Q[i].astype(np.float64)
+        v0 = o.evaluate_batch(qd[None])[0]
+        vp = o.evaluate_batch(qd[None] + eps * np.eye(o.q_dim))
+        num = ((vp - v0) / eps).T  # [2, q_dim]
+        for t in range(2):
+            if not np.isnan(v0[t]):
+                n_bad += int(np.abs(jac_gpu[i, t] - num[t]).max() > JAC_TOL)
+    assert n_bad <= 1

@@ -242,6 +242,37 @@ def test_is_valid_equals_all_evaluate_positive(base_type, with_self):
     assert n_agree > 90
 
 
+@pytest.mark.parametrize("base_type", [BaseType.FIXED, BaseType.PLANAR, BaseType.FLOATING])
+@pytest.mark.parametrize("with_self", [False, True])
+def test_evaluate_jacobian_matches_numerical(base_type, with_self):
+    # the reference's own Jacobian check, tests/test_constraints.py:22-44 (eps 1e-7, 4 decimals) on
+    # the case of :148-160 (PR2 right arm + unit box, std 1.0 fixed base / 0.1 moving base):
+    # pins evaluate_ext_collision / evaluate_self_collision gradients and get_attached_point_jacobian
+    spec = PR2RarmSpec(base_type=base_type)
+    cst = spec.create_collision_const(self_collision=with_self, use_cache=False)
+    cst.set_sdf(psdf.BoxSDF([1, 1, 1], psdf.Pose([0.5, 0.5, 0.5])))
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(11)
+    dim = o.q_dim
+    std = 1.0 if base_type == BaseType.FIXED else 0.1
+    Q = rng.standard_normal((100, dim)) * std
+    vals, jac = o.evaluate_grad_batch(Q)
+    eps = 1e-7
+    n_rows = 2 if with_self else 1
+    n_nonzero = 0
+    for i in range(Q.shape[0]):
+        Qp = np.repeat(Q[i : i + 1], dim, axis=0) + eps * np.eye(dim)
+        vp = o.evaluate_batch(Qp)
+        for t in range(2):
+            if np.isnan(vals[i, t]):
+                assert t == 1 and not with_self
+                continue
+            num = (vp[:, t] - vals[i, t]) / eps
+            np.testing.assert_almost_equal(jac[i, t], num, decimal=4)
+            n_nonzero += int(np.abs(jac[i, t]).max() > 0)
+    assert n_nonzero > 20 * n_rows  # most samples are closer than the 0.1 cutoff, so the rows are not trivially zero
+
+
 def test_no_sdf_no_pairs_is_always_valid():
     # tests/test_constraints.py:163-175, SURVEY App. C-7
     spec = PR2RarmSpec()

@@ -85,6 +85,7 @@ class KinematicModel:
     def __init__(self, urdf_xml_string: str):
         if not urdf_xml_string:
             raise RuntimeError("xml string is empty")  # kinematics.cpp:186-188
+        self._urdf_xml = urdf_xml_string  # kept so that the same text can be handed to another parser
         root = ET.fromstring(urdf_xml_string)
         link_names = [el.get("name") for el in root.findall("link")]
         joints = []

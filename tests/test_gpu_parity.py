@@ -1,5 +1,7 @@
-"""GPU parity tests: the CUDA path (through the C ABI) against the FP64 oracle and the committed
-golden vectors, on the BASELINE.json configurations.
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden vectors
+(REFERENCE output, tools/make_golden.py), the FP64 oracle (pinned to the compiled reference by
+tests/test_reference_pin.py) and, where the prebuilt oracle/_ref/libplainmp_ref.so travelled to the
+box, the compiled reference itself, on the BASELINE.json configurations.
 
 Parity rule (BASELINE.json north_star): validity bit-exact except items whose signed distance
 lies within EPS of the contact threshold; signed distances and sphere centres within TOL.
@@ -9,7 +11,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from oracle import bridge
+from oracle import bridge, ref_bridge
 from plainmp_b200 import _capi, psdf, tables, workloads
 from plainmp_b200.constraint import SphereAttachmentSpec, SphereCollisionCst
 from plainmp_b200.kdtree import KDTree
@@ -63,6 +65,49 @@ def test_configs_against_golden_and_oracle(cuda_lib, name):
     Qd = Q2.astype(np.float64)
     assert_validity_parity(cst.is_valid_batch(Q2), o.is_valid_batch(Qd), o.margin_batch(Qd), name + "/live")
     np.testing.assert_allclose(cst.evaluate_batch(Q2), o.evaluate_batch(Qd), atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("name", list(MAKERS))
+def test_golden_is_reference_output_and_jacobian_rows(cuda_lib, name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    assert str(g["source"]).startswith("reference")
+    spec, cst = MAKERS[name]()
+    k = g["jac_head"].shape[0]
+    Q = workloads.random_configs(spec, int(g["n"]), int(g["seed"]))[:k]
+    vals, jac = cst.evaluate_grad_batch(Q)
+    np.testing.assert_allclose(vals, g["dist"][:k], atol=TOL, rtol=0, equal_nan=True)
+    err = np.abs(np.nan_to_num(jac) - np.nan_to_num(g["jac_head"])).max(axis=2)
+    assert (err > 5e-4).mean() < 0.02, f"{name}: Jacobian rows vs reference, max err {err.max():.3e}"
+
+
+@pytest.mark.skipif(not ref_bridge.available(), reason="prebuilt oracle/_ref/libplainmp_ref.so did not travel to this box")
+@pytest.mark.parametrize("name", list(MAKERS))
+def test_configs_against_compiled_reference(cuda_lib, name):
+    """CUDA path vs the reference's own compiled C++ (not the restatement) on a fresh seed."""
+    spec, cst = MAKERS[name]()
+    r = ref_bridge.RefCst(cst)
+    o = bridge.OracleCst(cst, n_threads=4)  # only for the contact-band margin
+    Q = workloads.random_configs(spec, 6000, 4321)
+    Qd = Q.astype(np.float64)
+    assert_validity_parity(cst.is_valid_batch(Q), r.is_valid_batch(Qd), o.margin_batch(Qd), name + "/ref")
+    np.testing.assert_allclose(cst.evaluate_batch(Q[:2000]), r.evaluate_batch(Qd[:2000]), atol=TOL, rtol=0)
+    np.testing.assert_allclose(cst.get_all_spheres_batch(Q[:32], accurate=False), r.spheres_batch(Qd[:32], False), atol=TOL, rtol=0)
+
+
+@pytest.mark.skipif(not ref_bridge.available(), reason="prebuilt oracle/_ref/libplainmp_ref.so did not travel to this box")
+@pytest.mark.parametrize("vtype", [ValidatorType.BOX, ValidatorType.EUCLIDEAN])
+def test_edges_against_compiled_reference(cuda_lib, vtype):
+    spec, cst = workloads.make_panda(ceiled=True)
+    r = ref_bridge.RefCst(cst)
+    widths = [0.05, 0.07, 0.05, 0.1, 0.05, 0.2, 0.05]
+    mv = MotionValidator(cst, ValidatorConfig(vtype, 0.08, widths))
+    for planner_like in (False, True):
+        q0, q1 = workloads.random_edges(spec, 3000, 99, planner_like, (lambda q: cst.is_valid_batch(q)) if planner_like else None)
+        got, n_checked = mv.check_motion_batch(q0, q1)
+        want, n_ref = r.check_motion_batch(0 if vtype == ValidatorType.BOX else 1, widths, 0.08, q0.astype(np.float64), q1.astype(np.float64))
+        # an edge may differ only if one of its waypoints sits in the contact band: bounded, tiny
+        assert (got != want).mean() < 0.004, f"{(got != want).sum()} edge mismatches"
+        assert got.mean() == pytest.approx(want.mean(), abs=0.004)
 
 
 def test_single_item_api_equals_batch(cuda_lib):

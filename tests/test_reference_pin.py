@@ -1,0 +1,301 @@
+"""Pin the restated FP64 oracle (oracle/plainmp_oracle.cpp) against the REFERENCE ITSELF: the
+reference's own C++ sources for the hot path, compiled where they lie under /root/reference into
+oracle/_ref/libplainmp_ref.so (oracle/Makefile.ref; Eigen and OMPL are replaced by the minimal API
+stand-ins of oracle/ref_shim/).  CPU only.
+
+Every comparison here is FP64 vs FP64 and is expected to agree to rounding (1e-12), validity bit
+for bit.  What this pins that the KATs cannot: the URDF parser and link/joint numbering
+(third/urdf_parser + kinematics.cpp:29-223), lazy FK (algorithm.cpp:88-210), the sphere-group tables
+and reorder (primitive_sphere_collision.cpp:53-179), both broad phases and the early exits
+(.cpp:181-254), evaluate + Jacobian rows (.cpp:256-399, algorithm.cpp:346-433), every primitive's
+is_outside/evaluate/AABB (primitive_sdf.hpp), the kd-tree (kdtree.cpp) and both motion validators
+(motion_validator.cpp).
+
+The library is built in the authoring container (it needs /root/reference) and travels to the GPU
+box as a prebuilt, git-ignored file; where neither the library nor the reference tree exists the
+module is skipped, and the committed tests/golden/*.npz (reference-generated) carry the pin.
+"""
+import numpy as np
+import pytest
+
+from oracle import bridge, ref_bridge
+from plainmp_b200 import psdf, workloads
+from plainmp_b200.constraint import SphereAttachmentSpec, SphereCollisionCst
+from plainmp_b200.kinematics import BaseType, KinematicModel
+from plainmp_b200.robot_spec import FetchSpec, OpenArmV10DualSpec, PandaSpec, PR2DualarmSpec, PR2RarmSpec, rpy_matrix
+
+pytestmark = pytest.mark.skipif(
+    not (ref_bridge.available() or ref_bridge.can_build()),
+    reason="oracle/_ref/libplainmp_ref.so is absent and /root/reference is not mounted",
+)
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_ref():
+    ref_bridge.build()
+    yield
+
+
+MAKERS = {
+    "panda_dualbars": (workloads.make_panda, 1, 4000),
+    "panda_ceiled": (lambda: workloads.make_panda(ceiled=True), 3, 2000),
+    "fetch_table": (workloads.make_fetch, 2, 4000),
+    "pr2_cloud20k": (lambda: workloads.make_pr2_cloud(20000), 4, 1500),
+    "pr2_table": (workloads.make_pr2_table, 9, 2000),
+    "openarm_dual": (workloads.make_openarm, 6, 2000),
+}
+
+
+@pytest.mark.parametrize("name", list(MAKERS))
+def test_is_valid_evaluate_spheres_match_reference(name):
+    maker, seed, n = MAKERS[name]
+    spec, cst = maker()
+    Q = workloads.random_configs(spec, n, seed).astype(np.float64)
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    assert (o.q_dim, o.n_spheres) == (r.q_dim, r.n_spheres)
+    v_o, v_r = o.is_valid_batch(Q), r.is_valid_batch(Q)
+    assert (v_o == v_r).all(), f"{(v_o != v_r).sum()} validity mismatches"
+    assert 0.02 < v_r.mean() < 0.98  # both outcomes exercised
+    m = min(n, 600)
+    vals_o, jac_o = o.evaluate_grad_batch(Q[:m])
+    vals_r, jac_r = r.evaluate_grad_batch(Q[:m])
+    assert (np.isnan(vals_o) == np.isnan(vals_r)).all()
+    np.testing.assert_allclose(vals_o, vals_r, atol=TOL, rtol=0)
+    # the reference differentiates the SDF by forward differences with step 1e-6 (.cpp:305-312): its
+    # own rounding noise is ~1e-16 / 1e-6 per unit of Jacobian, both sides execute the same formula
+    np.testing.assert_allclose(jac_o, jac_r, atol=1e-8, rtol=0)
+    for accurate in (False, True):
+        np.testing.assert_allclose(o.spheres_batch(Q[:64], accurate), r.spheres_batch(Q[:64], accurate), atol=TOL, rtol=0)
+        g_o = np.stack([o.group_spheres(q, accurate) for q in Q[:16]])
+        np.testing.assert_allclose(g_o, r.group_spheres_batch(Q[:16], accurate), atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("base_type", [BaseType.FIXED, BaseType.PLANAR, BaseType.FLOATING])
+@pytest.mark.parametrize("with_self", [False, True])
+def test_moving_base_matches_reference(base_type, with_self):
+    # the reference's own constraint-test case (tests/test_constraints.py:47-53,148-160)
+    spec = PR2RarmSpec(base_type=base_type)
+    cst = spec.create_collision_const(self_collision=with_self, use_cache=False)
+    cst.set_sdf(psdf.BoxSDF([1, 1, 1], psdf.Pose([0.5, 0.5, 0.5])))
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    rng = np.random.default_rng(21)
+    Q = rng.standard_normal((400, o.q_dim)) * (1.0 if base_type == BaseType.FIXED else 0.3)
+    assert (o.is_valid_batch(Q) == r.is_valid_batch(Q)).all()
+    vals_o, jac_o = o.evaluate_grad_batch(Q)
+    vals_r, jac_r = r.evaluate_grad_batch(Q)
+    assert (np.isnan(vals_o) == np.isnan(vals_r)).all()
+    np.testing.assert_allclose(vals_o, vals_r, atol=TOL, rtol=0)
+    # base-rotation columns are forward differences with step 1e-7 (algorithm.cpp:392-431)
+    np.testing.assert_allclose(jac_o, jac_r, atol=1e-7, rtol=0)
+    np.testing.assert_allclose(o.spheres_batch(Q[:32], True), r.spheres_batch(Q[:32], True), atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("Spec", [PandaSpec, FetchSpec, PR2DualarmSpec, OpenArmV10DualSpec])
+def test_urdf_parse_and_fk_match_reference(Spec):
+    """Same URDF text through the reference's urdf_parser and through the host mirror's parser:
+    every link pose, joint limits, approximate and exact FK."""
+    spec = Spec()
+    kin = spec.get_kin()
+    names = spec.control_joint_names
+    ids = kin.get_joint_ids(names)
+    rk = ref_bridge.RefKin(kin)
+    ok = bridge.OracleKin(kin)
+    lim = rk.joint_limits(names)
+    np.testing.assert_array_equal(lim, np.array(kin.get_joint_position_limits(ids)))
+    rng = np.random.default_rng(5)
+    link_names = [L.name for L in kin.links]
+    for trial in range(6):
+        q = rng.uniform(-2.5, 2.5, size=len(names))
+        accurate = trial % 2 == 0
+        rk.set_joint_positions(names, q, accurate)
+        ok.set_joint_angles(ids, q, accurate)
+        for lid, ln in enumerate(link_names):
+            np.testing.assert_allclose(ok.link_pose(lid), rk.link_pose(ln), atol=TOL, rtol=0, err_msg=ln)
+
+
+def test_added_links_and_base_pose_match_reference():
+    spec = PandaSpec()
+    xml = spec.get_kin()._urdf_xml
+    kin = KinematicModel(xml)
+    kin.add_new_link("tool", "panda_hand", [0.01, -0.02, 0.1], [0.3, -0.2, 0.5], True)
+    kin.add_new_link("tool_tip", "tool", [0.0, 0.0, 0.05], [0.0, 0.0, 0.0], True)
+    kin.set_base_pose([0.1, 0.2, 0.3, *(np.array([0.1, 0.2, 0.3, 0.9]) / np.linalg.norm([0.1, 0.2, 0.3, 0.9]))])
+    names = spec.control_joint_names
+    q = np.linspace(-1.0, 1.0, 7)
+    kin.set_joint_positions(kin.get_joint_ids(names), q, True)
+    rk, ok = ref_bridge.RefKin(kin), bridge.OracleKin(kin)
+    for ln in ("tool", "tool_tip", "panda_link8"):
+        np.testing.assert_allclose(ok.link_pose(kin.get_link_ids([ln])[0]), rk.link_pose(ln), atol=TOL, rtol=0)
+    with pytest.raises(RuntimeError):  # kinematics.cpp:313-320
+        rk.add_new_link("tool", "panda_hand", [0, 0, 0], [0, 0, 0], True)
+    with pytest.raises(ValueError):  # std::invalid_argument, kinematics.cpp:270-272
+        rk.link_pose("no_such_link")
+    with pytest.raises(ValueError):  # kinematics.cpp:243-245
+        rk.set_joint_positions(["no_such_joint"], [0.0])
+
+
+def _random_prims(rng):
+    out = []
+    for k in range(24):
+        pos = rng.uniform(-0.5, 0.5, 3)
+        mode = k % 3
+        rot = np.eye(3) if mode == 0 else (rpy_matrix(0, 0, rng.uniform(-3, 3)) if mode == 1 else rpy_matrix(*rng.uniform(-3, 3, 3)))
+        kind = (k // 3) % 3
+        if kind == 0:
+            out.append(psdf.BoxSDF(rng.uniform(0.1, 0.8, 3), psdf.Pose(pos, rot)))
+        elif kind == 1:
+            out.append(psdf.CylinderSDF(rng.uniform(0.05, 0.4), rng.uniform(0.1, 0.9), psdf.Pose(pos, rot)))
+        else:
+            out.append(psdf.SphereSDF(rng.uniform(0.05, 0.5), psdf.Pose(pos, rot)))
+    out.append(psdf.GroundSDF(0.0))
+    out.append(psdf.GroundSDF(0.37))
+    return out
+
+
+def test_primitive_sdfs_match_reference():
+    rng = np.random.default_rng(31)
+    P = rng.uniform(-1.2, 1.2, size=(3000, 3))
+    radii = np.where(rng.random(3000) < 0.2, 0.0, rng.uniform(0.0, 0.3, 3000))
+    prims = _random_prims(rng)
+    for s in prims:
+        o, r = bridge.OracleSDF.from_psdf(s), ref_bridge.RefSDF.from_psdf(s)
+        np.testing.assert_allclose(o.evaluate_batch(P), r.evaluate_batch(P), atol=TOL, rtol=0)
+        np.testing.assert_allclose(r.evaluate_batch(P), r.evaluate_batch(P, each=True), atol=TOL, rtol=0)
+        assert (o.is_outside_batch(P, radii) == r.is_outside_batch(P, radii)).all()
+        for a, b in zip(o.aabb(), r.aabb()):
+            np.testing.assert_allclose(a, b, atol=TOL, rtol=0)
+        if s.get_type() != psdf.T_GROUND:
+            po, pr = o.pose(), r.pose()
+            assert po[2:] == pr[2:]
+            np.testing.assert_allclose(po[1], pr[1], atol=TOL, rtol=0)
+    u = psdf.UnionSDF(prims[:7])
+    o, r = bridge.OracleSDF.from_psdf(u), ref_bridge.RefSDF.from_psdf(u)
+    np.testing.assert_allclose(o.evaluate_batch(P), r.evaluate_batch(P), atol=TOL, rtol=0)
+    assert (o.is_outside_batch(P, radii) == r.is_outside_batch(P, radii)).all()
+    # scene mutation: translate / rotate_z on the union, clone independence
+    for obj in (o, r):
+        obj.translate([0.1, -0.2, 0.05])
+        obj.rotate_z(0.7)
+    np.testing.assert_allclose(o.evaluate_batch(P), r.evaluate_batch(P), atol=TOL, rtol=0)
+    oc, rc = o.clone(), r.clone()
+    o.translate([1.0, 0, 0])
+    r.translate([1.0, 0, 0])
+    np.testing.assert_allclose(oc.evaluate_batch(P), rc.evaluate_batch(P), atol=TOL, rtol=0)
+    np.testing.assert_allclose(o.evaluate_batch(P), r.evaluate_batch(P), atol=TOL, rtol=0)
+
+
+def test_reference_error_behaviour_matches_host_mirror():
+    g = ref_bridge.RefSDF.from_psdf(psdf.GroundSDF(0.0))
+    with pytest.raises(RuntimeError):  # primitive_sdf.hpp:234-240
+        g.translate([0, 0, 1])
+    with pytest.raises(RuntimeError):
+        g.rotate_z(0.1)
+    c = ref_bridge.RefSDF.from_psdf(psdf.CloudSDF(np.random.default_rng(0).random((10, 3)), 0.01))
+    for call in (lambda: c.translate([0, 0, 1]), lambda: c.rotate_z(0.1), c.clone):  # :585-595
+        with pytest.raises(RuntimeError):
+            call()
+    with pytest.raises(RuntimeError):
+        psdf.GroundSDF(0.0).translate([0, 0, 1])
+    with pytest.raises(RuntimeError):
+        psdf.CloudSDF(np.random.default_rng(0).random((10, 3)), 0.01).clone()
+    # bad pair name -> runtime_error (.cpp:171-174); unknown link in a spec -> invalid_argument
+    spec = PandaSpec()
+    kin = spec.get_kin()
+    one = SphereAttachmentSpec("panda_link1", np.zeros((3, 1)), np.array([0.1]), False)
+    good = SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED, [one], [], None, True)
+    ref_bridge.RefCst(good)
+    good._group_link_names = ["nope"]  # the reference resolves the name itself: get_link_ids throws
+    with pytest.raises(ValueError):
+        ref_bridge.RefCst(good)
+    with pytest.raises(RuntimeError):
+        SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED, [one], [("panda_link1", "nope")], None, True)
+    with pytest.raises(ValueError):
+        SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED,
+                           [SphereAttachmentSpec("nope", np.zeros((3, 1)), np.array([0.1]), False)], [], None, True)
+
+
+def test_kdtree_and_cloud_match_reference():
+    rng = np.random.default_rng(41)
+    for n in (1, 2, 7, 1000, 20000):
+        pts = rng.uniform(-1, 1, size=(n, 3))
+        Pq = rng.uniform(-1.5, 1.5, size=(500, 3))
+        o, r = bridge.OracleKDTree(pts), ref_bridge.RefKDTree(pts)
+        sq_r = r.sqdist_batch(Pq)
+        np.testing.assert_allclose(o.sqdist_batch(Pq), sq_r, atol=TOL, rtol=0)
+        brute = ((Pq[:, None, :] - pts[None, :, :]) ** 2).sum(-1).min(1)
+        np.testing.assert_allclose(sq_r, brute, atol=1e-12, rtol=0)  # tests/test_kdtree.py:6-20
+        nn = r.query_batch(Pq)
+        np.testing.assert_allclose(((nn - Pq) ** 2).sum(1), sq_r, atol=1e-12, rtol=0)
+    cloud = psdf.CloudSDF(workloads.table_cloud(5000), 0.002)
+    o, r = bridge.OracleSDF.from_psdf(cloud), ref_bridge.RefSDF.from_psdf(cloud)
+    P = rng.uniform([0.2, -1.1, 0.6], [1.4, 1.1, 1.3], size=(2000, 3))
+    np.testing.assert_allclose(o.evaluate_batch(P), r.evaluate_batch(P), atol=TOL, rtol=0)
+    rad = rng.uniform(0, 0.1, 2000)
+    assert (o.is_outside_batch(P, rad) == r.is_outside_batch(P, rad)).all()
+    for a, b in zip(o.aabb(), r.aabb()):
+        np.testing.assert_allclose(a, b, atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("vtype", [0, 1])
+def test_motion_validators_match_reference(vtype):
+    """checkMotion compiled from ompl/motion_validator.cpp (over the ompl::base stand-in): validity
+    AND the number of is_valid calls, i.e. the waypoint order with its early exit."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    widths = np.array([0.05, 0.07, 0.05, 0.1, 0.05, 0.2, 0.05])
+    res = 0.1
+    ov = bridge.OracleValidator(vtype, 7, widths, res)
+    for planner_like, n in ((False, 600), (True, 600)):
+        q0, q1 = workloads.random_edges(spec, n, 3, planner_like, (lambda q: o.is_valid_batch(q.astype(np.float64))) if planner_like else None)
+        q0, q1 = q0.astype(np.float64), q1.astype(np.float64)
+        want, n_ref = r.check_motion_batch(vtype, widths, res, q0, q1)
+        got, n_orc = ov.check_motion_batch(o, q0, q1)
+        assert (got == want).all()
+        assert n_orc == n_ref
+        for i in range(0, n, 37):
+            assert ov.step_ratio(q0[i], q1[i]) == ref_bridge.step_ratio(vtype, widths, res, q0[i], q1[i])
+    # degenerate edges: identical endpoints (ratio inf -> valid without any check), very long edges
+    # (n_test >= 129 -> natural order), tiny box widths
+    z = np.zeros((1, 7))
+    for s1, s2, w in [(z, z, widths), (z, z + 1e-7, widths), (z - 2.0, z + 2.0, np.full(7, 0.01)), (z, z + 0.3, np.full(7, 0.3))]:
+        ovv = bridge.OracleValidator(vtype, 7, w, 0.01)
+        want, n_ref = r.check_motion_batch(vtype, w, 0.01, s1, s2)
+        got, n_orc = ovv.check_motion_batch(o, s1, s2)
+        assert (got == want).all() and n_orc == n_ref
+
+
+def test_fetch_long_edges_natural_order_match_reference():
+    # fetch has continuous joints clipped to +-2 pi: n_test up to 253 > 128 -> untabulated order
+    spec, cst = workloads.make_fetch()
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    q0, q1 = workloads.random_edges(spec, 300, 12, False)
+    q0, q1 = q0.astype(np.float64), q1.astype(np.float64)
+    w = np.full(8, 0.05)
+    want, n_ref = r.check_motion_batch(0, w, 0.0, q0, q1)
+    got, n_orc = bridge.OracleValidator(0, 8, w).check_motion_batch(o, q0, q1)
+    assert (got == want).all() and n_orc == n_ref
+
+
+def test_zero_radius_self_only_and_no_scene_match_reference():
+    spec = PR2RarmSpec()
+    kin = spec.get_kin()
+    rng = np.random.default_rng(3)
+    specs = [
+        SphereAttachmentSpec("r_gripper_palm_link", rng.uniform(-0.1, 0.1, (3, 5)), np.zeros(5), False),
+        SphereAttachmentSpec("r_forearm_link", rng.uniform(-0.1, 0.1, (3, 4)), rng.uniform(0.02, 0.08, 4), False),
+        SphereAttachmentSpec("base_link", rng.uniform(-0.3, 0.3, (3, 6)), rng.uniform(0.05, 0.2, 6), True),
+    ]
+    pairs = [("r_gripper_palm_link", "base_link"), ("r_forearm_link", "base_link")]
+    for reorder in (True, False):
+        cst = SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED, specs, pairs, None, reorder)
+        Q = rng.standard_normal((500, 7))
+        for sdf in (None, psdf.UnionSDF([psdf.BoxSDF([0.4, 0.4, 0.4], psdf.Pose([0.6, -0.2, 0.8], rpy_matrix(0.2, 0.3, 0.4))), psdf.SphereSDF(0.2, psdf.Pose([0.5, 0.3, 1.0]))])):
+            cst.set_sdf(sdf)
+            o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+            assert (o.is_valid_batch(Q) == r.is_valid_batch(Q)).all()
+            vo, vr = o.evaluate_batch(Q), r.evaluate_batch(Q)
+            assert (np.isnan(vo) == np.isnan(vr)).all()
+            np.testing.assert_allclose(vo, vr, atol=TOL, rtol=0)
+            np.testing.assert_allclose(o.spheres_batch(Q[:8], True), r.spheres_batch(Q[:8], True), atol=TOL, rtol=0)

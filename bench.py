@@ -62,51 +62,116 @@ def make_workload(name):
 
 # ---- clocks ---------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms
+    from a thread (tens of samples even for a 50 ms region); `nvidia-smi -lms` as the fallback."""
+
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index: int):
-        self.rows = []
+    def __init__(self, gpu_index: int, uuid: str | None = None):
+        self.rows = []  # (sm_mhz, max_mhz, power_w, reasons-set)
         self.proc = None
         self.gpu = gpu_index
+        self.uuid = uuid
+        self.nvml = None
+        self._stop = threading.Event()
+        self.source = None
+
+    def _nvml_open(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                u = self.uuid if str(self.uuid).startswith("GPU-") else "GPU-" + str(self.uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+            except Exception:
+                h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.nvml, self.h = pynvml, h
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {
+            "hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                except Exception:
+                    mask = 0
+                self.rows.append((sm, self.max_mhz, pw, {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self._nvml_open()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                reasons = {nm for nm, v in zip(names, r[5:9]) if v.lower().startswith("active")}
+                pw = float(r[3]) if r[3].replace(".", "").isdigit() else None
+                self.rows.append((float(r[1]), float(r[2]), pw, reasons))
             except Exception:
                 pass
+
+    def stop(self):
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi and NVML unavailable"]}
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=1)
+        sm = [r[0] for r in self.rows]
+        reasons = set().union(*[r[3] for r in self.rows]) if self.rows else set()
+        pw = [r[2] for r in self.rows if r[2] is not None]
         return {
             "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
-            "power_w_max": max((float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()), default=None),
+            "sm_max_mhz": float(max(r[1] for r in self.rows)) if self.rows else None,
+            "power_w_max": max(pw) if pw else None,
             "samples": len(sm),
+            "source": self.source,
             "reasons": sorted(reasons),
         }
 
@@ -235,8 +300,9 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION or WARN) on stdout: send its log to stderr
+        # so that rank 0's stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.load()
 
@@ -276,7 +342,11 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     if rank == 0:
         sampler.start()
     launches0 = lib.pmp_launch_count()

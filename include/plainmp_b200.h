@@ -202,6 +202,31 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene,
                          const float* q1_host, int64_t n, uint32_t* valid_bits_host,
                          uint64_t* n_valid, uint64_t* n_checked);
 
+/* ---- validator sessions: what an OMPL-facing adaptor binds ---------------------
+ * The reference installs its validators inside CollisionAwareSpaceInformation
+ * (ompl/ompl_thin_wrap.hpp:80-91): isValid(state) -> IneqConstraintBase::is_valid (:114-120) and
+ * checkMotion(s1, s2) -> CustomValidatorBase::checkMotion (ompl/motion_validator.cpp:17-79), one
+ * state / one edge per call, states held as double[dim] by RealVectorStateSpace.  A session is the
+ * batched, low-latency form of that pair: it owns a stream and pinned + device staging sized at
+ * creation, takes the caller's FP64 states as they are, and answers with one byte per item.
+ * include/plainmp_b200_ompl.hpp wraps it as ompl::base::MotionValidator / StateValidityChecker.
+ *  - validator may be NULL for a session that only answers is_valid.
+ *  - capacity = items per launch; larger calls are chunked.  Calls on one session are serialised.
+ *  - check_motion: the step ratio and n_test are computed on the host in FP64 from the caller's
+ *    doubles exactly as determine_step_ratio does (:89-126).  Small batches (up to 2^17 waypoints)
+ *    test every waypoint of every edge in one wave (result identical: checkMotion is an AND);
+ *    larger ones use the early-exit kernel of pmp_check_edges.  n_checked reports the waypoint
+ *    checks actually executed, so it exceeds the reference's is_valid call count on the first path. */
+typedef struct pmp_session pmp_session_t;
+int pmp_session_create(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                       int64_t capacity, pmp_session_t** out);
+void pmp_session_destroy(pmp_session_t* session);
+/* Swap the scene the session checks against (the handle must outlive the session's use of it). */
+int pmp_session_set_scene(pmp_session_t* session, const pmp_scene_t* scene);
+int pmp_session_is_valid(pmp_session_t* session, const double* states_host, int64_t n, uint8_t* valid_host);
+int pmp_session_check_motion(pmp_session_t* session, const double* s1_host, const double* s2_host, int64_t n,
+                             uint8_t* valid_host, uint64_t* n_checked);
+
 /* ---- psdf / kdtree surface ------------------------------------------------------------------ */
 
 /* UnionSDF::evaluate_batch over the scene's primitives and cloud: out_dev[i] = min_P sdf_P(p_i).

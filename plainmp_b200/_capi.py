@@ -139,6 +139,11 @@ SYMBOLS = {
         _i32,
         [_p, _p, C.POINTER(Validator), _p, _p, _i64, _p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     ),
+    "pmp_session_create": (_i32, [_p, _p, C.POINTER(Validator), _i64, C.POINTER(_p)]),
+    "pmp_session_destroy": (None, [_p]),
+    "pmp_session_set_scene": (_i32, [_p, _p]),
+    "pmp_session_is_valid": (_i32, [_p, _p, _i64, _p]),
+    "pmp_session_check_motion": (_i32, [_p, _p, _p, _i64, _p, C.POINTER(C.c_uint64)]),
     "pmp_sdf_evaluate": (_i32, [_p, _p, _i64, _p, _p]),
     "pmp_sdf_is_outside": (_i32, [_p, _p, _p, _i64, _p, _p]),
     "pmp_cloud_nearest": (_i32, [_p, _p, _i64, _p, _p, _p]),

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pmp_cloud_build.h"
@@ -51,12 +52,33 @@ int ensure_device() {
   return PMP_OK;
 }
 
+// Occupancy per (kernel, dynamic smem, block) is queried once and remembered: the two runtime calls
+// cost several microseconds, which is most of a small launch on the session's latency path.
+struct GridCacheEntry {
+  int smem_attr = 0;                                  // MaxDynamicSharedMemorySize currently set
+  std::vector<std::pair<std::pair<size_t, int>, int>> per_sm;  // ((smem, block), CTAs per SM)
+};
+std::mutex g_grid_mu;
+std::unordered_map<const void*, GridCacheEntry> g_grid_cache;
+
 template <class K>
 int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kBlock) {
-  CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
-  if (per_sm < 1) return fail(PMP_ERR_LIMIT, "kernel does not fit on an SM with these tables");
+  {
+    std::lock_guard<std::mutex> lk(g_grid_mu);
+    GridCacheEntry& e = g_grid_cache[reinterpret_cast<const void*>(kernel)];
+    if ((int)smem > e.smem_attr) {
+      CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      e.smem_attr = (int)smem;
+    }
+    for (auto& kv : e.per_sm)
+      if (kv.first.first == smem && kv.first.second == block) per_sm = kv.second;
+    if (!per_sm) {
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+      if (per_sm < 1) return fail(PMP_ERR_LIMIT, "kernel does not fit on an SM with these tables");
+      e.per_sm.push_back({{smem, block}, per_sm});
+    }
+  }
   long long g = (long long)g_num_sms * per_sm;
   *grid = (int)std::max<long long>(1, std::min<long long>(g, n_tiles));
   return PMP_OK;
@@ -856,6 +878,271 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, con
   CUDA_OK(cudaMemcpy(g_ws.counters_host, g_ws.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (n_valid) *n_valid = g_ws.counters_host[0] + g_ws.counters_host[1];
   if (n_checked) *n_checked = g_ws.counters_host[2] + g_ws.counters_host[3];
+  return PMP_OK;
+}
+
+// ---- validator sessions (the OMPL-facing adaptor's back end) ----------------------------------------
+// A session owns a stream, one pinned + device-mapped host arena and one device arena sized at
+// creation.  A call packs FP64 -> FP32 into the arena and then either
+//   zero-copy (tiny batches): ONE kernel that reads its inputs from, and writes its results to, the
+//                             mapped host arena, and a stream synchronise;
+//   staged:                   ONE H2D copy of the compactly packed inputs, ONE kernel, ONE D2H copy;
+// no allocation, no memset, no shared workspace lock, occupancy queries cached (grid_for).
+struct pmp_session {
+  const pmp_robot_t* robot = nullptr;
+  const pmp_scene_t* scene = nullptr;
+  bool has_validator = false;
+  pmp_validator_t vdesc{};
+  std::vector<double> width, inv_width;
+  int64_t cap = 0;  // states / edges per launch; larger calls are chunked
+  int qd = 0;
+  cudaStream_t stream = nullptr;
+  char* host = nullptr;      // pinned, mapped
+  char* host_dev = nullptr;  // the device's view of `host`
+  char* dev = nullptr;
+  size_t arena = 0;
+  unsigned long long* counters = nullptr;       // device [2]: n_valid, n_checked of the early-exit path
+  unsigned long long* counters_host = nullptr;  // pinned [2]
+  std::mutex mu;
+};
+
+namespace {
+constexpr long long kFlatMaxWaypoints = 1 << 17;  // beyond this the early-exit kernel wins
+constexpr long long kZeroCopyWaypoints = 4096;    // flat path: results come back as bytes in mapped memory
+constexpr int64_t kZeroCopyStates = 2048;
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// BoxMotionValidator / EuclideanMotionValidator::determine_step_ratio in FP64 on the caller's
+// doubles (ompl/motion_validator.cpp:89-126)
+double host_step_ratio(const pmp_session* s, const double* a, const double* b) {
+  if (s->vdesc.type == PMP_VALIDATOR_BOX) {
+    double diff_longest = 0.0, max_diff = -std::numeric_limits<double>::infinity();
+    int longest = 0;
+    for (int i = 0; i < s->qd; i++) {  // first maximum wins (strict >)
+      const double diff = b[i] - a[i];
+      const double sc = std::abs(diff) * s->inv_width[i];
+      if (sc > max_diff) {
+        max_diff = sc;
+        longest = i;
+        diff_longest = diff;
+      }
+    }
+    if (std::abs(diff_longest) < 1e-6) return std::numeric_limits<double>::infinity();
+    return s->width[longest] / std::abs(diff_longest);
+  }
+  double d2 = 0.0;
+  for (int i = 0; i < s->qd; i++) {
+    const double d = a[i] - b[i];
+    d2 += d * d;
+  }
+  return s->vdesc.resolution / std::sqrt(d2);
+}
+}  // namespace
+
+int pmp_session_create(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                       int64_t capacity, pmp_session_t** out) {
+  if (!out) return fail(PMP_ERR_INVALID, "out is null");
+  *out = nullptr;
+  CHECK_COMMON(robot, capacity);
+  if (capacity < 1) return fail(PMP_ERR_INVALID, "capacity must be positive");
+  auto* s = new pmp_session();
+  s->robot = robot;
+  s->scene = scene;
+  s->qd = robot->fast.dev.q_dim;
+  s->cap = (capacity + 31) / 32 * 32;
+  if (validator) {
+    ValidatorDev V;  // validates the description (dimension, widths, type) like pmp_check_edges does
+    if (int rc = validator_to_dev(validator, s->qd, &V)) {
+      delete s;
+      return rc;
+    }
+    s->has_validator = true;
+    s->vdesc = *validator;
+    if (validator->type == PMP_VALIDATOR_BOX) {
+      s->width.assign(validator->box_width, validator->box_width + s->qd);
+      for (double w : s->width) s->inv_width.push_back(1.0 / w);
+      s->vdesc.box_width = s->width.data();
+    }
+  }
+  // worst-case compact layout: q0, q1, ratio, off, bits, and the zero-copy result bytes
+  const size_t qbytes = align256((size_t)s->cap * std::max(1, s->qd) * 4);
+  s->arena = 2 * qbytes + align256((size_t)s->cap * 8) + align256((size_t)(s->cap + 1) * 4) +
+             align256((size_t)(s->cap / 32) * 4) + align256((size_t)kZeroCopyWaypoints);
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaHostAlloc(&s->host, s->arena, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&s->host_dev, s->host, 0);
+  if (e == cudaSuccess) e = cudaMalloc(&s->dev, s->arena);
+  if (e == cudaSuccess) e = cudaMalloc(&s->counters, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&s->counters_host, 2 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    pmp_session_destroy(s);
+    return fail(PMP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  *out = s;
+  return PMP_OK;
+}
+
+void pmp_session_destroy(pmp_session_t* s) {
+  if (!s) return;
+  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->host) cudaFreeHost(s->host);
+  if (s->dev) cudaFree(s->dev);
+  if (s->counters) cudaFree(s->counters);
+  if (s->counters_host) cudaFreeHost(s->counters_host);
+  delete s;
+}
+
+int pmp_session_set_scene(pmp_session_t* s, const pmp_scene_t* scene) {
+  if (!s) return fail(PMP_ERR_INVALID, "session handle is null");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->scene = scene;
+  return PMP_OK;
+}
+
+int pmp_session_is_valid(pmp_session_t* s, const double* states, int64_t n, uint8_t* valid) {
+  if (!s) return fail(PMP_ERR_INVALID, "session handle is null");
+  if (n < 0) return fail(PMP_ERR_INVALID, "negative item count");
+  if (n == 0) return PMP_OK;
+  if ((!states && s->qd > 0) || !valid) return fail(PMP_ERR_INVALID, "null host pointer");
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (int rc = ensure_device()) return rc;
+  float* hq = reinterpret_cast<float*>(s->host);
+  for (int64_t off = 0; off < n; off += s->cap) {
+    const int64_t m = std::min<int64_t>(s->cap, n - off);
+    const size_t nq = (size_t)m * s->qd;
+    const size_t o_bits = align256(std::max<size_t>(nq, 1) * 4);
+    const size_t words = (size_t)((m + 31) / 32);
+    for (size_t i = 0; i < nq; i++) hq[i] = (float)states[off * s->qd + i];
+    const uint32_t* hbits = reinterpret_cast<const uint32_t*>(s->host + o_bits);
+    if (m <= kZeroCopyStates) {
+      if (int rc = pmp_check_configs(s->robot, s->scene, reinterpret_cast<const float*>(s->host_dev), m,
+                                     reinterpret_cast<uint32_t*>(s->host_dev + o_bits), nullptr, s->stream))
+        return rc;
+    } else {
+      if (nq) CUDA_OK(cudaMemcpyAsync(s->dev, hq, nq * 4, cudaMemcpyHostToDevice, s->stream));
+      if (int rc = pmp_check_configs(s->robot, s->scene, reinterpret_cast<const float*>(s->dev), m,
+                                     reinterpret_cast<uint32_t*>(s->dev + o_bits), nullptr, s->stream))
+        return rc;
+      CUDA_OK(cudaMemcpyAsync(s->host + o_bits, s->dev + o_bits, words * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < m; i++) valid[off + i] = (hbits[i >> 5] >> (i & 31)) & 1u;
+  }
+  return PMP_OK;
+}
+
+int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s2, int64_t n, uint8_t* valid,
+                             uint64_t* n_checked) {
+  if (!s) return fail(PMP_ERR_INVALID, "session handle is null");
+  if (n < 0) return fail(PMP_ERR_INVALID, "negative item count");
+  if (!s->has_validator) return fail(PMP_ERR_INVALID, "the session was created without a validator");
+  if (n_checked) *n_checked = 0;
+  if (n == 0) return PMP_OK;
+  if (((!s1 || !s2) && s->qd > 0) || !valid) return fail(PMP_ERR_INVALID, "null host pointer");
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (int rc = ensure_device()) return rc;
+  const pmp_robot_t* robot = s->robot;
+  const SceneDev S = s->scene ? s->scene->dev : empty_scene();
+  const int block = pick_block(robot->fast, S);
+  const size_t smem = smem_bytes(robot->fast, S, block);
+  if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  const bool approx = robot->fast.dev.base_type == PMP_BASE_FIXED;
+  const bool cloud = S.cloud.enabled != 0;
+  uint64_t checked = 0;
+  for (int64_t off = 0; off < n; off += s->cap) {
+    const int64_t m = std::min<int64_t>(s->cap, n - off);
+    // compact layout for this chunk
+    const size_t qb = align256((size_t)m * std::max(1, s->qd) * 4);
+    const size_t o_q1 = qb, o_ratio = 2 * qb, o_off = o_ratio + align256((size_t)m * 8);
+    const size_t o_bits = o_off + align256((size_t)(m + 1) * 4);
+    const size_t words = (size_t)((m + 31) / 32);
+    const size_t o_way = o_bits + align256(words * 4);
+    float* h0 = reinterpret_cast<float*>(s->host);
+    float* h1 = reinterpret_cast<float*>(s->host + o_q1);
+    double* hr = reinterpret_cast<double*>(s->host + o_ratio);
+    int* ho = reinterpret_cast<int*>(s->host + o_off);
+    uint32_t* hbits = reinterpret_cast<uint32_t*>(s->host + o_bits);
+    long long total = 0;
+    ho[0] = 0;
+    for (int64_t e = 0; e < m; e++) {
+      const double* a = s1 + (off + e) * s->qd;
+      const double* b = s2 + (off + e) * s->qd;
+      for (int i = 0; i < s->qd; i++) {
+        h0[e * s->qd + i] = (float)a[i];
+        h1[e * s->qd + i] = (float)b[i];
+      }
+      const double r = host_step_ratio(s, a, b);
+      hr[e] = r;
+      if (r != std::numeric_limits<double>::infinity()) {  // motion_validator.cpp:41-45
+        const double nt = std::floor(1.0 / r) + 2.0;
+        total += (nt < 2147483000.0) ? (long long)nt - 1 : 2147483000LL;  // s2 + the n_test - 2 interior points
+      }
+      if (total > 2147483000LL) total = 2147483000LL;
+      ho[e + 1] = (int)total;
+    }
+    if (total <= kFlatMaxWaypoints) {
+      // latency path: every waypoint in one wave
+      const bool zero_copy = total <= kZeroCopyWaypoints && m <= kFlatSmemEdges;
+      char* base = zero_copy ? s->host_dev : s->dev;
+      if (!zero_copy) {
+        for (size_t w = 0; w < words; w++) hbits[w] = 0;
+        CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_bits + words * 4, cudaMemcpyHostToDevice, s->stream));
+      }
+      if (total > 0) {
+        const long long tiles = (total + block - 1) / block;
+        int grid = 0;
+        const float* d0 = reinterpret_cast<const float*>(base);
+        const float* d1 = reinterpret_cast<const float*>(base + o_q1);
+        const double* dr = reinterpret_cast<const double*>(base + o_ratio);
+        const int* dof = reinterpret_cast<const int*>(base + o_off);
+        uint32_t* db = reinterpret_cast<uint32_t*>(base + o_bits);
+        uint8_t* dway = zero_copy ? reinterpret_cast<uint8_t*>(base + o_way) : nullptr;
+        const size_t smem_flat = smem;  // the static offset table is accounted for by the occupancy query
+#define PMP_F3(BB, AP, CL)                                                                                      \
+  do {                                                                                                          \
+    if (int rc = grid_for(k_check_waypoints_flat<BB, AP, CL>, smem_flat, tiles, &grid, block)) return rc;       \
+    k_check_waypoints_flat<BB, AP, CL><<<grid, block, smem_flat, s->stream>>>(robot->fast.dev, S, d0, d1, dr, dof, (int)m, db, dway); \
+  } while (0)
+#define PMP_F3_B(BB)                                                                 \
+  do {                                                                               \
+    if (approx) { if (cloud) PMP_F3(BB, true, true); else PMP_F3(BB, true, false); } \
+    else { if (cloud) PMP_F3(BB, false, true); else PMP_F3(BB, false, false); }      \
+  } while (0)
+        if (block == 128) PMP_F3_B(128); else PMP_F3_B(64);
+#undef PMP_F3_B
+#undef PMP_F3
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+      }
+      if (!zero_copy) CUDA_OK(cudaMemcpyAsync(hbits, s->dev + o_bits, words * 4, cudaMemcpyDeviceToHost, s->stream));
+      if (total > 0 || !zero_copy) CUDA_OK(cudaStreamSynchronize(s->stream));
+      if (zero_copy) {
+        const uint8_t* way = reinterpret_cast<const uint8_t*>(s->host + o_way);
+        for (int64_t e = 0; e < m; e++) {
+          uint8_t ok = 1;
+          for (int t = ho[e]; t < ho[e + 1]; t++) ok &= way[t];
+          valid[off + e] = ok;
+        }
+      } else {
+        for (int64_t e = 0; e < m; e++) valid[off + e] = ((hbits[e >> 5] >> (e & 31)) & 1u) ? 0 : 1;
+      }
+      checked += (uint64_t)total;
+    } else {
+      // throughput path: lane = edge with early exit (k_check_edges_v3)
+      CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_ratio, cudaMemcpyHostToDevice, s->stream));
+      CUDA_OK(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned long long), s->stream));
+      if (int rc = pmp_check_edges(robot, s->scene, &s->vdesc, reinterpret_cast<const float*>(s->dev),
+                                   reinterpret_cast<const float*>(s->dev + o_q1), m,
+                                   reinterpret_cast<uint32_t*>(s->dev + o_bits), s->counters, s->counters + 1, s->stream))
+        return rc;
+      CUDA_OK(cudaMemcpyAsync(hbits, s->dev + o_bits, words * 4, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_OK(cudaMemcpyAsync(s->counters_host, s->counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+      CUDA_OK(cudaStreamSynchronize(s->stream));
+      for (int64_t e = 0; e < m; e++) valid[off + e] = (hbits[e >> 5] >> (e & 31)) & 1u;
+      checked += s->counters_host[1];
+    }
+  }
+  if (n_checked) *n_checked = checked;
   return PMP_OK;
 }
 

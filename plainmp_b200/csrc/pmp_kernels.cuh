@@ -571,6 +571,59 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const
   }
 }
 
+// ---- motion edges, waypoint-parallel: the latency path of the validator session --------------------
+// The early-exit kernel above is the throughput path; a planner that asks about ONE edge (or a few
+// hundred) wants the answer after one configuration-check latency instead.  Here lane = one
+// (edge, waypoint): every waypoint the reference could test (s2 and t = j * ratio, j = 1 .. n_test-2;
+// the farthest-first table visits the same set in another order, motion_validator.cpp:45-78) is
+// tested in the same wave and an edge is valid iff none of its waypoints reports a collision —
+// checkMotion's result is an AND, so the answer is the reference's.  The step ratio and the waypoint
+// counts come from the host in FP64 (computed from the caller's doubles exactly as
+// determine_step_ratio does); off[e] .. off[e + 1] are edge e's waypoints.
+// way_ok != nullptr (zero-copy mode, tiny batches): every waypoint writes one byte into host-mapped
+// memory with a plain store and the host ANDs them per edge — no atomics on system memory, no D2H
+// copy.  n_edges <= kFlatSmemEdges: the offset table is staged in shared memory so the search does
+// not walk host memory.
+constexpr int kFlatSmemEdges = 1024;
+
+template <int B, bool APPROX, bool CLOUD>
+__global__ void __launch_bounds__(B, 512 / B)
+k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restrict__ q0, const float* __restrict__ q1,
+                       const double* __restrict__ ratio, const int* __restrict__ off, const int n_edges,
+                       uint32_t* __restrict__ bad_bits, uint8_t* __restrict__ way_ok) {
+  extern __shared__ float4 sm[];
+  __shared__ int s_off[kFlatSmemEdges + 1];
+  const bool off_in_smem = n_edges <= kFlatSmemEdges;
+  if (off_in_smem)
+    for (int i = threadIdx.x; i <= n_edges; i += B) s_off[i] = off[i];
+  const Smem T = stage_tables(R, S, sm);  // ends with a CTA barrier
+  const int* o = off_in_smem ? s_off : off;
+  const long long total = o[n_edges];
+  const long long n_tiles = (total + B - 1) / B;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long t = tile * B + threadIdx.x;
+    const bool active = t < total;
+    int e = 0;
+    if (active) {  // largest e with off[e] <= t
+      int lo = 0, hi = n_edges;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)o[mid] <= t) lo = mid; else hi = mid;
+      }
+      e = lo;
+    }
+    const int j = active ? (int)(t - o[e]) : 0;
+    const float rate = j == 0 ? 1.f : (float)((double)j * __ldg(ratio + e));
+    QEdge acc{q0 + (long long)e * R.q_dim, q1 + (long long)e * R.q_dim, rate, j == 0};
+    const bool ok = warp_check_v3<B, APPROX, CLOUD>(R, S, T, acc, active);
+    if (active) {
+      if (way_ok) way_ok[t] = ok ? 1 : 0;
+      else if (!ok) atomicOr(bad_bits + (e >> 5), 1u << (e & 31));
+    }
+    __syncwarp();
+  }
+}
+
 // ---- psdf / kdtree surface ------------------------------------------------------------------------
 __global__ void k_sdf_evaluate(const SceneDev S, const float* __restrict__ pts, const long long n,
                                float* __restrict__ out) {

@@ -518,3 +518,93 @@ def test_evaluate_jacobian_moving_base_and_numerical(cuda_lib, base_type, with_s
             if not np.isnan(v0[t]):
                 n_bad += int(np.abs(jac_gpu[i, t] - num[t]).max() > JAC_TOL)
     assert n_bad <= 1
+
+
+# ---- validator session + OMPL adaptor ------------------------------------------------
+from plainmp_b200.ompl import ValidatorSession  # noqa: E402
+
+
+def _edge_truth(cst, vtype, widths, res, q0, q1):
+    """Reference edge validity (compiled reference if it travelled, else the pinned restatement)."""
+    if ref_bridge.available():
+        return ref_bridge.RefCst(cst).check_motion_batch(int(vtype), widths, res, q0, q1)[0]
+    o = bridge.OracleCst(cst)
+    return bridge.OracleValidator(int(vtype), q0.shape[1], widths, res).check_motion_batch(o, q0, q1)[0]
+
+
+@pytest.mark.parametrize("vtype", [ValidatorType.BOX, ValidatorType.EUCLIDEAN])
+def test_session_matches_reference_small_and_large_batches(cuda_lib, vtype):
+    spec, cst = workloads.make_panda(ceiled=True)
+    widths = [0.05, 0.07, 0.05, 0.1, 0.05, 0.2, 0.05]
+    ses = ValidatorSession(cst, ValidatorConfig(vtype, 0.08, widths), capacity=8192)
+    mv = MotionValidator(cst, ValidatorConfig(vtype, 0.08, widths))
+    o = bridge.OracleCst(cst, n_threads=4)
+    # is_valid on FP64 states, one by one and batched
+    Q = workloads.random_configs(spec, 3000, 17).astype(np.float64)
+    got = got_states = ses.is_valid(Q)
+    assert_validity_parity(got, o.is_valid_batch(Q), o.margin_batch(Q), "session.is_valid")
+    assert [ses.is_valid(q) for q in Q[:50]] == list(got[:50])
+    assert ses.is_valid_call_count == 3050
+    for planner_like, n in ((True, 1500), (False, 1500), (True, 20000)):  # 20000 edges: chunked + early-exit path
+        q0, q1 = workloads.random_edges(spec, n, 5, planner_like, (lambda q: cst.is_valid_batch(q)) if planner_like else None)
+        q0, q1 = q0.astype(np.float64), q1.astype(np.float64)
+        got = ses.check_motion(q0, q1)
+        want = _edge_truth(cst, vtype, widths, 0.08, q0[:3000], q1[:3000])
+        assert (got[:3000] != want).mean() < 0.004
+        # and the device-tensor path agrees with the session up to in-band waypoints
+        assert (got != mv.check_motion_batch(q0.astype(np.float32), q1.astype(np.float32))[0]).mean() < 0.002
+        assert [ses.check_motion(a, b) for a, b in zip(q0[:40], q1[:40])] == list(got[:40])
+    # degenerate edges
+    bad = Q[np.where(~got_states)[0][0]]   # a colliding state
+    good = Q[np.where(got_states)[0][0]]
+    assert ses.check_motion(bad, bad) is True  # zero length: valid without any check (motion_validator.cpp:19-22)
+    assert ses.check_motion(good, good + 1e-7) is True
+    # |diff| < 1e-6: the box validator returns inf (no check at all), the euclidean one tests s2
+    assert ses.check_motion(bad, bad + 1e-7) is (vtype == ValidatorType.BOX)
+    ses.close()
+
+
+def test_session_follows_scene_updates(cuda_lib):
+    spec, cst = workloads.make_panda()
+    ses = ValidatorSession(cst, None, capacity=1024)
+    Q = workloads.random_configs(spec, 1000, 23).astype(np.float64)
+    before = ses.is_valid(Q)
+    with pytest.raises(Exception):
+        ses.check_motion(Q[0], Q[1])  # created without a validator
+    cst.get_sdf().translate([0.0, 0.0, 0.4])
+    ses.refresh()
+    after = ses.is_valid(Q)
+    assert (after == cst.is_valid_batch(Q.astype(np.float32))).all()
+    assert (after != before).any()
+
+
+def test_ompl_adaptor_header_through_ompl_base_interface(cuda_lib, tmp_path):
+    """include/plainmp_b200_ompl.hpp compiled with g++ against the ompl::base stand-in and driven the
+    way ompl_thin_wrap.hpp:80-91 installs the reference validators."""
+    import ctypes as C
+    import subprocess
+
+    root = Path(__file__).resolve().parent.parent
+    so = tmp_path / "libprobe.so"
+    subprocess.run(
+        ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{root / 'include'}", f"-I{root / 'oracle' / 'ref_shim'}",
+         "-o", str(so), str(root / "tests" / "cpp" / "ompl_adaptor_probe.cpp"),
+         f"-L{root / 'plainmp_b200'}", "-lplainmp_b200", f"-Wl,-rpath,{root / 'plainmp_b200'}"],
+        check=True,
+    )
+    probe = C.CDLL(str(so))
+    spec, cst = workloads.make_panda(ceiled=True)
+    widths = [0.05] * 7
+    ses = ValidatorSession(cst, ValidatorConfig(ValidatorType.BOX, 0.0, widths), capacity=2048)
+    q0, q1 = workloads.random_edges(spec, 400, 31, True, lambda q: cst.is_valid_batch(q))
+    q0, q1 = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+    single, batch, s2v = (np.zeros(400, dtype=np.uint8) for _ in range(3))
+    calls = C.c_uint64(0)
+    probe.probe_validators.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    rc = probe.probe_validators(ses._h, 7, q0.ctypes.data, q1.ctypes.data, 400, single.ctypes.data, batch.ctypes.data, s2v.ctypes.data, C.byref(calls))
+    assert rc == 0 and calls.value == 400
+    assert (single == batch).all()
+    want = _edge_truth(cst, 0, np.array(widths), 0.0, q0, q1)
+    assert (single.astype(bool) != want).sum() <= 2
+    assert (s2v.astype(bool) == ses.is_valid(q1)).all()
+    assert not (single.astype(bool) & ~s2v.astype(bool)).any()  # a valid edge has a valid end state

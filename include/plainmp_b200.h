@@ -142,6 +142,19 @@ typedef struct pmp_scene pmp_scene_t;
 int pmp_scene_create(const pmp_scene_desc_t* desc, pmp_scene_t** out);
 void pmp_scene_destroy(pmp_scene_t* scene);
 
+/* Scene mutation.  The reference's constraint holds the SDF objects by pointer, so
+ * SDFBase::translate / rotate_z on a leaf (primitive_sdf.hpp:135-145, 265-273) are visible to the next
+ * is_valid without re-flattening; these two calls are that path for a device-resident scene.
+ * update_prims overwrites the primitive records in place (same count and order as at creation;
+ * adding or removing leaves needs a new scene, as adding to a Union after set_sdf needs a new
+ * set_sdf upstream, primitive_sphere_collision.cpp:426-448); it is stream-ordered on `stream`.
+ * update_cloud replaces the CloudSDF's points (a new depth frame): the Morton sort, box tree and
+ * distance field are rebuilt on the device and swapped in after a device synchronise; n = 0 removes
+ * the cloud.  Handles that reference the scene (sessions) stay valid. */
+int pmp_scene_update_prims(pmp_scene_t* scene, const pmp_prim_t* prims, int32_t n_prims, void* stream);
+int pmp_scene_update_cloud(pmp_scene_t* scene, const float* cloud_points, int64_t n_cloud_points,
+                           float cloud_radius, float cloud_cell);
+
 /* ---- the hot path ------------------------------------------------------------------------ */
 
 /* Batched SphereCollisionCst::is_valid.  scene may be NULL (self-collision only).

@@ -127,6 +127,8 @@ SYMBOLS = {
     "pmp_robot_n_spheres": (_i32, [_p]),
     "pmp_scene_create": (_i32, [C.POINTER(SceneDesc), C.POINTER(_p)]),
     "pmp_scene_destroy": (None, [_p]),
+    "pmp_scene_update_prims": (_i32, [_p, _p, _i32, _p]),
+    "pmp_scene_update_cloud": (_i32, [_p, _p, _i64, C.c_float, C.c_float]),
     "pmp_check_configs": (_i32, [_p, _p, _p, _i64, _p, _p, _p]),
     "pmp_eval_configs": (_i32, [_p, _p, _p, _i64, _p, _p]),
     "pmp_eval_grad_configs": (_i32, [_p, _p, _p, _i64, _p, _p, _p]),

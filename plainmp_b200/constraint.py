@@ -142,8 +142,13 @@ class SphereCollisionCst(IneqConstraintBase):
         if not leaves:
             return None
         key = tuple(l._state_key() for l in leaves)
-        if self._scene_cache is None or self._scene_cache[0] != key:
+        if self._scene_cache is None:
             self._scene_cache = (key, tables.SceneTable(leaves))
+        elif self._scene_cache[0] != key:
+            # moved primitives / a new cloud frame are written into the resident scene in place, so
+            # handles that point at it (validator sessions) follow; a changed primitive list rebuilds
+            table = self._scene_cache[1]
+            self._scene_cache = (key, table if table.try_update(leaves) else tables.SceneTable(leaves))
         return self._scene_cache[1]
 
     # ---- binding surface ----

@@ -420,6 +420,44 @@ int pmp_robot_q_dim(const pmp_robot_t* r) { return r ? r->full.dev.q_dim : -1; }
 int pmp_robot_n_spheres(const pmp_robot_t* r) { return r ? r->full.dev.n_spheres : -1; }
 
 // ---------------------------------------------------------------------------------------------
+// repack pmp_prim_t into the device record (pmp_device.cuh): type | flags | test variant in p0.w,
+// AABB as centre / half extent
+static void pack_prims(const pmp_prim_t* prims, int n, std::vector<float4>* out) {
+  std::vector<float4>& rec = *out;
+  rec.assign((size_t)n * kPrimWords, make_float4(0.f, 0.f, 0.f, 0.f));
+  for (int i = 0; i < n; i++) {
+    const pmp_prim_t& P = prims[i];
+    int flags = P.flags;
+    // a z-aligned cylinder is evaluated in world axes for all three coordinates (primitive_sdf.hpp:446-449,466-472)
+    if (P.type == PMP_PRIM_CYLINDER && (flags & PMP_PRIMFLAG_Z_ALIGNED)) flags |= PMP_PRIMFLAG_AXIS_ALIGNED;
+    int kind = P.type;
+    if (P.type == PMP_PRIM_BOX && (flags & PMP_PRIMFLAG_AXIS_ALIGNED)) kind = PMP_KIND_BOX_AA;
+    if (P.type == PMP_PRIM_CYLINDER && (flags & PMP_PRIMFLAG_AXIS_ALIGNED)) kind = PMP_KIND_CYL_AA;
+    const int tf = P.type | (flags << 8) | (kind << 16);
+    float tfw;
+    memcpy(&tfw, &tf, 4);
+    float4* w = rec.data() + (size_t)kPrimWords * i;
+    w[0] = make_float4(P.position[0], P.position[1], P.position[2], tfw);
+    w[1] = make_float4(P.param0, P.param1, P.param2, 0.f);
+    w[2] = make_float4(P.rot_col0[0], P.rot_col0[1], P.rot_col0[2], 0.f);
+    w[3] = make_float4(P.rot_col1[0], P.rot_col1[1], P.rot_col1[2], 0.f);
+    w[4] = make_float4(P.rot_col2[0], P.rot_col2[1], P.rot_col2[2], 0.f);
+    float ctr[3], half[3];
+    for (int a = 0; a < 3; a++) {
+      const double lo = P.lb[a], hi = P.ub[a];
+      if (!(lo > -1e37) || !(hi < 1e37)) {  // unbounded axis (Ground x, y)
+        ctr[a] = 0.f;
+        half[a] = INFINITY;
+      } else {
+        ctr[a] = (float)(0.5 * (lo + hi));
+        half[a] = (float)(0.5 * (hi - lo) + 1e-6 + 1e-6 * std::max(std::fabs(lo), std::fabs(hi)));
+      }
+    }
+    w[5] = make_float4(ctr[0], ctr[1], ctr[2], 0.f);
+    w[6] = make_float4(half[0], half[1], half[2], 0.f);
+  }
+}
+
 int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
   if (!d || !out) return fail(PMP_ERR_INVALID, "null argument");
   if (d->n_prims < 0 || d->n_cloud_points < 0) return fail(PMP_ERR_INVALID, "negative table size");
@@ -430,39 +468,8 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
   s->dev = empty_scene();
   static_assert(sizeof(pmp_prim_t) == 96, "pmp_prim_t layout");
   if (d->n_prims > 0) {
-    // repack pmp_prim_t into the device record (pmp_device.cuh): type | flags in p0.w, AABB as centre / half extent
-    std::vector<float4> rec((size_t)d->n_prims * kPrimWords, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int i = 0; i < d->n_prims; i++) {
-      const pmp_prim_t& P = d->prims[i];
-      int flags = P.flags;
-      // a z-aligned cylinder is evaluated in world axes for all three coordinates (primitive_sdf.hpp:446-449,466-472)
-      if (P.type == PMP_PRIM_CYLINDER && (flags & PMP_PRIMFLAG_Z_ALIGNED)) flags |= PMP_PRIMFLAG_AXIS_ALIGNED;
-      int kind = P.type;
-      if (P.type == PMP_PRIM_BOX && (flags & PMP_PRIMFLAG_AXIS_ALIGNED)) kind = PMP_KIND_BOX_AA;
-      if (P.type == PMP_PRIM_CYLINDER && (flags & PMP_PRIMFLAG_AXIS_ALIGNED)) kind = PMP_KIND_CYL_AA;
-      const int tf = P.type | (flags << 8) | (kind << 16);
-      float tfw;
-      memcpy(&tfw, &tf, 4);
-      float4* w = rec.data() + (size_t)kPrimWords * i;
-      w[0] = make_float4(P.position[0], P.position[1], P.position[2], tfw);
-      w[1] = make_float4(P.param0, P.param1, P.param2, 0.f);
-      w[2] = make_float4(P.rot_col0[0], P.rot_col0[1], P.rot_col0[2], 0.f);
-      w[3] = make_float4(P.rot_col1[0], P.rot_col1[1], P.rot_col1[2], 0.f);
-      w[4] = make_float4(P.rot_col2[0], P.rot_col2[1], P.rot_col2[2], 0.f);
-      float ctr[3], half[3];
-      for (int a = 0; a < 3; a++) {
-        const double lo = P.lb[a], hi = P.ub[a];
-        if (!(lo > -1e37) || !(hi < 1e37)) {  // unbounded axis (Ground x, y)
-          ctr[a] = 0.f;
-          half[a] = INFINITY;
-        } else {
-          ctr[a] = (float)(0.5 * (lo + hi));
-          half[a] = (float)(0.5 * (hi - lo) + 1e-6 + 1e-6 * std::max(std::fabs(lo), std::fabs(hi)));
-        }
-      }
-      w[5] = make_float4(ctr[0], ctr[1], ctr[2], 0.f);
-      w[6] = make_float4(half[0], half[1], half[2], 0.f);
-    }
+    std::vector<float4> rec;
+    pack_prims(d->prims, d->n_prims, &rec);
     cudaError_t e = cudaMalloc(&s->prims_dev, rec.size() * sizeof(float4));
     if (e == cudaSuccess) e = cudaMemcpy(s->prims_dev, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -499,6 +506,46 @@ void pmp_scene_destroy(pmp_scene_t* s) {
   if (s->prims_dev) cudaFree(s->prims_dev);
   cloud_free(&s->cloud);
   delete s;
+}
+
+// Scene mutation without re-creating the handle: translate / rotate_z on the leaves (and a new depth
+// frame for the cloud) are visible to the reference's constraint immediately because it holds the
+// SDF objects by pointer (primitive_sdf.hpp:135-145,265-273; primitive_sphere_collision.cpp:426-448).
+int pmp_scene_update_prims(pmp_scene_t* s, const pmp_prim_t* prims, int32_t n_prims, void* stream) {
+  if (!s) return fail(PMP_ERR_INVALID, "scene handle is null");
+  if (n_prims != s->dev.n_prims) return fail(PMP_ERR_INVALID, "primitive count differs from the scene's: create a new scene");
+  if (n_prims == 0) return PMP_OK;
+  if (!prims) return fail(PMP_ERR_INVALID, "prims is null");
+  for (int i = 0; i < n_prims; i++)
+    if (prims[i].type < PMP_PRIM_BOX || prims[i].type > PMP_PRIM_GROUND) return fail(PMP_ERR_INVALID, "bad primitive type");
+  std::vector<float4> rec;
+  pack_prims(prims, n_prims, &rec);
+  // pageable source: the runtime stages the bytes before returning, so `rec` may die here
+  CUDA_OK(cudaMemcpyAsync(s->prims_dev, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return PMP_OK;
+}
+
+int pmp_scene_update_cloud(pmp_scene_t* s, const float* points, int64_t n, float radius, float cell) {
+  if (!s) return fail(PMP_ERR_INVALID, "scene handle is null");
+  if (n < 0 || n >= (int64_t)1 << 31) return fail(PMP_ERR_INVALID, "bad cloud size");
+  if (n > 0 && !points) return fail(PMP_ERR_INVALID, "cloud_points is null");
+  if (int rc = ensure_device()) return rc;
+  CloudDev fresh{};
+  CloudBuffers bufs;
+  if (n > 0) {
+    std::string err;
+    int launches = 0;
+    if (cloud_build(points, n, radius, cell, g_num_sms, &fresh, &bufs, &launches, &err))
+      return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
+    g_launches += launches;
+  } else {
+    fresh.enabled = 0;
+  }
+  CUDA_OK(cudaDeviceSynchronize());  // nothing in flight may still walk the old tree
+  cloud_free(&s->cloud);
+  s->cloud = bufs;
+  s->dev.cloud = fresh;
+  return PMP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

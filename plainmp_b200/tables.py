@@ -292,6 +292,38 @@ class SceneTable:
         _capi.check(lib.pmp_scene_create(C.byref(desc), C.byref(h)))
         self._h = h
         self._lib = lib
+        self._cloud_id = id(cloud) if cloud is not None else None
+        self._cloud_cell = cloud_cell
+        self.n_updates = 0
+
+    def try_update(self, leaves) -> bool:
+        """Scene mutation in place (pmp_scene_update_prims / pmp_scene_update_cloud): the same
+        primitive list with moved poses, and / or a replaced CloudSDF.  Returns False when the
+        primitive list itself changed (count or types) — the caller then builds a new table."""
+        prims, cloud = flatten_primitives(leaves)
+        if prims.shape[0] != self.n_prims or (self.n_prims and not (prims["type"] == self.prims["type"]).all()):
+            return False
+        if self.n_prims and prims.tobytes() != self.prims.tobytes():
+            _capi.check(self._lib.pmp_scene_update_prims(self._h, prims.ctypes.data, self.n_prims, _stream_ptr()))
+            _torch().cuda.current_stream().synchronize()  # other streams (sessions) may read the records next
+            self.prims = prims
+            self.n_updates += 1
+        new_id = id(cloud) if cloud is not None else None
+        if new_id != self._cloud_id:
+            if cloud is None:
+                _capi.check(self._lib.pmp_scene_update_cloud(self._h, None, 0, 0.0, 0.0))
+                self._cloud_pts = None
+            else:
+                self._cloud_pts = np.ascontiguousarray(cloud.points, dtype=np.float32)
+                _capi.check(
+                    self._lib.pmp_scene_update_cloud(
+                        self._h, self._cloud_pts.ctypes.data, self._cloud_pts.shape[0], cloud.radius, self._cloud_cell
+                    )
+                )
+            self._cloud_id = new_id
+            self.has_cloud = cloud is not None
+            self.n_updates += 1
+        return True
 
     @property
     def handle(self) -> C.c_void_p:

@@ -608,3 +608,60 @@ def test_ompl_adaptor_header_through_ompl_base_interface(cuda_lib, tmp_path):
     assert (single.astype(bool) != want).sum() <= 2
     assert (s2v.astype(bool) == ses.is_valid(q1)).all()
     assert not (single.astype(bool) & ~s2v.astype(bool)).any()  # a valid edge has a valid end state
+
+
+# ---- scene update path ----------------------------------------------------------------
+def test_scene_updates_in_place_match_oracle(cuda_lib):
+    spec, cst = workloads.make_panda()
+    Q = workloads.random_configs(spec, 4000, 61)
+    Qd = Q.astype(np.float64)
+    first = cst.is_valid_batch(Q)
+    table = cst._scene()
+    handle = table.handle.value
+    sdf = cst.get_sdf()
+    # move one leaf, then the whole union (translate + rotate_z recompute the AABBs, primitive_sdf.hpp:265-273)
+    sdf.sdfs[1].translate([0.1, -0.25, 0.0])
+    sdf.rotate_z(0.6)
+    sdf.translate([0.0, 0.05, 0.1])
+    got = cst.is_valid_batch(Q)
+    assert cst._scene() is table and table.handle.value == handle and table.n_updates == 1
+    o = bridge.OracleCst(cst, n_threads=4)
+    assert_validity_parity(got, o.is_valid_batch(Qd), o.margin_batch(Qd), "scene update")
+    assert (got != first).any()
+    np.testing.assert_allclose(cst.evaluate_batch(Q[:1000]), o.evaluate_batch(Qd[:1000]), atol=TOL, rtol=0)
+    # a changed primitive LIST is a new table
+    sdf.add(psdf.SphereSDF(0.15, psdf.Pose([0.4, 0.0, 0.6])))
+    cst.set_sdf(sdf)
+    got2 = cst.is_valid_batch(Q)
+    assert cst._scene() is not table
+    o2 = bridge.OracleCst(cst, n_threads=4)
+    assert_validity_parity(got2, o2.is_valid_batch(Qd), o2.margin_batch(Qd), "scene rebuild")
+
+
+def test_cloud_replacement_in_place_matches_oracle(cuda_lib):
+    spec, cst = workloads.make_pr2_cloud(20000)
+    Q = workloads.random_configs(spec, 1500, 62)
+    Qd = Q.astype(np.float64)
+    cst.is_valid_batch(Q)
+    table = cst._scene()
+    for n_pts, seed in ((5000, 9), (30000, 10)):  # a new depth frame: smaller, then larger than the first
+        pts = workloads.table_cloud(n_pts, seed) + np.array([0.0, 0.1, 0.02])
+        cst.set_sdf(psdf.CloudSDF(pts, 0.003))
+        got = cst.is_valid_batch(Q)
+        assert cst._scene() is table
+        o = bridge.OracleCst(cst, n_threads=4)
+        assert_validity_parity(got, o.is_valid_batch(Qd), o.margin_batch(Qd), f"cloud frame {n_pts}")
+        np.testing.assert_allclose(cst.evaluate_batch(Q[:300]), o.evaluate_batch(Qd[:300]), atol=TOL, rtol=0)
+    # cloud removed, primitives-only scene keeps working through the same handle
+    spec2, cst2 = workloads.make_fetch()
+    Q2 = workloads.random_configs(spec2, 1000, 63)
+    base = cst2.is_valid_batch(Q2)
+    t2 = cst2._scene()
+    cst2.set_sdf(psdf.UnionSDF([workloads.fetch_table_sdf(), psdf.CloudSDF(workloads.table_cloud(4000, 3), 0.002)]))
+    with_cloud = cst2.is_valid_batch(Q2)
+    assert cst2._scene() is t2 and t2.has_cloud
+    o = bridge.OracleCst(cst2, n_threads=4)
+    Q2d = Q2.astype(np.float64)
+    assert_validity_parity(with_cloud, o.is_valid_batch(Q2d), o.margin_batch(Q2d), "cloud added")
+    cst2.set_sdf(workloads.fetch_table_sdf())
+    assert (cst2.is_valid_batch(Q2) == base).all() and cst2._scene() is t2 and not t2.has_cloud

@@ -58,7 +58,30 @@ def main():
             row["reference_cpu_check_motion_us_per_call"] = 1e6 * t_ref
             row["reference_cpu_is_valid_us_per_call"] = 1e6 * t_ref_s
         rows.append(row)
-    print(json.dumps({"workload": "panda ceiled dual-bars, box validator 0.05, planner-like edges (valid start, |dq| <= 0.5)", "rows": rows}))
+    # scene update path: in-place primitive update and cloud re-index, per call
+    from plainmp_b200 import psdf
+
+    spec2, cst2 = workloads.make_panda()
+    cst2.is_valid_batch(q0[:32].astype(np.float32))
+    leaf = cst2.get_sdf().sdfs[1]
+
+    def move():
+        leaf.translate([1e-3, 0.0, 0.0])
+        cst2._scene()
+
+    upd = {"prims_update_us": 1e6 * timeit(move, 200)}
+    spec3, cst3 = workloads.make_pr2_cloud(1000)
+    cst3.is_valid_batch(workloads.random_configs(spec3, 32, 1))
+    for npts in (100000, 1000000):
+        clouds = [psdf.CloudSDF(workloads.table_cloud(npts, s), 0.002) for s in (1, 2, 3)]
+        it = iter(clouds * 4)
+
+        def frame():
+            cst3.set_sdf(next(it))
+            cst3._scene()
+
+        upd[f"cloud_reindex_{npts}_points_ms"] = 1e3 * timeit(frame, 6)
+    print(json.dumps({"scene_update": upd, "workload": "panda ceiled dual-bars, box validator 0.05, planner-like edges (valid start, |dq| <= 0.5)", "rows": rows}))
 
 
 if __name__ == "__main__":

@@ -33,19 +33,76 @@ def rpy_matrix(yaw: float, pitch: float, roll: float) -> np.ndarray:
     return rz @ ry @ rx
 
 
+def load_conf_yaml(conf_file: Path) -> dict:
+    """A robot configuration in the REFERENCE's own YAML schema, loaded the way RobotSpec.__init__
+    does (robot_spec.py:93-114: one level of ``include``, key conflicts are errors) and normalised
+    to the dict this module consumes: ``self_collision_group_pairs`` expanded and duplicates
+    rejected (:387-411), ``collision_spheres.<link>.spheres`` rows [x, y, z, r] (:345-382),
+    ``default_joint_positions`` as a mapping (fetch.yaml lists one-key dicts)."""
+    import yaml
+
+    conf_file = Path(conf_file)
+    with open(conf_file) as f:
+        d = yaml.safe_load(f)
+    for rel in d.pop("include", []):
+        with open(conf_file.parent / rel) as f:
+            dep = yaml.safe_load(f)
+        if set(d) & set(dep):
+            raise AssertionError("conflict")
+        if "include" in dep:
+            raise AssertionError("recursive include is not supported yet")
+        d.update(dep)
+    out = {"control_joint_names": list(d["control_joint_names"])}
+    pairs = [list(p) for p in d.get("self_collision_pairs", [])]
+    for gp in d.get("self_collision_group_pairs", []):
+        pairs += [[l1, l2] for l1 in gp["group1"] for l2 in gp["group2"]]
+    seen = set()
+    for p in pairs:
+        key = tuple(sorted(p))
+        if key in seen:
+            raise AssertionError(f"duplicated pair {key}")
+        seen.add(key)
+    out["self_collision_pairs"] = pairs
+    out["only_self_collision_links"] = list(d.get("only_self_collision_links", []))
+    out["collision_spheres"] = {
+        link: [[float(x) for x in row] for row in v["spheres"]] for link, v in d["collision_spheres"].items()
+    }
+    out["self_body_collision_primitives"] = d.get("self_body_collision_primitives", [])
+    djp = d.get("default_joint_positions", {})
+    if isinstance(djp, list):
+        merged = {}
+        for e in djp:
+            merged.update(e)
+        djp = merged
+    out["default_joint_positions"] = {k: float(v) for k, v in djp.items()}
+    out["custom_links"] = d.get("custom_links", {})
+    for k in ("urdf_path", "robot_name"):
+        if k in d:
+            out[k] = d[k]
+    return out
+
+
 class RobotSpec:
     conf_name: str = ""
     urdf_name: str = ""
 
-    def __init__(self, base_type: BaseType = BaseType.FIXED):
-        with open(DATA_DIR / "conf" / f"{self.conf_name}.json") as f:
-            self.conf_dict = json.load(f)
+    def __init__(self, base_type: BaseType = BaseType.FIXED, conf_file: Optional[Path] = None, urdf_file: Optional[Path] = None):
+        """Stock robots load the imported tables under data/; ``conf_file`` (the reference's YAML
+        schema, robot_spec.py:93-114) + ``urdf_file`` describe any other robot."""
+        if conf_file is not None:
+            self.conf_dict = load_conf_yaml(Path(conf_file))
+        else:
+            with open(DATA_DIR / "conf" / f"{self.conf_name}.json") as f:
+                self.conf_dict = json.load(f)
+        self._urdf_file = Path(urdf_file) if urdf_file is not None else None
         self.base_type = BaseType(base_type)
         self._kin: Optional[KinematicModel] = None
         self._csts: Dict[bool, SphereCollisionCst] = {}
 
     @property
     def urdf_path(self) -> Path:
+        if self._urdf_file is not None:  # robot_spec.py:119-122 urdf_path_override
+            return self._urdf_file
         return DATA_DIR / "urdf" / f"{self.urdf_name}.urdf"
 
     def get_kin(self) -> KinematicModel:

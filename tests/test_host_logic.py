@@ -246,3 +246,41 @@ def test_unpack_bits_roundtrip():
         for i in np.where(v)[0]:
             words[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
         assert (tables.unpack_bits(words.view(np.int32), n) == v).all()
+
+
+def test_yaml_conf_loader_matches_imported_tables(tmp_path):
+    """RobotSpec(conf_file=..., urdf_file=...) reads the reference's YAML schema at run time
+    (include, group pairs, sphere rows).  With /root/reference mounted the reference's own YAMLs are
+    loaded and must reproduce the imported JSON tables; a synthetic conf covers the schema anywhere."""
+    import json
+
+    from plainmp_b200 import robot_spec as rs
+
+    ref_conf = Path("/root/reference/src/plainmp/conf")
+    if ref_conf.is_dir():
+        for name, rel in [("panda", "panda.yaml"), ("fetch", "fetch.yaml"), ("pr2_dualarm", "pr2_dualarm.yaml"),
+                          ("openarm_v10_dual", "openarm_v10/openarm_v10_dual.yaml")]:
+            got = rs.load_conf_yaml(ref_conf / rel)
+            want = json.loads((rs.DATA_DIR / "conf" / f"{name}.json").read_text())
+            for k in want:
+                assert got[k] == want[k], (name, k)
+    (tmp_path / "common.yaml").write_text(
+        "collision_spheres:\n  panda_link1:\n    spheres:\n      - [0.0, 0.0, -0.1, 0.06]\n      - [0.0, -0.05, 0.0, 0.06]\n"
+        "  panda_link5:\n    spheres:\n      - [0.0, 0.0, -0.2, 0.05]\n"
+    )
+    (tmp_path / "robot.yaml").write_text(
+        "include: [common.yaml]\ncontrol_joint_names: [panda_joint1, panda_joint2, panda_joint3, panda_joint4, panda_joint5, panda_joint6, panda_joint7]\n"
+        "self_collision_group_pairs:\n  - group1: [panda_link1]\n    group2: [panda_link5]\n"
+        "only_self_collision_links: [panda_link1]\n"
+        "custom_links:\n  tool:\n    parent_link: panda_hand\n    position: [0, 0, 0.1]\n    rpy: [0, 0, 0]\n"
+    )
+    spec = rs.RobotSpec(conf_file=tmp_path / "robot.yaml", urdf_file=rs.DATA_DIR / "urdf" / "panda.urdf")
+    assert spec.get_self_collision_pairs() == [["panda_link1", "panda_link5"]]
+    cst = spec.create_collision_const(use_cache=False)
+    assert cst._group_link_names == ["panda_link1", "panda_link5"] and cst._group_only_self == [True, False]
+    assert spec.get_kin().get_link_ids(["tool"])[0] >= 0
+    (tmp_path / "dup.yaml").write_text(
+        "control_joint_names: []\ncollision_spheres: {}\nself_collision_pairs: [[a, b], [b, a]]\n"
+    )
+    with pytest.raises(AssertionError):
+        rs.load_conf_yaml(tmp_path / "dup.yaml")

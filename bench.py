@@ -29,6 +29,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+_REAL_STDOUT = None
 METRIC = "collision_checked_configs_per_sec"
 UNIT = "configs/s"
 # dense algorithmic work of one panda dual-bars configuration
@@ -299,10 +300,16 @@ def run_b200(args):
     _capi.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from plainmp_b200.parallel import bind_to_gpu_numa_node
+
+    numa_node = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
     if world > 1:
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION or WARN) on stdout: send its log to stderr
-        # so that rank 0's stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION or WARN) on stdout from native code: point
+        # fd 1 at stderr for the rest of the run and keep the real stdout for the one JSON line
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.load()
 
@@ -395,6 +402,11 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_global * e2e_steps / float(e2e_s.item())
     assert torch.equal(words_host.to(dev), bits), "host-buffer path and device path disagree"
+    # the bound of the e2e path: a bare pinned H2D copy of the same input bytes on this box
+    scratch = torch.empty_like(q_dev)
+    h2d_s = time_cuda(torch, lambda: scratch.copy_(q_host, non_blocking=True), steps=5, warmup=2)
+    h2d_gbs = q_host.numel() * 4 / h2d_s / 1e9
+    del scratch
     clocks = sampler.stop() if rank == 0 else None
 
     extras = {}
@@ -441,7 +453,7 @@ def run_b200(args):
                 "robot": "panda", "per_gpu_configs": n_local, "global_configs": n_global,
                 "l2": "inputs (28 B/config x per_gpu_configs) exceed the 126 MB L2; no flush needed",
                 "parallelism": f"item-sharded x{world}, tables replicated" + (", NCCL all_gather(bits)+all_reduce(count) per step" if world > 1 else ""),
-                "valid_fraction": valid_frac,
+                "numa_node_rank0": numa_node, "valid_fraction": valid_frac,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
@@ -456,7 +468,9 @@ def run_b200(args):
                 "frac": per_gpu_rate * F_CFG_DENSE / 1e12 / fp32_peak,
                 "note": "dense-equivalent: 14.7 kflop/config (SURVEY 8d, no culling) x configs/s; peak = FFMA micro-benchmark on this GPU" if extras.get("fp32_ffma_tflops_measured") else "dense-equivalent; nominal peak",
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * lb.shape[0] * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 16) * world, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * lb.shape[0] * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 16) * world, "steps": e2e_steps,
+                    "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs,
+                    "frac_of_h2d_copy": (e2e_value / world) * lb.shape[0] * 4 / 1e9 / h2d_gbs},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -464,7 +478,7 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_baseline
         if extras:
             line["extras"] = extras
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT or sys.stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

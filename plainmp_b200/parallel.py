@@ -18,6 +18,35 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates
+    pinned host buffers, so that the host side of every H2D / D2H copy is node-local.  With one
+    process per GPU on a two-socket box, unbound ranks end up copying across the socket link and
+    the end-to-end (host buffer) rate stops scaling past a few GPUs.  Returns the node, or None when
+    it cannot be determined (single-node hosts report -1)."""
+    import os
+
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(path + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous block of ceil(n / world) items rounded up to a multiple of 32, so that packed
     validity words never straddle ranks."""

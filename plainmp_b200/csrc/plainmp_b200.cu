@@ -835,7 +835,7 @@ struct Workspace {  // grow-only device scratch shared by the *_host calls (seri
     return PMP_OK;
   }
 } g_ws;
-constexpr int64_t kHostChunk = 1 << 21;  // items per pipelined chunk (multiple of 32)
+constexpr int64_t kHostChunk = 1 << 19;  // items per pipelined chunk (multiple of 32): the tail that cannot overlap is one chunk's kernel
 }  // namespace
 
 int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n,

@@ -35,6 +35,8 @@ UNIT = "configs/s"
 # dense algorithmic work of one panda dual-bars configuration
 F_CFG_DENSE = 14.7e3          # flop/config (no culling, no early exit)
 BYTES_PER_CFG = 7 * 4 + 1 / 8  # q in + 1 validity bit out
+# measured once with ncu --set full on the same kernel (profiles/r01_s18_panda_ncu.md): percentages of peak
+NCU_PIPE_FIGURES = {"source": "profiles/r01_s18_panda_ncu.md", "issue_active_pct": None, "fma_pipe_pct": None, "alu_pipe_pct": None, "warp_inst_per_config": None}
 DRAM_BYTES_PER_CFG_NCU = 28.9   # measured once with ncu --set full (profiles/r01_v3_check_configs_ncu.md), per configuration
 
 
@@ -221,6 +223,28 @@ class CpuArm:
         v = self.is_valid(Q)
         dt = time.perf_counter() - t
         return n / dt, float(v.mean())
+
+
+def work_model(cst, spec, n=20000, seed=5):
+    """flop per configuration under the stated convention, from the oracle's instrumented
+    counters on a sample — `executed` = what the reference's algorithm actually does for is_valid
+    (lazy FK, group broad phase, AABB pre-tests, early exit), `dense` = FK + every placement (counted)
+    + every env group and env sphere against every primitive + every listed pair and sphere pair."""
+    from oracle import bridge
+    from plainmp_b200 import psdf, workloads
+
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, n, seed).astype(np.float64)
+    ex, de = o.work_counts(Q), o.work_counts(Q, dense=True)
+    env = [g for g, only in zip(cst._group_spheres, cst._group_only_self) if not only]
+    g_env, s_env = len(env), sum(len(g) for g in env)
+    cost = {psdf.T_BOX: 22, psdf.T_CYLINDER: 25, psdf.T_SPHERE: 11, psdf.T_GROUND: 4}
+    prim_cost = sum(cost.get(leaf.get_type(), 0) for leaf in cst._leaves())
+    p_g = len(cst._pairs)
+    p_s = sum(len(cst._group_spheres[a]) * len(cst._group_spheres[b]) for a, b in cst._pairs)
+    dense = de["flops"] / n + prim_cost * (g_env + s_env) + 11 * (p_g + p_s)
+    return {"executed_flop_per_config": ex["flops"] / n, "dense_flop_per_config": dense,
+            "counters_per_config": {k: ex[k] / n for k in bridge.OracleCst.WORK_FIELDS}, "sample": n}
 
 
 def cpu_baseline_block(cst, spec, n, cores):
@@ -425,6 +449,7 @@ def run_b200(args):
             extras.update(side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorConfig, ValidatorType))
         # CPU baseline: the reference's own CPU path (oracle/_ref, else the restatement), bounded sample
         cpu_baseline, _ = cpu_baseline_block(cst, spec, args.cpu_sample, os.cpu_count() or 1)
+        extras["work_model"] = work_model(cst, spec)
     if rank == 0:
         peaks = {}
         try:
@@ -467,6 +492,11 @@ def run_b200(args):
                 "bound": "fp32_simt", "achieved": per_gpu_rate * F_CFG_DENSE / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": per_gpu_rate * F_CFG_DENSE / 1e12 / fp32_peak,
                 "note": "dense-equivalent: 14.7 kflop/config (SURVEY 8d, no culling) x configs/s; peak = FFMA micro-benchmark on this GPU" if extras.get("fp32_ffma_tflops_measured") else "dense-equivalent; nominal peak",
+                # the other two readings of the same rate: arithmetic the reference's algorithm executes
+                # (oracle counters, culling and early exit included), and what the pipes did (ncu)
+                "executed_flop_per_config": (extras.get("work_model") or {}).get("executed_flop_per_config"),
+                "executed_frac": (per_gpu_rate * extras["work_model"]["executed_flop_per_config"] / 1e12 / fp32_peak) if extras.get("work_model") else None,
+                "ncu": NCU_PIPE_FIGURES,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * lb.shape[0] * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 16) * world, "steps": e2e_steps,
                     "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs,

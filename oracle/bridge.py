@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
             "orc_cst_evaluate_grad_batch": (None, [vp, vp, i64, i, vp, vp]),
             "orc_cst_margin_batch": (None, [vp, vp, i64, i, vp]),
             "orc_cst_spheres_batch": (None, [vp, vp, i64, i, vp]),
+            "orc_cst_work_counts": (i64, [vp, vp, i64, i, vp]),
             "orc_validator_create": (vp, [i, i, vp, d]),
             "orc_validator_destroy": (None, [vp]),
             "orc_validator_step_ratio": (d, [vp, vp, vp]),
@@ -335,6 +336,28 @@ class OracleCst:
         out = np.zeros(Q.shape[0])
         lib().orc_cst_margin_batch(self.h, _p(Q), Q.shape[0], n_threads or self.n_threads, _p(out))
         return out
+
+    WORK_FIELDS = ("joints_rot", "joints_pri", "links_rot", "links_ident", "groups_placed", "spheres_placed", "aabb_tests",
+                   "box_tests", "cylinder_tests", "sphere_tests", "ground_tests", "cloud_tests", "pair_tests",
+                   "sphere_pair_tests", "valid")
+    # SURVEY 8d flop convention: FMA = 2, add/mul/abs/cmp/min/max/sqrt = 1
+    WORK_FLOPS = {"joints_rot": 53, "joints_pri": 11, "links_rot": 61, "links_ident": 33, "groups_placed": 24 + 18,
+                  "spheres_placed": 18, "aabb_tests": 12, "box_tests": 22, "cylinder_tests": 25, "sphere_tests": 11,
+                  "ground_tests": 4, "cloud_tests": 0, "pair_tests": 11, "sphere_pair_tests": 11}
+
+    def work_counts(self, Q, dense: bool = False) -> dict:
+        """Instrumented counters of SURVEY 8d summed over Q: the work the reference executes for
+        is_valid (lazy FK, broad phases, early exit), or with dense=True the FK + placement part of
+        the dense count.  'flops' applies the SURVEY's per-unit convention."""
+        Q = _f64(Q)
+        out = np.zeros(15, dtype=np.uint64)
+        diff = lib().orc_cst_work_counts(self.h, _p(Q), Q.shape[0], 1 if dense else 0, _p(out))
+        if diff:
+            raise AssertionError(f"instrumented is_valid disagrees with is_valid on {diff} items")
+        d = {k: int(v) for k, v in zip(self.WORK_FIELDS, out)}
+        d["flops"] = float(sum(self.WORK_FLOPS[k] * d[k] for k in self.WORK_FLOPS))
+        d["n"] = int(Q.shape[0])
+        return d
 
     def spheres_batch(self, Q, accurate: bool) -> np.ndarray:
         Q = _f64(Q)

@@ -1055,6 +1055,97 @@ struct SphereCollisionCst {
     return true;
   }
 
+  // ---- instrumented twin of is_valid: the same control flow as check_ext_collision /
+  // check_self_collision above with a counter at every unit of work the reference executes, so that
+  // bench.py can report executed vs dense arithmetic.  w[0..1] joints set (revolute+continuous,
+  // prismatic), w[2..3] link products built lazily (with rotation, identity-flagged), w[4] group
+  // centres placed (incl. toRotationMatrix), w[5] spheres placed, w[6] AABB pre-tests,
+  // w[7..11] is_outside calls on box / cylinder / sphere / ground / cloud, w[12] group-pair tests,
+  // w[13] sphere-pair tests, w[14] valid.  Returns the validity, which must equal is_valid(q).
+  bool count_is_valid(const double* q, uint64_t* w) {
+    update_kintree(q, false);
+    post_update_kintree();
+    for (size_t jid : control_joint_ids) w[kin->joint_types[jid] == J_PRISMATIC ? 1 : 0]++;
+    auto place_group = [&](SphereGroup& g) {
+      if (g.is_group_sphere_position_dirty) w[4]++;
+      g.create_group_sphere_position_cache(*kin);
+    };
+    auto place_spheres = [&](SphereGroup& g) {
+      if (g.is_sphere_positions_dirty) w[5] += g.radii.size();
+      g.create_sphere_position_cache(*kin);
+    };
+    auto outside = [&](const std::shared_ptr<PrimitiveSDFBase>& s, const V3& c, double r) {
+      w[6]++;
+      if (s->is_outside_aabb(c, r)) return true;
+      const int t = (int)s->get_type();
+      w[t == T_BOX ? 7 : t == T_CYLINDER ? 8 : t == T_SPHERE ? 9 : t == T_GROUND ? 10 : 11]++;
+      return s->is_outside(c, r);
+    };
+    bool valid = true;
+    if (ext_collision_enabled()) {
+      for (auto& group : sphere_groups) {
+        if (!valid) break;
+        if (group.only_self_collision) continue;
+        place_group(group);
+        for (auto& s : all_sdfs_cache) {
+          if (!valid) break;
+          if (!outside(s, group.group_sphere_position_cache, group.group_radius)) {
+            place_spheres(group);
+            for (size_t i = 0; i < group.radii.size(); i++)
+              if (!outside(s, group.sphere_positions_cache[i], group.radii[i])) {
+                valid = false;
+                break;
+              }
+          }
+        }
+      }
+    }
+    if (valid && self_collision_enabled()) {
+      for (auto& pr : selcol_group_id_pairs) {
+        if (!valid) break;
+        auto& group1 = sphere_groups[pr.first];
+        auto& group2 = sphere_groups[pr.second];
+        place_group(group1);
+        place_group(group2);
+        w[12]++;
+        double outer_sqdist = eig::sqnorm(group1.group_sphere_position_cache - group2.group_sphere_position_cache);
+        double outer_r_sum = group1.group_radius + group2.group_radius;
+        if (outer_sqdist > outer_r_sum * outer_r_sum) continue;
+        place_spheres(group1);
+        place_spheres(group2);
+        for (size_t i = 0; i < group1.radii.size() && valid; i++)
+          for (size_t j = 0; j < group2.radii.size(); j++) {
+            w[13]++;
+            double sqdist = eig::sqnorm(group1.sphere_positions_cache[i] - group2.sphere_positions_cache[j]);
+            double r_sum = group1.radii[i] + group2.radii[j];
+            if (sqdist < r_sum * r_sum) {
+              valid = false;
+              break;
+            }
+          }
+      }
+    }
+    // lazily built links: everything cached except the root
+    for (size_t l = 0; l < kin->cache_pred.size(); l++)
+      if (kin->cache_pred[l] && l != kin->root_link_id) w[kin->tf_plink_to_hlink_cache[l].is_quat_identity ? 3 : 2]++;
+    w[14] += valid ? 1 : 0;
+    return valid;
+  }
+  // the dense counterpart: every group and sphere placed (no culling), links counted the same way
+  void count_dense_fk(const double* q, uint64_t* w) {
+    update_kintree(q, false);
+    post_update_kintree();
+    for (size_t jid : control_joint_ids) w[kin->joint_types[jid] == J_PRISMATIC ? 1 : 0]++;
+    for (auto& g : sphere_groups) {
+      g.create_group_sphere_position_cache(*kin);
+      g.create_sphere_position_cache(*kin);
+      w[4]++;
+      w[5] += g.radii.size();
+    }
+    for (size_t l = 0; l < kin->cache_pred.size(); l++)
+      if (kin->cache_pred[l] && l != kin->root_link_id) w[kin->tf_plink_to_hlink_cache[l].is_quat_identity ? 3 : 2]++;
+  }
+
   // primitive.hpp:74-79 + .cpp:385-399 (values only; Jacobian rows are out of scope)
   int evaluate(const double* q, double* vals) {
     update_kintree(q, true);
@@ -1682,6 +1773,25 @@ void orc_cst_margin_batch(void* h, const double* q, int64_t n, int n_threads, do
     auto c = base->clone_for_thread();
     for (int64_t i = lo; i < hi; i++) out[i] = c->validity_margin(q + i * d);
   });
+}
+// SURVEY 8d instrumented counters, summed over the batch: dense = 0 -> the reference's executed work
+// (count_is_valid), dense = 1 -> FK + every placement without culling (count_dense_fk).  out[15].
+// Returns the number of items whose counted validity differs from is_valid (must be 0).
+int64_t orc_cst_work_counts(void* h, const double* q, int64_t n, int dense, uint64_t* out) {
+  auto* base = (SphereCollisionCst*)h;
+  const size_t d = base->q_dim();
+  auto c = base->clone_for_thread();
+  for (int k = 0; k < 15; k++) out[k] = 0;
+  int64_t diff = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (dense) {
+      c->count_dense_fk(q + i * d, out);
+    } else {
+      const bool v = c->count_is_valid(q + i * d, out);
+      if (v != c->is_valid(q + i * d)) diff++;
+    }
+  }
+  return diff;
 }
 void orc_cst_spheres_batch(void* h, const double* q, int64_t n, int high_accuracy, double* out4) {
   auto* base = (SphereCollisionCst*)h;

@@ -102,6 +102,10 @@ def lib() -> C.CDLL:
             "ref_cst_is_valid_batch": (None, [vp, vp, i64, vp]),
             "ref_cst_evaluate_batch": (None, [vp, vp, i64, vp, vp]),
             "ref_cst_spheres_batch": (None, [vp, vp, i64, i, i, vp]),
+            "ref_cst_flatten": (vp, [vp]),
+            "ref_flat_destroy": (None, [vp]),
+            "ref_flat_sizes": (None, [vp, vp]),
+            "ref_flat_copy": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
             "ref_check_motion_batch": (None, [vp, i, i, vp, d, vp, vp, i64, vp, C.POINTER(C.c_uint64)]),
             "ref_step_ratio": (d, [i, i, vp, d, vp, vp]),
         }
@@ -332,6 +336,37 @@ class RefCst:
         out = np.zeros((Q.shape[0], self.n_groups, 4))
         lib().ref_cst_spheres_batch(self.h, _p(Q), Q.shape[0], int(accurate), 1, _p(out))
         return out
+
+    def flatten(self) -> dict:
+        """include/plainmp_b200_plainmp.hpp run on the reference's own objects: the C-ABI tables
+        (numpy arrays in the dtypes of plainmp_b200._capi) a plainmp-side binding would hand to
+        pmp_robot_create / pmp_scene_create."""
+        from plainmp_b200 import _capi
+
+        f = lib().ref_cst_flatten(self.h)
+        if not f:
+            _raise()
+        try:
+            sz = np.zeros(8, dtype=np.int64)
+            lib().ref_flat_sizes(f, _p(sz))
+            out = {
+                "ops": np.zeros(sz[0], dtype=_capi.LINK_OP_DTYPE),
+                "groups": np.zeros(sz[1], dtype=_capi.GROUP_DTYPE),
+                "spheres": np.zeros((sz[2], 4), dtype=np.float32),
+                "pairs": np.zeros((sz[3], 2), dtype=np.int32),
+                "prims": np.zeros(sz[4], dtype=_capi.PRIM_DTYPE),
+                "cloud_points": np.zeros((sz[5], 3), dtype=np.float32),
+                "base_pose": np.zeros(7, dtype=np.float32),
+                "dof": int(sz[6]),
+                "base_type": int(sz[7]),
+            }
+            cr = np.zeros(1, dtype=np.float32)
+            lib().ref_flat_copy(f, _p(out["ops"]), _p(out["groups"]), _p(out["spheres"]), _p(out["pairs"]), _p(out["prims"]),
+                                _p(out["cloud_points"]), _p(out["base_pose"]), _p(cr))
+            out["cloud_radius"] = float(cr[0])
+            return out
+        finally:
+            lib().ref_flat_destroy(f)
 
     def check_motion_batch(self, vtype: int, box_width, resolution: float, S1, S2) -> Tuple[np.ndarray, int]:
         S1, S2 = _f64(S1), _f64(S2)

@@ -17,11 +17,29 @@
 #include <string>
 #include <vector>
 
+// The flatten header (include/plainmp_b200_plainmp.hpp) reads a few private members that a plainmp
+// maintainer would expose with a `friend` declaration; the reference headers stay unmodified here, so
+// this one translation unit sees them with private/protected spelled public (std headers come first).
+#include <algorithm>
+#include <array>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <optional>
+#include <stack>
+#include <stdexcept>
+#include <unordered_map>
+#include <utility>
+#define private public
+#define protected public
 #include "plainmp/collision/kdtree.hpp"
 #include "plainmp/collision/primitive_sdf.hpp"
 #include "plainmp/constraints/primitive_sphere_collision.hpp"
 #include "plainmp/kinematics/kinematic_model_wrapper.hpp"
 #include "plainmp/ompl/motion_validator.hpp"
+#include "plainmp_b200_plainmp.hpp"
+#undef private
+#undef protected
 
 namespace kin = plainmp::kinematics;
 namespace col = plainmp::collision;
@@ -313,6 +331,38 @@ void ref_cst_spheres_batch(void* h, const double* Q, int64_t n, int accurate, in
       out[w++] = s.second;
     }
   }
+}
+
+// ---- reference objects -> C-ABI tables (include/plainmp_b200_plainmp.hpp) ------------------------
+void* ref_cst_flatten(void* h) {
+  REF_TRY
+  return new plainmp_b200::Flat(plainmp_b200::Flatten::run(**static_cast<CstPtr*>(h)));
+  REF_CATCH(nullptr)
+}
+void ref_flat_destroy(void* f) { delete static_cast<plainmp_b200::Flat*>(f); }
+// out[8]: n_ops, n_groups, n_spheres, n_pairs, n_prims, n_cloud_points, dof, base_type
+void ref_flat_sizes(void* f, int64_t* out) {
+  auto* F = static_cast<plainmp_b200::Flat*>(f);
+  out[0] = (int64_t)F->ops.size();
+  out[1] = (int64_t)F->groups.size();
+  out[2] = (int64_t)F->spheres.size() / 4;
+  out[3] = (int64_t)F->pairs.size() / 2;
+  out[4] = (int64_t)F->prims.size();
+  out[5] = (int64_t)F->cloud_points.size() / 3;
+  out[6] = F->dof;
+  out[7] = F->base_type;
+}
+void ref_flat_copy(void* f, void* ops, void* groups, float* spheres, int32_t* pairs, void* prims, float* cloud,
+                   float* base_pose7, float* cloud_radius) {
+  auto* F = static_cast<plainmp_b200::Flat*>(f);
+  std::memcpy(ops, F->ops.data(), F->ops.size() * sizeof(pmp_link_op_t));
+  std::memcpy(groups, F->groups.data(), F->groups.size() * sizeof(pmp_group_t));
+  std::memcpy(spheres, F->spheres.data(), F->spheres.size() * sizeof(float));
+  std::memcpy(pairs, F->pairs.data(), F->pairs.size() * sizeof(int32_t));
+  std::memcpy(prims, F->prims.data(), F->prims.size() * sizeof(pmp_prim_t));
+  std::memcpy(cloud, F->cloud_points.data(), F->cloud_points.size() * sizeof(float));
+  std::memcpy(base_pose7, F->base_pose, sizeof(F->base_pose));
+  *cloud_radius = F->cloud_radius;
 }
 
 // ---- motion validators (ompl/motion_validator.cpp, installed as in ompl_thin_wrap.hpp:80-120) ----

@@ -188,6 +188,56 @@ class RobotTable:
             self._lib.pmp_robot_destroy(h)
 
 
+class RawTables:
+    """pmp_robot_t / pmp_scene_t built directly from C-ABI tables (numpy arrays in the _capi dtypes),
+    e.g. the output of include/plainmp_b200_plainmp.hpp run on plainmp's own objects.  Quacks like
+    (RobotTable, SceneTable) for check_configs / eval_configs / check_edges."""
+
+    class _Handle:
+        def __init__(self, h, lib, destroy, **attrs):
+            self._h, self._lib, self._destroy = h, lib, destroy
+            self.__dict__.update(attrs)
+
+        @property
+        def handle(self):
+            return self._h
+
+        def __del__(self):
+            h, self._h = getattr(self, "_h", None), None
+            if h:
+                getattr(self._lib, self._destroy)(h)
+
+    def __init__(self, flat: dict):
+        lib = _capi.load()
+        _device()
+        self._keep = flat
+        d = _capi.RobotDesc()
+        d.dof, d.base_type = flat["dof"], flat["base_type"]
+        for i in range(7):
+            d.base_pose[i] = float(flat["base_pose"][i])
+        d.n_ops, d.ops = len(flat["ops"]), flat["ops"].ctypes.data
+        d.n_groups, d.groups = len(flat["groups"]), flat["groups"].ctypes.data
+        d.n_spheres, d.spheres = len(flat["spheres"]), flat["spheres"].ctypes.data
+        d.n_pairs, d.pairs = len(flat["pairs"]), flat["pairs"].ctypes.data
+        h = C.c_void_p()
+        _capi.check(lib.pmp_robot_create(C.byref(d), C.byref(h)))
+        q_dim = lib.pmp_robot_q_dim(h)
+        self.robot = RawTables._Handle(h, lib, "pmp_robot_destroy", q_dim=q_dim, n_spheres=len(flat["spheres"]),
+                                       n_ops=len(flat["ops"]), dof=flat["dof"])
+        self.scene = None
+        if len(flat["prims"]) or len(flat["cloud_points"]):
+            sd = _capi.SceneDesc()
+            sd.n_prims = len(flat["prims"])
+            sd.prims = flat["prims"].ctypes.data if len(flat["prims"]) else None
+            sd.n_cloud_points = len(flat["cloud_points"])
+            sd.cloud_points = flat["cloud_points"].ctypes.data if len(flat["cloud_points"]) else None
+            sd.cloud_radius = flat["cloud_radius"]
+            sd.cloud_cell = 0.0
+            hs = C.c_void_p()
+            _capi.check(lib.pmp_scene_create(C.byref(sd), C.byref(hs)))
+            self.scene = RawTables._Handle(hs, lib, "pmp_scene_destroy")
+
+
 def group_bounding_sphere(sp: np.ndarray) -> Tuple[np.ndarray, float]:
     """Group centre = mean of member centres, radius = max(|p_j - centre| + r_j)
     (primitive_sphere_collision.cpp:130-144), float64."""

@@ -665,3 +665,23 @@ def test_cloud_replacement_in_place_matches_oracle(cuda_lib):
     assert_validity_parity(with_cloud, o.is_valid_batch(Q2d), o.margin_batch(Q2d), "cloud added")
     cst2.set_sdf(workloads.fetch_table_sdf())
     assert (cst2.is_valid_batch(Q2) == base).all() and cst2._scene() is t2 and not t2.has_cloud
+
+
+# ---- the drop-in, end to end: reference objects -> C++ flatten -> C ABI -> CUDA ------------------------
+@pytest.mark.skipif(not ref_bridge.available(), reason="prebuilt oracle/_ref/libplainmp_ref.so did not travel to this box")
+@pytest.mark.parametrize("name", list(MAKERS))
+def test_reference_objects_flattened_in_cpp_run_on_cuda(cuda_lib, name):
+    """SphereCollisionCst / KinematicModel / SDF objects of the COMPILED REFERENCE are flattened by
+    include/plainmp_b200_plainmp.hpp (C++, inside the reference build) and handed to the C ABI; the
+    CUDA result is compared with is_valid / evaluate of those same reference objects."""
+    spec, cst = MAKERS[name]()
+    r = ref_bridge.RefCst(cst)
+    raw = tables.RawTables(r.flatten())
+    Q = workloads.random_configs(spec, 5000, 808)
+    Qd = Q.astype(np.float64)
+    got = tables.check_configs(raw.robot, raw.scene, Q)
+    o = bridge.OracleCst(cst, n_threads=4)  # only for the contact-band margin
+    assert_validity_parity(got, r.is_valid_batch(Qd), o.margin_batch(Qd), name + "/flatten")
+    np.testing.assert_allclose(tables.eval_configs(raw.robot, raw.scene, Q[:1500]), r.evaluate_batch(Qd[:1500]), atol=TOL, rtol=0, equal_nan=True)
+    # and the same answer as this repo's own host-mirror tables, bit for bit
+    assert (got == cst.is_valid_batch(Q)).all()

@@ -299,3 +299,60 @@ def test_zero_radius_self_only_and_no_scene_match_reference():
             assert (np.isnan(vo) == np.isnan(vr)).all()
             np.testing.assert_allclose(vo, vr, atol=TOL, rtol=0)
             np.testing.assert_allclose(o.spheres_batch(Q[:8], True), r.spheres_batch(Q[:8], True), atol=TOL, rtol=0)
+
+
+# ---- reference objects -> C-ABI tables (include/plainmp_b200_plainmp.hpp) -----------------------------
+def _canon_ops(ops, names=None):
+    """Order-independent view of an op table: each op with its chain of ancestors' content."""
+    rows = []
+    for k in range(len(ops)):
+        chain, i = [], k
+        while i >= 0:
+            o = ops[i]
+            chain.append((tuple(np.round(o["origin_quat"], 6)), tuple(np.round(o["origin_xyz"], 6)), int(o["kind"]),
+                          tuple(np.round(o["axis"], 6)), int(o["q_index"]), int(o["flags"]) & 1))
+            i = int(o["parent"])
+        rows.append(tuple(chain))
+    return rows
+
+
+@pytest.mark.parametrize("name", ["panda_dualbars", "fetch_table", "pr2_cloud20k", "openarm_dual"])
+def test_reference_side_flatten_equals_host_mirror_tables(name):
+    """The C++ flatten a plainmp maintainer would compile into the reference (run here on the compiled
+    reference's own SphereCollisionCst / KinematicModel / SDF objects) produces the same C-ABI tables
+    as this repo's Python host mirror: same ops (per link chain), groups, spheres (reference's
+    re-ordered order), pairs and primitive records."""
+    from plainmp_b200 import tables
+
+    maker, seed, n = MAKERS[name]
+    spec, cst = maker()
+    flat = ref_bridge.RefCst(cst).flatten()
+    prog = tables.LinkProgram(cst.get_kin(), cst._control_joint_ids, cst._group_links)
+    assert flat["dof"] == len(cst._control_joint_ids) and flat["base_type"] == int(cst._base_type)
+    assert len(flat["ops"]) == len(prog.ops)
+    assert sorted(_canon_ops(flat["ops"])) == sorted(_canon_ops(prog.ops))
+    # groups: link chain of the op + centre + radius + flag + member spheres in order
+    ref_chain, host_chain = _canon_ops(flat["ops"]), _canon_ops(prog.ops)
+    assert len(flat["groups"]) == len(cst._group_links)
+    for g, G in enumerate(flat["groups"]):
+        host_op = prog.op_of_link[cst._group_links[g]]
+        assert ref_chain[int(G["op"])] == host_chain[host_op]
+        centre, radius = tables.group_bounding_sphere(cst._group_spheres[g])
+        np.testing.assert_allclose(G["center"], centre, atol=1e-7)
+        assert abs(float(G["radius"]) - radius) < 1e-7
+        assert bool(G["only_self_collision"]) == cst._group_only_self[g]
+        b, c = int(G["sphere_begin"]), int(G["sphere_count"])
+        np.testing.assert_allclose(flat["spheres"][b : b + c], cst._group_spheres[g].astype(np.float32), atol=1e-7)
+    assert [tuple(p) for p in flat["pairs"]] == [tuple(p) for p in cst._pairs]
+    prims, cloud = tables.flatten_primitives(cst._leaves())
+    assert len(flat["prims"]) == len(prims)
+    for a, b in zip(flat["prims"], prims):
+        for k in ("type", "flags"):
+            assert int(a[k]) == int(b[k]), k
+        for k in ("position", "rot_col0", "rot_col1", "rot_col2", "param0", "param1", "param2", "lb", "ub"):
+            np.testing.assert_allclose(a[k], b[k], atol=1e-6, err_msg=k)
+    if cloud is not None:
+        assert flat["cloud_radius"] == pytest.approx(cloud.radius)
+        np.testing.assert_allclose(np.sort(flat["cloud_points"], axis=0), np.sort(cloud.points.astype(np.float32), axis=0), atol=0)
+    else:
+        assert len(flat["cloud_points"]) == 0

@@ -90,7 +90,8 @@ int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kB
 struct RobotTables {
   RobotDev dev{};
   float4* blob_dev = nullptr;
-  size_t stash_floats_per_thread = 0;
+  size_t stash_floats_per_thread = 0;       // validity kernels (v3 layout) / FK kernels
+  size_t stash_floats_per_thread_eval = 0;  // evaluate kernel: one word per group (+1) after the group centres
 };
 
 struct pmp_robot {
@@ -122,8 +123,9 @@ static size_t extra_smem() {  // PMP_EXTRA_SMEM=<bytes>: occupancy experiments o
   }();
   return v;
 }
-static size_t smem_bytes(const RobotTables& r, const SceneDev& s, int block = kBlock) {
-  return (size_t)(r.dev.blob_words + s.n_prims * kPrimWords) * 16 + r.stash_floats_per_thread * 4 * block + extra_smem();
+static size_t smem_bytes(const RobotTables& r, const SceneDev& s, int block = kBlock, bool eval_kernel = false) {
+  const size_t stash = eval_kernel ? r.stash_floats_per_thread_eval : r.stash_floats_per_thread;
+  return (size_t)(r.dev.blob_words + s.n_prims * kPrimWords) * 16 + stash * 4 * block + extra_smem();
 }
 // 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
 static int pick_block(const RobotTables& r, const SceneDev& s) {
@@ -234,7 +236,9 @@ ProgramD fold_fixed_ops(const ProgramD& in) {
   return out;
 }
 
-int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, RobotTables* out) {
+// v3: the tables feed the validity kernels (pmp_v3.cuh), whose stash has the v3 layout and which
+// understand kSlotBase; otherwise the evaluate / FK kernels of pmp_kernels.cuh.
+int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v3, RobotTables* out) {
   const int n_ops = (int)P.ops.size(), n_groups = (int)P.groups.size(), n_spheres = (int)P.spheres.size() / 4,
             n_pairs = (int)P.pairs.size() / 2;
   // groups sorted by op (stable), pairs remapped
@@ -252,8 +256,15 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, RobotT
     if (P.ops[i].parent >= 0 && P.ops[i].parent != i - 1) need[P.ops[i].parent] = 1;
   for (int g = 0; g < n_groups; g++) need[P.groups[g].op] = 1;
   int n_slots = 0;
-  for (int i = 0; i < n_ops; i++)
-    if (need[i]) slot[i] = n_slots++;
+  for (int i = 0; i < n_ops; i++) {
+    if (!need[i]) continue;
+    const OpD& o = P.ops[i];
+    // the root op of a FIXED-base robot carries the base pose itself, the same for every
+    // configuration: the v3 kernels take it from the handle instead of stashing it per thread
+    const bool is_base = v3 && d->base_type == PMP_BASE_FIXED && o.parent < 0 && o.kind == PMP_OP_FIXED &&
+                         (o.flags & PMP_OPFLAG_ORIGIN_IDENTITY) && o.oxyz[0] == 0.0 && o.oxyz[1] == 0.0 && o.oxyz[2] == 0.0;
+    slot[i] = is_base ? kSlotBase : n_slots++;
+  }
 
   const int off_groups = n_ops * kOpWords;
   const int off_spheres = off_groups + n_groups * 2;
@@ -277,7 +288,8 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, RobotT
     const int pslot = (o.parent >= 0 && o.parent != i - 1) ? slot[o.parent] : -1;
     int flags = o.flags & PMP_OPFLAG_ORIGIN_IDENTITY;
     if ((float)o.oxyz[0] == 0.f && (float)o.oxyz[1] == 0.f && (float)o.oxyz[2] == 0.f) flags |= PMP_OPFLAG_ZERO_XYZ;
-    blob[kOpWords * i + 3] = make_float4(fi(o.parent), fi(flags), fi(slot[i]), fi(pslot));
+    // an op whose frame is the constant base pose is never stashed (own slot -1); readers get kSlotBase
+    blob[kOpWords * i + 3] = make_float4(fi(o.parent), fi(flags), fi(slot[i] == kSlotBase ? -1 : slot[i]), fi(pslot));
     // v3 sine basis: origin (x) (axis, 0) in FP64 (Eigen product, w = -o.a, vec = ow a + o x a)
     const double ax = o.axis[0], ay = o.axis[1], az = o.axis[2];
     blob[kOpWords * i + 4] = make_float4((float)(oq[3] * ax + oq[1] * az - oq[2] * ay), (float)(oq[3] * ay + oq[2] * ax - oq[0] * az),
@@ -286,7 +298,7 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, RobotT
   for (int k = 0; k < n_groups; k++) {
     const GroupD& G = P.groups[order[k]];
     blob[off_groups + 2 * k] = make_float4((float)G.center[0], (float)G.center[1], (float)G.center[2], (float)G.radius);
-    const int sl = slot[G.op] < 0 ? 0 : slot[G.op];
+    const int sl = slot[G.op] < 0 ? 0 : slot[G.op];  // kSlotBase = 0xffff fits the 16-bit field
     const int fl = (G.only_self ? 1 : 0) | (sl << 8);
     blob[off_groups + 2 * k + 1] = make_float4(fi(G.op), fi(G.sphere_begin), fi(G.sphere_count), fi(fl));
   }
@@ -322,8 +334,10 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, RobotT
   memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
   // per thread: frames [slot][7], group centres [group][3], + the per-warp scratch row and queues
   // (the evaluate kernel keeps one word per group instead)
-  out->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)n_groups * 3 + std::max<size_t>((size_t)n_groups + 1, kV3WordsPerThread);
-  if (smem_bytes(*out, empty_scene()) > (size_t)kMaxSmem)
+  out->stash_floats_per_thread_eval = (size_t)n_slots * 7 + (size_t)n_groups * 3 + (size_t)n_groups + 1;
+  out->stash_floats_per_thread =
+      v3 ? (size_t)n_slots * 7 + (size_t)n_groups * 3 + (size_t)kV3WordsPerThread : out->stash_floats_per_thread_eval;
+  if (smem_bytes(*out, empty_scene(), kBlock, true) > (size_t)kMaxSmem || smem_bytes(*out, empty_scene()) > (size_t)kMaxSmem)
     return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
   return PMP_OK;
 }
@@ -400,8 +414,8 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
   P.pairs.assign(d->pairs, d->pairs + (size_t)2 * d->n_pairs);
 
   auto* r = new pmp_robot();
-  int rc = build_tables(P, d, q_dim, &r->full);
-  if (rc == PMP_OK) rc = build_tables(fold_fixed_ops(P), d, q_dim, &r->fast);
+  int rc = build_tables(P, d, q_dim, false, &r->full);
+  if (rc == PMP_OK) rc = build_tables(fold_fixed_ops(P), d, q_dim, true, &r->fast);
   if (rc != PMP_OK) {
     pmp_robot_destroy(r);
     return rc;
@@ -597,7 +611,7 @@ static int eval_launch(const pmp_robot_t* robot, const pmp_scene_t* scene, const
   if (n == 0) return PMP_OK;
   if ((!q_dev && robot->fast.dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const size_t smem = smem_bytes(robot->fast, S);
+  const size_t smem = smem_bytes(robot->fast, S, kBlock, true);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   int grid = 0;
   if (jac_dev) {

@@ -63,6 +63,10 @@ __device__ __forceinline__ Smem stage_tables(const RobotDev& R, const SceneDev& 
   return t;
 }
 
+// slot code of a frame that is not stashed because it is the same for every configuration: the root
+// op of a FIXED-base robot in the folded (`fast`) tables (frame = base pose)
+constexpr int kSlotBase = 0xffff;
+
 __device__ __forceinline__ void stash_put(float* stash, int slot, const Frame& f) {
   float* p = stash + (slot * 7) * blockDim.x + threadIdx.x;
   const int n = blockDim.x;
@@ -119,7 +123,7 @@ __device__ __forceinline__ void walk_links(const RobotDev& R, const Smem& T, con
     const int4 w3 = *reinterpret_cast<const int4*>(&T.ops[kOpWords * i + 3]);
     const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
     Frame parent = cur;
-    if (w3.x != i - 1) parent = (w3.x < 0) ? base : stash_get(T.stash, w3.w);
+    if (w3.x != i - 1) parent = (w3.x < 0 || w3.w == kSlotBase) ? base : stash_get(T.stash, w3.w);
     const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
     cur = apply_op<APPROX>(parent, w0, w1, w2, kind, w3.y, qv);
     if (w3.z >= 0) stash_put(T.stash, w3.z, cur);
@@ -287,7 +291,9 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
       if (dx * dx + dy * dy + dz * dz > rs * rs) continue;
       const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * pr.x + 1]);
       const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * pr.y + 1]);
-      const Frame fa = stash_get(T.stash, wa.w >> 8), fb = stash_get(T.stash, wb.w >> 8);
+      const Frame fbase = base_frame(R, acc);
+      const Frame fa = (wa.w >> 8) == kSlotBase ? fbase : stash_get(T.stash, wa.w >> 8);
+      const Frame fb = (wb.w >> 8) == kSlotBase ? fbase : stash_get(T.stash, wb.w >> 8);
       const Rot ra = rotmat(fa), rb = rotmat(fb);
       for (int i = 0; i < wa.z; i++) {
         const float4 sa = T.spheres[wa.y + i];

@@ -30,7 +30,11 @@ namespace pmp {
 
 constexpr int kQE = 128;  // env items per warp:  lane | group << 5 | primitive << 16
 constexpr int kQS = 32;   // self items per warp: lane | pair << 5
-constexpr int kV3WordsPerThread = (32 * 4 + kQE + kQS) / 32;  // scratch float4[32] + queues, per warp
+// The self drain's scratch row (float4[32] per warp) lives in the bytes of the env queue: every env
+// item has been drained before the first self item is looked at, so the two are never live together.
+static_assert(kQE * 4 == 32 * 16, "the env queue and the scratch row share their bytes");
+constexpr int kV3WordsPerThread = (kQE + kQS) / 32;  // env queue (= scratch row) + self queue, per warp
+// (kSlotBase, pmp_kernels.cuh: the root frame of a FIXED-base robot is taken from the handle)
 constexpr unsigned kItemCloud = 0xffffu;     // primitive field: the scene's point cloud
 constexpr unsigned kItemOverflow = 0xfffeu;  // primitive field: every primitive with index >= 30
 constexpr int kMaxGroupsV3 = 2048;           // the group field of an env item has 11 bits
@@ -43,7 +47,7 @@ template <int B>
 struct V3View {
   float* frames;    // [slot][7][B]
   float* gc;        // [group][3][B]
-  float4* scratch;  // [warp][32]
+  float4* scratch;  // [warp][32]   (aliases qenv)
   unsigned* qenv;   // [warp][kQE]
   unsigned* qself;  // [warp][kQS]
 };
@@ -54,7 +58,7 @@ __device__ __forceinline__ V3View<B> v3_view(const RobotDev& R, const Smem& T) {
   v.frames = T.stash;
   v.gc = T.stash + R.n_slots * 7 * B;
   v.scratch = reinterpret_cast<float4*>(v.gc + R.n_groups * 3 * B);
-  v.qenv = reinterpret_cast<unsigned*>(v.scratch + B);
+  v.qenv = reinterpret_cast<unsigned*>(v.scratch);
   v.qself = v.qenv + kQE * (B / 32);
   return v;
 }
@@ -66,6 +70,13 @@ __device__ __forceinline__ Frame v3_frame_at(const V3View<B>& v, int slot, int t
   f.qx = p[0]; f.qy = p[B]; f.qz = p[2 * B]; f.qw = p[3 * B];
   f.tx = p[4 * B]; f.ty = p[5 * B]; f.tz = p[6 * B];
   return f;
+}
+
+// frame of a group's op: the stash, or the constant base frame for kSlotBase
+template <int B>
+__device__ __forceinline__ Frame v3_group_frame(const V3View<B>& v, const Frame& basef, int slot, int tid) {
+  if (slot == kSlotBase) return basef;
+  return v3_frame_at(v, slot, tid);
 }
 
 // t + q * v  (Eigen's q * v, algebraically equal to toRotationMatrix() * v for any q)
@@ -114,8 +125,9 @@ __device__ __forceinline__ Frame apply_op_v3(const Frame& p, const float4 wB, co
 // env items: 8 lanes per (configuration, group, primitive) item, one sphere per lane per round.
 // Sub-warps are independent; they meet again at the REDUX that retires configurations.
 template <int B, bool CLOUD>
-__device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const unsigned* qenv,
-                                              const int n_env, unsigned bad, const int lane, const int wbase) {
+__device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const Frame& basef,
+                                              const unsigned* qenv, const int n_env, unsigned bad, const int lane,
+                                              const int wbase) {
   constexpr unsigned full = 0xffffffffu;
   const int sub = lane & 7, k = lane >> 3;
   for (int b0 = 0; b0 < n_env; b0 += 4) {
@@ -126,7 +138,7 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
       const int src = h & 31;
       if (!((bad >> src) & 1u)) {
         const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * ((h >> 5) & (kMaxGroupsV3 - 1)) + 1]);
-        const Frame f = v3_frame_at(V, gw.w >> 8, wbase + src);
+        const Frame f = v3_group_frame(V, basef, gw.w >> 8, wbase + src);
         const unsigned kp = h >> 16;
         bool hit = false;
         if (kp < 30u) {
@@ -184,8 +196,9 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
 // then every lane owns one sphere of B (culled against A's bounding sphere) and tests it against the
 // compacted A spheres (strict <, .cpp:240-248).
 template <int B>
-__device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V, const unsigned* qself, float4* scratch,
-                                               const int n_self, unsigned bad, const int lane, const int wbase) {
+__device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V, const Frame& basef, const unsigned* qself,
+                                               float4* scratch, const int n_self, unsigned bad, const int lane,
+                                               const int wbase) {
   constexpr unsigned full = 0xffffffffu;
   const int sub = lane & 7, k = lane >> 3;
   const unsigned smask = 0xffu << (k * 8);
@@ -203,7 +216,7 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
         const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * ga + 1]);
         const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * gb + 1]);
         const int stid = wbase + src;
-        const Frame fa = v3_frame_at(V, wa.w >> 8, stid), fb = v3_frame_at(V, wb.w >> 8, stid);
+        const Frame fa = v3_group_frame(V, basef, wa.w >> 8, stid), fb = v3_group_frame(V, basef, wb.w >> 8, stid);
         const float* pa = V.gc + ga * (3 * B) + stid;
         const float* pb = V.gc + gb * (3 * B) + stid;
         const float3 gca = make3(pa[0], pa[B], pa[2 * B]);
@@ -369,7 +382,7 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
         const int4 w3 = *reinterpret_cast<const int4*>(ow + 3);
         const float4 wA = ow[4];
         const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
-        if (w3.x != i - 1) cur = (w3.x < 0) ? base : v3_frame_at(X.V, w3.w, X.tid);
+        if (w3.x != i - 1) cur = (w3.x < 0 || w3.w == kSlotBase) ? base : v3_frame_at(X.V, w3.w, X.tid);
         const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
         cur = apply_op_v3<APPROX>(cur, wB, w1, w2, wA, kind, w3.y, qv);
         if (w3.z >= 0) v3_stash_frame(X, w3.z, cur);
@@ -393,7 +406,7 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
       ready = false;
     }
     __syncwarp();
-    X.bad = drain_env<B, CLOUD>(S, T, X.V, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
+    X.bad = drain_env<B, CLOUD>(S, T, X.V, base, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
     X.n_env = 0;
     if (!stalled) break;
     __syncwarp();
@@ -409,7 +422,7 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
       if (!v3_push_self(X, p, alive & !(dx * dx + dy * dy + dz * dz > pw.z))) break;
     }
     __syncwarp();
-    X.bad = drain_self<B>(T, X.V, X.qself, X.scratch, X.n_self, X.bad, X.lane, X.wbase);
+    X.bad = drain_self<B>(T, X.V, base, X.qself, X.scratch, X.n_self, X.bad, X.lane, X.wbase);
     X.n_self = 0;
     if (p >= R.n_pairs) break;
     __syncwarp();

@@ -90,6 +90,7 @@ int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kB
 struct RobotTables {
   RobotDev dev{};
   float4* blob_dev = nullptr;
+  int v3_mode = 0;                          // MODE of the validity kernels (pmp_v3.cuh: warp_check_interp)
   size_t stash_floats_per_thread = 0;       // validity kernels (v3 layout) / FK kernels
   size_t stash_floats_per_thread_eval = 0;  // evaluate kernel: one word per group (+1) after the group centres
 };
@@ -310,7 +311,7 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
       pw[2 * p] = pos[P.pairs[2 * p]];
       pw[2 * p + 1] = pos[P.pairs[2 * p + 1]];
       const float rs = (float)P.groups[P.pairs[2 * p]].radius + (float)P.groups[P.pairs[2 * p + 1]].radius;
-      blob[off_pairs4 + p] = make_float4(fi(pw[2 * p]), fi(pw[2 * p + 1]), rs * rs, 0.f);
+      blob[off_pairs4 + p] = make_float4(fi(pw[2 * p]), fi(pw[2 * p + 1]), rs * rs, (rs + kGc16Pair) * (rs + kGc16Pair));
     }
   }
   cudaError_t e = cudaMalloc(&out->blob_dev, blob.size() * sizeof(float4));
@@ -335,8 +336,22 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   // per thread: frames [slot][7], group centres [group][3], + the per-warp scratch row and queues
   // (the evaluate kernel keeps one word per group instead)
   out->stash_floats_per_thread_eval = (size_t)n_slots * 7 + (size_t)n_groups * 3 + (size_t)n_groups + 1;
-  out->stash_floats_per_thread =
-      v3 ? (size_t)n_slots * 7 + (size_t)n_groups * 3 + (size_t)kV3WordsPerThread : out->stash_floats_per_thread_eval;
+  out->stash_floats_per_thread = out->stash_floats_per_thread_eval;
+  if (v3) {
+    // FP16 group centres (MODE 2) cost a few instructions per pair; they are used only where the
+    // bytes they save buy another resident CTA per SM (estimated with a 4-primitive scene and the
+    // register limit of these kernels: 5 CTAs of 128 threads at 85-86 registers)
+    const bool fixed = d->base_type == PMP_BASE_FIXED;
+    auto ctas = [&](bool gc16) {
+      const size_t stash = (size_t)n_slots * 7 + (size_t)v3_gc_floats(n_groups, gc16) + (size_t)kV3WordsPerThread;
+      const size_t cta = (size_t)words * 16 + 4 * kPrimWords * 16 + stash * 4 * kBlock + 1024;
+      return std::min<size_t>(5, (size_t)233472 / cta);
+    };
+    bool gc16 = fixed && ctas(true) > ctas(false);
+    if (const char* e = getenv("PMP_V3_MODE")) gc16 = fixed && atoi(e) == 2;  // A/B experiments and tests only
+    out->v3_mode = !fixed ? 0 : (gc16 ? 2 : 1);
+    out->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)v3_gc_floats(n_groups, gc16) + (size_t)kV3WordsPerThread;
+  }
   if (smem_bytes(*out, empty_scene(), kBlock, true) > (size_t)kMaxSmem || smem_bytes(*out, empty_scene()) > (size_t)kMaxSmem)
     return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
   return PMP_OK;
@@ -581,7 +596,7 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
   int grid = 0;
   cudaStream_t st = (cudaStream_t)stream;
   // is_valid uses the polynomial sin/cos only for a FIXED base (constraints/primitive.hpp:39-60)
-  const bool approx = robot->fast.dev.base_type == PMP_BASE_FIXED;
+  const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
 #define PMP_LAUNCH_CHECK(KERNEL)                                                                  \
   do {                                                                                            \
     if (int rc = grid_for(KERNEL, smem, n_tiles, &grid, block)) return rc;                        \
@@ -590,10 +605,11 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
   {
       const bool cloud = S.cloud.enabled != 0;
 #define PMP_V3(BB, AP, CL) PMP_LAUNCH_CHECK((k_check_configs_v3<BB, AP, CL>))
-#define PMP_V3_B(BB)                                                         \
-  do {                                                                       \
-    if (approx) { if (cloud) PMP_V3(BB, true, true); else PMP_V3(BB, true, false); }   \
-    else { if (cloud) PMP_V3(BB, false, true); else PMP_V3(BB, false, false); }        \
+#define PMP_V3_B(BB)                                                                      \
+  do {                                                                                    \
+    if (mode == 2) { if (cloud) PMP_V3(BB, 2, true); else PMP_V3(BB, 2, false); }         \
+    else if (mode == 1) { if (cloud) PMP_V3(BB, 1, true); else PMP_V3(BB, 1, false); }    \
+    else { if (cloud) PMP_V3(BB, 0, true); else PMP_V3(BB, 0, false); }                   \
   } while (0)
       if (block == 128) PMP_V3_B(128); else PMP_V3_B(64);
 #undef PMP_V3_B
@@ -792,7 +808,7 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
   const long long n_words = (n + 31) / 32;
   const long long tiles = (n_words + (block / 32) - 1) / (block / 32);  // one warp per 32 edges at most
   int grid = 0;
-  const bool approx = robot->fast.dev.base_type == PMP_BASE_FIXED;
+  const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
   const bool cloud = S.cloud.enabled != 0;
   // lane = edge with dynamic refill (k_check_edges_v3); valid edges atomicOr their bit into zeroed words
   cudaStream_t st = (cudaStream_t)stream;
@@ -807,10 +823,11 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
     k_check_edges_v3<BB, AP, CL><<<grid, block, smem, st>>>(robot->fast.dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
                                                             n_valid_dev, n_checked_dev, counter);           \
   } while (0)
-#define PMP_E3_B(BB)                                                                       \
-  do {                                                                                     \
-    if (approx) { if (cloud) PMP_E3(BB, true, true); else PMP_E3(BB, true, false); }       \
-    else { if (cloud) PMP_E3(BB, false, true); else PMP_E3(BB, false, false); }            \
+#define PMP_E3_B(BB)                                                                      \
+  do {                                                                                    \
+    if (mode == 2) { if (cloud) PMP_E3(BB, 2, true); else PMP_E3(BB, 2, false); }         \
+    else if (mode == 1) { if (cloud) PMP_E3(BB, 1, true); else PMP_E3(BB, 1, false); }    \
+    else { if (cloud) PMP_E3(BB, 0, true); else PMP_E3(BB, 0, false); }                   \
   } while (0)
       if (block == 128) PMP_E3_B(128); else PMP_E3_B(64);
 #undef PMP_E3_B
@@ -1107,7 +1124,7 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
   const int block = pick_block(robot->fast, S);
   const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
-  const bool approx = robot->fast.dev.base_type == PMP_BASE_FIXED;
+  const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
   const bool cloud = S.cloud.enabled != 0;
   uint64_t checked = 0;
   for (int64_t off = 0; off < n; off += s->cap) {
@@ -1164,10 +1181,11 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
     if (int rc = grid_for(k_check_waypoints_flat<BB, AP, CL>, smem_flat, tiles, &grid, block)) return rc;       \
     k_check_waypoints_flat<BB, AP, CL><<<grid, block, smem_flat, s->stream>>>(robot->fast.dev, S, d0, d1, dr, dof, (int)m, db, dway); \
   } while (0)
-#define PMP_F3_B(BB)                                                                 \
-  do {                                                                               \
-    if (approx) { if (cloud) PMP_F3(BB, true, true); else PMP_F3(BB, true, false); } \
-    else { if (cloud) PMP_F3(BB, false, true); else PMP_F3(BB, false, false); }      \
+#define PMP_F3_B(BB)                                                                      \
+  do {                                                                                    \
+    if (mode == 2) { if (cloud) PMP_F3(BB, 2, true); else PMP_F3(BB, 2, false); }         \
+    else if (mode == 1) { if (cloud) PMP_F3(BB, 1, true); else PMP_F3(BB, 1, false); }    \
+    else { if (cloud) PMP_F3(BB, 0, true); else PMP_F3(BB, 0, false); }                   \
   } while (0)
         if (block == 128) PMP_F3_B(128); else PMP_F3_B(64);
 #undef PMP_F3_B

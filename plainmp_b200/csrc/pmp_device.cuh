@@ -10,6 +10,7 @@
 //   prim_evaluate      collision/primitive_sdf.hpp:245, :299-311, :444-462, :540-544
 // Quaternions are never renormalised along the chain.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -150,10 +150,10 @@ struct QEdge {
 };
 
 // ---- kernels ------------------------------------------------------------------------------------
-// v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  B = blockDim.x (compile-time so that the
+// v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  MODE: see warp_check_interp.  B = blockDim.x (compile-time so that the
 // stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
 // out of the primitives-only kernel).
-template <int B, bool APPROX, bool CLOUD>
+template <int B, int MODE, bool CLOUD>
 __global__ void __launch_bounds__(B, 512 / B)
 k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
                    uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
@@ -165,7 +165,7 @@ k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__
     const long long item = tile * B + threadIdx.x;
     const bool active = item < n;
     QDirect acc{q + (active ? item : 0) * R.q_dim};
-    const bool ok = warp_check_v3<B, APPROX, CLOUD>(R, S, T, acc, active);
+    const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, active);
     const unsigned b = __ballot_sync(0xffffffffu, ok);
     if ((threadIdx.x & 31) == 0 && active) {
       bits[item >> 5] = b;
@@ -491,7 +491,7 @@ __device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const f
 // Valid edges set their bit with one atomicOr (the host wrapper zeroes the words first).
 constexpr int kEdgeChunk = 256;
 
-template <int B, bool APPROX, bool CLOUD>
+template <int B, int MODE, bool CLOUD>
 __global__ void __launch_bounds__(B, 512 / B)
 k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const float* __restrict__ q0,
                  const float* __restrict__ q1, const long long n, uint32_t* __restrict__ bits,
@@ -555,7 +555,7 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const
     }
     const long long ee = work ? e : 0;
     QEdge acc{q0 + ee * R.q_dim, q1 + ee * R.q_dim, t, w == 0};
-    const bool ok = warp_check_v3<B, APPROX, CLOUD>(R, S, T, acc, work);
+    const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, work);
     if (work) {
       cnt_checked++;
       if (!ok) {
@@ -592,7 +592,7 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const
 // not walk host memory.
 constexpr int kFlatSmemEdges = 1024;
 
-template <int B, bool APPROX, bool CLOUD>
+template <int B, int MODE, bool CLOUD>
 __global__ void __launch_bounds__(B, 512 / B)
 k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restrict__ q0, const float* __restrict__ q1,
                        const double* __restrict__ ratio, const int* __restrict__ off, const int n_edges,
@@ -621,7 +621,7 @@ k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restri
     const int j = active ? (int)(t - o[e]) : 0;
     const float rate = j == 0 ? 1.f : (float)((double)j * __ldg(ratio + e));
     QEdge acc{q0 + (long long)e * R.q_dim, q1 + (long long)e * R.q_dim, rate, j == 0};
-    const bool ok = warp_check_v3<B, APPROX, CLOUD>(R, S, T, acc, active);
+    const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, active);
     if (active) {
       if (way_ok) way_ok[t] = ok ? 1 : 0;
       else if (!ok) atomicOr(bad_bits + (e >> 5), 1u << (e & 31));

@@ -35,6 +35,20 @@ constexpr int kQS = 32;   // self items per warp: lane | pair << 5
 static_assert(kQE * 4 == 32 * 16, "the env queue and the scratch row share their bytes");
 constexpr int kV3WordsPerThread = (kQE + kQS) / 32;  // env queue (= scratch row) + self queue, per warp
 // (kSlotBase, pmp_kernels.cuh: the root frame of a FIXED-base robot is taken from the handle)
+//
+// Group centres in the stash.  They are read back only by the SELF broad phase (bounding spheres of a
+// listed pair; culling of member spheres against the other group's bounding sphere), which merely
+// has to be conservative: everything that survives goes through the exact FP32 narrow phase.  For a
+// FIXED base (GC16) they are therefore kept as FP16 offsets from the base position — half the bytes,
+// which buys one more resident CTA per SM — and every test that uses them is inflated by a bound on
+// the rounding: |offset component| < kGc16Range  =>  component error <= 2^-12 * 4 m, centre error
+// <= 1.7 mm, pair distance error <= 3.4 mm < kGc16Pair.  A configuration with a group centre farther
+// than kGc16Range from the base (none of the stock robots can reach that) is flagged `far` and skips
+// these culls altogether.  Moving bases keep FP32 centres.
+constexpr float kGc16Range = 4.0f;
+constexpr float kGc16Pair = 4.0e-3f;    // added to Ra + Rb of a pair test (host: pairs4.w)
+constexpr float kGc16Sphere = 2.0e-3f;  // added to r + R of a sphere-vs-bounding-sphere cull
+constexpr unsigned kSelfItemFar = 1u << 31;
 constexpr unsigned kItemCloud = 0xffffu;     // primitive field: the scene's point cloud
 constexpr unsigned kItemOverflow = 0xfffeu;  // primitive field: every primitive with index >= 30
 constexpr int kMaxGroupsV3 = 2048;           // the group field of an env item has 11 bits
@@ -46,18 +60,21 @@ constexpr unsigned kMaskOverflow = 1u << 31;
 template <int B>
 struct V3View {
   float* frames;    // [slot][7][B]
-  float* gc;        // [group][3][B]
+  float* gc;        // [group][3][B] floats, or (GC16) the same shape in halves
   float4* scratch;  // [warp][32]   (aliases qenv)
   unsigned* qenv;   // [warp][kQE]
   unsigned* qself;  // [warp][kQS]
 };
 
+// floats per thread taken by the group centres
+__host__ __device__ constexpr int v3_gc_floats(int n_groups, bool gc16) { return gc16 ? (3 * n_groups + 1) / 2 : 3 * n_groups; }
+
 template <int B>
-__device__ __forceinline__ V3View<B> v3_view(const RobotDev& R, const Smem& T) {
+__device__ __forceinline__ V3View<B> v3_view(const RobotDev& R, const Smem& T, const bool gc16) {
   V3View<B> v;
   v.frames = T.stash;
   v.gc = T.stash + R.n_slots * 7 * B;
-  v.scratch = reinterpret_cast<float4*>(v.gc + R.n_groups * 3 * B);
+  v.scratch = reinterpret_cast<float4*>(v.gc + v3_gc_floats(R.n_groups, gc16) * B);
   v.qenv = reinterpret_cast<unsigned*>(v.scratch);
   v.qself = v.qenv + kQE * (B / 32);
   return v;
@@ -77,6 +94,17 @@ template <int B>
 __device__ __forceinline__ Frame v3_group_frame(const V3View<B>& v, const Frame& basef, int slot, int tid) {
   if (slot == kSlotBase) return basef;
   return v3_frame_at(v, slot, tid);
+}
+
+// group centre of thread `stid` as stored: absolute (FP32) or relative to the base position (GC16)
+template <int B, bool GC16>
+__device__ __forceinline__ float3 v3_load_gc(const V3View<B>& V, const int g, const int stid) {
+  if (GC16) {
+    const __half* p = reinterpret_cast<const __half*>(V.gc) + g * (3 * B) + stid;
+    return make3(__half2float(p[0]), __half2float(p[B]), __half2float(p[2 * B]));
+  }
+  const float* p = V.gc + g * (3 * B) + stid;
+  return make3(p[0], p[B], p[2 * B]);
 }
 
 // t + q * v  (Eigen's q * v, algebraically equal to toRotationMatrix() * v for any q)
@@ -195,7 +223,7 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
 // cull them against B's bounding sphere and compact the survivors into the sub-warp's scratch row;
 // then every lane owns one sphere of B (culled against A's bounding sphere) and tests it against the
 // compacted A spheres (strict <, .cpp:240-248).
-template <int B>
+template <int B, bool GC16>
 __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V, const Frame& basef, const unsigned* qself,
                                                float4* scratch, const int n_self, unsigned bad, const int lane,
                                                const int wbase) {
@@ -210,24 +238,27 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
       const unsigned h = qself[it];
       const int src = h & 31;
       if (!((bad >> src) & 1u)) {
-        const float4 pw = T.pairs4[h >> 5];
+        const float4 pw = T.pairs4[(h & ~kSelfItemFar) >> 5];
+        const bool far = (h & kSelfItemFar) != 0u;  // GC16 only: the stored centres are not usable
         const int ga = __float_as_int(pw.x), gb = __float_as_int(pw.y);
         const float Ra = T.groups[2 * ga].w, Rb = T.groups[2 * gb].w;
         const int4 wa = *reinterpret_cast<const int4*>(&T.groups[2 * ga + 1]);
         const int4 wb = *reinterpret_cast<const int4*>(&T.groups[2 * gb + 1]);
         const int stid = wbase + src;
         const Frame fa = v3_group_frame(V, basef, wa.w >> 8, stid), fb = v3_group_frame(V, basef, wb.w >> 8, stid);
-        const float* pa = V.gc + ga * (3 * B) + stid;
-        const float* pb = V.gc + gb * (3 * B) + stid;
-        const float3 gca = make3(pa[0], pa[B], pa[2 * B]);
-        const float3 gcb = make3(pb[0], pb[B], pb[2 * B]);
+        float3 gca = v3_load_gc<B, GC16>(V, ga, stid), gcb = v3_load_gc<B, GC16>(V, gb, stid);
+        const float slack = GC16 ? kGc16Sphere : 0.f;
+        if (GC16) {
+          gca = make3(gca.x + basef.tx, gca.y + basef.ty, gca.z + basef.tz);
+          gcb = make3(gcb.x + basef.tx, gcb.y + basef.ty, gcb.z + basef.tz);
+        }
         bool hit = false;
         for (int i0 = 0; i0 < wa.z; i0 += 8) {
           const int i = i0 + sub;
           const float4 sa = T.spheres[wa.y + i];  // reads past the group stay inside the CTA's tables and are masked
           const float3 ca = place(fa, sa.x, sa.y, sa.z);
-          const float ex = ca.x - gcb.x, ey = ca.y - gcb.y, ez = ca.z - gcb.z, er = sa.w + Rb;
-          const bool keep_a = (i < wa.z) & !(ex * ex + ey * ey + ez * ez > er * er);
+          const float ex = ca.x - gcb.x, ey = ca.y - gcb.y, ez = ca.z - gcb.z, er = sa.w + Rb + slack;
+          const bool keep_a = (i < wa.z) & (far | !(ex * ex + ey * ey + ez * ez > er * er));
           const unsigned MA = (__ballot_sync(smask, keep_a) >> (k * 8)) & 0xffu;
           if (!MA) continue;
           __syncwarp(smask);  // readers of the previous chunk are done
@@ -238,8 +269,8 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
             const int j = j0 + sub;
             const float4 sb = T.spheres[wb.y + j];
             const float3 cb = place(fb, sb.x, sb.y, sb.z);
-            const float fx = cb.x - gca.x, fy = cb.y - gca.y, fz = cb.z - gca.z, fr = sb.w + Ra;
-            if ((j < wb.z) & !(fx * fx + fy * fy + fz * fz > fr * fr)) {
+            const float fx = cb.x - gca.x, fy = cb.y - gca.y, fz = cb.z - gca.z, fr = sb.w + Ra + slack;
+            if ((j < wb.z) & (far | !(fx * fx + fy * fy + fz * fz > fr * fr))) {
               for (int t = 0; t < ka; t++) {
                 const float4 a = my[t];
                 const float hx = a.x - cb.x, hy = a.y - cb.y, hz = a.z - cb.z, hr = a.w + sb.w;
@@ -274,13 +305,13 @@ struct V3Ctx {
 };
 
 template <int B>
-__device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, const bool active) {
+__device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, const bool active, const bool gc16) {
   V3Ctx<B> X;
   X.tid = threadIdx.x;
   X.lane = X.tid & 31;
   X.wbase = X.tid & ~31;
   X.lt = (1u << X.lane) - 1u;
-  X.V = v3_view<B>(R, T);
+  X.V = v3_view<B>(R, T, gc16);
   const int warp = X.tid >> 5;
   X.qenv = X.V.qenv + warp * kQE;
   X.qself = X.V.qself + warp * kQS;
@@ -300,10 +331,19 @@ __device__ __forceinline__ void v3_stash_frame(const V3Ctx<B>& X, const int slot
   p[4 * B] = f.tx; p[5 * B] = f.ty; p[6 * B] = f.tz;
 }
 
-template <int B>
-__device__ __forceinline__ void v3_store_gc(const V3Ctx<B>& X, const int gi, const float3 gc) {
+// GC16: offset from the base position in FP16; returns true when the offset leaves the range the
+// inflation constants cover (the configuration is then `far`)
+template <int B, bool GC16>
+__device__ __forceinline__ bool v3_store_gc(const V3Ctx<B>& X, const Frame& basef, const int gi, const float3 gc) {
+  if (GC16) {
+    __half* p = reinterpret_cast<__half*>(X.V.gc) + gi * (3 * B) + X.tid;
+    const float rx = gc.x - basef.tx, ry = gc.y - basef.ty, rz = gc.z - basef.tz;
+    p[0] = __float2half_rn(rx); p[B] = __float2half_rn(ry); p[2 * B] = __float2half_rn(rz);
+    return !(fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) < kGc16Range);
+  }
   float* p = X.V.gc + gi * (3 * B) + X.tid;
   p[0] = gc.x; p[B] = gc.y; p[2 * B] = gc.z;
+  return false;
 }
 
 // Group-level cull of a bounding sphere against every primitive's AABB and the cloud's distance
@@ -350,12 +390,12 @@ __device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, const uns
 // One listed group pair p; `near` = this lane's bounding spheres are within reach and the
 // configuration is still alive.  Returns false when the items do not fit (drain, call again).
 template <int B>
-__device__ __forceinline__ bool v3_push_self(V3Ctx<B>& X, const int p, const bool near) {
+__device__ __forceinline__ bool v3_push_self(V3Ctx<B>& X, const int p, const bool near, const bool far = false) {
   const unsigned ball = __ballot_sync(0xffffffffu, near);
   if (ball) {
     const int cnt = __popc(ball);
     if (X.n_self + cnt > kQS) return false;
-    if (near) X.qself[X.n_self + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)p << 5);
+    if (near) X.qself[X.n_self + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)p << 5) | (far ? kSelfItemFar : 0u);
     X.n_self += cnt;
   }
   return true;
@@ -364,12 +404,17 @@ __device__ __forceinline__ bool v3_push_self(V3Ctx<B>& X, const int p, const boo
 // Table interpreter: FK over the link program, groups in op order, single drain site per queue
 // (phase 1 is resumable: when a push does not fit, the queue is drained and the group redone).
 // All 32 lanes of the warp must call this (lanes without a configuration pass active = false).
-template <int B, bool APPROX, bool CLOUD, class QAcc>
+// MODE 0: exact sin/cos (moving base), FP32 group centres; 1: polynomial sin/cos (FIXED base), FP32
+// group centres; 2: FIXED base with FP16 group centres (chosen by the host when it buys a CTA per SM)
+template <int B, int MODE, bool CLOUD, class QAcc>
 __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
                                                   const bool active) {
-  V3Ctx<B> X = v3_begin<B>(R, T, active);
+  constexpr bool APPROX = MODE != 0;  // FIXED base (constraints/primitive.hpp:39-60)
+  constexpr bool GC16 = MODE == 2;
+  V3Ctx<B> X = v3_begin<B>(R, T, active, GC16);
   const bool ext = (S.n_prims > 0) || CLOUD;
   const Frame base = base_frame(R, q);
+  bool far = false;
   Frame cur = base;
   int i = 0, gi = 0;
   bool ready = false;
@@ -393,7 +438,7 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
         if (gw.x != i) break;
         const float4 g = T.groups[2 * gi];
         const float3 gc = place(cur, g.x, g.y, g.z);
-        v3_store_gc(X, gi, gc);
+        far |= v3_store_gc<B, GC16>(X, base, gi, gc);
         if (ext && !(gw.w & 1)) {
           if (!v3_push_env(X, gi, v3_cull_mask<CLOUD>(S, T, gc, g.w))) {
             stalled = true;
@@ -416,13 +461,15 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
     const bool alive = active && !((X.bad >> X.lane) & 1u);
     for (; p < R.n_pairs; p++) {
       const float4 pw = T.pairs4[p];
-      const float* pa = X.V.gc + __float_as_int(pw.x) * (3 * B) + X.tid;
-      const float* pb = X.V.gc + __float_as_int(pw.y) * (3 * B) + X.tid;
-      const float dx = pa[0] - pb[0], dy = pa[B] - pb[B], dz = pa[2 * B] - pb[2 * B];
-      if (!v3_push_self(X, p, alive & !(dx * dx + dy * dy + dz * dz > pw.z))) break;
+      const float3 ca = v3_load_gc<B, GC16>(X.V, __float_as_int(pw.x), X.tid);
+      const float3 cb = v3_load_gc<B, GC16>(X.V, __float_as_int(pw.y), X.tid);
+      const float dx = ca.x - cb.x, dy = ca.y - cb.y, dz = ca.z - cb.z;
+      // pw.z = (Ra + Rb)^2, pw.w = (Ra + Rb + kGc16Pair)^2
+      const bool near = far | !(dx * dx + dy * dy + dz * dz > (GC16 ? pw.w : pw.z));
+      if (!v3_push_self(X, p, alive & near, GC16 && far)) break;
     }
     __syncwarp();
-    X.bad = drain_self<B>(T, X.V, base, X.qself, X.scratch, X.n_self, X.bad, X.lane, X.wbase);
+    X.bad = drain_self<B, GC16>(T, X.V, base, X.qself, X.scratch, X.n_self, X.bad, X.lane, X.wbase);
     X.n_self = 0;
     if (p >= R.n_pairs) break;
     __syncwarp();
@@ -450,10 +497,10 @@ __device__ __forceinline__ bool warp_check_v3(const RobotDev& R, const SceneDev&
   return ok;
 }
 #else
-template <int B, bool APPROX, bool CLOUD, class QAcc>
+template <int B, int MODE, bool CLOUD, class QAcc>
 __device__ __forceinline__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
                                               const bool active) {
-  return warp_check_interp<B, APPROX, CLOUD>(R, S, T, q, active);
+  return warp_check_interp<B, MODE, CLOUD>(R, S, T, q, active);
 }
 #endif
 

@@ -685,3 +685,51 @@ def test_reference_objects_flattened_in_cpp_run_on_cuda(cuda_lib, name):
     np.testing.assert_allclose(tables.eval_configs(raw.robot, raw.scene, Q[:1500]), r.evaluate_batch(Qd[:1500]), atol=TOL, rtol=0, equal_nan=True)
     # and the same answer as this repo's own host-mirror tables, bit for bit
     assert (got == cst.is_valid_batch(Q)).all()
+
+
+# ---- FP16 group-centre stash (MODE 2 of the validity kernels) -------------------------------------------
+def test_far_group_centres_skip_the_fp16_culls(cuda_lib, monkeypatch):
+    """A FIXED-base robot whose group centres lie farther than the FP16 range covers (4 m) from the
+    base must take the `far` path (no self broad-phase culling) and still agree with the oracle;
+    PMP_V3_MODE=2 forces the FP16 layout whatever the occupancy heuristic would pick."""
+    monkeypatch.setenv("PMP_V3_MODE", "2")
+    spec = PR2RarmSpec()
+    kin = spec.get_kin()
+    name = "far_payload_link"
+    try:
+        kin.get_link_ids([name])
+    except ValueError:
+        kin.add_new_link(name, "r_gripper_palm_link", [5.5, 0.0, 0.0], [0.0, 0.0, 0.0], True)
+    rng = np.random.default_rng(71)
+    specs = [
+        SphereAttachmentSpec("r_gripper_palm_link", rng.uniform(-0.05, 0.05, (3, 6)), rng.uniform(0.03, 0.06, 6), False),
+        SphereAttachmentSpec(name, rng.uniform(-0.3, 0.3, (3, 9)), rng.uniform(0.1, 0.3, 9), False),
+        SphereAttachmentSpec("base_link", rng.uniform(-0.3, 0.3, (3, 5)) + np.array([[4.5], [0.0], [0.8]]), rng.uniform(1.0, 2.0, 5), True),
+        SphereAttachmentSpec("r_forearm_link", rng.uniform(-0.1, 0.1, (3, 4)), rng.uniform(0.03, 0.06, 4), False),
+    ]
+    pairs = [(name, "base_link"), ("r_gripper_palm_link", "base_link"), ("r_forearm_link", name)]
+    cst = SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED, specs, pairs, None, True)
+    cst.set_sdf(psdf.BoxSDF([3, 3, 3], psdf.Pose([5.0, 2.0, 1.0])))
+    Q = workloads.random_configs(spec, 6000, 72)
+    Qd = Q.astype(np.float64)
+    o = bridge.OracleCst(cst, n_threads=4)
+    want = o.is_valid_batch(Qd)
+    assert 0.03 < want.mean() < 0.97
+    assert_validity_parity(cst.is_valid_batch(Q), want, o.margin_batch(Qd), "far centres")
+    cst.set_sdf(None)  # self-collision only: every invalid item is found through the `far` path
+    o = bridge.OracleCst(cst, n_threads=4)
+    want = o.is_valid_batch(Qd)
+    assert 0.01 < (~want).mean()
+    assert_validity_parity(cst.is_valid_batch(Q), want, o.margin_batch(Qd), "far centres, self only")
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("name", list(MAKERS))
+def test_both_group_centre_layouts_agree_with_the_reference_output(cuda_lib, monkeypatch, name, mode):
+    monkeypatch.setenv("PMP_V3_MODE", mode)
+    g = np.load(GOLDEN / f"{name}.npz")
+    spec, cst = MAKERS[name]()
+    n = int(g["n"])
+    Q = workloads.random_configs(spec, n, int(g["seed"]))
+    want = np.unpackbits(g["valid_bits"], bitorder="little")[:n].astype(bool)
+    assert_validity_parity(cst.is_valid_batch(Q), want, g["margin"], f"{name}/mode{mode}")

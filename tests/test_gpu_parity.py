@@ -733,3 +733,36 @@ def test_both_group_centre_layouts_agree_with_the_reference_output(cuda_lib, mon
     Q = workloads.random_configs(spec, n, int(g["seed"]))
     want = np.unpackbits(g["valid_bits"], bitorder="little")[:n].astype(bool)
     assert_validity_parity(cst.is_valid_batch(Q), want, g["margin"], f"{name}/mode{mode}")
+
+
+def test_non_finite_and_out_of_range_inputs_follow_the_reference(cuda_lib):
+    """The reference does no input validation: NaN / inf joint values flow through FK into comparisons
+    that are all false (AABB and is_outside report 'not outside' -> collision with the environment;
+    self-collision's strict < reports none).  Angles far outside the joint limits go through the
+    range reduction of compute_approx_sin_cos (kinematics/algorithm.cpp:62-76).  Same answers here."""
+    spec, cst = workloads.make_panda()
+    rng = np.random.default_rng(5)
+    Q = workloads.random_configs(spec, 512, 91)
+    Q[0::8, rng.integers(0, 7)] = np.nan
+    Q[1::8, 3] = np.inf
+    Q[2::8, 6] = -np.inf
+    Q[3::8] *= 40.0           # up to +-116 rad: range reduction with floor()
+    Q[4::8, 0] = 1.0e6        # beyond what FP32 can reduce accurately: still must not crash
+    o = bridge.OracleCst(cst)
+    Qd = Q.astype(np.float64)
+    got, want = cst.is_valid_batch(Q), o.is_valid_batch(Qd)
+    finite_small = np.isfinite(Q).all(axis=1) & (np.abs(Q).max(axis=1) < 200.0)
+    nonfinite = ~np.isfinite(Q).all(axis=1)
+    assert (got[nonfinite] == want[nonfinite]).all() and not want[nonfinite].any()
+    m = o.margin_batch(Qd)
+    # large but finite angles: FP32 range reduction of a 100 rad angle is good to ~1e-5 rad, so allow
+    # the items whose margin is within that lever-arm error
+    bad = np.where((got != want) & finite_small)[0]
+    assert all(m[i] < 2e-4 for i in bad), (bad, m[bad])
+    # self-collision only: non-finite items are reported valid by both
+    spec2 = PR2RarmSpec()
+    cst2 = spec2.create_collision_const(self_collision=True, use_cache=False)
+    Q2 = workloads.random_configs(spec2, 64, 92)
+    Q2[::2, 1] = np.nan
+    o2 = bridge.OracleCst(cst2)
+    assert (cst2.is_valid_batch(Q2) == o2.is_valid_batch(Q2.astype(np.float64))).all()

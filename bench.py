@@ -567,6 +567,18 @@ def side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorC
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         dt = time_cuda(torch, lambda: tables.check_configs_device(robot, scene, q, bits, cnt), steps=3, warmup=1)
         out["pr2_cloud_1M_points"] = {"configs_per_s": n_p / dt, "n": n_p}
+        # BASELINE config 4, the query itself: exact nearest-point distance (KDTree::sqdist) for the
+        # sphere centres of PR2 configurations against the same 1 M-point cloud, and evaluate()
+        n_s = 1 << 16
+        centres = torch.empty((n_s, robot.n_spheres, 4), dtype=torch.float32, device=dev)
+        _check(lib, lib.pmp_fk_spheres(robot.handle, q.data_ptr(), n_s, 1, centres.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        pts = centres[:, :, :3].reshape(-1, 3).contiguous()
+        sq = torch.empty(pts.shape[0], dtype=torch.float32, device=dev)
+        dt = time_cuda(torch, lambda: _check(lib, lib.pmp_cloud_nearest(scene.handle, pts.data_ptr(), pts.shape[0], sq.data_ptr(), None, torch.cuda.current_stream().cuda_stream)), steps=3, warmup=1)
+        out["pr2_cloud_1M_points"]["nearest_point_queries_per_s"] = pts.shape[0] / dt
+        dist = torch.empty((n_s, 2), dtype=torch.float32, device=dev)
+        dt = time_cuda(torch, lambda: _check(lib, lib.pmp_eval_configs(robot.handle, scene.handle, q.data_ptr(), n_s, dist.data_ptr(), torch.cuda.current_stream().cuda_stream)), steps=3, warmup=1)
+        out["pr2_cloud_1M_points"]["evaluate_configs_per_s"] = n_s / dt
     except Exception as e:  # side metrics must never break the headline line
         out["error"] = repr(e)
     return out

@@ -288,8 +288,7 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
 }
 
 // ---- per-warp context and the building blocks of phase 1 -------------------------------------------
-// Used by the table interpreter below and by the per-robot code that pmp_jit.cu generates
-// (straight-line FK with the robot's constants folded in, calling the same helpers).
+// Used by the table interpreter below.
 template <int B>
 struct V3Ctx {
   V3View<B> V;
@@ -301,7 +300,6 @@ struct V3Ctx {
   unsigned bad;       // warp-uniform: bit l set = lane l's configuration is known to be invalid
   int n_env, n_self;  // warp-uniform queue fills
   bool active;
-  bool redo;          // generated code only: an item of this lane did not fit into a queue
 };
 
 template <int B>
@@ -320,7 +318,6 @@ __device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, c
   X.n_env = 0;
   X.n_self = 0;
   X.active = active;
-  X.redo = false;
   return X;
 }
 
@@ -477,31 +474,10 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
   return active && !((X.bad >> X.lane) & 1u);
 }
 
-#ifdef PMP_JIT
-}  // namespace pmp
-#include "pmp_jit_robot.cuh"  // generated: pmp::jit_phase1<B, APPROX, CLOUD>(X, R, S, T, q)
-namespace pmp {
-
-// Generated straight-line phase 1 + the same drains.  A lane whose item did not fit into a queue
-// (X.redo) is simply run again through the interpreter, which can drain in the middle of phase 1.
-template <int B, bool APPROX, bool CLOUD, class QAcc>
-__device__ __forceinline__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
-                                              const bool active) {
-  V3Ctx<B> X = v3_begin<B>(R, T, active);
-  jit_phase1<B, APPROX, CLOUD>(X, R, S, T, q);
-  bool ok = active && !((X.bad >> X.lane) & 1u);
-  if (__any_sync(0xffffffffu, X.redo)) {
-    const bool again = warp_check_interp<B, APPROX, CLOUD>(R, S, T, q, X.redo && ok);
-    if (X.redo) ok = ok && again;
-  }
-  return ok;
-}
-#else
 template <int B, int MODE, bool CLOUD, class QAcc>
 __device__ __forceinline__ bool warp_check_v3(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& q,
                                               const bool active) {
   return warp_check_interp<B, MODE, CLOUD>(R, S, T, q, active);
 }
-#endif
 
 }  // namespace pmp

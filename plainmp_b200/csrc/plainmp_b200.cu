@@ -137,6 +137,7 @@ namespace {
 // Host-side (FP64) description of a program, the common input of build_tables.
 struct OpD {
   double oq[4], oxyz[3], axis[3];
+  double axis_child[3];  // the joint axis in the op's OWN frame (= axis unless folding moved a prismatic axis)
   int kind, q_index, parent, flags;
 };
 struct GroupD {
@@ -211,7 +212,10 @@ ProgramD fold_fixed_ops(const ProgramD& in) {
     OpD c = o;
     for (int a = 0; a < 4; a++) c.oq[a] = L.q[a];
     for (int a = 0; a < 3; a++) c.oxyz[a] = L.t[a];
-    if (o.kind == PMP_OP_PRISMATIC) qrot(P.q, o.axis, c.axis);  // the axis lives in the parent link's frame
+    // a prismatic joint translates along its axis in the PARENT link's frame (the joint has no rotation
+    // of its own): fold the parent's constant rotation into the axis used for the translation; the
+    // Jacobian pass wants the axis in the op's own frame, which is the unrotated one
+    if (o.kind == PMP_OP_PRISMATIC) qrot(P.q, o.axis, c.axis);
     c.parent = P.anchor;
     c.flags = (L.q[0] == 0.0 && L.q[1] == 0.0 && L.q[2] == 0.0 && L.q[3] == 1.0) ? PMP_OPFLAG_ORIGIN_IDENTITY : 0;
     out.ops.push_back(c);
@@ -295,6 +299,9 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
     const double ax = o.axis[0], ay = o.axis[1], az = o.axis[2];
     blob[kOpWords * i + 4] = make_float4((float)(oq[3] * ax + oq[1] * az - oq[2] * ay), (float)(oq[3] * ay + oq[2] * ax - oq[0] * az),
                                          (float)(oq[3] * az + oq[0] * ay - oq[1] * ax), (float)(-oq[0] * ax - oq[1] * ay - oq[2] * az));
+    // prismatic ops have no sine basis: word 4 carries the axis in the op's own frame (Jacobian pass)
+    if (o.kind == PMP_OP_PRISMATIC)
+      blob[kOpWords * i + 4] = make_float4((float)o.axis_child[0], (float)o.axis_child[1], (float)o.axis_child[2], 0.f);
   }
   for (int k = 0; k < n_groups; k++) {
     const GroupD& G = P.groups[order[k]];
@@ -408,7 +415,7 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
     OpD& c = P.ops[i];
     for (int a = 0; a < 4; a++) c.oq[a] = o.origin_quat[a];
     for (int a = 0; a < 3; a++) c.oxyz[a] = o.origin_xyz[a];
-    for (int a = 0; a < 3; a++) c.axis[a] = o.axis[a];
+    for (int a = 0; a < 3; a++) c.axis[a] = c.axis_child[a] = o.axis[a];
     c.kind = o.kind;
     c.q_index = o.q_index;
     c.parent = o.parent;
@@ -649,7 +656,8 @@ int pmp_eval_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const f
 
 int pmp_eval_grad_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n,
                           float* dist_dev, float* jac_dev, void* stream) {
-  if (!jac_dev && n > 0) return fail(PMP_ERR_INVALID, "null device pointer");
+  if (!jac_dev && n > 0 && robot && robot->fast.dev.q_dim > 0) return fail(PMP_ERR_INVALID, "null device pointer");
+  if (!jac_dev) return eval_launch(robot, scene, q_dev, n, dist_dev, nullptr, stream);  // q_dim == 0: no columns
   return eval_launch(robot, scene, q_dev, n, dist_dev, jac_dev, stream);
 }
 

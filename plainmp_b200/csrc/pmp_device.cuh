@@ -141,15 +141,15 @@ __device__ __forceinline__ Frame apply_op(const Frame& p, const float4 w0, const
       lw = ow;
     }
     quat_mul(p.qx, p.qy, p.qz, p.qw, lx, ly, lz, lw, f.qx, f.qy, f.qz, f.qw);
-  } else if (kind == PMP_OP_PRISMATIC) {
-    ltx = fmaf(w2.x, qv, ltx);
-    lty = fmaf(w2.y, qv, lty);
-    ltz = fmaf(w2.z, qv, ltz);
-    f.qx = p.qx;
-    f.qy = p.qy;
-    f.qz = p.qz;
-    f.qw = p.qw;
-  } else {  // fixed
+  } else {
+    // prismatic: translation origin + axis * q.  The joint itself carries no rotation
+    // (kinematics/algorithm.cpp:149-155), but in the folded tables the constant rotation of the fixed
+    // links above it lives in this op's origin quaternion, so it is applied like a fixed op's.
+    if (kind == PMP_OP_PRISMATIC) {
+      ltx = fmaf(w2.x, qv, ltx);
+      lty = fmaf(w2.y, qv, lty);
+      ltz = fmaf(w2.z, qv, ltz);
+    }
     if (flags & PMP_OPFLAG_ORIGIN_IDENTITY) {
       f.qx = p.qx;
       f.qy = p.qy;

@@ -346,7 +346,10 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
       if (kind == PMP_OP_FIXED) return true;
       const float4 w2 = T.ops[kOpWords * op + 2];
       const int qi = __float_as_int(w2.w);
-      const float3 wa = quat_rot(f.qx, f.qy, f.qz, f.qw, make3(w2.x, w2.y, w2.z));  // axis w.r.t. the root
+      // joint axis in the op's own frame: word 2 for a revolute joint; a prismatic op keeps it in word 4
+      // (word 2 holds the axis folded into the parent's frame, which is what the translation needs)
+      const float4 wj = (kind == PMP_OP_PRISMATIC) ? T.ops[kOpWords * op + 4] : w2;
+      const float3 wa = quat_rot(f.qx, f.qy, f.qz, f.qw, make3(wj.x, wj.y, wj.z));  // axis w.r.t. the root
       auto column = [&](const float3 c) -> float3 {
         if (kind == PMP_OP_PRISMATIC) return wa;
         const float rx = c.x - f.tx, ry = c.y - f.ty, rz = c.z - f.tz;

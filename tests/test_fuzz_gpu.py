@@ -1,0 +1,68 @@
+"""Differential test on RANDOM robots and scenes (tests/fuzz_util.py): the CUDA path against the
+compiled reference where it travelled to the box, else the restated oracle (pinned to it by
+tests/test_fuzz_cpu.py on the same seeds)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bridge, ref_bridge
+from fuzz_util import random_case, sample_q
+from plainmp_b200.kinematics import BaseType
+from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorSession, ValidatorType
+
+# PMP_FUZZ_SEEDS=start:count widens the sweep for a one-off hunt (default: 40 fixed seeds)
+_s, _c = (int(x) for x in os.environ.get("PMP_FUZZ_SEEDS", "1000:40").split(":"))
+SEEDS = range(_s, _s + _c)
+
+pytestmark = pytest.mark.gpu
+
+EPS_BAND = 1e-5
+TOL = 2e-5  # random chains reach 3-4 m with up to 12 links: FP32 accumulates a little more than on the stock arms
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_cuda_equals_reference_on_random_robot(cuda_lib, seed):
+    cst, lb, ub, desc = random_case(seed)
+    o = bridge.OracleCst(cst, n_threads=4)
+    r = ref_bridge.RefCst(cst) if ref_bridge.available() else o
+    Q = sample_q(lb, ub, 3000, seed)
+    Qd = Q.astype(np.float64)
+    got, want = cst.is_valid_batch(Q), r.is_valid_batch(Qd)
+    margin = o.margin_batch(Qd)
+    bad = [int(i) for i in np.where(got != want)[0] if margin[i] > EPS_BAND]
+    assert not bad, f"{desc}: {len(bad)} validity mismatches outside the band, e.g. {bad[:4]} margins {margin[bad[:4]]}"
+    np.testing.assert_allclose(cst.evaluate_batch(Q[:1000]), r.evaluate_batch(Qd[:1000]), atol=TOL, rtol=0, equal_nan=True, err_msg=desc)
+    for accurate in (False, True):
+        np.testing.assert_allclose(cst.get_all_spheres_batch(Q[:16], accurate=accurate), r.spheres_batch(Qd[:16], accurate), atol=TOL, rtol=0, err_msg=desc)
+    # Jacobian rows of evaluate(): analytic here, forward differences in the reference; rows may differ
+    # where the arg-min is nearly tied or the finite difference straddles a kink of the SDF
+    vals, jac = cst.evaluate_grad_batch(Q[:600])
+    want_v, want_j = o.evaluate_grad_batch(Qd[:600])
+    np.testing.assert_allclose(vals, want_v, atol=TOL, rtol=0, equal_nan=True, err_msg=desc)
+    assert (np.isnan(jac) == np.isnan(want_j)).all(), desc
+    if jac.size:
+        err = np.abs(np.nan_to_num(jac) - np.nan_to_num(want_j)).max(axis=2)
+        assert (err > 1e-3).mean() < 0.03, f"{desc}: {(err > 1e-3).mean():.2%} Jacobian rows differ (max {err.max():.3e})"
+
+
+@pytest.mark.parametrize("seed", range(1000, 1012))
+def test_edges_and_session_on_random_robot(cuda_lib, seed):
+    cst, lb, ub, desc = random_case(seed)
+    dim = len(lb)
+    if dim == 0:
+        pytest.skip("no degrees of freedom")
+    o = bridge.OracleCst(cst, n_threads=4)
+    rng = np.random.default_rng(seed)
+    widths = rng.uniform(0.03, 0.2, dim)
+    q0 = sample_q(lb, ub, 1500, seed + 1)
+    q1 = np.clip(q0.astype(np.float64) + rng.uniform(-0.6, 0.6, q0.shape), lb, ub).astype(np.float32)
+    for vtype, res in ((ValidatorType.BOX, 0.0), (ValidatorType.EUCLIDEAN, 0.07)):
+        want, _ = bridge.OracleValidator(int(vtype), dim, widths, res).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64), n_threads=4)
+        cfg = ValidatorConfig(vtype, res, list(widths))
+        got, _ = MotionValidator(cst, cfg).check_motion_batch(q0, q1)
+        assert (got != want).mean() < 0.006, desc
+        ses = ValidatorSession(cst, cfg, capacity=512)
+        got_s = ses.check_motion(q0.astype(np.float64), q1.astype(np.float64))
+        assert (got_s != want).mean() < 0.006, desc
+        ses.close()

@@ -128,6 +128,13 @@ static size_t smem_bytes(const RobotTables& r, const SceneDev& s, int block = kB
   const size_t stash = eval_kernel ? r.stash_floats_per_thread_eval : r.stash_floats_per_thread;
   return (size_t)(r.dev.blob_words + s.n_prims * kPrimWords) * 16 + stash * 4 * block + extra_smem();
 }
+// Per-thread kernels (evaluate, FK dumps) read blockDim.x at run time: take the largest CTA whose
+// stash fits the budget, so that very large robots (dozens of links with sphere groups) still run.
+static int pick_block_per_thread(const RobotTables& r, const SceneDev& s, bool eval_kernel) {
+  for (int b : {128, 64, 32})
+    if (smem_bytes(r, s, b, eval_kernel) <= (size_t)kMaxSmem) return b;
+  return 0;
+}
 // 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
 static int pick_block(const RobotTables& r, const SceneDev& s) {
   return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
@@ -359,7 +366,7 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
     out->v3_mode = !fixed ? 0 : (gc16 ? 2 : 1);
     out->stash_floats_per_thread = (size_t)n_slots * 7 + (size_t)v3_gc_floats(n_groups, gc16) + (size_t)kV3WordsPerThread;
   }
-  if (smem_bytes(*out, empty_scene(), kBlock, true) > (size_t)kMaxSmem || smem_bytes(*out, empty_scene()) > (size_t)kMaxSmem)
+  if (pick_block_per_thread(*out, empty_scene(), true) == 0 || smem_bytes(*out, empty_scene(), 64) > (size_t)kMaxSmem)
     return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget of one CTA");
   return PMP_OK;
 }
@@ -634,15 +641,16 @@ static int eval_launch(const pmp_robot_t* robot, const pmp_scene_t* scene, const
   if (n == 0) return PMP_OK;
   if ((!q_dev && robot->fast.dev.q_dim > 0) || !dist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
-  const size_t smem = smem_bytes(robot->fast, S, kBlock, true);
-  if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  const int block = pick_block_per_thread(robot->fast, S, true);
+  if (!block) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  const size_t smem = smem_bytes(robot->fast, S, block, true);
   int grid = 0;
   if (jac_dev) {
-    if (int rc = grid_for(k_eval_configs<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_eval_configs<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, jac_dev);
+    if (int rc = grid_for(k_eval_configs<true>, smem, (n + block - 1) / block, &grid, block)) return rc;
+    k_eval_configs<true><<<grid, block, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, jac_dev);
   } else {
-    if (int rc = grid_for(k_eval_configs<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_eval_configs<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, nullptr);
+    if (int rc = grid_for(k_eval_configs<false>, smem, (n + block - 1) / block, &grid, block)) return rc;
+    k_eval_configs<false><<<grid, block, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, nullptr);
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -666,16 +674,18 @@ int pmp_fk_spheres(const pmp_robot_t* robot, const float* q_dev, int64_t n, int 
   if (n == 0) return PMP_OK;
   if ((!q_dev && robot->full.dev.q_dim > 0) || !spheres_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = empty_scene();
-  const size_t smem = smem_bytes(robot->full, S);
+  const int block = pick_block_per_thread(robot->full, S, false);
+  if (!block) return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget");
+  const size_t smem = smem_bytes(robot->full, S, block);
   int grid = 0;
   // a moving base always uses exact sin/cos (constraints/primitive.hpp:42)
   const bool approx = !accurate && robot->full.dev.base_type == PMP_BASE_FIXED;
   if (approx) {
-    if (int rc = grid_for(k_fk_spheres<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_spheres<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, (float4*)spheres_dev);
+    if (int rc = grid_for(k_fk_spheres<true>, smem, (n + block - 1) / block, &grid, block)) return rc;
+    k_fk_spheres<true><<<grid, block, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, (float4*)spheres_dev);
   } else {
-    if (int rc = grid_for(k_fk_spheres<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_spheres<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, (float4*)spheres_dev);
+    if (int rc = grid_for(k_fk_spheres<false>, smem, (n + block - 1) / block, &grid, block)) return rc;
+    k_fk_spheres<false><<<grid, block, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, (float4*)spheres_dev);
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -687,15 +697,17 @@ int pmp_fk_frames(const pmp_robot_t* robot, const float* q_dev, int64_t n, int a
   if (n == 0) return PMP_OK;
   if ((!q_dev && robot->full.dev.q_dim > 0) || !frames_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = empty_scene();
-  const size_t smem = smem_bytes(robot->full, S);
+  const int block = pick_block_per_thread(robot->full, S, false);
+  if (!block) return fail(PMP_ERR_LIMIT, "robot tables exceed the shared-memory budget");
+  const size_t smem = smem_bytes(robot->full, S, block);
   int grid = 0;
   const bool approx = !accurate && robot->full.dev.base_type == PMP_BASE_FIXED;
   if (approx) {
-    if (int rc = grid_for(k_fk_frames<true>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_frames<true><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, frames_dev);
+    if (int rc = grid_for(k_fk_frames<true>, smem, (n + block - 1) / block, &grid, block)) return rc;
+    k_fk_frames<true><<<grid, block, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, frames_dev);
   } else {
-    if (int rc = grid_for(k_fk_frames<false>, smem, (n + kBlock - 1) / kBlock, &grid)) return rc;
-    k_fk_frames<false><<<grid, kBlock, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, frames_dev);
+    if (int rc = grid_for(k_fk_frames<false>, smem, (n + block - 1) / block, &grid, block)) return rc;
+    k_fk_frames<false><<<grid, block, smem, (cudaStream_t)stream>>>(robot->full.dev, S, q_dev, n, frames_dev);
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());

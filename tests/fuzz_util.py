@@ -43,20 +43,21 @@ def random_urdf(rng: np.random.Generator, n_links: int) -> str:
     return "\n".join(lines) + "\n"
 
 
-def random_scene(rng: np.random.Generator, with_cloud: bool):
+def random_scene(rng: np.random.Generator, with_cloud: bool, big: bool = False):
     prims = []
-    for _ in range(int(rng.integers(1, 7))):
-        pos = rng.uniform(-1.0, 1.0, 3)
+    for _ in range(int(rng.integers(28, 45)) if big else int(rng.integers(1, 7))):
+        pos = rng.uniform(-1.0, 1.0, 3) * (2.5 if big else 1.0)
         mode = rng.integers(0, 3)
         rot = np.eye(3) if mode == 0 else (rpy_matrix(0, 0, rng.uniform(-3, 3)) if mode == 1 else rpy_matrix(*rng.uniform(-3, 3, 3)))
         kind = rng.integers(0, 3)
+        k = 0.4 if big else 1.0  # many small obstacles instead of a few large ones
         if kind == 0:
-            prims.append(psdf.BoxSDF(rng.uniform(0.1, 0.9, 3), psdf.Pose(pos, rot)))
+            prims.append(psdf.BoxSDF(rng.uniform(0.1, 0.9, 3) * k, psdf.Pose(pos, rot)))
         elif kind == 1:
-            prims.append(psdf.CylinderSDF(rng.uniform(0.05, 0.4), rng.uniform(0.1, 1.0), psdf.Pose(pos, rot)))
+            prims.append(psdf.CylinderSDF(rng.uniform(0.05, 0.4) * k, rng.uniform(0.1, 1.0) * k, psdf.Pose(pos, rot)))
         else:
-            prims.append(psdf.SphereSDF(rng.uniform(0.05, 0.5), psdf.Pose(pos, rot)))
-    if rng.random() < 0.4:
+            prims.append(psdf.SphereSDF(rng.uniform(0.05, 0.5) * k, psdf.Pose(pos, rot)))
+    if rng.random() < (0.0 if big else 0.4):
         prims.append(psdf.GroundSDF(float(rng.uniform(0.0, 1.5))))
     if with_cloud:
         n = int(rng.integers(1, 4000))
@@ -65,11 +66,12 @@ def random_scene(rng: np.random.Generator, with_cloud: bool):
     return psdf.UnionSDF(prims) if len(prims) > 1 or rng.random() < 0.5 else prims[0]
 
 
-def random_case(seed: int):
+def random_case(seed: int, big: bool = False):
     """(cst, lb, ub, description): a SphereCollisionCst on a random robot with a random scene, and
-    sampling bounds for q."""
+    sampling bounds for q.  big: 20-45 links, up to 35 groups of up to 20 spheres, dozens of pairs and
+    28-44 primitives — the 64-thread CTAs, the queue-overflow path and the >30-primitive path."""
     rng = np.random.default_rng(seed)
-    n_links = int(rng.integers(2, 13))
+    n_links = int(rng.integers(20, 46)) if big else int(rng.integers(2, 13))
     kin = KinematicModel(random_urdf(rng, n_links))
     movable = sorted(kin._joint_ids.keys(), key=lambda n: kin._joint_ids[n])
     # added links (RobotSpec custom_links), one of them a child of another
@@ -89,19 +91,21 @@ def random_case(seed: int):
         qb /= np.linalg.norm(qb)
         kin.set_base_pose([*rng.uniform(-0.5, 0.5, 3), *qb])
     # sphere groups on a random subset of links
-    n_groups = int(rng.integers(1, min(len(link_names), 8) + 1))
+    n_groups = int(rng.integers(12, min(len(link_names), 35) + 1)) if big else int(rng.integers(1, min(len(link_names), 8) + 1))
     glinks = list(rng.choice(link_names, size=n_groups, replace=False))
     specs = []
     for ln in glinks:
-        m = int(rng.integers(1, 13))
-        rad = rng.uniform(0.02, 0.15, m)
+        m = int(rng.integers(1, 21 if big else 13))
+        rad = rng.uniform(0.02, 0.15, m) * (0.3 if big else 1.0)
         if rng.random() < 0.15:
             rad[:] = 0.0  # zero-radius attachments take the r < 1e-6 shortcuts
-        specs.append(SphereAttachmentSpec(ln, rng.uniform(-0.15, 0.15, (3, m)), rad, bool(rng.random() < 0.2) and base_type == BaseType.FIXED))
+        specs.append(SphereAttachmentSpec(ln, rng.uniform(-0.15, 0.15, (3, m)) * (0.4 if big else 1.0), rad, bool(rng.random() < 0.2) and base_type == BaseType.FIXED))
     pairs = []
     if n_groups >= 2 and rng.random() < 0.8:
-        for _ in range(int(rng.integers(1, 2 * n_groups))):
+        for _ in range(int(rng.integers(1, (3 if big else 2) * n_groups))):
             a, b = rng.choice(n_groups, size=2, replace=False)
+            if big and abs(int(glinks[a][1:]) - int(glinks[b][1:])) < 8:
+                continue  # neighbouring links of a random chain overlap all the time
             if (glinks[a], glinks[b]) not in pairs and (glinks[b], glinks[a]) not in pairs:
                 pairs.append((glinks[a], glinks[b]))
     fixed_sdf = psdf.UnionSDF([psdf.BoxSDF(rng.uniform(0.1, 0.4, 3), psdf.Pose(rng.uniform(-0.6, 0.6, 3)))]) if (
@@ -109,7 +113,7 @@ def random_case(seed: int):
     cst = SphereCollisionCst(kin, control, base_type, specs, pairs, fixed_sdf, bool(rng.random() < 0.8))
     scene_kind = rng.integers(0, 4)  # 0: none, 1-2: primitives, 3: primitives + cloud
     if scene_kind > 0:
-        cst.set_sdf(random_scene(rng, with_cloud=scene_kind == 3))
+        cst.set_sdf(random_scene(rng, with_cloud=scene_kind == 3, big=big))
     limits = kin.get_joint_position_limits(kin.get_joint_ids(control))
     lb = np.array([max(l[0], -2 * np.pi) for l in limits] + ([-1.0, -1.0, -np.pi] if base_type == BaseType.PLANAR else []) +
                   ([-1.0, -1.0, -1.0, -np.pi, -1.5, -np.pi] if base_type == BaseType.FLOATING else []))

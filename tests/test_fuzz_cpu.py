@@ -13,6 +13,7 @@ from fuzz_util import random_case, sample_q
 # PMP_FUZZ_SEEDS=start:count widens the sweep for a one-off hunt (default: 40 fixed seeds)
 _s, _c = (int(x) for x in os.environ.get("PMP_FUZZ_SEEDS", "1000:40").split(":"))
 SEEDS = range(_s, _s + _c)
+BIG_SEEDS = range(3000, 3000 + max(12, _c // 4))
 
 pytestmark = pytest.mark.skipif(
     not (ref_bridge.available() or ref_bridge.can_build()),
@@ -36,3 +37,13 @@ def test_oracle_equals_reference_on_random_robot(seed):
     # the C++ flatten of the reference objects describes the same robot as the host mirror
     flat = r.flatten()
     assert flat["dof"] == len(cst._control_joint_ids) and len(flat["groups"]) == len(cst._group_links), desc
+
+
+@pytest.mark.parametrize("seed", BIG_SEEDS)
+def test_oracle_equals_reference_on_big_random_robot(seed):
+    ref_bridge.build()
+    cst, lb, ub, desc = random_case(seed, big=True)
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    Q = sample_q(lb, ub, 200, seed).astype(np.float64)
+    assert (o.is_valid_batch(Q) == r.is_valid_batch(Q)).all(), desc
+    np.testing.assert_allclose(o.evaluate_batch(Q[:60]), r.evaluate_batch(Q[:60]), atol=1e-12, rtol=0, err_msg=desc)

@@ -14,6 +14,7 @@ from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorSession
 # PMP_FUZZ_SEEDS=start:count widens the sweep for a one-off hunt (default: 40 fixed seeds)
 _s, _c = (int(x) for x in os.environ.get("PMP_FUZZ_SEEDS", "1000:40").split(":"))
 SEEDS = range(_s, _s + _c)
+BIG_SEEDS = range(3000, 3000 + max(12, _c // 4))
 
 pytestmark = pytest.mark.gpu
 
@@ -66,3 +67,19 @@ def test_edges_and_session_on_random_robot(cuda_lib, seed):
         got_s = ses.check_motion(q0.astype(np.float64), q1.astype(np.float64))
         assert (got_s != want).mean() < 0.006, desc
         ses.close()
+
+
+@pytest.mark.parametrize("seed", BIG_SEEDS)
+def test_cuda_equals_reference_on_big_random_robot(cuda_lib, seed):
+    """20-45 links, up to 35 sphere groups, dozens of pairs, 28-44 primitives: the 64-thread CTAs, the
+    queue-overflow path of phase 1 and the >30-primitive overflow item."""
+    cst, lb, ub, desc = random_case(seed, big=True)
+    o = bridge.OracleCst(cst, n_threads=4)
+    r = ref_bridge.RefCst(cst) if ref_bridge.available() else o
+    Q = sample_q(lb, ub, 1500, seed)
+    Qd = Q.astype(np.float64)
+    got, want = cst.is_valid_batch(Q), r.is_valid_batch(Qd)
+    margin = o.margin_batch(Qd)
+    bad = [int(i) for i in np.where(got != want)[0] if margin[i] > 2 * EPS_BAND]  # chains of 30+ links
+    assert not bad, f"{desc}: {len(bad)} validity mismatches outside the band, e.g. {bad[:4]} margins {margin[bad[:4]]}"
+    np.testing.assert_allclose(cst.evaluate_batch(Q[:300]), r.evaluate_batch(Qd[:300]), atol=5e-5, rtol=0, equal_nan=True, err_msg=desc)

@@ -83,3 +83,86 @@ def test_cuda_equals_reference_on_big_random_robot(cuda_lib, seed):
     bad = [int(i) for i in np.where(got != want)[0] if margin[i] > 2 * EPS_BAND]  # chains of 30+ links
     assert not bad, f"{desc}: {len(bad)} validity mismatches outside the band, e.g. {bad[:4]} margins {margin[bad[:4]]}"
     np.testing.assert_allclose(cst.evaluate_batch(Q[:300]), r.evaluate_batch(Qd[:300]), atol=5e-5, rtol=0, equal_nan=True, err_msg=desc)
+
+
+@pytest.mark.parametrize("seed", range(4000, 4020))
+def test_psdf_and_kdtree_surface_on_random_scenes(cuda_lib, seed):
+    """The psdf / kdtree binding surface (evaluate_batch, is_outside, KDTree.sqdist / query) on random
+    unions and on degenerate clouds, against the compiled reference (else the pinned oracle)."""
+    from fuzz_util import random_scene
+    from plainmp_b200 import psdf
+    from plainmp_b200.kdtree import KDTree
+
+    rng = np.random.default_rng(seed)
+    sdf = random_scene(rng, with_cloud=bool(seed % 2))
+    if sdf.get_type() != psdf.T_UNION:
+        sdf = psdf.UnionSDF([sdf])
+    R = ref_bridge.RefSDF.from_psdf(sdf) if ref_bridge.available() else bridge.OracleSDF.from_psdf(sdf)
+    P = rng.uniform(-1.6, 1.6, size=(4000, 3)).astype(np.float32).astype(np.float64)
+    want = R.evaluate_batch(P)
+    np.testing.assert_allclose(sdf.evaluate_batch(P.T), want, atol=1e-5, rtol=0)
+    radii = np.where(rng.random(4000) < 0.25, 0.0, rng.uniform(0.0, 0.3, 4000))
+    want_out = R.is_outside_batch(P, radii)
+    got_out = np.array([sdf.is_outside(p, r) for p, r in zip(P[:400], radii[:400])])
+    near = np.abs(want[:400] - radii[:400]) < 1e-5
+    assert ((got_out == want_out[:400]) | near).all()
+    # kd-tree on degenerate clouds
+    kind = seed % 5
+    n = int(rng.integers(1, 3000))
+    if kind == 0:
+        pts = np.repeat(rng.uniform(-1, 1, (1, 3)), n, axis=0)                       # all points identical
+    elif kind == 1:
+        pts = rng.uniform(-1, 1, (1, 3)) + np.outer(rng.uniform(-1, 1, n), rng.standard_normal(3))  # collinear
+    elif kind == 2:
+        pts = np.repeat(rng.uniform(-1, 1, (max(1, n // 7), 3)), 7, axis=0)           # heavy duplication
+    elif kind == 3:
+        pts = 1.0e3 + rng.uniform(-0.5, 0.5, (n, 3))                                  # far from the origin
+    else:
+        pts = rng.uniform(-1, 1, (n, 3)) * np.array([1.0, 1.0, 0.0])                  # planar
+    pts = pts.astype(np.float32).astype(np.float64)
+    tree = KDTree(pts)
+    Pq = (pts.mean(axis=0) + rng.uniform(-1.5, 1.5, (300, 3))).astype(np.float32).astype(np.float64)
+    brute = ((Pq[:, None, :] - pts[None, :, :]) ** 2).sum(-1).min(1)
+    got = np.array([tree.sqdist(p) for p in Pq[:100]])
+    scale = max(1.0, float(np.abs(pts).max()))
+    tol = 2e-5 * scale * (1 + np.sqrt(brute))  # FP32 squared distances: error grows with the coordinates' magnitude
+    assert (np.abs(got - brute[:100]) <= tol[:100]).all(), np.abs(got - brute[:100]).max()
+    nn = np.array([tree.query(p) for p in Pq[:50]])
+    assert (np.abs(((nn - Pq[:50]) ** 2).sum(1) - brute[:50]) <= tol[:50]).all()
+
+
+@pytest.mark.parametrize("seed", range(4100, 4108))
+def test_random_scene_mutations_follow_the_reference(cuda_lib, seed):
+    """A random sequence of translate / rotate_z on leaves and on the union, set_sdf with a new scene and
+    back: after every step the CUDA answer equals the oracle's for the mutated scene."""
+    from fuzz_util import random_scene
+
+    cst, lb, ub, desc = random_case(seed)
+    rng = np.random.default_rng(seed)
+    scene = random_scene(rng, with_cloud=False)
+    cst.set_sdf(scene)
+    Q = sample_q(lb, ub, 1500, seed)
+    Qd = Q.astype(np.float64)
+    for step in range(6):
+        op = rng.integers(0, 4)
+        target = scene
+        if op == 0 and hasattr(scene, "sdfs"):
+            movable = [s for s in scene.sdfs if hasattr(s, "_pose")]
+            if movable:
+                movable[int(rng.integers(0, len(movable)))].translate(rng.uniform(-0.3, 0.3, 3))
+        elif op == 1 and hasattr(scene, "sdfs"):
+            movable = [s for s in scene.sdfs if hasattr(s, "_pose")]
+            if movable:
+                movable[int(rng.integers(0, len(movable)))].rotate_z(float(rng.uniform(-1, 1)))
+        elif op == 2:
+            try:
+                target.rotate_z(float(rng.uniform(-1, 1)))
+            except RuntimeError:
+                pass  # a union holding a GroundSDF refuses, like the reference
+        else:
+            scene = random_scene(rng, with_cloud=bool(step % 2))
+            cst.set_sdf(scene)
+        o = bridge.OracleCst(cst, n_threads=4)
+        got, want, margin = cst.is_valid_batch(Q), o.is_valid_batch(Qd), o.margin_batch(Qd)
+        bad = [int(i) for i in np.where(got != want)[0] if margin[i] > EPS_BAND]
+        assert not bad, f"{desc}, step {step} op {op}: {len(bad)} mismatches"

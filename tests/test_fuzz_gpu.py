@@ -36,6 +36,12 @@ def test_cuda_equals_reference_on_random_robot(cuda_lib, seed):
     np.testing.assert_allclose(cst.evaluate_batch(Q[:1000]), r.evaluate_batch(Qd[:1000]), atol=TOL, rtol=0, equal_nan=True, err_msg=desc)
     for accurate in (False, True):
         np.testing.assert_allclose(cst.get_all_spheres_batch(Q[:16], accurate=accurate), r.spheres_batch(Qd[:16], accurate), atol=TOL, rtol=0, err_msg=desc)
+    if ref_bridge.available():
+        # the drop-in chain on the same robot: reference objects -> C++ flatten -> C ABI -> CUDA
+        from plainmp_b200 import tables
+
+        raw = tables.RawTables(r.flatten())
+        assert (tables.check_configs(raw.robot, raw.scene, Q) == got).all(), desc
     # Jacobian rows of evaluate(): analytic here, forward differences in the reference; rows may differ
     # where the arg-min is nearly tied or the finite difference straddles a kink of the SDF
     vals, jac = cst.evaluate_grad_batch(Q[:600])

@@ -35,10 +35,10 @@ UNIT = "configs/s"
 # dense algorithmic work of one panda dual-bars configuration
 F_CFG_DENSE = 14.7e3          # flop/config (no culling, no early exit)
 BYTES_PER_CFG = 7 * 4 + 1 / 8  # q in + 1 validity bit out
-# measured once with ncu --set full on the same kernel (profiles/r01_s18_panda_ncu.md): percentages of peak
-NCU_PIPE_FIGURES = {"source": "profiles/r01_s18_panda_ncu.md", "issue_active_pct": 60.8, "fma_pipe_pct": 22.6, "alu_pipe_pct": 37.3, "lsu_pipe_pct": 23.7,
-                    "warp_inst_per_config": 176.2, "lanes_active_per_inst": 24.35, "warps_active_pct": 23.8}
-DRAM_BYTES_PER_CFG_NCU = 28.9   # measured once with ncu --set full (profiles/r01_s18_panda_ncu.md), per configuration
+# measured once with ncu --set full on the same kernel (profiles/r01_s34_panda_ncu.md): percentages of peak
+NCU_PIPE_FIGURES = {"source": "profiles/r01_s34_panda_ncu.md", "issue_active_pct": 68.7, "fma_pipe_pct": 25.5, "alu_pipe_pct": 42.4, "lsu_pipe_pct": 25.4,
+                    "warp_inst_per_config": 183.3, "lanes_active_per_inst": 24.29, "warps_active_pct": 28.8}
+DRAM_BYTES_PER_CFG_NCU = 29.4   # measured once with ncu --set full (profiles/r01_s34_panda_ncu.md), per configuration
 
 
 def parse_args():
@@ -484,7 +484,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": DRAM_BYTES_PER_CFG_NCU * n_local / 1e9, "traffic_unit": "GB per launch",
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 28.9 B/config (profiles/r01_s18_panda_ncu.md), scaled to this launch",
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 29.4 B/config (profiles/r01_s34_panda_ncu.md), scaled to this launch",
                 "algorithmic_gb_per_launch": BYTES_PER_CFG * n_local / 1e9,
                 "peak_source": hbm_src, "kernel_ms": kernel_ms,
                 "note": "algorithmic bytes = 28.125 B/config; the kernel is FP32-SIMT issue bound, see roofline_fp32",

@@ -183,7 +183,20 @@ class SphereCollisionCst(IneqConstraintBase):
         self._last_accurate = accurate
 
     def is_valid(self, q: Sequence[float]) -> bool:
-        return bool(self.is_valid_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))[0])
+        """One configuration, same call as the binding (constraint.cpp:82).  Goes through a cached
+        validator session (pinned, mapped staging; one kernel launch and a stream synchronise, no
+        torch tensors) so that callers that loop over single states pay ~20 us, not a tensor round
+        trip; the session is rebuilt when the robot or scene tables it points at are replaced."""
+        from .ompl import ValidatorSession  # late import: ompl imports tables
+
+        robot, scene = self._robot(), self._scene()
+        c = getattr(self, "_single_session", None)
+        if c is None or c[0] is not robot or c[1] is not scene:
+            if c is not None:
+                c[2].close()
+            c = (robot, scene, ValidatorSession(self, None, capacity=256))
+            self._single_session = c
+        return bool(c[2].is_valid(np.asarray(q, dtype=np.float64).reshape(-1)))
 
     def evaluate(self, q: Sequence[float]):
         """``(vals, jac)`` like the binding (constraint.cpp:33): one row per enabled term

@@ -106,7 +106,11 @@ struct pmp_robot {
 struct pmp_scene {
   SceneDev dev{};
   float4* prims_dev = nullptr;
-  CloudBuffers cloud;
+  // two grow-only buffer sets: a new cloud is indexed into the idle set while kernels in flight may
+  // still walk the current one, then the sets swap; the build temporaries are kept too
+  CloudBuffers cloud[2];
+  int cloud_cur = 0;
+  CloudScratch cloud_scratch;
 };
 
 static SceneDev empty_scene() {
@@ -533,7 +537,7 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
     }
     std::string err;
     int launches = 0;
-    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_cell, g_num_sms, &s->dev.cloud, &s->cloud,
+    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_cell, g_num_sms, &s->dev.cloud, &s->cloud[0], &s->cloud_scratch,
                     &launches, &err)) {
       pmp_scene_destroy(s);
       return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
@@ -547,7 +551,9 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
 void pmp_scene_destroy(pmp_scene_t* s) {
   if (!s) return;
   if (s->prims_dev) cudaFree(s->prims_dev);
-  cloud_free(&s->cloud);
+  cloud_free(&s->cloud[0]);
+  cloud_free(&s->cloud[1]);
+  cloud_free(&s->cloud_scratch);
   delete s;
 }
 
@@ -574,19 +580,18 @@ int pmp_scene_update_cloud(pmp_scene_t* s, const float* points, int64_t n, float
   if (n > 0 && !points) return fail(PMP_ERR_INVALID, "cloud_points is null");
   if (int rc = ensure_device()) return rc;
   CloudDev fresh{};
-  CloudBuffers bufs;
+  const int idle = 1 - s->cloud_cur;
   if (n > 0) {
     std::string err;
     int launches = 0;
-    if (cloud_build(points, n, radius, cell, g_num_sms, &fresh, &bufs, &launches, &err))
+    if (cloud_build(points, n, radius, cell, g_num_sms, &fresh, &s->cloud[idle], &s->cloud_scratch, &launches, &err))
       return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
     g_launches += launches;
   } else {
     fresh.enabled = 0;
   }
-  CUDA_OK(cudaDeviceSynchronize());  // nothing in flight may still walk the old tree
-  cloud_free(&s->cloud);
-  s->cloud = bufs;
+  CUDA_OK(cudaDeviceSynchronize());  // nothing in flight may still walk the old tree when it becomes the idle set
+  s->cloud_cur = idle;
   s->dev.cloud = fresh;
   return PMP_OK;
 }

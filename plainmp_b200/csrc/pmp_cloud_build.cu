@@ -100,16 +100,37 @@ void cloud_free(CloudBuffers* b) {
   if (b->pts) cudaFree(b->pts);
   if (b->nodes) cudaFree(b->nodes);
   if (b->dist) cudaFree(b->dist);
-  b->pts = nullptr;
-  b->nodes = nullptr;
-  b->dist = nullptr;
+  *b = CloudBuffers{};
 }
 
+void cloud_free(CloudScratch* s) {
+  if (s->raw) cudaFree(s->raw);
+  if (s->keys) cudaFree(s->keys);
+  if (s->keys2) cudaFree(s->keys2);
+  if (s->vals) cudaFree(s->vals);
+  if (s->vals2) cudaFree(s->vals2);
+  if (s->tmp) cudaFree(s->tmp);
+  *s = CloudScratch{};
+}
+
+namespace {
+template <class T>
+cudaError_t reserve(T** p, size_t* cap, size_t bytes) {  // grow-only; 25 % headroom so that frames of
+  if (*cap >= bytes) return cudaSuccess;                 // slightly different sizes do not reallocate
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), want);
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
+}  // namespace
+
 int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num_sms, CloudDev* Cout, CloudBuffers* bufs,
-                int* n_launches, std::string* err) {
+                CloudScratch* scr, int* n_launches, std::string* err) {
   auto bad = [&](const std::string& m, cudaError_t e) {
     *err = m + (e == cudaSuccess ? "" : std::string(": ") + cudaGetErrorString(e));
-    cloud_free(bufs);
     return -1;
   };
   *n_launches = 0;
@@ -143,32 +164,22 @@ int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num
   const int64_t n_pad = (n + 7) / 8 * 8;
 
   // ---- sort + boxes ----
-  float* raw = nullptr;
-  unsigned *keys = nullptr, *keys2 = nullptr, *vals = nullptr, *vals2 = nullptr;
-  void* tmp = nullptr;
   size_t tmp_bytes = 0;
-  auto free_tmp = [&] {
-    if (raw) cudaFree(raw);
-    if (keys) cudaFree(keys);
-    if (keys2) cudaFree(keys2);
-    if (vals) cudaFree(vals);
-    if (vals2) cudaFree(vals2);
-    if (tmp) cudaFree(tmp);
-  };
-  cudaError_t e = cudaMalloc(&raw, n * 12);
-  if (e == cudaSuccess) e = cudaMemcpy(raw, host_pts, n * 12, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&keys, n * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&keys2, n * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&vals, n * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&vals2, n * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&bufs->pts, n_pad * sizeof(float4));
-  if (e == cudaSuccess) e = cudaMalloc(&bufs->nodes, (size_t)total_nodes * 2 * sizeof(float4));
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 30);
-  if (e == cudaSuccess) e = cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16));
-  if (e != cudaSuccess) {
-    free_tmp();
-    return bad("cloud build allocation", e);
-  }
+  cudaError_t e = reserve(&scr->raw, &scr->cap_raw, (size_t)n * 12);
+  if (e == cudaSuccess) e = cudaMemcpy(scr->raw, host_pts, (size_t)n * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = reserve(&scr->keys, &scr->cap_keys, (size_t)n * 4);
+  if (e == cudaSuccess) e = reserve(&scr->keys2, &scr->cap_keys2, (size_t)n * 4);
+  if (e == cudaSuccess) e = reserve(&scr->vals, &scr->cap_vals, (size_t)n * 4);
+  if (e == cudaSuccess) e = reserve(&scr->vals2, &scr->cap_vals2, (size_t)n * 4);
+  if (e == cudaSuccess) e = reserve(&bufs->pts, &bufs->cap_pts, (size_t)n_pad * sizeof(float4));
+  if (e == cudaSuccess) e = reserve(&bufs->nodes, &bufs->cap_nodes, (size_t)total_nodes * 2 * sizeof(float4));
+  if (e == cudaSuccess)
+    e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, scr->keys, scr->keys2, scr->vals, scr->vals2, (int)n, 0, 30);
+  if (e == cudaSuccess) e = reserve(&scr->tmp, &scr->cap_tmp, std::max<size_t>(tmp_bytes, 16));
+  if (e != cudaSuccess) return bad("cloud build allocation", e);
+  float* raw = scr->raw;
+  unsigned *keys = scr->keys, *keys2 = scr->keys2, *vals = scr->vals, *vals2 = scr->vals2;
+  void* tmp = scr->tmp;
   const int grid = num_sms * 8;
   const float3 qlo = make_float3(lo[0], lo[1], lo[2]);
   const float3 qsc = make_float3(1023.999f / std::max(hi[0] - lo[0], 1e-20f), 1023.999f / std::max(hi[1] - lo[1], 1e-20f),
@@ -184,7 +195,6 @@ int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num
     *n_launches += 1;
   }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  free_tmp();
   if (e != cudaSuccess) return bad("cloud tree build", e);
   C.pts = bufs->pts;
   C.nodes = bufs->nodes;
@@ -203,7 +213,7 @@ int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num
   C.ny = (int)std::ceil(ext[1] / h) + 1;
   C.nz = (int)std::ceil(ext[2] / h) + 1;
   const int64_t n_cells = (int64_t)C.nx * C.ny * C.nz;
-  e = cudaMalloc(&bufs->dist, n_cells * sizeof(float));
+  e = reserve(&bufs->dist, &bufs->cap_dist, (size_t)n_cells * sizeof(float));
   if (e != cudaSuccess) return bad("cloud field allocation", e);
   k_cloud_field<<<num_sms * 16, 128>>>(C, bufs->dist);
   *n_launches += 1;

@@ -58,6 +58,9 @@ def main():
             row["reference_cpu_check_motion_us_per_call"] = 1e6 * t_ref
             row["reference_cpu_is_valid_us_per_call"] = 1e6 * t_ref_s
         rows.append(row)
+    # the plain per-item call of the host mirror, cst.is_valid(q) (routed through a cached session)
+    t_single = timeit(lambda: cst.is_valid(q1[0]), 2000)
+    rows.append({"cst_is_valid_single_call_us": 1e6 * t_single})
     # scene update path: in-place primitive update and cloud re-index, per call
     from plainmp_b200 import psdf
 

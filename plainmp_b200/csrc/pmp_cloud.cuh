@@ -275,14 +275,49 @@ __device__ __forceinline__ bool cloud_surely_outside(const CloudDev& C, const fl
 
 // Exact NN squared distance, unbounded (KDTree::sqdist).  The field's upper bound (or, far from
 // every point, the distance to the far corner of the bounding box) starts the search.
+// Upper bound of NN(p) from one greedy descent: at every level step into the child box nearest to p
+// and, at the leaf, take the nearest of its 8 points.  n_levels x 8 box tests; for a query far from
+// the cloud (outside the distance field) this is what makes the bounded search below prune.
+__device__ inline float cloud_greedy_bound2(const CloudDev& C, const float3 p) {
+  int n = 0;
+  for (int l = C.n_levels - 1; l > 0; l--) {
+    const float4* b = C.nodes + 2 * (size_t)(C.level_off[l - 1] + 8 * n);
+    float bd = INFINITY;
+    int bj = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float d2 = box_dist2(__ldg(b + 2 * j), __ldg(b + 2 * j + 1), p);  // padding boxes give +inf
+      if (d2 < bd) {
+        bd = d2;
+        bj = j;
+      }
+    }
+    n = 8 * n + bj;
+  }
+  const float4* q = C.pts + 8 * (size_t)n;
+  float best = INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float4 x = __ldg(q + k);  // padding points are +inf
+    const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+    best = fminf(best, dx * dx + dy * dy + dz * dz);
+  }
+  return best;
+}
+
 __device__ inline float cloud_nn_exact(const CloudDev& C, const float3 p, int* idx) {
   float lo, hi;
   cloud_bounds(C, p, lo, hi);
   if (!(hi < INFINITY)) {
-    const float bx = fmaxf(fabsf(p.x - (C.lbx + C.rho)), fabsf(p.x - (C.ubx - C.rho)));
-    const float by = fmaxf(fabsf(p.y - (C.lby + C.rho)), fabsf(p.y - (C.uby - C.rho)));
-    const float bz = fmaxf(fabsf(p.z - (C.lbz + C.rho)), fabsf(p.z - (C.ubz - C.rho)));
-    hi = sqrtf(bx * bx + by * by + bz * bz);
+    const float g2 = cloud_greedy_bound2(C, p);
+    if (g2 < INFINITY) {
+      hi = sqrtf(g2);
+    } else {
+      const float bx = fmaxf(fabsf(p.x - (C.lbx + C.rho)), fabsf(p.x - (C.ubx - C.rho)));
+      const float by = fmaxf(fabsf(p.y - (C.lby + C.rho)), fabsf(p.y - (C.uby - C.rho)));
+      const float bz = fmaxf(fabsf(p.z - (C.lbz + C.rho)), fabsf(p.z - (C.ubz - C.rho)));
+      hi = sqrtf(bx * bx + by * by + bz * bz);
+    }
   }
   const float b = hi * (1.f + 1e-6f) + 1e-6f;
   return cloud_nn_within(C, p, b * b, idx);

@@ -576,6 +576,16 @@ def side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorC
         sq = torch.empty(pts.shape[0], dtype=torch.float32, device=dev)
         dt = time_cuda(torch, lambda: _check(lib, lib.pmp_cloud_nearest(scene.handle, pts.data_ptr(), pts.shape[0], sq.data_ptr(), None, torch.cuda.current_stream().cuda_stream)), steps=3, warmup=1)
         out["pr2_cloud_1M_points"]["nearest_point_queries_per_s"] = pts.shape[0] / dt
+        # the queries evaluate() really makes: sphere centres within the 0.1 cutoff of the cloud's AABB
+        # (far queries are the worst case of any exact NN structure and are culled before they happen)
+        cl = torch.from_numpy(cst.get_sdf().points.astype(np.float32)).to(dev)
+        lo, hi = cl.min(dim=0).values - 0.1, cl.max(dim=0).values + 0.1
+        near = pts[((pts >= lo) & (pts <= hi)).all(dim=1)].contiguous()
+        if near.shape[0] > 0:
+            sqn = torch.empty(near.shape[0], dtype=torch.float32, device=dev)
+            dt = time_cuda(torch, lambda: _check(lib, lib.pmp_cloud_nearest(scene.handle, near.data_ptr(), near.shape[0], sqn.data_ptr(), None, torch.cuda.current_stream().cuda_stream)), steps=3, warmup=1)
+            out["pr2_cloud_1M_points"]["nearest_point_queries_per_s_near_cloud"] = near.shape[0] / dt
+            out["pr2_cloud_1M_points"]["near_cloud_fraction"] = near.shape[0] / pts.shape[0]
         dist = torch.empty((n_s, 2), dtype=torch.float32, device=dev)
         dt = time_cuda(torch, lambda: _check(lib, lib.pmp_eval_configs(robot.handle, scene.handle, q.data_ptr(), n_s, dist.data_ptr(), torch.cuda.current_stream().cuda_stream)), steps=3, warmup=1)
         out["pr2_cloud_1M_points"]["evaluate_configs_per_s"] = n_s / dt

@@ -1286,7 +1286,7 @@ int pmp_cloud_nearest(const pmp_scene_t* scene, const float* points_dev, int64_t
   if (int rc = ensure_device()) return rc;
   if (n == 0) return PMP_OK;
   if (!points_dev || !sqdist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
-  const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)g_num_sms * 16);
+  const int grid = (int)std::min<int64_t>((n + 15) / 16, (int64_t)g_num_sms * 16);  // 16 queries per CTA of 128 threads
   k_cloud_nearest<<<grid, 128, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, n, sqdist_dev, nearest_index_dev);
   g_launches++;
   CUDA_OK(cudaGetLastError());

@@ -248,6 +248,94 @@ __device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, cons
   }
 }
 
+// 8-lane cooperative exact nearest neighbour: the sub-warp shares one query p; lane j tests child box j
+// of the current node (strict test against the running best), a leaf is one point per lane followed by
+// a sub-warp arg-min.  `best` enters as an exclusive upper bound on the squared distance and is sub-warp
+// uniform throughout.  Returns the squared NN distance (or the bound if nothing beat it) and the
+// original index of the nearest point through *idx (-1 if none).
+__device__ inline float cloud_nn8(const CloudDev& C, const float3 p, float best, const unsigned smask, const int sub,
+                                  const int kshift, int* idx) {
+  const int top = C.n_levels - 1;
+  int best_i = -1;
+  int l = top, n = 0;
+  unsigned long long masks = 0;
+  auto child_mask = [&](const int level, const int first) -> unsigned {
+    const float4* b = C.nodes + 2 * (size_t)(C.level_off[level] + first + sub);
+    const float d2 = box_dist2(__ldg(b), __ldg(b + 1), p);
+    return (__ballot_sync(smask, d2 < best) >> kshift) & 0xffu;
+  };
+  if (top == 0) {
+    masks = 1ull << 8;
+    l = 1;
+  } else {
+    masks = (unsigned long long)child_mask(l - 1, 0) << (8 * l);
+  }
+  const int vtop = l;
+  for (;;) {
+    const unsigned m = (unsigned)(masks >> (8 * l)) & 0xffu;
+    if (!m) {
+      if (l == vtop) break;
+      n >>= 3;
+      l++;
+      continue;
+    }
+    const int j = __ffs(m) - 1;
+    masks &= ~(1ull << (8 * l + j));
+    const int child = n * 8 + j;
+    if (l == 1) {
+      const float4 x = __ldg(C.pts + 8 * (size_t)child + sub);  // padding points are +inf
+      const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+      float d2 = dx * dx + dy * dy + dz * dz;
+      int di = __float_as_int(x.w);
+#pragma unroll
+      for (int off = 4; off; off >>= 1) {
+        const float od = __shfl_xor_sync(smask, d2, off);
+        const int oi = __shfl_xor_sync(smask, di, off);
+        if (od < d2 || (od == d2 && oi < di)) {  // ties -> smaller original index, the same on every lane
+          d2 = od;
+          di = oi;
+        }
+      }
+      if (d2 < best) {
+        best = d2;
+        best_i = di;
+      }
+    } else {
+      l--;
+      n = child;
+      masks = (masks & ~(0xffull << (8 * l))) | ((unsigned long long)child_mask(l - 1, n * 8) << (8 * l));
+    }
+  }
+  *idx = best_i;
+  return best;
+}
+
+// cooperative form of cloud_greedy_bound2: lane j looks at child j, the sub-warp steps into the nearest
+__device__ inline float cloud_greedy_bound2_8(const CloudDev& C, const float3 p, const unsigned smask, const int sub) {
+  int n = 0;
+  for (int l = C.n_levels - 1; l > 0; l--) {
+    const float4* b = C.nodes + 2 * (size_t)(C.level_off[l - 1] + 8 * n + sub);
+    float d2 = box_dist2(__ldg(b), __ldg(b + 1), p);
+    int dj = sub;
+#pragma unroll
+    for (int off = 4; off; off >>= 1) {
+      const float od = __shfl_xor_sync(smask, d2, off);
+      const int oj = __shfl_xor_sync(smask, dj, off);
+      if (od < d2 || (od == d2 && oj < dj)) {
+        d2 = od;
+        dj = oj;
+      }
+    }
+    n = 8 * n + dj;
+  }
+  const float4 x = __ldg(C.pts + 8 * (size_t)n + sub);
+  const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+  float d2 = dx * dx + dy * dy + dz * dz;
+#pragma unroll
+  for (int off = 4; off; off >>= 1) d2 = fminf(d2, __shfl_xor_sync(smask, d2, off));
+  return d2;
+}
+
 // The O(1) part of cloud_is_outside: 0 = certainly outside, 1 = certainly not outside, 2 = the
 // distance field cannot decide (p lies within +-e of the r + rho iso-surface): ask the tree with
 // bound (r + rho)^2.
@@ -308,11 +396,13 @@ __device__ inline float cloud_greedy_bound2(const CloudDev& C, const float3 p) {
 __device__ inline float cloud_nn_exact(const CloudDev& C, const float3 p, int* idx) {
   float lo, hi;
   cloud_bounds(C, p, lo, hi);
-  if (!(hi < INFINITY)) {
+  {
+    // one greedy descent: outside the field it is the only bound, inside it usually beats the field's
+    // +-cell-diagonal bound by orders of magnitude and turns the search into a verification
     const float g2 = cloud_greedy_bound2(C, p);
     if (g2 < INFINITY) {
-      hi = sqrtf(g2);
-    } else {
+      hi = fminf(hi, sqrtf(g2));
+    } else if (!(hi < INFINITY)) {
       const float bx = fmaxf(fabsf(p.x - (C.lbx + C.rho)), fabsf(p.x - (C.ubx - C.rho)));
       const float by = fmaxf(fabsf(p.y - (C.lby + C.rho)), fabsf(p.y - (C.uby - C.rho)));
       const float bz = fmaxf(fabsf(p.z - (C.lbz + C.rho)), fabsf(p.z - (C.ubz - C.rho)));

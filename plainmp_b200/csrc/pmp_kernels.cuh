@@ -674,13 +674,34 @@ __global__ void k_sdf_is_outside(const SceneDev S, const float* __restrict__ pts
   }
 }
 
-__global__ void k_cloud_nearest(const SceneDev S, const float* __restrict__ pts, const long long n,
-                                float* __restrict__ sqd, int* __restrict__ idx) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float3 p = make3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+// KDTree::sqdist / query for a batch: 8 lanes per query (4 queries per warp in flight), see cloud_nn8.
+__global__ void __launch_bounds__(128)
+k_cloud_nearest(const SceneDev S, const float* __restrict__ pts, const long long n, float* __restrict__ sqd,
+                int* __restrict__ idx) {
+  const CloudDev& C = S.cloud;
+  const int lane = threadIdx.x & 31, sub = lane & 7, k = lane >> 3;
+  const unsigned smask = 0xffu << (8 * k);
+  const long long n_sub = (long long)gridDim.x * (blockDim.x / 8);
+  for (long long i = (long long)blockIdx.x * (blockDim.x / 8) + (threadIdx.x >> 3); i < n; i += n_sub) {
+    const float3 p = make3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2));
+    float lo, hi;
+    cloud_bounds(C, p, lo, hi);  // the distance field's upper bound starts the search ...
+    // ... tightened by one greedy descent (n_levels node visits): the field only knows NN to within
+    // the cell diagonal, and on flat geometry a shell that thick holds hundreds of leaf boxes; the
+    // greedy leaf is usually the nearest point itself, which makes the search below a verification
+    float bound2 = cloud_greedy_bound2_8(C, p, smask, sub);
+    if (hi < INFINITY) {
+      const float b = hi * (1.f + 1e-6f) + 1e-6f;
+      bound2 = fminf(bound2, b * b);
+    }
+    // strict search against a bound nudged up by one ulp, so that a point AT the bound is found
+    bound2 = __uint_as_float(__float_as_uint(fminf(fmaxf(bound2, 0.f), 3.0e38f)) + 1u);
     int bi;
-    sqd[i] = cloud_nn_exact(S.cloud, p, &bi);
-    if (idx) idx[i] = bi;
+    const float d2 = cloud_nn8(C, p, bound2, smask, sub, 8 * k, &bi);
+    if (sub == 0) {
+      sqd[i] = d2;
+      if (idx) idx[i] = bi;
+    }
   }
 }
 

@@ -50,7 +50,7 @@ def parse_args():
     p.add_argument("--per-gpu", type=int, default=1 << 24, help="configurations per GPU per step")
     p.add_argument("--workload", default="panda_dual_bars", choices=["panda_dual_bars", "panda_ceiled", "fetch_table"])
     p.add_argument("--extras", type=int, default=1, help="also measure edges/s, fetch and cloud side metrics (N=1)")
-    p.add_argument("--cpu-sample", type=int, default=1 << 22)
+    p.add_argument("--cpu-sample", type=int, default=1 << 24, help="configurations per CPU-baseline pass (about 10 s of CPU work on 16 cores)")
     return p.parse_args()
 
 

@@ -766,3 +766,29 @@ def test_non_finite_and_out_of_range_inputs_follow_the_reference(cuda_lib):
     Q2[::2, 1] = np.nan
     o2 = bridge.OracleCst(cst2)
     assert (cst2.is_valid_batch(Q2) == o2.is_valid_batch(Q2.astype(np.float64))).all()
+
+
+def test_bench_prints_one_contract_line(cuda_lib):
+    """The driver's contract: one JSON line on stdout with value / e2e / roofline / cpu_baseline /
+    clocks / gpu_launches (small batch so that the test stays short)."""
+    import json
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run(
+        [sys.executable, str(root / "bench.py"), "--steps", "2", "--warmup", "3", "--per-gpu", "1048576", "--extras", "0", "--cpu-sample", "20000"],
+        capture_output=True, text=True, check=True, timeout=900,
+    ).stdout.strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["gpu_launches"] == 2 and d["value"] > 1e8
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert d["e2e"]["h2d_bytes_per_step"] == 1048576 * 28 and d["e2e"]["value"] > 1e7
+    assert d["clocks"]["samples"] >= 1 and "workload" in d["config"]

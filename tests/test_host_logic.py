@@ -284,3 +284,25 @@ def test_yaml_conf_loader_matches_imported_tables(tmp_path):
     )
     with pytest.raises(AssertionError):
         rs.load_conf_yaml(tmp_path / "dup.yaml")
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference runs on CPU only (the reference's compiled C++ if oracle/_ref is
+    there, else the restatement) and prints exactly one JSON line with the driver's contract keys."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run(
+        [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "20000"],
+        capture_output=True, text=True, check=True, timeout=600,
+    ).stdout.strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "collision_checked_configs_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]

@@ -499,6 +499,16 @@ def run_b200(args):
                 "executed_frac": (per_gpu_rate * extras["work_model"]["executed_flop_per_config"] / 1e12 / fp32_peak) if extras.get("work_model") else None,
                 "ncu": NCU_PIPE_FIGURES,
             },
+            # the resource that actually binds the kernel: warp-instruction issue slots (4 schedulers per SM,
+            # one warp instruction per cycle each).  achieved = ncu's warp instructions per configuration for
+            # this kernel x the configurations/s measured in this run; peak at the sampled SM clock.
+            "roofline_issue": {
+                "bound": "issue_slots", "unit": "Gwarp-inst/s",
+                "achieved": per_gpu_rate * NCU_PIPE_FIGURES["warp_inst_per_config"] / 1e9,
+                "peak": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                "frac": per_gpu_rate * NCU_PIPE_FIGURES["warp_inst_per_config"] / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
+                "note": "warp_inst_per_config from " + NCU_PIPE_FIGURES["source"] + "; ncu's own smsp__issue_active for the same kernel: %.1f %%" % NCU_PIPE_FIGURES["issue_active_pct"],
+            },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * lb.shape[0] * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 16) * world, "steps": e2e_steps,
                     "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs,
                     "frac_of_h2d_copy": (e2e_value / world) * lb.shape[0] * 4 / 1e9 / h2d_gbs},

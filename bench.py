@@ -561,6 +561,20 @@ def side_metrics(torch, dev, lib, tables, workloads, MotionValidator, ValidatorC
             dt = time_cuda(torch, run)
             c = ctr.cpu().numpy()
             out[f"edges_{tag}"] = {"edges_per_s": n_e / dt, "valid_fraction": float(c[0]) / n_e, "waypoint_checks_per_edge": float(c[1]) / n_e, "waypoint_checks_per_s": float(c[1]) / dt, "n": n_e}
+            # the same edges end to end through the host-buffer entry point (pinned host in, bits out)
+            h0, h1 = torch.from_numpy(q0).pin_memory(), torch.from_numpy(q1).pin_memory()
+            hbits = torch.empty((n_e + 31) // 32, dtype=torch.int32, pin_memory=True)
+            nv, nc = C.c_uint64(0), C.c_uint64(0)
+
+            def run_host():
+                _check(lib, lib.pmp_check_edges_host(robot.handle, scene.handle, C.byref(mv._v), h0.data_ptr(), h1.data_ptr(), n_e, hbits.data_ptr(), C.byref(nv), C.byref(nc)))
+
+            run_host()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                run_host()
+            out[f"edges_{tag}"]["e2e_edges_per_s"] = 3 * n_e / (time.perf_counter() - t0)
+            assert torch.equal(hbits.to(dev), bits), "edge host path and device path disagree"
         spec, cst = workloads.make_fetch()
         robot, scene = cst._robot(), cst._scene()
         n_f = 1 << 22

@@ -892,6 +892,7 @@ struct Workspace {  // grow-only device scratch shared by the *_host calls (seri
   }
 } g_ws;
 constexpr int64_t kHostChunk = 1 << 19;  // items per pipelined chunk (multiple of 32): the tail that cannot overlap is one chunk's kernel
+constexpr int64_t kHostChunkEdges = 1 << 19;  // measured: 128K- and 256K-edge chunks are slower (per-chunk memsets and launches outweigh the better overlap)
 }  // namespace
 
 int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n,
@@ -963,8 +964,8 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, con
   CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
   CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
   int k = 0;
-  for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
-    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+  for (int64_t off = 0; off < n; off += kHostChunkEdges, k ^= 1) {
+    const int64_t m = std::min<int64_t>(kHostChunkEdges, n - off);
     for (int a = 0; a < 2; a++)
       if (int rc = g_ws.reserve(&g_ws.in[k][a], &g_ws.in_cap[k][a], (size_t)m * qd * 4)) return rc;
     if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;

@@ -792,3 +792,16 @@ def test_bench_prints_one_contract_line(cuda_lib):
         assert k in d["cpu_baseline"], k
     assert d["e2e"]["h2d_bytes_per_step"] == 1048576 * 28 and d["e2e"]["value"] > 1e7
     assert d["clocks"]["samples"] >= 1 and "workload" in d["config"]
+
+
+def test_robot_without_any_sphere_group(cuda_lib):
+    """No sphere specs at all: is_valid is vacuously true, evaluate reports the cutoff for the enabled
+    environment term and nothing for self-collision — same as the reference's loops over nothing."""
+    spec = PandaSpec()
+    cst = SphereCollisionCst(spec.get_kin(), spec.control_joint_names, BaseType.FIXED, [], [], None, True)
+    cst.set_sdf(workloads.panda_dual_bars_sdf())
+    Q = workloads.random_configs(spec, 257, 5)
+    o = bridge.OracleCst(cst)
+    assert cst.is_valid_batch(Q).all() and o.is_valid_batch(Q.astype(np.float64)).all()
+    np.testing.assert_allclose(cst.evaluate_batch(Q), o.evaluate_batch(Q.astype(np.float64)), atol=TOL, equal_nan=True)
+    assert cst.is_valid(Q[0]) is True

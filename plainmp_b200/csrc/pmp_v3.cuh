@@ -361,25 +361,27 @@ __device__ __forceinline__ unsigned v3_cull_mask(const SceneDev& S, const Smem& 
   return pm;
 }
 
-// Push one queue item per set bit of this lane's cull mask for group gi.  Returns false (without
-// pushing the rest) when the items of the next round do not fit: the caller drains and calls again
-// with the same mask (items already queued are then only re-tested).
+// Push one queue item per set bit of this lane's cull mask `pm` for group gi, consuming the bits as
+// they are queued.  Returns false when the items of the next round do not fit; `pm` then holds what
+// is still to be queued.  The caller drains and either restarts the group from its full mask (items
+// queued before are then only re-tested) or, for a group that cannot fit even into an empty queue,
+// calls again with the remaining bits.
 template <int B>
-__device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, const unsigned pm) {
+__device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, unsigned& pm) {
   constexpr unsigned full = 0xffffffffu;
-  unsigned rem = (X.active && !((X.bad >> X.lane) & 1u)) ? pm : 0u;
-  unsigned ball = __ballot_sync(full, rem != 0u);
+  if (!(X.active && !((X.bad >> X.lane) & 1u))) pm = 0u;
+  unsigned ball = __ballot_sync(full, pm != 0u);
   while (ball) {
     const int cnt = __popc(ball);
     if (X.n_env + cnt > kQE) return false;
-    if (rem) {
-      const unsigned b = __ffs(rem) - 1;
-      rem &= rem - 1u;
+    if (pm) {
+      const unsigned b = __ffs(pm) - 1;
+      pm &= pm - 1u;
       const unsigned kp = (b < 30u) ? b : (b == 30u ? kItemCloud : kItemOverflow);
       X.qenv[X.n_env + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)gi << 5) | (kp << 16);
     }
     X.n_env += cnt;
-    ball = __ballot_sync(full, rem != 0u);
+    ball = __ballot_sync(full, pm != 0u);
   }
   return true;
 }
@@ -412,6 +414,9 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
   const bool ext = (S.n_prims > 0) || CLOUD;
   const Frame base = base_frame(R, q);
   bool far = false;
+  unsigned pm = 0u;     // cull mask of the group being queued (what is left of it when resuming)
+  int stall_gi = -1;    // group at which the queue last overflowed (warp-uniform)
+  bool resume = false;  // warp-uniform: the group stalled twice in a row, keep pm across the drain
   Frame cur = base;
   int i = 0, gi = 0;
   bool ready = false;
@@ -433,15 +438,23 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
       while (gi < R.n_groups) {
         const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
         if (gw.x != i) break;
-        const float4 g = T.groups[2 * gi];
-        const float3 gc = place(cur, g.x, g.y, g.z);
-        far |= v3_store_gc<B, GC16>(X, base, gi, gc);
-        if (ext && !(gw.w & 1)) {
-          if (!v3_push_env(X, gi, v3_cull_mask<CLOUD>(S, T, gc, g.w))) {
-            stalled = true;
-            break;
-          }
+        if (!resume) {
+          const float4 g = T.groups[2 * gi];
+          const float3 gc = place(cur, g.x, g.y, g.z);
+          far |= v3_store_gc<B, GC16>(X, base, gi, gc);
+          pm = (ext && !(gw.w & 1)) ? v3_cull_mask<CLOUD>(S, T, gc, g.w) : 0u;
         }
+        if (!v3_push_env(X, gi, pm)) {
+          // After the drain the group is normally restarted from its full mask.  A group that yields
+          // more items than the whole queue holds (e.g. 5+ primitives passing the cull on all 32
+          // lanes) would stall again in exactly the same place for ever if no lane died in between:
+          // from its second consecutive stall on, continue with the bits that are still to be queued.
+          resume = (stall_gi == gi);
+          stall_gi = gi;
+          stalled = true;
+          break;
+        }
+        resume = false;
         gi++;
       }
       if (stalled) break;

@@ -805,3 +805,60 @@ def test_robot_without_any_sphere_group(cuda_lib):
     assert cst.is_valid_batch(Q).all() and o.is_valid_batch(Q.astype(np.float64)).all()
     np.testing.assert_allclose(cst.evaluate_batch(Q), o.evaluate_batch(Q.astype(np.float64)), atol=TOL, equal_nan=True)
     assert cst.is_valid(Q[0]) is True
+
+
+def test_group_larger_than_the_queue_does_not_livelock(cuda_lib):
+    """Found by the 600-seed fuzz hunt (seed 40289): one sphere group whose cull mask passes 5+
+    primitives on all 32 lanes yields more items than the 128-entry warp queue holds; restarting the
+    group after every drain then stalls in the same place for ever unless a lane dies.  The kernel now
+    resumes such a group with the bits that are still to be queued.  The case runs in a child process
+    with a timeout so that a regression shows up as a failure of this test, not as a hung suite."""
+    import subprocess
+    import sys
+    import textwrap
+
+    root = Path(__file__).resolve().parent.parent
+    code = textwrap.dedent(
+        f"""
+        import sys
+        sys.path.insert(0, {str(root)!r}); sys.path.insert(0, {str(root / 'tests')!r})
+        import numpy as np
+        from oracle import bridge
+        from fuzz_util import random_case, sample_q
+        from plainmp_b200 import psdf, workloads
+        from plainmp_b200.constraint import SphereAttachmentSpec, SphereCollisionCst
+        from plainmp_b200.kinematics import BaseType
+        from plainmp_b200.robot_spec import PandaSpec
+        worst = 0
+        for seed in (40289, 40288, 40290):
+            cst, lb, ub, desc = random_case(seed)
+            Q = sample_q(lb, ub, 3000, seed)
+            o = bridge.OracleCst(cst, n_threads=4)
+            got, want, m = cst.is_valid_batch(Q), o.is_valid_batch(Q.astype(np.float64)), o.margin_batch(Q.astype(np.float64))
+            assert all(m[i] < 1e-5 for i in np.where(got != want)[0]), desc
+        # and a constructed worst case: a static group at the origin inside the AABBs of 8 thin plates
+        # that stand diagonally around it (surfaces 0.7 - 0.9 m away): 8 items x 32 lanes = 256 > 128,
+        # every lane stays alive
+        spec = PandaSpec()
+        one = SphereAttachmentSpec("panda_link0", np.zeros((3, 4)) + np.array([[0.0], [0.0], [0.3]]), np.full(4, 0.01), False)
+        cst = SphereCollisionCst(spec.get_kin(), spec.control_joint_names, BaseType.FIXED, [one], [], None, True)
+        shells, big, rot = [], [], []
+        for r in (1.0, 1.3):
+            for k in range(4):
+                phi = 0.5 * np.pi * k
+                plate = psdf.BoxSDF([0.05, 4.0, 4.0], psdf.Pose([r * np.cos(phi), r * np.sin(phi), 0.3]))
+                plate.rotate_z(phi + 0.25 * np.pi)
+                rot.append(plate)
+        cst.set_sdf(psdf.UnionSDF(shells + big + rot))
+        Q = workloads.random_configs(spec, 4096, 3)
+        o = bridge.OracleCst(cst, n_threads=4)
+        got, want = cst.is_valid_batch(Q), o.is_valid_batch(Q.astype(np.float64))
+        assert (got == want).all() and want.mean() > 0.9, want.mean()
+        print("OK")
+        """
+    )
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    except subprocess.TimeoutExpired:
+        pytest.fail("the validity kernel did not return within 240 s: queue-overflow livelock")
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]

@@ -306,3 +306,69 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_queue_overflow_protocol_lane_level_model():
+    """A lane-level model of phase 1's env-queue protocol (csrc/pmp_v3.cuh: v3_push_env +
+    warp_check_interp): 32 lanes, a 128-entry queue, drain on overflow.  Restarting an overflowing group
+    from its full mask after every drain (the original handling) livelocks when one group alone yields
+    more than 128 items and no lane dies; resuming with the remaining bits from the second
+    consecutive stall on terminates and drains every (lane, group, primitive) item."""
+    import random
+
+    KQE = 128
+
+    def simulate(masks, resume_enabled, die_prob=0.0, max_iters=2000, seed=0):
+        rng = random.Random(seed)
+        bad, drained, queue = [False] * 32, set(), []
+        pm, gi, resume, stall_gi, iters = [0] * 32, 0, False, -1, 0
+
+        def push(g):
+            for lane in range(32):
+                if bad[lane]:
+                    pm[lane] = 0
+            while any(pm):
+                cnt = sum(1 for lane in range(32) if pm[lane])
+                if len(queue) + cnt > KQE:
+                    return False
+                for lane in range(32):
+                    if pm[lane]:
+                        b = (pm[lane] & -pm[lane]).bit_length() - 1
+                        pm[lane] &= pm[lane] - 1
+                        queue.append((lane, g, b))
+            return True
+
+        while True:
+            iters += 1
+            if iters > max_iters:
+                return False, drained
+            stalled = False
+            while gi < len(masks):
+                if not (resume_enabled and resume):
+                    pm[:] = masks[gi]
+                if not push(gi):
+                    resume, stall_gi, stalled = (stall_gi == gi), gi, True
+                    break
+                resume = False
+                gi += 1
+            for it in queue:
+                if not bad[it[0]]:
+                    drained.add(it)
+                    if rng.random() < die_prob:
+                        bad[it[0]] = True
+            queue.clear()
+            if not stalled:
+                return True, drained
+
+    worst = [[0x7F] * 32]  # 7 primitives pass on every lane: 224 items from one group
+    assert simulate(worst, resume_enabled=False)[0] is False  # the livelock
+    ok, drained = simulate(worst, resume_enabled=True)
+    assert ok and len(drained) == 224
+    rng = random.Random(1)
+    for trial in range(300):
+        masks = [[rng.getrandbits(rng.choice([3, 7, 12, 31])) if rng.random() < rng.choice([0.2, 0.9, 1.0]) else 0 for _ in range(32)]
+                 for _ in range(rng.randint(1, 12))]
+        ok, drained = simulate(masks, True)
+        want = {(lane, g, b) for g, row in enumerate(masks) for lane in range(32) for b in range(32) if (row[lane] >> b) & 1}
+        assert ok and drained == want
+        assert simulate(masks, True, die_prob=0.02, seed=trial)[0]

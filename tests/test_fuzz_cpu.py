@@ -47,3 +47,23 @@ def test_oracle_equals_reference_on_big_random_robot(seed):
     Q = sample_q(lb, ub, 200, seed).astype(np.float64)
     assert (o.is_valid_batch(Q) == r.is_valid_batch(Q)).all(), desc
     np.testing.assert_allclose(o.evaluate_batch(Q[:60]), r.evaluate_batch(Q[:60]), atol=1e-12, rtol=0, err_msg=desc)
+
+
+@pytest.mark.parametrize("seed", range(6000, 6020))
+def test_validators_oracle_equals_reference_on_random_robot(seed):
+    """Both motion validators on random robots: edge validity AND the number of is_valid calls (the
+    waypoint order with its early exit) of the restatement equal the compiled reference's."""
+    ref_bridge.build()
+    cst, lb, ub, desc = random_case(seed)
+    dim = len(lb)
+    if dim == 0:
+        pytest.skip("no degrees of freedom")
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    rng = np.random.default_rng(seed)
+    widths = rng.uniform(0.02, 0.3, dim)
+    q0 = sample_q(lb, ub, 300, seed + 1).astype(np.float64)
+    q1 = np.clip(q0 + rng.uniform(-0.8, 0.8, q0.shape) * rng.choice([0.05, 1.0, 3.0]), lb, ub)
+    for vtype, res in ((0, 0.0), (1, float(rng.uniform(0.02, 0.3)))):
+        want, n_ref = r.check_motion_batch(vtype, widths, res, q0, q1)
+        got, n_orc = bridge.OracleValidator(vtype, dim, widths, res).check_motion_batch(o, q0, q1)
+        assert (got == want).all() and n_orc == n_ref, desc

@@ -372,3 +372,19 @@ def test_queue_overflow_protocol_lane_level_model():
         want = {(lane, g, b) for g, row in enumerate(masks) for lane in range(32) for b in range(32) if (row[lane] >> b) & 1}
         assert ok and drained == want
         assert simulate(masks, True, die_prob=0.02, seed=trial)[0]
+
+
+def test_ompl_adaptor_header_compiles_against_the_ompl_stand_in(tmp_path):
+    """include/plainmp_b200_ompl.hpp + the test probe compile with g++ against oracle/ref_shim's
+    ompl::base stand-in and link against the C-ABI library (no GPU needed to compile / load)."""
+    import subprocess
+
+    so = tmp_path / "libprobe.so"
+    subprocess.run(
+        ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", f"-I{ROOT / 'include'}", f"-I{ROOT / 'oracle' / 'ref_shim'}",
+         "-o", str(so), str(ROOT / "tests" / "cpp" / "ompl_adaptor_probe.cpp"),
+         f"-L{ROOT / 'plainmp_b200'}", "-lplainmp_b200", f"-Wl,-rpath,{ROOT / 'plainmp_b200'}"],
+        check=True,
+    )
+    _capi.load()
+    assert C.CDLL(str(so)).probe_validators is not None

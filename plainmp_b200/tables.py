@@ -128,35 +128,18 @@ class RobotTable:
         pairs: Sequence[Tuple[int, int]],
         extra_links: Sequence[int] = (),
     ):
-        self.program = LinkProgram(kin, control_joint_ids, list(group_links) + list(extra_links))
-        n_groups = len(group_links)
-        groups = np.zeros(n_groups, dtype=_capi.GROUP_DTYPE)
-        flat: List[np.ndarray] = []
-        begin = 0
-        for g in range(n_groups):
-            sp = np.asarray(group_spheres[g], dtype=np.float64).reshape(-1, 4)
-            centre, radius = group_bounding_sphere(sp)
-            groups[g]["center"] = centre
-            groups[g]["radius"] = radius
-            groups[g]["op"] = self.program.op_of_link[group_links[g]]
-            groups[g]["sphere_begin"] = begin
-            groups[g]["sphere_count"] = sp.shape[0]
-            groups[g]["only_self_collision"] = 1 if group_only_self[g] else 0
-            begin += sp.shape[0]
-            flat.append(sp)
-        self.groups = groups
-        self.spheres = (
-            np.ascontiguousarray(np.concatenate(flat, axis=0), dtype=np.float32)
-            if flat
-            else np.zeros((0, 4), dtype=np.float32)
-        )
-        self.pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
-        self.dof = len(control_joint_ids)
-        self.base_type = BaseType(base_type)
-        self.q_dim = self.dof + (3 if base_type == BaseType.PLANAR else 0) + (6 if base_type == BaseType.FLOATING else 0)
+        arrays = RobotTable.build_arrays(kin, control_joint_ids, base_type, group_links, group_spheres, group_only_self, pairs, extra_links)
+        self.program = arrays["program"]
+        self.groups = arrays["groups"]
+        self.spheres = arrays["spheres"]
+        self.pairs = arrays["pairs"]
+        self.dof = arrays["dof"]
+        self.base_type = arrays["base_type"]
+        self.q_dim = arrays["q_dim"]
         self.n_spheres = int(self.spheres.shape[0])
         self.n_ops = int(self.program.ops.shape[0])
-        self.base_pose = np.asarray(kin.get_base_pose(), dtype=np.float32)
+        self.base_pose = arrays["base_pose"]
+        n_groups = len(group_links)
 
         lib = _capi.load()
         desc = _capi.RobotDesc()
@@ -177,6 +160,42 @@ class RobotTable:
         _capi.check(lib.pmp_robot_create(C.byref(desc), C.byref(h)))
         self._h = h
         self._lib = lib
+
+    @staticmethod
+    def build_arrays(kin, control_joint_ids, base_type, group_links, group_spheres, group_only_self, pairs, extra_links=()):
+        """The C-ABI tables of a robot as numpy arrays (no device needed): link program, groups with
+        their bounding spheres, spheres, pairs."""
+        program = LinkProgram(kin, control_joint_ids, list(group_links) + list(extra_links))
+        n_groups = len(group_links)
+        groups = np.zeros(n_groups, dtype=_capi.GROUP_DTYPE)
+        flat: List[np.ndarray] = []
+        begin = 0
+        for g in range(n_groups):
+            sp = np.asarray(group_spheres[g], dtype=np.float64).reshape(-1, 4)
+            centre, radius = group_bounding_sphere(sp)
+            groups[g]["center"] = centre
+            groups[g]["radius"] = radius
+            groups[g]["op"] = program.op_of_link[group_links[g]]
+            groups[g]["sphere_begin"] = begin
+            groups[g]["sphere_count"] = sp.shape[0]
+            groups[g]["only_self_collision"] = 1 if group_only_self[g] else 0
+            begin += sp.shape[0]
+            flat.append(sp)
+        spheres = (
+            np.ascontiguousarray(np.concatenate(flat, axis=0), dtype=np.float32) if flat else np.zeros((0, 4), dtype=np.float32)
+        )
+        dof = len(control_joint_ids)
+        bt = BaseType(base_type)
+        return {
+            "program": program,
+            "groups": groups,
+            "spheres": spheres,
+            "pairs": np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2)),
+            "dof": dof,
+            "base_type": bt,
+            "q_dim": dof + (3 if bt == BaseType.PLANAR else 0) + (6 if bt == BaseType.FLOATING else 0),
+            "base_pose": np.asarray(kin.get_base_pose(), dtype=np.float32),
+        }
 
     @property
     def handle(self) -> C.c_void_p:

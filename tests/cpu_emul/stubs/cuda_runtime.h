@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE: see ../cuda_emul.h
+#pragma once
+#include "cuda_emul.h"

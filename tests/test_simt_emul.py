@@ -1,0 +1,223 @@
+"""The kernel sources of plainmp_b200/csrc/ compiled UNCHANGED for a SIMT emulator (tests/cpu_emul/:
+one OS thread per CUDA thread, warp collectives as rendezvous) and run on the CPU against the FP64
+oracle.  Test infrastructure only: the product never loads this library and still refuses to compute
+without a CUDA device (test_no_cpu_fallback_without_device).  What it buys: the kernels' control flow
+— warp-local queues and their overflow handling, sub-warp drains, dynamic edge refill, the session's
+flat waypoint kernel — is exercised in the CPU tier, a few hundred items at a time; in particular the
+queue-overflow livelock found by fuzzing on the GPU is reproduced and its fix verified here.
+FP32 results differ from the GPU's in the last bits (no FMA contraction on the host), which the
+1e-5 contact band absorbs."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import bridge
+from plainmp_b200 import _capi, psdf, tables, workloads
+from plainmp_b200.constraint import SphereAttachmentSpec, SphereCollisionCst
+from plainmp_b200.kinematics import BaseType
+from plainmp_b200.robot_spec import PandaSpec
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from cpu_emul import build as emul_build  # noqa: E402
+from fuzz_util import random_case, sample_q  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = C.CDLL(str(emul_build.build()))
+    for name, (res, args) in _capi.SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+class EmuTables:
+    """pmp_robot_t / pmp_scene_t of the EMULATED library for a host-mirror constraint."""
+
+    def __init__(self, lib, cst):
+        self.lib = lib
+        a = tables.RobotTable.build_arrays(
+            cst.get_kin(), cst._control_joint_ids, cst._base_type, cst._group_links, cst._group_spheres, cst._group_only_self, cst._pairs
+        )
+        self._keep = a
+        d = _capi.RobotDesc()
+        d.dof, d.base_type = a["dof"], int(a["base_type"])
+        for i in range(7):
+            d.base_pose[i] = float(a["base_pose"][i])
+        ops = a["program"].ops
+        d.n_ops, d.ops = len(ops), ops.ctypes.data
+        d.n_groups, d.groups = len(a["groups"]), a["groups"].ctypes.data
+        d.n_spheres, d.spheres = len(a["spheres"]), a["spheres"].ctypes.data
+        d.n_pairs, d.pairs = len(a["pairs"]), a["pairs"].ctypes.data
+        self.q_dim = a["q_dim"]
+        self.robot = C.c_void_p()
+        assert lib.pmp_robot_create(C.byref(d), C.byref(self.robot)) == 0, lib.pmp_last_error()
+        self.scene = None
+        leaves = cst._leaves()
+        if leaves:
+            prims, cloud = tables.flatten_primitives(leaves)
+            assert cloud is None, "no clouds in the emulation"
+            self._prims = prims
+            sd = _capi.SceneDesc()
+            sd.n_prims, sd.prims = len(prims), prims.ctypes.data
+            self.scene = C.c_void_p()
+            assert lib.pmp_scene_create(C.byref(sd), C.byref(self.scene)) == 0, lib.pmp_last_error()
+
+    def check(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        n = Q.shape[0]
+        bits = np.zeros((n + 31) // 32, dtype=np.uint32)
+        cnt = C.c_uint64(0)
+        rc = self.lib.pmp_check_configs_host(self.robot, self.scene, Q.ctypes.data, n, bits.ctypes.data, C.byref(cnt))
+        assert rc == 0, self.lib.pmp_last_error()
+        v = tables.unpack_bits(bits, n)
+        assert int(cnt.value) == int(v.sum())
+        return v
+
+    def evaluate(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        out = np.zeros((Q.shape[0], 2), dtype=np.float32)
+        assert self.lib.pmp_eval_configs_host(self.robot, self.scene, Q.ctypes.data, Q.shape[0], out.ctypes.data) == 0
+        return out.astype(np.float64)
+
+    def check_edges(self, vtype, widths, res, q0, q1):
+        q0, q1 = np.ascontiguousarray(q0, dtype=np.float32), np.ascontiguousarray(q1, dtype=np.float32)
+        v, keep = tables.make_validator(vtype, q0.shape[1], widths if vtype == 0 else None, res)
+        n = q0.shape[0]
+        bits = np.zeros((n + 31) // 32, dtype=np.uint32)
+        nv, nc = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.pmp_check_edges_host(self.robot, self.scene, C.byref(v), q0.ctypes.data, q1.ctypes.data, n, bits.ctypes.data, C.byref(nv), C.byref(nc))
+        assert rc == 0, self.lib.pmp_last_error()
+        return tables.unpack_bits(bits, n), int(nc.value)
+
+    def __del__(self):
+        if getattr(self, "scene", None):
+            self.lib.pmp_scene_destroy(self.scene)
+        if getattr(self, "robot", None):
+            self.lib.pmp_robot_destroy(self.robot)
+
+
+def _parity(got, want, margin, what):
+    bad = [int(i) for i in np.where(got != want)[0] if margin[i] > 1e-5]
+    assert not bad, f"{what}: validity mismatches outside the band at {bad[:5]}"
+
+
+@pytest.mark.parametrize("maker", ["panda", "panda_ceiled", "fetch"])
+def test_emulated_validity_and_distances_match_oracle(emu, maker):
+    spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch}[maker]()
+    t = EmuTables(emu, cst)
+    Q = workloads.random_configs(spec, 300, 11)  # two full tiles + a ragged one
+    o = bridge.OracleCst(cst)
+    Qd = Q.astype(np.float64)
+    want = o.is_valid_batch(Qd)
+    _parity(t.check(Q), want, o.margin_batch(Qd), maker)
+    assert 0.1 < want.mean() < 0.9
+    np.testing.assert_allclose(t.evaluate(Q[:128]), o.evaluate_batch(Qd[:128]), atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_group_larger_than_the_queue_terminates_in_the_emulation(emu, monkeypatch, mode):
+    """The livelock of DESIGN section 8: a group inside the AABBs of 8 plates (8 x 32 = 256 items > the
+    128-entry queue) with every lane alive.  Before the resume fix this never returned."""
+    monkeypatch.setenv("PMP_V3_MODE", mode)
+    spec = PandaSpec()
+    one = SphereAttachmentSpec("panda_link0", np.zeros((3, 4)) + np.array([[0.0], [0.0], [0.3]]), np.full(4, 0.01), False)
+    arm = SphereAttachmentSpec("panda_link5", np.array([[0.0, 0.0], [0.0, 0.05], [-0.1, 0.0]]), np.array([0.06, 0.05]), False)
+    cst = SphereCollisionCst(spec.get_kin(), spec.control_joint_names, BaseType.FIXED, [one, arm], [("panda_link0", "panda_link5")], None, True)
+    plates = []
+    for r in (1.0, 1.3):
+        for k in range(4):
+            phi = 0.5 * np.pi * k
+            plate = psdf.BoxSDF([0.05, 4.0, 4.0], psdf.Pose([r * np.cos(phi), r * np.sin(phi), 0.3]))
+            plate.rotate_z(phi + 0.25 * np.pi)
+            plates.append(plate)
+    cst.set_sdf(psdf.UnionSDF(plates))
+    t = EmuTables(emu, cst)
+    Q = workloads.random_configs(spec, 96, 3)
+    o = bridge.OracleCst(cst)
+    want = o.is_valid_batch(Q.astype(np.float64))
+    _parity(t.check(Q), want, o.margin_batch(Q.astype(np.float64)), "8 plates")
+    assert want.mean() > 0.5
+
+
+import os  # noqa: E402
+
+_s, _c = (int(x) for x in os.environ.get("PMP_FUZZ_SEEDS", "1000:40").split(":"))
+
+
+@pytest.mark.parametrize("seed", [40289] + list(range(_s, _s + _c)))
+def test_emulated_random_robots(emu, seed):
+    """The suite's fuzz seeds (among them 1003 / 1012 / 1018, which exposed evaluate on folded prismatic
+    joints on the GPU) and 40289 (the queue livelock), replayed on the emulated kernels; clouds are
+    dropped from the scenes (their index is built with cub on the device)."""
+    cst, lb, ub, desc = random_case(seed)
+    if any(leaf.get_type() == psdf.T_CLOUD for leaf in cst._leaves()):
+        cst.set_sdf(psdf.UnionSDF([leaf for leaf in cst.get_sdf()._leaves() if leaf.get_type() != psdf.T_CLOUD] or [psdf.GroundSDF(2.0)]))
+    t = EmuTables(emu, cst)
+    Q = sample_q(lb, ub, 160, seed)
+    o = bridge.OracleCst(cst)
+    Qd = Q.astype(np.float64)
+    _parity(t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), desc)
+    np.testing.assert_allclose(t.evaluate(Q[:64]), o.evaluate_batch(Qd[:64]), atol=2e-5, rtol=0, equal_nan=True, err_msg=desc)
+
+
+def test_emulated_edges_follow_the_reference_order(emu):
+    """The lane = edge kernel with dynamic refill: validity and the NUMBER of waypoint checks equal the
+    oracle's (which equals the compiled reference's), i.e. the visiting order with its early exit."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    widths = np.full(7, 0.05)
+    q0, q1 = workloads.random_edges(spec, 80, 3, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    got, n_checks = t.check_edges(0, widths, 0.0, q0, q1)
+    want, n_orc = bridge.OracleValidator(0, 7, widths).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64))
+    assert (got != want).sum() <= 1
+    if (got == want).all():
+        assert abs(n_checks - n_orc) <= 2  # FP32 step ratio may move n_test by one on an edge at a boundary
+
+
+def test_emulated_session_flat_and_early_exit_paths(emu):
+    """pmp_session_*: FP64 states in, bytes out; the waypoint-parallel flat kernel (zero-copy and staged)
+    and the early-exit kernel behind one entry point."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    widths = np.full(7, 0.05)
+    v, keep = tables.make_validator(0, 7, widths, 0.0)
+    ses = C.c_void_p()
+    assert emu.pmp_session_create(t.robot, t.scene, C.byref(v), 64, C.byref(ses)) == 0, emu.pmp_last_error()
+    q0, q1 = workloads.random_edges(spec, 40, 5, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    q0, q1 = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+    out = np.zeros(40, dtype=np.uint8)
+    nc = C.c_uint64(0)
+    assert emu.pmp_session_check_motion(ses, q0.ctypes.data, q1.ctypes.data, 40, out.ctypes.data, C.byref(nc)) == 0
+    want, _ = bridge.OracleValidator(0, 7, widths).check_motion_batch(o, q0, q1)
+    assert (out.astype(bool) != want).sum() <= 1
+    one = np.zeros(1, dtype=np.uint8)
+    for i in range(5):  # single edges: the zero-copy path
+        assert emu.pmp_session_check_motion(ses, q0[i].ctypes.data, q1[i].ctypes.data, 1, one.ctypes.data, None) == 0
+        assert bool(one[0]) == bool(out[i])
+    st = np.zeros(40, dtype=np.uint8)
+    assert emu.pmp_session_is_valid(ses, q1.ctypes.data, 40, st.ctypes.data) == 0
+    Qd = q1
+    bad = np.where(st.astype(bool) != o.is_valid_batch(Qd))[0]
+    assert all(o.margin_batch(Qd)[i] < 1e-5 for i in bad)
+    emu.pmp_session_destroy(ses)
+
+
+@pytest.mark.parametrize("base_type", [BaseType.PLANAR, BaseType.FLOATING])
+def test_emulated_moving_base(emu, base_type):
+    from plainmp_b200.robot_spec import PR2RarmSpec
+
+    spec = PR2RarmSpec(base_type=base_type)
+    cst = spec.create_collision_const(self_collision=True, use_cache=False)
+    cst.set_sdf(psdf.BoxSDF([1, 1, 1], psdf.Pose([0.5, 0.5, 0.5])))
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(2)
+    Q = (rng.standard_normal((128, o.q_dim)) * 0.4).astype(np.float32)
+    Qd = Q.astype(np.float64)
+    _parity(t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), str(base_type))

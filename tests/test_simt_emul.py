@@ -221,3 +221,19 @@ def test_emulated_moving_base(emu, base_type):
     Q = (rng.standard_normal((128, o.q_dim)) * 0.4).astype(np.float32)
     Qd = Q.astype(np.float64)
     _parity(t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), str(base_type))
+
+
+@pytest.mark.parametrize("seed", list(range(3000, 3000 + max(6, _c // 8))))
+def test_emulated_big_random_robots(emu, seed):
+    """20-45 links, up to 35 groups, 28-44 primitives (the > 30-primitive overflow item, frequent queue
+    overflows, 64-thread CTAs) on the emulated kernels."""
+    cst, lb, ub, desc = random_case(seed, big=True)
+    if any(leaf.get_type() == psdf.T_CLOUD for leaf in cst._leaves()):
+        cst.set_sdf(psdf.UnionSDF([leaf for leaf in cst.get_sdf()._leaves() if leaf.get_type() != psdf.T_CLOUD]))
+    t = EmuTables(emu, cst)
+    Q = sample_q(lb, ub, 96, seed)
+    o = bridge.OracleCst(cst)
+    Qd = Q.astype(np.float64)
+    got, want, m = t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd)
+    bad = [int(i) for i in np.where(got != want)[0] if m[i] > 2e-5]
+    assert not bad, desc

@@ -24,8 +24,8 @@ def _rewrite(text: str) -> str:
 
 
 def build(force: bool = False) -> Path:
-    srcs = [p for p in sorted(CSRC.glob("*.cu*")) if p.name != "pmp_cloud_build.cu"] + [CSRC / "pmp_cloud_build.h"]
-    deps = srcs + [HERE / "cuda_emul.h", HERE / "emul_extra.cpp", Path(__file__)]
+    srcs = sorted(CSRC.glob("*.cu*")) + [CSRC / "pmp_cloud_build.h"]
+    deps = srcs + [HERE / "cuda_emul.h", HERE / "emul_extra.cpp", HERE / "stubs" / "cub" / "device" / "device_radix_sort.cuh", Path(__file__)]
     if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return LIB
     OUT.mkdir(exist_ok=True)
@@ -35,7 +35,7 @@ def build(force: bool = False) -> Path:
     cmd = [
         "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-w", "-ffp-contract=off",
         f"-I{HERE}", f"-I{HERE / 'stubs'}", f"-I{OUT}",
-        "-o", str(LIB), str(OUT / "plainmp_b200.cpp"), str(HERE / "emul_extra.cpp"),
+        "-o", str(LIB), str(OUT / "plainmp_b200.cpp"), str(OUT / "pmp_cloud_build.cpp"), str(HERE / "emul_extra.cpp"),
     ]
     subprocess.run(cmd, check=True)
     return LIB

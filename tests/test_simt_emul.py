@@ -59,10 +59,13 @@ class EmuTables:
         leaves = cst._leaves()
         if leaves:
             prims, cloud = tables.flatten_primitives(leaves)
-            assert cloud is None, "no clouds in the emulation"
             self._prims = prims
             sd = _capi.SceneDesc()
-            sd.n_prims, sd.prims = len(prims), prims.ctypes.data
+            sd.n_prims, sd.prims = len(prims), (prims.ctypes.data if len(prims) else None)
+            if cloud is not None:
+                self._cloud = np.ascontiguousarray(cloud.points, dtype=np.float32)
+                sd.n_cloud_points, sd.cloud_points = len(self._cloud), self._cloud.ctypes.data
+                sd.cloud_radius, sd.cloud_cell = cloud.radius, 0.02  # coarse field: fewer cells to fill in emulation
             self.scene = C.c_void_p()
             assert lib.pmp_scene_create(C.byref(sd), C.byref(self.scene)) == 0, lib.pmp_last_error()
 
@@ -151,11 +154,9 @@ _s, _c = (int(x) for x in os.environ.get("PMP_FUZZ_SEEDS", "1000:40").split(":")
 @pytest.mark.parametrize("seed", [40289] + list(range(_s, _s + _c)))
 def test_emulated_random_robots(emu, seed):
     """The suite's fuzz seeds (among them 1003 / 1012 / 1018, which exposed evaluate on folded prismatic
-    joints on the GPU) and 40289 (the queue livelock), replayed on the emulated kernels; clouds are
-    dropped from the scenes (their index is built with cub on the device)."""
+    joints on the GPU) and 40289 (the queue livelock), replayed on the emulated kernels, clouds included
+    (the index build runs in the emulation too, with a host stand-in for the one CUB sort)."""
     cst, lb, ub, desc = random_case(seed)
-    if any(leaf.get_type() == psdf.T_CLOUD for leaf in cst._leaves()):
-        cst.set_sdf(psdf.UnionSDF([leaf for leaf in cst.get_sdf()._leaves() if leaf.get_type() != psdf.T_CLOUD] or [psdf.GroundSDF(2.0)]))
     t = EmuTables(emu, cst)
     Q = sample_q(lb, ub, 160, seed)
     o = bridge.OracleCst(cst)
@@ -228,8 +229,6 @@ def test_emulated_big_random_robots(emu, seed):
     """20-45 links, up to 35 groups, 28-44 primitives (the > 30-primitive overflow item, frequent queue
     overflows, 64-thread CTAs) on the emulated kernels."""
     cst, lb, ub, desc = random_case(seed, big=True)
-    if any(leaf.get_type() == psdf.T_CLOUD for leaf in cst._leaves()):
-        cst.set_sdf(psdf.UnionSDF([leaf for leaf in cst.get_sdf()._leaves() if leaf.get_type() != psdf.T_CLOUD]))
     t = EmuTables(emu, cst)
     Q = sample_q(lb, ub, 96, seed)
     o = bridge.OracleCst(cst)
@@ -237,3 +236,26 @@ def test_emulated_big_random_robots(emu, seed):
     got, want, m = t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd)
     bad = [int(i) for i in np.where(got != want)[0] if m[i] > 2e-5]
     assert not bad, desc
+
+
+def test_emulated_cloud_scene_and_nearest_queries(emu):
+    """PR2 dual arm against a 3 000-point table cloud: the cooperative 8-lane tree traversal of the
+    narrow phase, the distance field, and the 8-lane nearest-point kernel."""
+    spec, cst = workloads.make_pr2_cloud(3000)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, 96, 4)
+    Qd = Q.astype(np.float64)
+    want = o.is_valid_batch(Qd)
+    _parity(t.check(Q), want, o.margin_batch(Qd), "pr2 cloud")
+    assert 0.05 < want.mean() < 0.95
+    np.testing.assert_allclose(t.evaluate(Q[:32]), o.evaluate_batch(Qd[:32]), atol=1e-5, rtol=0)
+    pts = cst.get_sdf().points
+    rng = np.random.default_rng(1)
+    P = (pts.mean(axis=0) + rng.uniform(-1.2, 1.2, (200, 3))).astype(np.float32)
+    sq = np.zeros(200, dtype=np.float32)
+    idx = np.zeros(200, dtype=np.int32)
+    assert emu.pmp_cloud_nearest(t.scene, P.ctypes.data, 200, sq.ctypes.data, idx.ctypes.data, None) == 0
+    brute = ((P[:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(sq, brute.min(1), atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(brute[np.arange(200), idx], brute.min(1), atol=2e-5, rtol=1e-5)

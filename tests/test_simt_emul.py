@@ -259,3 +259,34 @@ def test_emulated_cloud_scene_and_nearest_queries(emu):
     brute = ((P[:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(-1)
     np.testing.assert_allclose(sq, brute.min(1), atol=2e-5, rtol=1e-5)
     np.testing.assert_allclose(brute[np.arange(200), idx], brute.min(1), atol=2e-5, rtol=1e-5)
+
+
+def test_emulated_far_group_centres_fp16_layout(emu, monkeypatch):
+    """MODE 2 (FP16 group centres) with centres farther than the 4 m the inflation constants cover: the
+    `far` flag must switch the self broad-phase culls off (same case as the GPU test)."""
+    from plainmp_b200.robot_spec import PR2RarmSpec
+
+    monkeypatch.setenv("PMP_V3_MODE", "2")
+    spec = PR2RarmSpec()
+    kin = spec.get_kin()
+    name = "far_payload_link_emul"
+    try:
+        kin.get_link_ids([name])
+    except ValueError:
+        kin.add_new_link(name, "r_gripper_palm_link", [5.5, 0.0, 0.0], [0.0, 0.0, 0.0], True)
+    rng = np.random.default_rng(71)
+    specs = [
+        SphereAttachmentSpec("r_gripper_palm_link", rng.uniform(-0.05, 0.05, (3, 6)), rng.uniform(0.03, 0.06, 6), False),
+        SphereAttachmentSpec(name, rng.uniform(-0.3, 0.3, (3, 9)), rng.uniform(0.1, 0.3, 9), False),
+        SphereAttachmentSpec("base_link", rng.uniform(-0.3, 0.3, (3, 5)) + np.array([[4.5], [0.0], [0.8]]), rng.uniform(1.0, 2.0, 5), True),
+        SphereAttachmentSpec("r_forearm_link", rng.uniform(-0.1, 0.1, (3, 4)), rng.uniform(0.03, 0.06, 4), False),
+    ]
+    pairs = [(name, "base_link"), ("r_gripper_palm_link", "base_link"), ("r_forearm_link", name)]
+    cst = SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED, specs, pairs, None, True)
+    t = EmuTables(emu, cst)
+    Q = workloads.random_configs(spec, 512, 72)
+    o = bridge.OracleCst(cst)
+    Qd = Q.astype(np.float64)
+    want = o.is_valid_batch(Qd)
+    assert (~want).sum() >= 5  # some self collisions, all found through the far path
+    _parity(t.check(Q), want, o.margin_batch(Qd), "far centres")

@@ -290,3 +290,32 @@ def test_emulated_far_group_centres_fp16_layout(emu, monkeypatch):
     want = o.is_valid_batch(Qd)
     assert (~want).sum() >= 5  # some self collisions, all found through the far path
     _parity(t.check(Q), want, o.margin_batch(Qd), "far centres")
+
+
+@pytest.mark.parametrize("seed", list(range(7000, 7000 + max(8, _c // 5))))
+def test_emulated_edges_on_random_robots(emu, seed):
+    """Both validators on random robots through the emulated lane = edge kernel (dynamic refill, the
+    reference's visiting order, natural order for n_test >= 129) and through the session's flat kernel."""
+    cst, lb, ub, desc = random_case(seed)
+    dim = len(lb)
+    if dim == 0:
+        pytest.skip("no degrees of freedom")
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(seed)
+    widths = rng.uniform(0.01, 0.3, dim)
+    res = float(rng.uniform(0.01, 0.3))
+    q0 = sample_q(lb, ub, 48, seed + 1)
+    q1 = np.clip(q0.astype(np.float64) + rng.uniform(-0.8, 0.8, q0.shape) * rng.choice([0.05, 1.0, 3.0]), lb, ub).astype(np.float32)
+    for vtype in (0, 1):
+        want, _ = bridge.OracleValidator(vtype, dim, widths, res).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64))
+        got, _ = t.check_edges(vtype, widths, res, q0, q1)
+        assert (got != want).sum() <= 1, desc  # a waypoint inside the contact band may flip one edge
+        v, keep = tables.make_validator(vtype, dim, widths if vtype == 0 else None, res)
+        ses = C.c_void_p()
+        assert emu.pmp_session_create(t.robot, t.scene, C.byref(v), 64, C.byref(ses)) == 0
+        a, b = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+        out = np.zeros(48, dtype=np.uint8)
+        assert emu.pmp_session_check_motion(ses, a.ctypes.data, b.ctypes.data, 48, out.ctypes.data, None) == 0
+        emu.pmp_session_destroy(ses)
+        assert (out.astype(bool) != want).sum() <= 1, desc

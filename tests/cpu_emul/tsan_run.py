@@ -20,3 +20,22 @@ t = T.EmuTables(lib, cst)
 o = bridge.OracleCst(cst)
 q0, q1 = workloads.random_edges(spec, 64, 3, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
 print("edges", t.check_edges(0, np.full(7, 0.05), 0.0, q0, q1)[0].mean(), flush=True)
+# cloud scene (index build, 8-lane traversal, nearest-point kernel) and the session's flat kernel
+spec, cst = workloads.make_pr2_cloud(1500)
+t = T.EmuTables(lib, cst)
+Q = workloads.random_configs(spec, 64, 4)
+print("pr2 cloud valid", t.check(Q).mean(), flush=True)
+P = np.random.default_rng(0).uniform(0.2, 1.4, (64, 3)).astype(np.float32)
+sq = np.zeros(64, dtype=np.float32)
+lib.pmp_cloud_nearest(t.scene, P.ctypes.data, 64, sq.ctypes.data, None, None)
+spec, cst = workloads.make_panda(ceiled=True)
+t = T.EmuTables(lib, cst)
+from plainmp_b200 import tables
+v, keep = tables.make_validator(0, 7, np.full(7, 0.05), 0.0)
+ses = C.c_void_p()
+lib.pmp_session_create(t.robot, t.scene, C.byref(v), 64, C.byref(ses))
+a, b = np.ascontiguousarray(q0[:32], dtype=np.float64), np.ascontiguousarray(q1[:32], dtype=np.float64)
+out = np.zeros(32, dtype=np.uint8)
+lib.pmp_session_check_motion(ses, a.ctypes.data, b.ctypes.data, 32, out.ctypes.data, None)
+print("session edges valid", out.mean(), flush=True)
+lib.pmp_session_destroy(ses)

@@ -319,3 +319,23 @@ def test_emulated_edges_on_random_robots(emu, seed):
         assert emu.pmp_session_check_motion(ses, a.ctypes.data, b.ctypes.data, 48, out.ctypes.data, None) == 0
         emu.pmp_session_destroy(ses)
         assert (out.astype(bool) != want).sum() <= 1, desc
+
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("name", ["panda_dualbars_seed1", "fetch_table_seed2", "pr2_cloud20k_seed4", "openarm_dual_seed6"])
+def test_emulated_kernels_against_reference_golden_vectors(emu, name):
+    """The kernel source (emulated) against the committed REFERENCE output: validity bits outside the
+    contact band and evaluate() distances for the head of every golden file."""
+    g = np.load(GOLDEN / f"{name}.npz")
+    maker = {"panda_dualbars_seed1": workloads.make_panda, "fetch_table_seed2": workloads.make_fetch,
+             "pr2_cloud20k_seed4": lambda: workloads.make_pr2_cloud(20000), "openarm_dual_seed6": workloads.make_openarm}[name]
+    spec, cst = maker()
+    n = 512 if "cloud" not in name else 192
+    Q = workloads.random_configs(spec, int(g["n"]), int(g["seed"]))[:n]
+    t = EmuTables(emu, cst)
+    want = np.unpackbits(g["valid_bits"], bitorder="little")[:n].astype(bool)
+    _parity(t.check(Q), want, g["margin"][:n], name)
+    m = min(n, 128)
+    np.testing.assert_allclose(t.evaluate(Q[:m]), g["dist"][:m], atol=1e-5, rtol=0)

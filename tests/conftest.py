@@ -29,3 +29,14 @@ def cuda_lib():
     lib = _capi.load()
     assert lib.pmp_device_count() >= 1, "gpu-marked test needs a CUDA device"
     return lib
+
+
+def pytest_collection_modifyitems(config, items):
+    # a kernel that never returns would otherwise hold the GPU box until the caller's own limit:
+    # every gpu-marked test gets a hard limit enforced from a watchdog thread (a blocked CUDA
+    # synchronise inside a ctypes call never sees a signal), which ends the process with a stack dump
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900, method="thread"))

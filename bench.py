@@ -625,10 +625,19 @@ def _check(lib, status):
 
 def main():
     args = parse_args()
+    # a kernel that never returns must end this process (stack dump on stderr, non-zero exit) rather than
+    # hold the GPU box until the caller's limit; PMP_BENCH_WATCHDOG_S=0 turns the watchdog off
+    limit = float(os.environ.get("PMP_BENCH_WATCHDOG_S", "3600"))
+    if limit > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(limit, exit=True, file=sys.stderr)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    if limit > 0:
+        faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":

@@ -128,3 +128,22 @@ def sample_q(lb, ub, n, seed):
     if lb.shape[0] == 0:
         return np.zeros((n, 0), dtype=np.float32)
     return rng.uniform(lb, ub, size=(n, lb.shape[0])).astype(np.float32)
+
+
+def stress_scene(rng, with_cloud):
+    """Many thin plates whose AABBs cover the whole workspace while their surfaces stay mostly clear of
+    it: every sphere group passes the cull test of almost every primitive on almost every lane, so the
+    128-entry environment queue overflows inside single groups and few lanes die early."""
+    plates = []
+    for _ in range(int(rng.integers(9, 28))):
+        r, phi = rng.uniform(1.6, 2.6), rng.uniform(0, 2 * np.pi)
+        if rng.random() < 0.7:
+            p = psdf.BoxSDF([0.04, 6.0, 6.0], psdf.Pose([r * np.cos(phi), r * np.sin(phi), rng.uniform(-0.3, 0.3)]))
+        else:
+            p = psdf.CylinderSDF(4.0, 0.05, psdf.Pose([r * np.cos(phi), r * np.sin(phi), 0.0]))
+        p.rotate_z(phi + rng.uniform(0.15, 0.35) * np.pi)
+        plates.append(p)
+    if with_cloud:
+        pts = rng.uniform(-1.0, 1.0, (int(rng.integers(50, 400)), 3)) + np.array([2.2, 0.0, 0.0])
+        plates.append(psdf.CloudSDF(pts, 0.01))
+    return psdf.UnionSDF(plates)

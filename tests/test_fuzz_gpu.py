@@ -91,6 +91,48 @@ def test_cuda_equals_reference_on_big_random_robot(cuda_lib, seed):
     np.testing.assert_allclose(cst.evaluate_batch(Q[:300]), r.evaluate_batch(Qd[:300]), atol=5e-5, rtol=0, equal_nan=True, err_msg=desc)
 
 
+@pytest.mark.parametrize("mode", ["", "2"])
+def test_queue_overflow_stress_on_random_robots(cuda_lib, mode):
+    """Scenes of fuzz_util.stress_scene (every group passes the cull test of 9-27 plates on nearly every
+    lane, so single groups overflow the 128-entry warp queue) on random robots of every base type, in
+    the default and the FP16 group-centre stash layout.  In a child process with a limit: a kernel that
+    stops making progress fails this test instead of hanging the suite (tests/test_simt_emul.py runs
+    the same cases on the emulated kernels in the CPU tier)."""
+    import subprocess
+    import sys
+    import textwrap
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    code = textwrap.dedent(
+        f"""
+        import sys
+        sys.path.insert(0, {str(root)!r}); sys.path.insert(0, {str(root / 'tests')!r})
+        import numpy as np
+        from oracle import bridge
+        from fuzz_util import random_case, sample_q, stress_scene
+        for seed in range(9000, 9024):
+            cst, lb, ub, desc = random_case(seed)
+            cst.set_sdf(stress_scene(np.random.default_rng(seed), seed % 3 == 0))
+            Q = sample_q(lb, ub, 4096, seed)
+            o = bridge.OracleCst(cst, n_threads=4)
+            Qd = Q.astype(np.float64)
+            got, want, m = cst.is_valid_batch(Q), o.is_valid_batch(Qd), o.margin_batch(Qd)
+            bad = [int(i) for i in np.where(got != want)[0] if m[i] > 1e-5]
+            assert not bad, (desc, bad[:4])
+        print("OK")
+        """
+    )
+    env = dict(os.environ)
+    if mode:
+        env["PMP_V3_MODE"] = mode
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=420, env=env)
+    except subprocess.TimeoutExpired:
+        pytest.fail("the validity kernel did not return within 420 s on a queue-overflow stress scene")
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("seed", range(4000, 4020))
 def test_psdf_and_kdtree_surface_on_random_scenes(cuda_lib, seed):
     """The psdf / kdtree binding surface (evaluate_batch, is_outside, KDTree.sqdist / query) on random

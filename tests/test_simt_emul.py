@@ -22,7 +22,7 @@ from plainmp_b200.robot_spec import PandaSpec
 
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 from cpu_emul import build as emul_build  # noqa: E402
-from fuzz_util import random_case, sample_q  # noqa: E402
+from fuzz_util import random_case, sample_q, stress_scene  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -341,25 +341,6 @@ def test_emulated_kernels_against_reference_golden_vectors(emu, name):
     np.testing.assert_allclose(t.evaluate(Q[:m]), g["dist"][:m], atol=1e-5, rtol=0)
 
 
-def _stress_scene(rng, with_cloud):
-    """Many thin plates whose AABBs cover the whole workspace while their surfaces stay mostly clear of
-    it: every sphere group passes the cull test of almost every primitive on almost every lane, so the
-    128-entry environment queue overflows inside single groups and few lanes die early."""
-    plates = []
-    for _ in range(int(rng.integers(9, 28))):
-        r, phi = rng.uniform(1.6, 2.6), rng.uniform(0, 2 * np.pi)
-        if rng.random() < 0.7:
-            p = psdf.BoxSDF([0.04, 6.0, 6.0], psdf.Pose([r * np.cos(phi), r * np.sin(phi), rng.uniform(-0.3, 0.3)]))
-        else:
-            p = psdf.CylinderSDF(4.0, 0.05, psdf.Pose([r * np.cos(phi), r * np.sin(phi), 0.0]))
-        p.rotate_z(phi + rng.uniform(0.15, 0.35) * np.pi)
-        plates.append(p)
-    if with_cloud:
-        pts = rng.uniform(-1.0, 1.0, (int(rng.integers(50, 400)), 3)) + np.array([2.2, 0.0, 0.0])
-        plates.append(psdf.CloudSDF(pts, 0.01))
-    return psdf.UnionSDF(plates)
-
-
 @pytest.mark.parametrize("mode", ["", "2"])
 @pytest.mark.parametrize("seed", list(range(9000, 9000 + max(10, _c // 4))))
 def test_emulated_queue_stress(emu, monkeypatch, seed, mode):
@@ -369,7 +350,7 @@ def test_emulated_queue_stress(emu, monkeypatch, seed, mode):
         monkeypatch.setenv("PMP_V3_MODE", mode)
     cst, lb, ub, desc = random_case(seed)
     rng = np.random.default_rng(seed)
-    cst.set_sdf(_stress_scene(rng, bool(seed % 3 == 0)))
+    cst.set_sdf(stress_scene(rng, bool(seed % 3 == 0)))
     t = EmuTables(emu, cst)
     Q = sample_q(lb, ub, 128, seed)
     o = bridge.OracleCst(cst)

@@ -86,6 +86,23 @@ class EmuTables:
         assert self.lib.pmp_eval_configs_host(self.robot, self.scene, Q.ctypes.data, Q.shape[0], out.ctypes.data) == 0
         return out.astype(np.float64)
 
+    # device-pointer entry points: in the emulation "device" memory is host memory and launches are
+    # synchronous, so numpy buffers go straight through
+    def evaluate_grad(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        out = np.zeros((Q.shape[0], 2), dtype=np.float32)
+        jac = np.zeros((Q.shape[0], 2, self.q_dim), dtype=np.float32)
+        rc = self.lib.pmp_eval_grad_configs(self.robot, self.scene, Q.ctypes.data, Q.shape[0], out.ctypes.data, jac.ctypes.data if jac.size else None, None)
+        assert rc == 0, self.lib.pmp_last_error()
+        return out.astype(np.float64), jac.astype(np.float64)
+
+    def fk_spheres(self, Q, accurate):
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        out = np.zeros((Q.shape[0], len(self._keep["spheres"]), 4), dtype=np.float32)
+        rc = self.lib.pmp_fk_spheres(self.robot, Q.ctypes.data, Q.shape[0], int(accurate), out.ctypes.data, None)
+        assert rc == 0, self.lib.pmp_last_error()
+        return out
+
     def check_edges(self, vtype, widths, res, q0, q1):
         q0, q1 = np.ascontiguousarray(q0, dtype=np.float32), np.ascontiguousarray(q1, dtype=np.float32)
         v, keep = tables.make_validator(vtype, q0.shape[1], widths if vtype == 0 else None, res)
@@ -356,3 +373,23 @@ def test_emulated_queue_stress(emu, monkeypatch, seed, mode):
     o = bridge.OracleCst(cst)
     Qd = Q.astype(np.float64)
     _parity(t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), desc)
+
+
+@pytest.mark.parametrize("seed", [1003, 1012, 1018] + list(range(5000, 5000 + max(10, _c // 4))))
+def test_emulated_jacobian_rows_and_sphere_placement(emu, seed):
+    """evaluate() with Jacobian rows (arg-min tracking + point-Jacobian pass) and get_all_spheres in
+    both FK precisions on the emulated kernels, random robots of every base type."""
+    cst, lb, ub, desc = random_case(seed)
+    t = EmuTables(emu, cst)
+    Q = sample_q(lb, ub, 96, seed)
+    Qd = Q.astype(np.float64)
+    o = bridge.OracleCst(cst)
+    vals, jac = t.evaluate_grad(Q)
+    want_v, want_j = o.evaluate_grad_batch(Qd)
+    np.testing.assert_allclose(vals, want_v, atol=2e-5, rtol=0, equal_nan=True, err_msg=desc)
+    assert (np.isnan(jac) == np.isnan(want_j)).all(), desc
+    if jac.size:
+        err = np.abs(np.nan_to_num(jac) - np.nan_to_num(want_j)).max(axis=2)
+        assert (err > 1e-3).mean() < 0.05, f"{desc}: {(err > 1e-3).mean():.2%} Jacobian rows differ (max {err.max():.3e})"
+    for accurate in (False, True):
+        np.testing.assert_allclose(t.fk_spheres(Q[:32], accurate), o.spheres_batch(Qd[:32], accurate), atol=2e-5, rtol=0, err_msg=desc)

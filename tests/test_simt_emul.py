@@ -393,3 +393,76 @@ def test_emulated_jacobian_rows_and_sphere_placement(emu, seed):
         assert (err > 1e-3).mean() < 0.05, f"{desc}: {(err > 1e-3).mean():.2%} Jacobian rows differ (max {err.max():.3e})"
     for accurate in (False, True):
         np.testing.assert_allclose(t.fk_spheres(Q[:32], accurate), o.spheres_batch(Qd[:32], accurate), atol=2e-5, rtol=0, err_msg=desc)
+
+
+def test_emulated_scene_updates_and_sdf_queries(emu):
+    """The scene update path (in-place primitive records; cloud re-index through the grow-only ping-pong
+    buffers, growing, shrinking and removal), a session following a scene swap, and the batched psdf
+    queries, all on the emulated kernels."""
+    spec, cst = workloads.make_panda()
+    rng = np.random.default_rng(5)
+
+    def cloud(n, shift):
+        return rng.uniform(-0.15, 0.15, (n, 3)) + np.array([0.45 + shift, 0.0, 0.55])
+
+    box = psdf.BoxSDF([0.2, 0.3, 0.25], psdf.Pose([0.5, -0.4, 0.3]))
+    cyl = psdf.CylinderSDF(0.12, 0.5, psdf.Pose([-0.3, 0.45, 0.25]))
+    pts = cloud(700, 0.0)
+    cst.set_sdf(psdf.UnionSDF([box, cyl, psdf.CloudSDF(pts, 0.01)]))
+    t = EmuTables(emu, cst)
+    Q = workloads.random_configs(spec, 96, 9)
+    Qd = Q.astype(np.float64)
+
+    def agree(what):
+        o = bridge.OracleCst(cst)
+        want = o.is_valid_batch(Qd)
+        _parity(t.check(Q), want, o.margin_batch(Qd), what)
+        np.testing.assert_allclose(t.evaluate(Q[:32]), o.evaluate_batch(Qd[:32]), atol=1e-5, rtol=0, err_msg=what)
+        return want
+
+    first = agree("initial")
+    # SDFBase::translate / rotate_z on leaves -> new records, same count and order
+    box.translate(np.array([-0.1, 0.25, 0.1]))
+    cyl.rotate_z(0.7)
+    cyl.translate(np.array([0.35, -0.2, 0.0]))
+    prims, _ = tables.flatten_primitives(cst._leaves())
+    assert emu.pmp_scene_update_prims(t.scene, prims.ctypes.data, len(prims), None) == 0, emu.pmp_last_error()
+    moved = agree("moved primitives")
+    assert (first != moved).any()
+    assert emu.pmp_scene_update_prims(t.scene, prims.ctypes.data, len(prims) + 1, None) != 0  # count is fixed
+    # new depth frames: same size, larger (buffers grow), smaller, none
+    for n, shift in ((700, 0.05), (2500, -0.05), (90, 0.1), (0, 0.0)):
+        leaves = [box, cyl] + ([psdf.CloudSDF(cloud(n, shift), 0.01)] if n else [])
+        cst.set_sdf(psdf.UnionSDF(leaves))
+        p32 = np.ascontiguousarray(leaves[-1].points, dtype=np.float32) if n else None
+        rc = emu.pmp_scene_update_cloud(t.scene, p32.ctypes.data if n else None, n, 0.01, 0.02)
+        assert rc == 0, emu.pmp_last_error()
+        agree(f"cloud of {n} points")
+    # a session keeps working across a scene swap
+    cst.set_sdf(psdf.UnionSDF([box, cyl, psdf.CloudSDF(cloud(400, 0.0), 0.01)]))
+    t2 = EmuTables(emu, cst)
+    v, keep = tables.make_validator(0, 7, np.full(7, 0.05), 0.0)
+    ses = C.c_void_p()
+    assert emu.pmp_session_create(t.robot, t.scene, C.byref(v), 64, C.byref(ses)) == 0
+    st = np.zeros(len(Qd), dtype=np.uint8)
+    assert emu.pmp_session_is_valid(ses, Qd.ctypes.data, len(Qd), st.ctypes.data) == 0
+    before = st.astype(bool).copy()
+    assert emu.pmp_session_set_scene(ses, t2.scene) == 0
+    assert emu.pmp_session_is_valid(ses, Qd.ctypes.data, len(Qd), st.ctypes.data) == 0
+    o = bridge.OracleCst(cst)
+    _parity(st.astype(bool), o.is_valid_batch(Qd), o.margin_batch(Qd), "session after set_scene")
+    assert (before != st.astype(bool)).any()
+    emu.pmp_session_destroy(ses)
+    # UnionSDF::evaluate_batch / is_outside over primitives + cloud
+    sdf = bridge.OracleSDF.from_psdf(cst.get_sdf())
+    P = rng.uniform(-0.8, 0.9, (300, 3))
+    P32 = np.ascontiguousarray(P, dtype=np.float32)
+    out = np.zeros(300, dtype=np.float32)
+    assert emu.pmp_sdf_evaluate(t2.scene, P32.ctypes.data, 300, out.ctypes.data, None) == 0
+    want = sdf.evaluate_batch(P32.astype(np.float64))
+    np.testing.assert_allclose(out, want, atol=1e-5, rtol=0)
+    r32 = rng.uniform(0.0, 0.2, 300).astype(np.float32)
+    flag = np.zeros(300, dtype=np.uint8)
+    assert emu.pmp_sdf_is_outside(t2.scene, P32.ctypes.data, r32.ctypes.data, 300, flag.ctypes.data, None) == 0
+    far = np.abs(want - r32) > 1e-5
+    assert ((flag.astype(bool) == (want > r32)) | ~far).all()

@@ -23,7 +23,13 @@ def _rewrite(text: str) -> str:
     return text
 
 
-def build(force: bool = False) -> Path:
+def build(force: bool = False, sanitize: str | None = None) -> Path:
+    """sanitize="address": the memcheck variant (tools/asan_emul.sh) — device allocations without slack,
+    unrequested dynamic shared memory poisoned; load it with libasan preloaded."""
+    import os
+
+    sanitize = sanitize or os.environ.get("PMP_EMUL_SANITIZE") or None
+    LIB = OUT / (f"libpmp_simt_emul_{sanitize}.so" if sanitize else "libpmp_simt_emul.so")
     srcs = sorted(CSRC.glob("*.cu*")) + [CSRC / "pmp_cloud_build.h"]
     deps = srcs + [HERE / "cuda_emul.h", HERE / "emul_extra.cpp", HERE / "stubs" / "cub" / "device" / "device_radix_sort.cuh", Path(__file__)]
     if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
@@ -37,6 +43,8 @@ def build(force: bool = False) -> Path:
         f"-I{HERE}", f"-I{HERE / 'stubs'}", f"-I{OUT}",
         "-o", str(LIB), str(OUT / "plainmp_b200.cpp"), str(OUT / "pmp_cloud_build.cpp"), str(HERE / "emul_extra.cpp"),
     ]
+    if sanitize:
+        cmd[1:1] = [f"-fsanitize={sanitize}", "-g", "-fno-omit-frame-pointer"] + (["-DPMP_EMUL_ASAN"] if "address" in sanitize else [])
     subprocess.run(cmd, check=True)
     return LIB
 

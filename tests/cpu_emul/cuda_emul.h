@@ -204,6 +204,10 @@ inline void __syncthreads() {
 }
 
 // ---- shared memory arena (one CTA at a time): defined in emul_extra.cpp as pmp::sm ------------------------
+namespace pmp { extern float4 sm[1 << 16]; }
+#ifdef PMP_EMUL_ASAN
+#include <sanitizer/asan_interface.h>
+#endif
 
 // ---- kernel launch: K % emu::Cfg(grid, block, smem, stream)(args...) ------------------------------------
 // (tests/cpu_emul/build.py rewrites `K<<<g, b, s, st>>>(args)` into that form)
@@ -211,19 +215,39 @@ namespace emu {
 template <class... A>
 struct Bound {
   unsigned grid, block;
+  size_t smem;
   std::tuple<A...> args;
 };
 struct Cfg {
   unsigned grid, block;
-  template <class G, class B> Cfg(G g, B b, size_t = 0, void* = nullptr) : grid((unsigned)g), block((unsigned)b) {}
+  size_t smem;
+  template <class G, class B> Cfg(G g, B b, size_t s = 0, void* = nullptr) : grid((unsigned)g), block((unsigned)b), smem(s) {}
   template <class... A> Bound<std::decay_t<A>...> operator()(A&&... a) const {
-    return Bound<std::decay_t<A>...>{grid, block, std::tuple<std::decay_t<A>...>(std::forward<A>(a)...)};
+    return Bound<std::decay_t<A>...>{grid, block, smem, std::tuple<std::decay_t<A>...>(std::forward<A>(a)...)};
   }
 };
+#ifdef PMP_EMUL_ASAN
+#ifndef PMP_EMUL_ASAN_SELFTEST
+#define PMP_EMUL_ASAN_SELFTEST 0  // 64: poison the last 64 requested bytes too (checks that the checker fires)
+#endif
+struct SmemGuard {
+  size_t used;
+  explicit SmemGuard(size_t n) : used((n + 7) / 8 * 8 - (n >= 64 ? PMP_EMUL_ASAN_SELFTEST : 0)) {
+    ASAN_POISON_MEMORY_REGION((char*)pmp::sm + used, sizeof(float4) * (1 << 16) - used);
+  }
+  ~SmemGuard() { ASAN_UNPOISON_MEMORY_REGION((char*)pmp::sm + used, sizeof(float4) * (1 << 16) - used); }
+};
+#endif
 constexpr unsigned kMaxGrid = 2;  // persistent / grid-stride kernels: a couple of CTAs cover every path
 template <class... P, class... A>
 inline void launch(void (*k)(P...), const Bound<A...>& b) {
   const unsigned grid = std::min(b.grid, kMaxGrid);
+#ifdef PMP_EMUL_ASAN
+  // memcheck mode: the dynamic shared memory the launch did not ask for is poisoned, device
+  // allocations carry no slack (cudaMalloc below), so AddressSanitizer reports what
+  // compute-sanitizer's memcheck would
+  emu::SmemGuard guard(b.smem);
+#endif
   for (unsigned bid = 0; bid < grid; bid++) {
     Cta cta;
     cta.n = (int)b.block;
@@ -256,7 +280,11 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cu
 enum { cudaStreamNonBlocking = 1, cudaHostAllocMapped = 2 };
 enum { cudaDevAttrMultiProcessorCount = 16, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+#ifdef PMP_EMUL_ASAN
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { void* q = nullptr; if (posix_memalign(&q, 256, n ? n : 1)) q = nullptr; *p = (T*)q; return q ? cudaSuccess : cudaErrorMemoryAllocation; }
+#else
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+#endif
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc(p, n); }
 template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { return cudaMalloc(p, n); }

@@ -39,3 +39,24 @@ out = np.zeros(32, dtype=np.uint8)
 lib.pmp_session_check_motion(ses, a.ctypes.data, b.ctypes.data, 32, out.ctypes.data, None)
 print("session edges valid", out.mean(), flush=True)
 lib.pmp_session_destroy(ses)
+# queue overflow with resume (stress scene), Jacobian rows, scene update path
+sys.path.insert(0, '/root/repo/tests')
+from fuzz_util import random_case, sample_q, stress_scene
+from plainmp_b200 import psdf
+for seed in (9004, 9007):
+    cst, lb, ub, desc = random_case(seed)
+    cst.set_sdf(stress_scene(np.random.default_rng(seed), seed % 3 == 0))
+    t = T.EmuTables(lib, cst)
+    print("stress", seed, t.check(sample_q(lb, ub, 64, seed)).mean(), flush=True)
+cst, lb, ub, desc = random_case(1012)
+t = T.EmuTables(lib, cst)
+vals, jac = t.evaluate_grad(sample_q(lb, ub, 64, 1012))
+print("jacobian rows", jac.shape, flush=True)
+spec, cst = workloads.make_panda()
+rng = np.random.default_rng(0)
+cst.set_sdf(psdf.UnionSDF([psdf.BoxSDF([0.2, 0.3, 0.25], psdf.Pose([0.5, -0.4, 0.3])), psdf.CloudSDF(rng.uniform(-0.15, 0.15, (500, 3)) + [0.45, 0, 0.55], 0.01)]))
+t = T.EmuTables(lib, cst)
+for n in (900, 200):
+    p32 = (rng.uniform(-0.15, 0.15, (n, 3)) + [0.5, 0, 0.55]).astype(np.float32)
+    assert lib.pmp_scene_update_cloud(t.scene, p32.ctypes.data, n, 0.01, 0.02) == 0
+    print("cloud update", n, t.check(workloads.random_configs(spec, 64, 2)).mean(), flush=True)

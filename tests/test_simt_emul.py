@@ -8,6 +8,7 @@ queue-overflow livelock found by fuzzing on the GPU is reproduced and its fix ve
 FP32 results differ from the GPU's in the last bits (no FMA contraction on the host), which the
 1e-5 contact band absorbs."""
 import ctypes as C
+import os
 import sys
 from pathlib import Path
 
@@ -27,7 +28,7 @@ from fuzz_util import random_case, sample_q, stress_scene  # noqa: E402
 
 @pytest.fixture(scope="module")
 def emu():
-    lib = C.CDLL(str(emul_build.build()))
+    lib = C.CDLL(os.environ.get("PMP_EMUL_LIB") or str(emul_build.build()))  # PMP_EMUL_LIB: tools/coverage_emul.sh
     for name, (res, args) in _capi.SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
@@ -466,3 +467,109 @@ def test_emulated_scene_updates_and_sdf_queries(emu):
     assert emu.pmp_sdf_is_outside(t2.scene, P32.ctypes.data, r32.ctypes.data, 300, flag.ctypes.data, None) == 0
     far = np.abs(want - r32) > 1e-5
     assert ((flag.astype(bool) == (want > r32)) | ~far).all()
+
+
+# ---- cases added from the line-coverage report (tools/coverage_emul.sh): every kernel line the suite did
+# ---- not reach before — link frames, zero-length and > 128-waypoint edges, the session's staged flat path,
+# ---- a ground plane through is_outside, single-leaf cloud trees
+def test_emulated_link_frames(emu):
+    spec, cst = workloads.make_panda()
+    t = EmuTables(emu, cst)
+    kin = cst.get_kin()
+    Q = workloads.random_configs(spec, 40, 21)
+    n_ops = len(t._keep["program"].ops)
+    ok = bridge.OracleKin(kin)
+    for accurate in (True, False):
+        out = np.zeros((len(Q), n_ops, 7), dtype=np.float32)
+        assert emu.pmp_fk_frames(t.robot, Q.ctypes.data, len(Q), int(accurate), out.ctypes.data, None) == 0, emu.pmp_last_error()
+        for i in (0, 17, 39):
+            ok.set_joint_angles(cst._control_joint_ids, Q[i].astype(np.float64), accurate)
+            for lid, op in t._keep["program"].op_of_link.items():
+                want = ok.link_pose(lid)
+                got = out[i, op].astype(np.float64)
+                np.testing.assert_allclose(got[:3], want[:3], atol=2e-6, rtol=0)
+                assert min(np.abs(got[3:] - want[3:]).max(), np.abs(got[3:] + want[3:]).max()) < 2e-6
+
+
+def test_emulated_edge_corner_cases(emu):
+    """Zero-length edges (valid without a check), edges of more than 128 waypoints (past the sequence
+    table: plain forward order) next to ordinary ones, both validators, waypoint counts included."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    q0, q1 = workloads.random_edges(spec, 24, 8, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    q1[::4] = q0[::4]  # zero length
+    for i in (1, 9):  # long: 0.3 rad over a 0.002 box -> 150+ waypoints
+        q1[i] = q0[i] + np.float32(0.3) * np.sign(q1[i] - q0[i] + 1e-9)
+    widths = np.full(7, 0.002)
+    got, nc = t.check_edges(0, widths, 0.0, q0, q1)
+    want, nc_want = bridge.OracleValidator(0, 7, widths).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64))
+    assert (got == want).all() and nc == nc_want
+    assert got[::4].all()
+    got, nc = t.check_edges(1, None, 0.004, q0, q1)
+    want, nc_want = bridge.OracleValidator(1, 7, None, 0.004).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64))
+    assert (got == want).all() and nc == nc_want
+
+
+def test_emulated_session_staged_flat_path(emu):
+    """More than 4096 waypoints in one call: the flat kernel reading a staged (copied) arena and
+    reporting through the per-edge bit mask instead of the zero-copy bytes."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    widths = np.full(7, 0.009)
+    v, keep = tables.make_validator(0, 7, widths, 0.0)
+    ses = C.c_void_p()
+    assert emu.pmp_session_create(t.robot, t.scene, C.byref(v), 4096, C.byref(ses)) == 0, emu.pmp_last_error()
+    q0, q1 = workloads.random_edges(spec, 110, 12, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    q0, q1 = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+    out = np.zeros(len(q0), dtype=np.uint8)
+    nc = C.c_uint64(0)
+    assert emu.pmp_session_check_motion(ses, q0.ctypes.data, q1.ctypes.data, len(q0), out.ctypes.data, C.byref(nc)) == 0
+    assert nc.value > 4096, nc.value
+    want, _ = bridge.OracleValidator(0, 7, widths).check_motion_batch(o, q0, q1)
+    assert (out.astype(bool) != want).sum() <= 1
+    # and more than 2048 states in one is_valid call: staged copy + the bulk validity kernel
+    Qd = np.ascontiguousarray(workloads.random_configs(spec, 2100, 13), dtype=np.float64)
+    st = np.zeros(len(Qd), dtype=np.uint8)
+    assert emu.pmp_session_is_valid(ses, Qd.ctypes.data, len(Qd), st.ctypes.data) == 0
+    _parity(st.astype(bool), o.is_valid_batch(Qd), o.margin_batch(Qd), "staged is_valid")
+    emu.pmp_session_destroy(ses)
+
+
+@pytest.mark.parametrize("n_points", [1, 5, 8, 9])
+def test_emulated_tiny_clouds_and_ground(emu, n_points):
+    """Clouds whose box tree is a single leaf (<= 8 points) or barely more, in every traversal (narrow
+    phase, evaluate, nearest point, psdf queries), and a ground plane through is_outside."""
+    spec, cst = workloads.make_panda()
+    rng = np.random.default_rng(n_points)
+    pts = rng.uniform(-0.05, 0.05, (n_points, 3)) + np.array([0.45, 0.0, 0.5])
+    cst.set_sdf(psdf.UnionSDF([psdf.GroundSDF(-0.02), psdf.CloudSDF(pts, 0.03)]))
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, 96, 6)
+    Qd = Q.astype(np.float64)
+    want = o.is_valid_batch(Qd)
+    _parity(t.check(Q), want, o.margin_batch(Qd), f"{n_points}-point cloud")
+    assert 0.0 < want.mean() < 1.0
+    np.testing.assert_allclose(t.evaluate(Q[:32]), o.evaluate_batch(Qd[:32]), atol=1e-5, rtol=0)
+    P = (np.array([0.45, 0.0, 0.5]) + rng.uniform(-0.6, 0.6, (64, 3))).astype(np.float32)
+    sq = np.zeros(64, dtype=np.float32)
+    idx = np.zeros(64, dtype=np.int32)
+    assert emu.pmp_cloud_nearest(t.scene, P.ctypes.data, 64, sq.ctypes.data, idx.ctypes.data, None) == 0
+    brute = ((P[:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(sq, brute.min(1), atol=2e-6, rtol=1e-5)
+    sdf = bridge.OracleSDF.from_psdf(cst.get_sdf())
+    val = np.zeros(64, dtype=np.float32)
+    assert emu.pmp_sdf_evaluate(t.scene, P.ctypes.data, 64, val.ctypes.data, None) == 0
+    wv = sdf.evaluate_batch(P.astype(np.float64))
+    np.testing.assert_allclose(val, wv, atol=1e-5, rtol=0)
+    # is_outside: many queries close to the cloud so that the field leaves some for the tree
+    P = (np.array([0.45, 0.0, 0.5]) + rng.uniform(-0.25, 0.25, (512, 3))).astype(np.float32)
+    wv = sdf.evaluate_batch(P.astype(np.float64))
+    r32 = (np.maximum(wv, 0.0) + rng.uniform(-0.02, 0.02, 512)).clip(0.0).astype(np.float32)
+    flag = np.zeros(512, dtype=np.uint8)
+    assert emu.pmp_sdf_is_outside(t.scene, P.ctypes.data, r32.ctypes.data, 512, flag.ctypes.data, None) == 0
+    far = np.abs(wv - r32) > 1e-5
+    assert ((flag.astype(bool) == (wv > r32)) | ~far).all()
+    assert 0.2 < flag.mean() < 0.8

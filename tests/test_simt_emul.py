@@ -573,3 +573,31 @@ def test_emulated_tiny_clouds_and_ground(emu, n_points):
     far = np.abs(wv - r32) > 1e-5
     assert ((flag.astype(bool) == (wv > r32)) | ~far).all()
     assert 0.2 < flag.mean() < 0.8
+
+
+@pytest.mark.parametrize("seed", [9001, 9004, 9006, 9007, 9010, 9013, 9016, 9019])
+def test_emulated_edges_under_queue_stress(emu, seed):
+    """The lane = edge kernel and the session's flat kernel on the queue-overflow scenes: every lane
+    carries a different waypoint of a different edge while single groups overflow the warp queue."""
+    cst, lb, ub, desc = random_case(seed)
+    dim = len(lb)
+    if dim == 0:
+        pytest.skip("no degrees of freedom")
+    rng = np.random.default_rng(seed)
+    cst.set_sdf(stress_scene(rng, bool(seed % 3 == 0)))
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    widths = rng.uniform(0.02, 0.2, dim)
+    q0 = sample_q(lb, ub, 64, seed + 1)
+    q1 = np.clip(q0.astype(np.float64) + rng.uniform(-0.5, 0.5, q0.shape), lb, ub).astype(np.float32)
+    want, nc_want = bridge.OracleValidator(0, dim, widths, 0.0).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64))
+    got, nc = t.check_edges(0, widths, 0.0, q0, q1)
+    assert (got != want).sum() <= 1, desc
+    v, keep = tables.make_validator(0, dim, widths, 0.0)
+    ses = C.c_void_p()
+    assert emu.pmp_session_create(t.robot, t.scene, C.byref(v), 64, C.byref(ses)) == 0
+    a, b = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+    out = np.zeros(64, dtype=np.uint8)
+    assert emu.pmp_session_check_motion(ses, a.ctypes.data, b.ctypes.data, 64, out.ctypes.data, None) == 0
+    emu.pmp_session_destroy(ses)
+    assert (out.astype(bool) != want).sum() <= 1, desc

@@ -120,6 +120,14 @@ def test_queue_overflow_stress_on_random_robots(cuda_lib, mode):
             got, want, m = cst.is_valid_batch(Q), o.is_valid_batch(Qd), o.margin_batch(Qd)
             bad = [int(i) for i in np.where(got != want)[0] if m[i] > 1e-5]
             assert not bad, (desc, bad[:4])
+            if len(lb) and seed % 2 == 0:  # the lane = edge kernel on the same scene
+                from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorType
+                rng = np.random.default_rng(seed)
+                widths = rng.uniform(0.02, 0.2, len(lb))
+                q1 = np.clip(Qd[:1024] + rng.uniform(-0.5, 0.5, (1024, len(lb))), lb, ub).astype(np.float32)
+                e_want, _ = bridge.OracleValidator(0, len(lb), widths, 0.0).check_motion_batch(o, Qd[:1024], q1.astype(np.float64), n_threads=4)
+                e_got, _ = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, list(widths))).check_motion_batch(Q[:1024], q1)
+                assert (e_got != e_want).mean() < 0.006, desc
         print("OK")
         """
     )

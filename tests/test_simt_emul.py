@@ -601,3 +601,89 @@ def test_emulated_edges_under_queue_stress(emu, seed):
     assert emu.pmp_session_check_motion(ses, a.ctypes.data, b.ctypes.data, 64, out.ctypes.data, None) == 0
     emu.pmp_session_destroy(ses)
     assert (out.astype(bool) != want).sum() <= 1, desc
+
+
+# ---- branches the gcov branch report showed untaken --------------------------------------------------
+def test_emulated_joint_angles_beyond_pi(emu):
+    """Joint angles up to +-4 pi on a FIXED base: the range reduction of the approximate sin/cos
+    (kinematics/algorithm.cpp:49-86) in all its branches, against the oracle's FP64 restatement."""
+    spec, cst = workloads.make_panda()
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(17)
+    Q = rng.uniform(-4 * np.pi, 4 * np.pi, (192, 7)).astype(np.float32)
+    Qd = Q.astype(np.float64)
+    _parity(t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), "angles beyond pi")
+    np.testing.assert_allclose(t.fk_spheres(Q[:48], False), o.spheres_batch(Qd[:48], False), atol=2e-5, rtol=0)
+
+
+def test_emulated_ground_as_nearest_primitive_and_optional_arguments(emu):
+    """evaluate() with Jacobian rows where the ground plane is the arg-min primitive; is_outside without
+    radii; nearest-point queries without the index output; duplicated cloud points (distance ties)."""
+    spec, cst = workloads.make_panda()
+    rng = np.random.default_rng(23)
+    base = rng.uniform(-0.05, 0.05, (40, 3)) + np.array([0.5, 0.0, 0.6])
+    pts = np.concatenate([base, base[:15], base[:5]])  # exact duplicates
+    cst.set_sdf(psdf.UnionSDF([psdf.GroundSDF(0.08), psdf.CloudSDF(pts, 0.01)]))
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, 96, 31)
+    Qd = Q.astype(np.float64)
+    vals, jac = t.evaluate_grad(Q)
+    want_v, want_j = o.evaluate_grad_batch(Qd)
+    np.testing.assert_allclose(vals, want_v, atol=1e-5, rtol=0)
+    err = np.abs(jac - want_j).max(axis=2)
+    assert (err > 1e-3).mean() < 0.05, err.max()
+    P = (np.array([0.5, 0.0, 0.4]) + rng.uniform(-0.5, 0.5, (200, 3))).astype(np.float32)
+    sdf = bridge.OracleSDF.from_psdf(cst.get_sdf())
+    wv = sdf.evaluate_batch(P.astype(np.float64))
+    flag = np.zeros(200, dtype=np.uint8)
+    assert emu.pmp_sdf_is_outside(t.scene, P.ctypes.data, None, 200, flag.ctypes.data, None) == 0
+    assert ((flag.astype(bool) == (wv > 0)) | (np.abs(wv) < 1e-5)).all()
+    sq = np.zeros(200, dtype=np.float32)
+    assert emu.pmp_cloud_nearest(t.scene, P.ctypes.data, 200, sq.ctypes.data, None, None) == 0
+    brute = ((P[:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(sq, brute.min(1), atol=2e-6, rtol=1e-5)
+    idx = np.zeros(200, dtype=np.int32)
+    assert emu.pmp_cloud_nearest(t.scene, P.ctypes.data, 200, sq.ctypes.data, idx.ctypes.data, None) == 0
+    np.testing.assert_allclose(brute[np.arange(200), idx], brute.min(1), atol=2e-6, rtol=1e-5)
+    # values only, with a primitive nearer than the cloud for most configurations
+    np.testing.assert_allclose(t.evaluate(Q), o.evaluate_batch(Qd), atol=1e-5, rtol=0)
+    # psdf queries on a scene without a cloud; edges without the optional counters
+    spec2, cst2 = workloads.make_panda(ceiled=True)
+    t2 = EmuTables(emu, cst2)
+    sdf2 = bridge.OracleSDF.from_psdf(cst2.get_sdf())
+    val = np.zeros(200, dtype=np.float32)
+    assert emu.pmp_sdf_evaluate(t2.scene, P.ctypes.data, 200, val.ctypes.data, None) == 0
+    wv2 = sdf2.evaluate_batch(P.astype(np.float64))
+    np.testing.assert_allclose(val, wv2, atol=1e-5, rtol=0)
+    assert emu.pmp_sdf_is_outside(t2.scene, P.ctypes.data, None, 200, flag.ctypes.data, None) == 0
+    assert ((flag.astype(bool) == (wv2 > 0)) | (np.abs(wv2) < 1e-5)).all()
+    o2 = bridge.OracleCst(cst2)
+    q0, q1 = workloads.random_edges(spec2, 40, 5, True, lambda q: o2.is_valid_batch(q.astype(np.float64)))
+    vd, keep = tables.make_validator(0, 7, np.full(7, 0.05), 0.0)
+    bits = np.zeros(2, dtype=np.uint32)
+    assert emu.pmp_check_edges_host(t2.robot, t2.scene, C.byref(vd), q0.ctypes.data, q1.ctypes.data, 40, bits.ctypes.data, None, None) == 0
+    assert (tables.unpack_bits(bits, 40) == t2.check_edges(0, np.full(7, 0.05), 0.0, q0, q1)[0]).all()
+
+
+def test_emulated_session_more_edges_than_the_offset_table(emu):
+    """More than 1024 (short) edges in one call: the flat kernel searches the waypoint offsets in global
+    memory instead of the shared-memory copy."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    widths = np.full(7, 0.05)
+    v, keep = tables.make_validator(0, 7, widths, 0.0)
+    ses = C.c_void_p()
+    assert emu.pmp_session_create(t.robot, t.scene, C.byref(v), 2048, C.byref(ses)) == 0, emu.pmp_last_error()
+    rng = np.random.default_rng(3)
+    q0 = workloads.random_configs(spec, 1100, 41).astype(np.float64)
+    q1 = q0 + rng.uniform(-0.06, 0.06, q0.shape)
+    out = np.zeros(len(q0), dtype=np.uint8)
+    nc = C.c_uint64(0)
+    assert emu.pmp_session_check_motion(ses, q0.ctypes.data, q1.ctypes.data, len(q0), out.ctypes.data, C.byref(nc)) == 0
+    want, _ = bridge.OracleValidator(0, 7, widths).check_motion_batch(o, q0, q1)
+    assert (out.astype(bool) != want).mean() < 0.01
+    assert 0.1 < want.mean() < 0.9
+    emu.pmp_session_destroy(ses)

@@ -15,6 +15,7 @@ g++ --coverage -O0 -std=c++17 -fPIC -pthread -w -Itests/cpu_emul -Itests/cpu_emu
 g++ --coverage -shared -pthread -o $B/libpmp_simt_emul_cov.so $C/plainmp_b200.o $C/pmp_cloud_build.o $C/emul_extra.o
 PMP_EMUL_LIB=$PWD/$B/libpmp_simt_emul_cov.so python -m pytest tests/test_simt_emul.py -x -q "$@" 1>&2
 mkdir -p $C/out
-gcov -o $C $C/plainmp_b200.o $C/pmp_cloud_build.o > $C/gcov.log 2>&1 || true
+gcov -b -c -o $C $C/plainmp_b200.o $C/pmp_cloud_build.o > $C/gcov.log 2>&1 || true
 mv ./*.gcov $C/out/
 python tools/coverage_report.py $C/out
+python tools/coverage_branches.py $C/out

@@ -54,6 +54,7 @@ class EmuTables:
         d.n_spheres, d.spheres = len(a["spheres"]), a["spheres"].ctypes.data
         d.n_pairs, d.pairs = len(a["pairs"]), a["pairs"].ctypes.data
         self.q_dim = a["q_dim"]
+        self._desc = d
         self.robot = C.c_void_p()
         assert lib.pmp_robot_create(C.byref(d), C.byref(self.robot)) == 0, lib.pmp_last_error()
         self.scene = None
@@ -687,3 +688,82 @@ def test_emulated_session_more_edges_than_the_offset_table(emu):
     assert (out.astype(bool) != want).mean() < 0.01
     assert 0.1 < want.mean() < 0.9
     emu.pmp_session_destroy(ses)
+
+
+def test_emulated_abi_argument_errors(emu):
+    """The C ABI's argument validation (status code + pmp_last_error text), reachable on the CPU through
+    the emulated build: malformed robot / scene tables, validators and calls are refused before any launch."""
+    import copy
+
+    spec, cst = workloads.make_panda()
+    t = EmuTables(emu, cst)
+
+    def refused(rc, text):
+        assert rc != 0 and text in emu.pmp_last_error().decode(), (rc, emu.pmp_last_error())
+
+    out = C.c_void_p()
+    refused(emu.pmp_robot_create(None, C.byref(out)), "null argument")
+    for field, value, text in (
+        ("n_ops", -1, "negative table size"),
+        ("base_type", 7, "bad base_type"),
+        ("n_groups", 4096, "too many sphere groups"),
+    ):
+        d = _capi.RobotDesc.from_buffer_copy(t._desc)
+        setattr(d, field, value)
+        refused(emu.pmp_robot_create(C.byref(d), C.byref(out)), text)
+    a = t._keep
+    for name, idx, field, value, text in (
+        ("groups", 0, "sphere_count", 10**6, "group sphere range out of bounds"),
+        ("groups", 1, "op", 999, "group refers to an unknown op"),
+    ):
+        arr = a[name].copy()
+        arr[idx][field] = value
+        d = _capi.RobotDesc.from_buffer_copy(t._desc)
+        d.groups = arr.ctypes.data
+        refused(emu.pmp_robot_create(C.byref(d), C.byref(out)), text)
+    ops = a["program"].ops.copy()
+    ops[3]["parent"] = 5
+    d = _capi.RobotDesc.from_buffer_copy(t._desc)
+    d.ops = ops.ctypes.data
+    refused(emu.pmp_robot_create(C.byref(d), C.byref(out)), "topological order")
+    pairs = a["pairs"].copy()
+    if len(pairs):
+        pairs.reshape(-1)[0] = 500
+        d = _capi.RobotDesc.from_buffer_copy(t._desc)
+        d.pairs = pairs.ctypes.data
+        refused(emu.pmp_robot_create(C.byref(d), C.byref(out)), "pair refers to an unknown group")
+    assert emu.pmp_robot_q_dim(None) == -1 and emu.pmp_robot_q_dim(t.robot) == 7
+    assert emu.pmp_robot_n_spheres(t.robot) == len(a["spheres"])
+    # scenes
+    sd = _capi.SceneDesc()
+    sd.n_prims = -1
+    refused(emu.pmp_scene_create(C.byref(sd), C.byref(out)), "negative table size")
+    prims = t._prims.copy()
+    prims[0]["type"] = 9
+    sd = _capi.SceneDesc()
+    sd.n_prims, sd.prims = len(prims), prims.ctypes.data
+    refused(emu.pmp_scene_create(C.byref(sd), C.byref(out)), "bad primitive type")
+    sd = _capi.SceneDesc()
+    sd.n_cloud_points, sd.cloud_points, sd.cloud_radius, sd.cloud_cell = 10, None, 0.01, 0.02
+    refused(emu.pmp_scene_create(C.byref(sd), C.byref(out)), "cloud_points is null")
+    bad = np.zeros((10, 3), dtype=np.float32)
+    bad[4, 1] = np.nan
+    sd.cloud_points = bad.ctypes.data
+    refused(emu.pmp_scene_create(C.byref(sd), C.byref(out)), "non-finite")
+    # validators and calls
+    Q = workloads.random_configs(spec, 8, 1)
+    bits = np.zeros(1, dtype=np.uint32)
+    v, keep = tables.make_validator(0, 7, np.full(7, 0.05), 0.0)
+    v.type = 5
+    refused(emu.pmp_check_edges_host(t.robot, t.scene, C.byref(v), Q.ctypes.data, Q.ctypes.data, 8, bits.ctypes.data, None, None), "unknown validator type")
+    v, keep = tables.make_validator(1, 7, None, 0.1)
+    v.resolution = 0.0
+    refused(emu.pmp_check_edges_host(t.robot, t.scene, C.byref(v), Q.ctypes.data, Q.ctypes.data, 8, bits.ctypes.data, None, None), "resolution must be positive")
+    refused(emu.pmp_check_configs_host(None, t.scene, Q.ctypes.data, 8, bits.ctypes.data, None), "")
+    refused(emu.pmp_check_configs_host(t.robot, t.scene, Q.ctypes.data, -3, bits.ctypes.data, None), "")
+    refused(emu.pmp_check_configs_host(t.robot, t.scene, None, 8, bits.ctypes.data, None), "")
+    ses = C.c_void_p()
+    v.type = 5
+    refused(emu.pmp_session_create(t.robot, t.scene, C.byref(v), 64, C.byref(ses)), "unknown validator type")
+    # and the handles still work afterwards
+    assert t.check(Q).shape == (8,)

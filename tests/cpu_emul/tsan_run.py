@@ -60,3 +60,10 @@ for n in (900, 200):
     p32 = (rng.uniform(-0.15, 0.15, (n, 3)) + [0.5, 0, 0.55]).astype(np.float32)
     assert lib.pmp_scene_update_cloud(t.scene, p32.ctypes.data, n, 0.01, 0.02) == 0
     print("cloud update", n, t.check(workloads.random_configs(spec, 64, 2)).mean(), flush=True)
+# the edge kernel (dynamic refill) on an overflow scene
+cst, lb, ub, desc = random_case(9004)
+cst.set_sdf(stress_scene(np.random.default_rng(9004), False))
+t = T.EmuTables(lib, cst)
+qa = sample_q(lb, ub, 48, 1)
+qb = np.clip(qa + np.random.default_rng(2).uniform(-0.4, 0.4, qa.shape), lb, ub).astype(np.float32)
+print("stress edges", t.check_edges(0, np.full(len(lb), 0.05), 0.0, qa, qb)[0].mean(), flush=True)

@@ -104,6 +104,15 @@ typedef struct {
 
 typedef struct pmp_robot pmp_robot_t;
 int pmp_robot_create(const pmp_robot_desc_t* desc, pmp_robot_t** out);
+/* The same with a collision filter: group_prim_mask[g] (may be NULL = all ones) says which entries of
+ * the scene group g is tested against — bit k (k < 30) = primitive k, bit 30 = the scene's point cloud.
+ * This is how a composite of several collision constraints on ONE kinematic model, each with its own
+ * scene (IneqCompositeCst, constraints/composite_constraint.hpp:27-44,98-105), is checked with a single
+ * forward-kinematics pass: the members' groups and pairs are concatenated into one robot table, their
+ * primitives into one scene, and every group keeps the bits of its own member's primitives.  Only the
+ * validity kernels (check_configs / check_edges / sessions) honour the mask; scenes used with a masked
+ * robot must have at most 30 primitives. */
+int pmp_robot_create_ex(const pmp_robot_desc_t* desc, const uint32_t* group_prim_mask, pmp_robot_t** out);
 void pmp_robot_destroy(pmp_robot_t* robot);
 int pmp_robot_q_dim(const pmp_robot_t* robot);
 int pmp_robot_n_spheres(const pmp_robot_t* robot);
@@ -204,6 +213,20 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene,
                     int64_t n, uint32_t* valid_bits_dev, unsigned long long* n_valid_dev,
                     unsigned long long* n_checked_dev, void* stream);
 
+/* The same with what the reference's own callers hold and what its tests observe:
+ *  - endpoints_f64 != 0: q0_dev / q1_dev are double [n][q_dim] (RealVectorStateSpace states).  The step
+ *    ratio and n_test are computed from the doubles exactly as determine_step_ratio does (:89-126), so
+ *    the waypoint count never depends on a rounding of the endpoints; the waypoints themselves are
+ *    interpolated and checked in FP32.
+ *  - calls_per_edge_dev (optional, [n]): how many times is_valid was called for edge i — the position
+ *    of the first failing waypoint in the reference's visiting order, else the waypoint count; the sum
+ *    is what n_checked_dev receives (si_->isValid calls, ompl_thin_wrap.hpp:114-120). */
+int pmp_check_edges_ex(const pmp_robot_t* robot, const pmp_scene_t* scene,
+                       const pmp_validator_t* validator, const void* q0_dev, const void* q1_dev,
+                       int endpoints_f64, int64_t n, uint32_t* valid_bits_dev,
+                       uint32_t* calls_per_edge_dev, unsigned long long* n_valid_dev,
+                       unsigned long long* n_checked_dev, void* stream);
+
 /* Host-buffer entry points (what the Python shim / an FFI caller binds): H2D copy of the
  * inputs, kernel, D2H copy of the results, all inside the call. */
 int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host,
@@ -214,6 +237,13 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene,
                          const pmp_validator_t* validator, const float* q0_host,
                          const float* q1_host, int64_t n, uint32_t* valid_bits_host,
                          uint64_t* n_valid, uint64_t* n_checked);
+
+/* FP64 host endpoints, as bindings hand them over (pybind11 converts numpy to Eigen::VectorXd,
+ * bindings/bindings.hpp:11-13): uploaded as doubles, converted on the device. */
+int pmp_check_edges_host_f64(const pmp_robot_t* robot, const pmp_scene_t* scene,
+                             const pmp_validator_t* validator, const double* q0_host,
+                             const double* q1_host, int64_t n, uint32_t* valid_bits_host,
+                             uint64_t* n_valid, uint64_t* n_checked);
 
 /* ---- validator sessions: what an OMPL-facing adaptor binds ---------------------
  * The reference installs its validators inside CollisionAwareSpaceInformation
@@ -228,8 +258,9 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene,
  *  - check_motion: the step ratio and n_test are computed on the host in FP64 from the caller's
  *    doubles exactly as determine_step_ratio does (:89-126).  Small batches (up to 2^17 waypoints)
  *    test every waypoint of every edge in one wave (result identical: checkMotion is an AND);
- *    larger ones use the early-exit kernel of pmp_check_edges.  n_checked reports the waypoint
- *    checks actually executed, so it exceeds the reference's is_valid call count on the first path. */
+ *    larger ones use the early-exit kernel of pmp_check_edges on the host-computed ratios.  n_checked
+ *    is the reference's is_valid call count on both paths (on the first one it is derived from the
+ *    per-waypoint results: position of the first failing waypoint in the reference's visiting order). */
 typedef struct pmp_session pmp_session_t;
 int pmp_session_create(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
                        int64_t capacity, pmp_session_t** out);

@@ -7,7 +7,7 @@
  *   si_->setMotionValidator(std::make_shared<BoxMotionValidator>(si_, vconfig.box_width));   // reference
  *   si_->setStateValidityChecker([this](const ob::State* s) { return this->is_valid(s); });
  * becomes
- *   auto mv = std::make_shared<plainmp_b200::SessionMotionValidator>(si_, session);
+ *   auto mv = std::make_shared<plainmp_b200::SessionMotionValidator>(si_, session, &is_valid_call_count_);
  *   si_->setMotionValidator(mv);
  *   si_->setStateValidityChecker(plainmp_b200::state_validity_fn(session, dim, &is_valid_call_count_));
  *
@@ -64,14 +64,19 @@ inline std::function<bool(const ob::State*)> state_validity_fn(pmp_session_t* se
 
 class SessionMotionValidator : public ob::MotionValidator {
  public:
-  SessionMotionValidator(const ob::SpaceInformationPtr& si, pmp_session_t* session)
-      : ob::MotionValidator(si), session_(session), dim_(si->getStateDimension()) {}
+  /* call_count (optional): the counter the state validity function bumps.  In the reference every
+   * waypoint of checkMotion goes through si_->isValid (motion_validator.cpp:52-71) and therefore through
+   * is_valid_call_count_ (ompl_thin_wrap.hpp:114-120), which is what a planner's max_is_valid_call budget
+   * looks at; the session reports exactly that number per call and it is added here. */
+  SessionMotionValidator(const ob::SpaceInformationPtr& si, pmp_session_t* session, std::size_t* call_count = nullptr)
+      : ob::MotionValidator(si), session_(session), dim_(si->getStateDimension()), call_count_(call_count) {}
 
   bool checkMotion(const ob::State* s1, const ob::State* s2) const override {
     std::uint8_t ok = 0;
     std::uint64_t n = 0;
     throw_on_error(pmp_session_check_motion(session_, values_of(s1), values_of(s2), 1, &ok, &n));
     checks_ += n;
+    if (call_count_) *call_count_ += (std::size_t)n;
     return ok != 0;
   }
   bool checkMotion(const ob::State* s1, const ob::State* s2, std::pair<ob::State*, double>& /*lastValid*/) const override {
@@ -91,6 +96,7 @@ class SessionMotionValidator : public ob::MotionValidator {
     std::uint64_t cnt = 0;
     throw_on_error(pmp_session_check_motion(session_, a.data(), b.data(), (std::int64_t)n, ok.data(), &cnt));
     checks_ += cnt;
+    if (call_count_) *call_count_ += (std::size_t)cnt;
     return std::vector<char>(ok.begin(), ok.end());
   }
 
@@ -99,6 +105,7 @@ class SessionMotionValidator : public ob::MotionValidator {
  private:
   pmp_session_t* session_;
   unsigned dim_;
+  std::size_t* call_count_;
   mutable std::uint64_t checks_ = 0;
 };
 

@@ -97,6 +97,11 @@ def lib() -> C.CDLL:
             "orc_validator_step_ratio": (d, [vp, vp, vp]),
             "orc_check_motion": (i, [vp, vp, vp, vp, C.POINTER(C.c_uint64)]),
             "orc_check_motion_batch": (None, [vp, vp, vp, vp, i64, i, vp, C.POINTER(C.c_uint64)]),
+            "orc_check_motion_batch_ex": (None, [vp, vp, vp, vp, i64, i, vp, vp, vp]),
+            "orc_composite_check": (i, [vp, i]),
+            "orc_composite_is_valid_batch": (None, [vp, i, vp, i64, i, vp]),
+            "orc_composite_margin_batch": (None, [vp, i, vp, i64, i, vp]),
+            "orc_composite_evaluate_batch": (None, [vp, i, vp, i64, i, vp]),
             "orc_sequence_row": (None, [i, vp]),
             "orc_farthest_sequence": (None, [i, vp]),
         }
@@ -269,8 +274,8 @@ class OracleKDTree:
 class OracleCst:
     """SphereCollisionCst of the oracle, mirrored from a plainmp_b200 SphereCollisionCst."""
 
-    def __init__(self, cst, n_threads: int = 1):
-        self.kin = OracleKin(cst.get_kin())
+    def __init__(self, cst, n_threads: int = 1, kin: "Optional[OracleKin]" = None):
+        self.kin = kin if kin is not None else OracleKin(cst.get_kin())  # `kin`: shared by the members of a composite
         self.n_threads = n_threads
         offs = [0]
         flat = []
@@ -403,10 +408,55 @@ class OracleValidator:
         lib().orc_check_motion_batch(self.h, cst.h, _p(S1), _p(S2), S1.shape[0], n_threads, _p(out), C.byref(n))
         return out.astype(bool), int(n.value)
 
+    def check_motion_batch_ex(self, cst: OracleCst, S1, S2, n_threads: int = 1, with_margin: bool = True):
+        """(valid [n], calls_per_edge [n], min_margin_per_edge [n] or None): the serial walk per edge, how
+        many is_valid calls it makes, and the smallest contact-band margin over the waypoints it visits."""
+        S1, S2 = _f64(S1), _f64(S2)
+        n = S1.shape[0]
+        out = np.zeros(n, dtype=np.uint8)
+        calls = np.zeros(n, dtype=np.uint32)
+        margin = np.zeros(n) if with_margin else None
+        lib().orc_check_motion_batch_ex(self.h, cst.h, _p(S1), _p(S2), n, n_threads, _p(out), _p(calls), _p(margin) if with_margin else None)
+        return out.astype(bool), calls, margin
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_validator_destroy(self.h)
             self.h = None
+
+
+class OracleComposite:
+    """IneqCompositeCst of the oracle (composite_constraint.hpp:27-44, 98-105) over OracleCst members
+    built on ONE shared OracleKin."""
+
+    def __init__(self, composite, n_threads: int = 1):
+        members = list(composite.constraints)
+        self.kin = OracleKin(members[0].get_kin())
+        self.members = [OracleCst(c, n_threads, kin=self.kin) for c in members]
+        self.n_threads = n_threads
+        self._h = (C.c_void_p * len(self.members))(*[m.h for m in self.members])
+        if lib().orc_composite_check(self._h, len(self.members)) != 0:
+            raise RuntimeError("All constraints must have the same kinematic chain")
+        self.q_dim = self.members[0].q_dim
+
+    def is_valid_batch(self, Q) -> np.ndarray:
+        Q = _f64(Q)
+        out = np.zeros(Q.shape[0], dtype=np.uint8)
+        lib().orc_composite_is_valid_batch(self._h, len(self.members), _p(Q), Q.shape[0], self.n_threads, _p(out))
+        return out.astype(bool)
+
+    def margin_batch(self, Q) -> np.ndarray:
+        Q = _f64(Q)
+        out = np.zeros(Q.shape[0])
+        lib().orc_composite_margin_batch(self._h, len(self.members), _p(Q), Q.shape[0], self.n_threads, _p(out))
+        return out
+
+    def evaluate_batch(self, Q) -> np.ndarray:
+        """[n, n_members, 2] (ext, self) per member, NaN where a term is disabled."""
+        Q = _f64(Q)
+        out = np.zeros((Q.shape[0], len(self.members), 2))
+        lib().orc_composite_evaluate_batch(self._h, len(self.members), _p(Q), Q.shape[0], self.n_threads, _p(out))
+        return out
 
 
 def sequence_row(n: int) -> List[int]:

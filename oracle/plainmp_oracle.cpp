@@ -1349,8 +1349,10 @@ struct SphereCollisionCst {
   // over every sphere/primitive and listed sphere/sphere test is_valid(q) can make, with the
   // same approximate FK.  Parity tests use it to decide whether an item lies in the epsilon
   // band where an FP32 implementation may legitimately disagree (BASELINE.json north_star).
-  double validity_margin(const double* q) {
-    update_kintree(q, false);
+  double validity_margin(const double* q) { return validity_margin_dirty_after(*this, q); }
+  // `driver` runs the FK update (the composite's first member, composite_constraint.hpp:39-44)
+  double validity_margin_dirty_after(SphereCollisionCst& driver, const double* q) {
+    driver.update_kintree(q, false);
     post_update_kintree();
     double m = std::numeric_limits<double>::infinity();
     for (auto& g : sphere_groups) {
@@ -1845,6 +1847,109 @@ void orc_check_motion_batch(void* v, void* cst, const double* s1, const double* 
     for (auto c : calls) *n_calls_total += c;
   }
 }
+// The same walk with what the parity tests need per edge: validity, how many is_valid calls the
+// reference's visiting order makes (position of the first failing waypoint, else the waypoint count),
+// and — ORACLE-ONLY — the smallest validity_margin over the waypoints visited.  An FP32 implementation
+// that walks the same order can differ from the reference on an edge (in validity or in call count)
+// only if one of those visited waypoints lies in the contact band.
+void orc_check_motion_batch_ex(void* v, void* cst, const double* s1, const double* s2, int64_t n, int n_threads,
+                               uint8_t* out, uint32_t* calls_per_edge, double* min_margin_per_edge) {
+  auto* V = (Validator*)v;
+  auto* base = (SphereCollisionCst*)cst;
+  const size_t d = V->dim;
+  parallel_for(n, n_threads, [&](int, int64_t lo, int64_t hi) {
+    auto c = base->clone_for_thread();
+    std::vector<double> tmp(d);
+    for (int64_t i = lo; i < hi; i++) {
+      const double* a = s1 + i * d;
+      const double* b = s2 + i * d;
+      uint64_t nc = 0;
+      out[i] = V->check_motion(*c, a, b, tmp.data(), &nc) ? 1 : 0;
+      if (calls_per_edge) calls_per_edge[i] = (uint32_t)nc;
+      if (!min_margin_per_edge) continue;
+      // replay the first nc waypoints of motion_validator.cpp:45-78
+      double m = std::numeric_limits<double>::infinity();
+      if (nc > 0) {
+        const double step_ratio = V->determine_step_ratio(a, b);
+        const size_t n_test = std::floor(1 / step_ratio) + 2;
+        const bool table = n_test < sequence_table().size() + 1;
+        m = std::min(m, c->validity_margin(b));
+        for (uint64_t k = 1; k < nc; k++) {
+          const double t = table ? sequence_table()[n_test - 1][k + 1] * step_ratio : k * step_ratio;
+          for (size_t j = 0; j < d; j++) tmp[j] = a[j] + (b[j] - a[j]) * t;
+          m = std::min(m, c->validity_margin(tmp.data()));
+        }
+      }
+      min_margin_per_edge[i] = m;
+    }
+  });
+}
+
+// ---- IneqCompositeCst (constraints/composite_constraint.hpp:27-44, 98-105) -----------------------
+// members share ONE kinematic model: update_kintree through the first member, post_update_kintree on
+// all, then AND of is_valid_dirty (is_valid) or the members' values stacked in order (evaluate)
+struct Composite {
+  std::vector<std::unique_ptr<SphereCollisionCst>> m;
+  static Composite clone_of(void** members, int n) {
+    Composite c;
+    for (int i = 0; i < n; i++) {
+      c.m.push_back(((SphereCollisionCst*)members[i])->clone_for_thread());
+      if (i > 0) c.m[i]->kin = c.m[0]->kin;
+    }
+    return c;
+  }
+  void update_kintree(const double* q, bool high_accuracy) {  // :39-44
+    m.front()->update_kintree(q, high_accuracy);
+    for (auto& c : m) c->post_update_kintree();
+  }
+  bool is_valid(const double* q) {  // :98-105
+    update_kintree(q, false);
+    for (auto& c : m)
+      if (!c->is_valid_dirty()) return false;
+    return true;
+  }
+};
+int orc_composite_check(void** members, int n) {  // ctor :27-37: same kinematic chain
+  for (int i = 1; i < n; i++)
+    if (((SphereCollisionCst*)members[i])->kin != ((SphereCollisionCst*)members[0])->kin) return -1;
+  return 0;
+}
+void orc_composite_is_valid_batch(void** members, int n_members, const double* q, int64_t n, int n_threads, uint8_t* out) {
+  const size_t d = ((SphereCollisionCst*)members[0])->q_dim();
+  parallel_for(n, n_threads, [&](int, int64_t lo, int64_t hi) {
+    Composite c = Composite::clone_of(members, n_members);
+    for (int64_t i = lo; i < hi; i++) out[i] = c.is_valid(q + i * d) ? 1 : 0;
+  });
+}
+// ORACLE-ONLY: min over the members of validity_margin under the shared (first member's) FK
+void orc_composite_margin_batch(void** members, int n_members, const double* q, int64_t n, int n_threads, double* out) {
+  const size_t d = ((SphereCollisionCst*)members[0])->q_dim();
+  parallel_for(n, n_threads, [&](int, int64_t lo, int64_t hi) {
+    Composite c = Composite::clone_of(members, n_members);
+    for (int64_t i = lo; i < hi; i++) {
+      double mm = std::numeric_limits<double>::infinity();
+      for (auto& k : c.m) mm = std::min(mm, k->validity_margin_dirty_after(*c.m.front(), q + i * d));
+      out[i] = mm;
+    }
+  });
+}
+// vals [n][2 * n_members]: (ext, self) per member, NaN where a term is disabled (:46-61 stacks only the
+// enabled ones; the bridge compacts)
+void orc_composite_evaluate_batch(void** members, int n_members, const double* q, int64_t n, int n_threads, double* vals) {
+  const size_t d = ((SphereCollisionCst*)members[0])->q_dim();
+  parallel_for(n, n_threads, [&](int, int64_t lo, int64_t hi) {
+    Composite c = Composite::clone_of(members, n_members);
+    for (int64_t i = lo; i < hi; i++) {
+      c.update_kintree(q + i * d, true);
+      for (int k = 0; k < n_members; k++) {
+        auto& mk = *c.m[k];
+        vals[(i * n_members + k) * 2] = mk.ext_collision_enabled() ? mk.evaluate_ext_collision() : std::nan("");
+        vals[(i * n_members + k) * 2 + 1] = mk.self_collision_enabled() ? mk.evaluate_self_collision() : std::nan("");
+      }
+    }
+  });
+}
+
 void orc_sequence_row(int n, int* out) {  // row n-1 of SEQUENCE_TABLE (first n entries)
   auto& t = sequence_table();
   for (int i = 0; i < n; i++) out[i] = t[n - 1][i];

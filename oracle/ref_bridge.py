@@ -107,6 +107,12 @@ def lib() -> C.CDLL:
             "ref_flat_sizes": (None, [vp, vp]),
             "ref_flat_copy": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
             "ref_check_motion_batch": (None, [vp, i, i, vp, d, vp, vp, i64, vp, C.POINTER(C.c_uint64)]),
+            "ref_check_motion_batch_ex": (None, [vp, i, i, vp, d, vp, vp, i64, vp, vp, C.POINTER(C.c_uint64)]),
+            "ref_composite_create": (vp, [vp, i]),
+            "ref_composite_destroy": (None, [vp]),
+            "ref_composite_dim": (i, [vp]),
+            "ref_composite_is_valid_batch": (None, [vp, vp, i64, vp]),
+            "ref_composite_evaluate_batch": (None, [vp, vp, i64, vp, vp]),
             "ref_step_ratio": (d, [i, i, vp, d, vp, vp]),
         }
         for name, (res, args) in sig.items():
@@ -275,8 +281,8 @@ class RefCst:
     """plainmp::constraint::SphereCollisionCst mirrored from a plainmp_b200 SphereCollisionCst
     (un-reordered specs, link/pair NAMES, SDF tree) on its own private kinematic model."""
 
-    def __init__(self, cst):
-        self.kin = RefKin(cst.get_kin())
+    def __init__(self, cst, kin: "Optional[RefKin]" = None):
+        self.kin = kin if kin is not None else RefKin(cst.get_kin())  # `kin`: shared by the members of a composite
         offs, flat = [0], []
         for sp in cst._group_spheres_unordered:
             flat.append(sp)
@@ -377,9 +383,55 @@ class RefCst:
         lib().ref_check_motion_batch(self.h, int(vtype), dim, _p(w), float(resolution), _p(S1), _p(S2), S1.shape[0], _p(out), C.byref(n))
         return out.astype(bool), int(n.value)
 
+    def check_motion_batch_ex(self, vtype: int, box_width, resolution: float, S1, S2):
+        """(valid [n], calls_per_edge [n]): checkMotion per edge and how many times it called isValid."""
+        S1, S2 = _f64(S1), _f64(S2)
+        dim = S1.shape[1]
+        w = _f64(box_width) if box_width is not None else np.zeros(dim)
+        out = np.zeros(S1.shape[0], dtype=np.uint8)
+        calls = np.zeros(S1.shape[0], dtype=np.uint32)
+        n = C.c_uint64(0)
+        lib().ref_check_motion_batch_ex(self.h, int(vtype), dim, _p(w), float(resolution), _p(S1), _p(S2), S1.shape[0], _p(out), _p(calls), C.byref(n))
+        return out.astype(bool), calls
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().ref_cst_destroy(self.h)
+            self.h = None
+
+
+class RefComposite:
+    """plainmp::constraint::IneqCompositeCst (composite_constraint.hpp:88-105) over RefCst members that
+    share ONE reference KinematicModel, as bindings/constraint.cpp:108-113 constructs it."""
+
+    def __init__(self, composite):
+        members = list(composite.constraints)
+        self.kin = RefKin(members[0].get_kin())
+        self.members = [RefCst(c, kin=self.kin) for c in members]
+        hs = (C.c_void_p * len(self.members))(*[m.h for m in self.members])
+        self.h = lib().ref_composite_create(hs, len(self.members))
+        if not self.h:
+            _raise()
+        self.dim = lib().ref_composite_dim(self.h)
+        self.q_dim = self.members[0].q_dim
+
+    def is_valid_batch(self, Q) -> np.ndarray:
+        Q = _f64(Q)
+        out = np.zeros(Q.shape[0], dtype=np.uint8)
+        lib().ref_composite_is_valid_batch(self.h, _p(Q), Q.shape[0], _p(out))
+        return out.astype(bool)
+
+    def evaluate_batch(self, Q, with_jac: bool = False):
+        """vals [n, cst_dim] (+ jac [n, cst_dim, q_dim]): the enabled terms of the members stacked in order."""
+        Q = _f64(Q)
+        vals = np.zeros((Q.shape[0], self.dim))
+        jac = np.zeros((Q.shape[0], self.dim, Q.shape[1])) if with_jac else None
+        lib().ref_composite_evaluate_batch(self.h, _p(Q), Q.shape[0], _p(vals), _p(jac) if with_jac else None)
+        return (vals, jac) if with_jac else vals
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_composite_destroy(self.h)
             self.h = None
 
 
@@ -409,3 +461,26 @@ def is_valid_batch_threads(cst, Q, n_threads: int) -> np.ndarray:
     for t in ths:
         t.join()
     return out
+
+
+def check_motion_batch_threads(cst, vtype: int, box_width, resolution: float, S1, S2, n_threads: int):
+    """check_motion_batch_ex over disjoint slices, one private reference kin + cst per thread."""
+    import threading
+
+    S1, S2 = _f64(S1), _f64(S2)
+    n_threads = max(1, min(n_threads, len(S1)))
+    insts = [RefCst(cst) for _ in range(n_threads)]
+    valid = np.zeros(len(S1), dtype=bool)
+    calls = np.zeros(len(S1), dtype=np.uint32)
+    bounds = np.linspace(0, len(S1), n_threads + 1).astype(int)
+
+    def work(t):
+        lo, hi = bounds[t], bounds[t + 1]
+        valid[lo:hi], calls[lo:hi] = insts[t].check_motion_batch_ex(vtype, box_width, resolution, S1[lo:hi], S2[lo:hi])
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return valid, calls

@@ -3,7 +3,7 @@
 // C entry points around the REFERENCE's own hot-path classes, compiled from the sources where they
 // lie under /root/reference (see oracle/Makefile.ref): plainmp::kinematics::utils::_KinematicModel,
 // plainmp::collision::{Box,Cylinder,Sphere,Ground,Cloud,Union}SDF and KDTree,
-// plainmp::constraint::SphereCollisionCst, plainmp::ompl_wrapper::{Box,Euclidean}MotionValidator.
+// plainmp::constraint::{SphereCollisionCst,IneqCompositeCst}, plainmp::ompl_wrapper::{Box,Euclidean}MotionValidator.
 // This file contains no algorithm: it only constructs those objects and loops over batches, the way
 // bindings/{kinematics,primitive,constraint,kdtree}.cpp and ompl/ompl_thin_wrap.hpp:80-120 do.
 // Output: oracle/_ref/libplainmp_ref.so (git-ignored).  Used by tests/ to pin the restated oracle
@@ -13,6 +13,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <numeric>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -34,6 +35,7 @@
 #define protected public
 #include "plainmp/collision/kdtree.hpp"
 #include "plainmp/collision/primitive_sdf.hpp"
+#include "plainmp/constraints/composite_constraint.hpp"
 #include "plainmp/constraints/primitive_sphere_collision.hpp"
 #include "plainmp/kinematics/kinematic_model_wrapper.hpp"
 #include "plainmp/ompl/motion_validator.hpp"
@@ -366,8 +368,18 @@ void ref_flat_copy(void* f, void* ops, void* groups, float* spheres, int32_t* pa
 }
 
 // ---- motion validators (ompl/motion_validator.cpp, installed as in ompl_thin_wrap.hpp:80-120) ----
+// calls_per_edge (optional): how many times checkMotion called isValid for edge i — the position of the
+// first failing waypoint in the reference's visiting order, else the waypoint count
+void ref_check_motion_batch_ex(void* cst_h, int type, int dim, const double* box_width, double resolution,
+                               const double* S1, const double* S2, int64_t n, uint8_t* out, uint32_t* calls_per_edge,
+                               uint64_t* n_checked);
 void ref_check_motion_batch(void* cst_h, int type, int dim, const double* box_width, double resolution,
                             const double* S1, const double* S2, int64_t n, uint8_t* out, uint64_t* n_checked) {
+  ref_check_motion_batch_ex(cst_h, type, dim, box_width, resolution, S1, S2, n, out, nullptr, n_checked);
+}
+void ref_check_motion_batch_ex(void* cst_h, int type, int dim, const double* box_width, double resolution,
+                               const double* S1, const double* S2, int64_t n, uint8_t* out, uint32_t* calls_per_edge,
+                               uint64_t* n_checked) {
   auto& c = *static_cast<CstPtr*>(cst_h);
   auto space = std::make_shared<ob::RealVectorStateSpace>((unsigned)dim);
   auto si = std::make_shared<ob::SpaceInformation>(space);
@@ -391,11 +403,44 @@ void ref_check_motion_batch(void* cst_h, int type, int dim, const double* box_wi
       a->values[k] = S1[i * dim + k];
       b->values[k] = S2[i * dim + k];
     }
+    const uint64_t before = count;
     out[i] = mv->checkMotion(a, b) ? 1 : 0;
+    if (calls_per_edge) calls_per_edge[i] = (uint32_t)(count - before);
   }
   si->freeState(a);
   si->freeState(b);
   if (n_checked) *n_checked = count;
+}
+
+// ---- IneqCompositeCst (constraints/composite_constraint.hpp:88-105, bindings/constraint.cpp:108-113) ----
+using CompPtr = std::shared_ptr<cst::IneqCompositeCst>;
+void* ref_composite_create(void** members, int n) {
+  REF_TRY
+  std::vector<cst::IneqConstraintBase::Ptr> v;
+  for (int i = 0; i < n; i++) v.push_back(*static_cast<CstPtr*>(members[i]));
+  return new CompPtr(std::make_shared<cst::IneqCompositeCst>(v));
+  REF_CATCH(nullptr)
+}
+void ref_composite_destroy(void* h) { delete static_cast<CompPtr*>(h); }
+int ref_composite_dim(void* h) { return (int)(*static_cast<CompPtr*>(h))->CompositeConstraintBase::cst_dim(); }
+void ref_composite_is_valid_batch(void* h, const double* Q, int64_t n, uint8_t* out) {
+  auto& c = *static_cast<CompPtr*>(h);
+  const int d = (int)c->q_dim();
+  for (int64_t i = 0; i < n; i++) out[i] = c->is_valid(row_of(Q, i, d)) ? 1 : 0;
+}
+// vals [n][cst_dim], jac [n][cst_dim][q_dim] (optional): members stacked in order, disabled terms absent
+void ref_composite_evaluate_batch(void* h, const double* Q, int64_t n, double* vals, double* jac) {
+  auto& c = *static_cast<CompPtr*>(h);
+  const int d = (int)c->q_dim();
+  const int m = (int)c->CompositeConstraintBase::cst_dim();
+  for (int64_t i = 0; i < n; i++) {
+    auto r = c->evaluate(row_of(Q, i, d));
+    for (int t = 0; t < m; t++) {
+      vals[i * m + t] = r.first[t];
+      if (jac)
+        for (int k = 0; k < d; k++) jac[(i * m + t) * d + k] = r.second(t, k);
+    }
+  }
 }
 
 double ref_step_ratio(int type, int dim, const double* box_width, double resolution, const double* s1, const double* s2) {

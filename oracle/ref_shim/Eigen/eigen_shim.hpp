@@ -296,6 +296,11 @@ struct DenseBase {
   View<S, BR, BC> block(Index i, Index j) {
     return {&coeffRef(i, j), BR, BC, derived().rstride_(), derived().cstride_()};
   }
+  // run-time sized block / segment (composite_constraint.hpp:57-58)
+  View<S, Dynamic, Dynamic> block(Index i, Index j, Index r, Index c) {
+    return {&coeffRef(i, j), r, c, derived().rstride_(), derived().cstride_()};
+  }
+  View<S, Dynamic, 1> segment(Index i, Index n) { return {&linRef(i), n, 1, cols() == 1 ? derived().rstride_() : derived().cstride_(), 0}; }
   View<S, Dynamic, 1> head(Index n) { return {&linRef(0), n, 1, cols() == 1 ? derived().rstride_() : derived().cstride_(), 0}; }
   View<S, Dynamic, 1> head(Index n) const { return const_cast<DenseBase*>(this)->head(n); }
   ArrayOf<S, RowsAtCompileTime, ColsAtCompileTime> array() {

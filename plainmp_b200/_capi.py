@@ -122,6 +122,7 @@ SYMBOLS = {
     "pmp_set_device": (_i32, [_i32]),
     "pmp_measure_fp32_peak": (_i32, [C.POINTER(C.c_double)]),
     "pmp_robot_create": (_i32, [C.POINTER(RobotDesc), C.POINTER(_p)]),
+    "pmp_robot_create_ex": (_i32, [C.POINTER(RobotDesc), _p, C.POINTER(_p)]),
     "pmp_robot_destroy": (None, [_p]),
     "pmp_robot_q_dim": (_i32, [_p]),
     "pmp_robot_n_spheres": (_i32, [_p]),
@@ -135,9 +136,14 @@ SYMBOLS = {
     "pmp_fk_spheres": (_i32, [_p, _p, _i64, _i32, _p, _p]),
     "pmp_fk_frames": (_i32, [_p, _p, _i64, _i32, _p, _p]),
     "pmp_check_edges": (_i32, [_p, _p, C.POINTER(Validator), _p, _p, _i64, _p, _p, _p, _p]),
+    "pmp_check_edges_ex": (_i32, [_p, _p, C.POINTER(Validator), _p, _p, _i32, _i64, _p, _p, _p, _p, _p]),
     "pmp_check_configs_host": (_i32, [_p, _p, _p, _i64, _p, C.POINTER(C.c_uint64)]),
     "pmp_eval_configs_host": (_i32, [_p, _p, _p, _i64, _p]),
     "pmp_check_edges_host": (
+        _i32,
+        [_p, _p, C.POINTER(Validator), _p, _p, _i64, _p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+    ),
+    "pmp_check_edges_host_f64": (
         _i32,
         [_p, _p, C.POINTER(Validator), _p, _p, _i64, _p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     ),

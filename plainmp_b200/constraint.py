@@ -254,19 +254,107 @@ class SphereCollisionCst(IneqConstraintBase):
 
 
 class IneqCompositeCst:
-    """composite_constraint.hpp:98-105: one FK, AND over members.  Only collision members are on
-    this repo's path; they must share the kinematic model."""
+    """composite_constraint.hpp:27-44, 98-105: ONE forward-kinematics update (through the first member),
+    then the AND of the members' ``is_valid_dirty``.  Only sphere-collision members are on this repo's
+    path; they must share the kinematic model (the reference's constructor check).
+
+    The members are merged into one device table — their sphere groups and listed pairs concatenated
+    over a single link program, their primitives concatenated into one scene, and every group masked to
+    the primitives of its own member (``pmp_robot_create_ex``) — so that ``is_valid`` /
+    ``is_valid_batch`` / edges run ONE kernel with ONE FK pass per configuration, as the reference does
+    one ``update_kintree``.  ``evaluate`` stacks the members' rows (composite_constraint.hpp:46-61)."""
+
+    MAX_MERGED_PRIMS = 30  # the direct bits of the kernels' cull mask
 
     def __init__(self, constraints: Sequence[SphereCollisionCst]):
         self.constraints = list(constraints)
+        if not self.constraints:
+            raise RuntimeError("IneqCompositeCst needs at least one constraint")
+        first = self.constraints[0]
         for c in self.constraints:
-            if c.get_kin() is not self.constraints[0].get_kin():
+            if c.get_kin() is not first.get_kin():
                 raise RuntimeError("All constraints must have the same kinematic chain")
+        self._merged_cache = None
+
+    # the reference drives the shared model through the FIRST member (update_kintree, :39-44): the other
+    # members see whatever joints / base that member controls.  A merged table can only represent
+    # members that agree on them, which is how the reference's own callers build composites.
+    def _mergeable(self) -> bool:
+        first = self.constraints[0]
+        same_q = all(c._control_joint_ids == first._control_joint_ids and c._base_type == first._base_type for c in self.constraints)
+        n_prims = sum(1 for c in self.constraints for leaf in c._leaves() if not _is_cloud(leaf))
+        n_clouds = sum(1 for c in self.constraints for leaf in c._leaves() if _is_cloud(leaf))
+        return same_q and n_prims <= self.MAX_MERGED_PRIMS and n_clouds <= 1
+
+    def _merge_parts(self):
+        """The members' tables concatenated (host arrays only, no device): group links / spheres /
+        only-self flags, pairs re-indexed, the flattened scene leaves in member order and the per-group
+        scene mask (bit k < 30 = k-th non-cloud leaf, bit 30 = the cloud)."""
+        leaves, links, spheres, only_self, pairs, masks = [], [], [], [], [], []
+        for c in self.constraints:
+            mask, base_g = 0, len(links)
+            for leaf in c._leaves():
+                if _is_cloud(leaf):
+                    mask |= 1 << 30
+                else:
+                    mask |= 1 << sum(1 for l in leaves if not _is_cloud(l))
+                leaves.append(leaf)
+            links += c._group_links
+            spheres += c._group_spheres
+            only_self += c._group_only_self
+            pairs += [(a + base_g, b + base_g) for a, b in c._pairs]
+            masks += [mask] * len(c._group_links)
+        return {"leaves": leaves, "links": links, "spheres": spheres, "only_self": only_self, "pairs": pairs, "masks": masks}
+
+    def _merged(self):
+        """(RobotTable with per-group scene masks, SceneTable or None) for the current member state."""
+        first = self.constraints[0]
+        m = self._merge_parts()
+        leaves, masks = m["leaves"], m["masks"]
+        key = (first._kin.state_key(first._control_joint_ids), tuple(id(c) for c in self.constraints), tuple(masks),
+               tuple(len(c._group_links) for c in self.constraints))
+        skey = tuple(l._state_key() for l in leaves)
+        mc = self._merged_cache
+        if mc is None or mc["key"] != key:
+            robot = tables.RobotTable(first._kin, first._control_joint_ids, first._base_type, m["links"], m["spheres"], m["only_self"],
+                                      m["pairs"], group_prim_mask=masks)
+            mc = {"key": key, "robot": robot, "skey": None, "scene": None}
+        if mc["skey"] != skey:
+            if not leaves:
+                mc["scene"] = None
+            elif mc["scene"] is None or not mc["scene"].try_update(leaves):
+                mc["scene"] = tables.SceneTable(leaves)
+            mc["skey"] = skey
+        self._merged_cache = mc
+        return mc["robot"], mc["scene"]
+
+    # the surface the validators / sessions use (same names as SphereCollisionCst)
+    def _robot(self):
+        return self._merged()[0]
+
+    def _scene(self):
+        return self._merged()[1]
+
+    def q_dim(self) -> int:
+        return self.constraints[0].q_dim()
+
+    def get_kin(self):
+        return self.constraints[0].get_kin()
+
+    def cst_dim(self) -> int:
+        return sum(c.cst_dim() for c in self.constraints)
 
     def is_valid(self, q) -> bool:
-        return all(c.is_valid(q) for c in self.constraints)
+        return bool(self.is_valid_batch(np.asarray(q, dtype=np.float64).reshape(1, -1))[0])
 
     def is_valid_batch(self, Q) -> np.ndarray:
+        if self._mergeable():
+            robot, scene = self._merged()
+            if scene is None and robot.pairs.shape[0] == 0:
+                return np.ones(np.asarray(Q).shape[0], dtype=bool)
+            return tables.check_configs(robot, scene, Q)
+        # members that cannot share one table (different control joints / base, more than 30 primitives or
+        # several clouds in total): one launch per member
         out = None
         for c in self.constraints:
             v = c.is_valid_batch(Q)
@@ -274,9 +362,19 @@ class IneqCompositeCst:
         return out
 
     def evaluate(self, q):
-        # composite_constraint.hpp:63-79: member values and Jacobian rows stacked in order
+        # composite_constraint.hpp:46-61: member values and Jacobian rows stacked in order
         parts = [c.evaluate(q) for c in self.constraints]
         dim = self.constraints[0].q_dim()
         v = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0)
         j = np.concatenate([p[1].reshape(-1, dim) for p in parts], axis=0) if parts else np.zeros((0, dim))
         return v, j
+
+    def evaluate_batch(self, Q) -> np.ndarray:
+        """[n, n_members, 2]: (ext, self) of every member, NaN where a term is disabled."""
+        return np.stack([c.evaluate_batch(Q) for c in self.constraints], axis=1)
+
+
+def _is_cloud(leaf) -> bool:
+    from . import psdf
+
+    return leaf.get_type() == psdf.T_CLOUD

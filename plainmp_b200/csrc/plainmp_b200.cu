@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -35,38 +36,81 @@ int fail(int code, const std::string& msg) {
 constexpr int kBlock = 128;
 constexpr int kMaxSmem = 200 * 1024;
 
-int g_num_sms = 0;
-int ensure_device() {
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] {
-    int n = 0;
-    err = cudaGetDeviceCount(&n);
-    if (err == cudaSuccess && n == 0) err = cudaErrorNoDevice;
-    if (err != cudaSuccess) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  });
-  if (err != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(err));
-  return PMP_OK;
-}
-
-// Occupancy per (kernel, dynamic smem, block) is queried once and remembered: the two runtime calls
-// cost several microseconds, which is most of a small launch on the session's latency path.
+// Everything the library caches on a device lives in a per-device record: the SM count, the occupancy
+// cache (cudaFuncSetAttribute is per device), the sequence table, the box-width copies and the host-call
+// workspaces.  The record of the calling thread's CURRENT device is used, so one process may drive
+// several GPUs (pmp_set_device).
 struct GridCacheEntry {
   int smem_attr = 0;                                  // MaxDynamicSharedMemorySize currently set
   std::vector<std::pair<std::pair<size_t, int>, int>> per_sm;  // ((smem, block), CTAs per SM)
 };
-std::mutex g_grid_mu;
-std::unordered_map<const void*, GridCacheEntry> g_grid_cache;
+struct ValidatorCache {  // device copies of box widths, keyed by content
+  std::vector<double> width;
+  double* dev = nullptr;  // [2][dim]: width, inv_width
+  uint64_t last_use = 0;
+};
+struct HostWorkspace;
+struct DeviceState {
+  int ordinal = -1;
+  int num_sms = 0;
+  std::mutex grid_mu;
+  std::unordered_map<const void*, GridCacheEntry> grid_cache;
+  std::mutex seq_mu;
+  uint8_t* seq_dev = nullptr;
+  std::mutex val_mu;
+  std::vector<ValidatorCache> val_cache;
+  uint64_t val_clock = 0;
+  std::mutex ws_mu;
+  std::vector<HostWorkspace*> ws_free;  // idle host-call workspaces (one is checked out per *_host call)
+};
+std::mutex g_dev_mu;
+std::vector<DeviceState*> g_devs;  // index = device ordinal; entries are never freed
 
+int device_state(DeviceState** out) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err == cudaSuccess && dev < 0) err = cudaErrorNoDevice;
+  if (err != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(err));
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if ((int)g_devs.size() <= dev) g_devs.resize(dev + 1, nullptr);
+  if (!g_devs[dev]) {
+    int n = 0;
+    err = cudaGetDeviceCount(&n);
+    if (err == cudaSuccess && n == 0) err = cudaErrorNoDevice;
+    if (err != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(err));
+    auto* d = new DeviceState();
+    d->ordinal = dev;
+    cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    // stream-ordered scratch (cudaMallocAsync) is handed back to the pool, not to the driver, between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    g_devs[dev] = d;
+  }
+  *out = g_devs[dev];
+  return PMP_OK;
+}
+int ensure_device() {
+  DeviceState* d;
+  return device_state(&d);
+}
+int num_sms() {
+  DeviceState* d;
+  return device_state(&d) == PMP_OK ? d->num_sms : 1;
+}
+
+// Occupancy per (kernel, dynamic smem, block) is queried once per device and remembered: the two runtime
+// calls cost several microseconds, which is most of a small launch on the session's latency path.
 template <class K>
 int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kBlock) {
+  DeviceState* D;
+  if (int rc = device_state(&D)) return rc;
   int per_sm = 0;
   {
-    std::lock_guard<std::mutex> lk(g_grid_mu);
-    GridCacheEntry& e = g_grid_cache[reinterpret_cast<const void*>(kernel)];
+    std::lock_guard<std::mutex> lk(D->grid_mu);
+    GridCacheEntry& e = D->grid_cache[reinterpret_cast<const void*>(kernel)];
     if ((int)smem > e.smem_attr) {
       CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       e.smem_attr = (int)smem;
@@ -79,7 +123,7 @@ int grid_for(K kernel, size_t smem, long long n_tiles, int* grid, int block = kB
       e.per_sm.push_back({{smem, block}, per_sm});
     }
   }
-  long long g = (long long)g_num_sms * per_sm;
+  long long g = (long long)D->num_sms * per_sm;
   *grid = (int)std::max<long long>(1, std::min<long long>(g, n_tiles));
   return PMP_OK;
 }
@@ -139,6 +183,8 @@ static int pick_block_per_thread(const RobotTables& r, const SceneDev& s, bool e
     if (smem_bytes(r, s, b, eval_kernel) <= (size_t)kMaxSmem) return b;
   return 0;
 }
+// a robot with per-group scene masks addresses primitives through the 30 direct bits of the cull mask
+static bool mask_limit_ok(const RobotTables& r, const SceneDev& s) { return r.dev.off_gmask < 0 || s.n_prims <= 30; }
 // 128 threads per CTA unless the per-thread stash would leave fewer than 3 CTAs per SM
 static int pick_block(const RobotTables& r, const SceneDev& s) {
   return smem_bytes(r, s, 128) * 3 <= (size_t)227 * 1024 ? 128 : 64;
@@ -154,6 +200,7 @@ struct OpD {
 struct GroupD {
   double center[3], radius;
   int op, sphere_begin, sphere_count, only_self;
+  unsigned prim_mask = 0xffffffffu;  // which scene entries the group is tested against (pmp_robot_create_ex)
 };
 struct ProgramD {
   std::vector<OpD> ops;
@@ -286,7 +333,10 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   const int off_spheres = off_groups + n_groups * 2;
   const int off_pairs = off_spheres + n_spheres;
   const int off_pairs4 = off_pairs + (n_pairs + 1) / 2;
-  const int words = off_pairs4 + n_pairs;
+  const int off_gmask = off_pairs4 + n_pairs;
+  bool has_gmask = false;
+  for (const GroupD& G : P.groups) has_gmask |= G.prim_mask != 0xffffffffu;
+  const int words = off_gmask + (has_gmask ? (n_groups + 3) / 4 : 0);
   std::vector<float4> blob(std::max(words, 1));
   auto fi = [](int v) {
     float f;
@@ -332,6 +382,10 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
       blob[off_pairs4 + p] = make_float4(fi(pw[2 * p]), fi(pw[2 * p + 1]), rs * rs, (rs + kGc16Pair) * (rs + kGc16Pair));
     }
   }
+  if (has_gmask) {
+    unsigned* gm = reinterpret_cast<unsigned*>(blob.data() + off_gmask);
+    for (int k = 0; k < n_groups; k++) gm[k] = P.groups[order[k]].prim_mask;
+  }
   cudaError_t e = cudaMalloc(&out->blob_dev, blob.size() * sizeof(float4));
   if (e == cudaSuccess) e = cudaMemcpy(out->blob_dev, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("robot table upload: ") + cudaGetErrorString(e));
@@ -346,6 +400,7 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   D.off_spheres = off_spheres;
   D.off_pairs = off_pairs;
   D.off_pairs4 = off_pairs4;
+  D.off_gmask = has_gmask ? off_gmask : -1;
   D.dof = d->dof;
   D.q_dim = q_dim;
   D.base_type = d->base_type;
@@ -388,13 +443,14 @@ int pmp_device_count(void) {
 }
 
 int pmp_set_device(int device) {
-  if (int rc = ensure_device()) return rc;
   CUDA_OK(cudaSetDevice(device));
-  return PMP_OK;
+  return ensure_device();  // creates this device's record (SM count, caches) on first use
 }
 
 // ---------------------------------------------------------------------------------------------
-int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
+int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) { return pmp_robot_create_ex(d, nullptr, out); }
+
+int pmp_robot_create_ex(const pmp_robot_desc_t* d, const uint32_t* group_prim_mask, pmp_robot_t** out) {
   if (!d || !out) return fail(PMP_ERR_INVALID, "null argument");
   if (d->n_ops < 0 || d->n_groups < 0 || d->n_spheres < 0 || d->n_pairs < 0 || d->dof < 0)
     return fail(PMP_ERR_INVALID, "negative table size");
@@ -442,6 +498,7 @@ int pmp_robot_create(const pmp_robot_desc_t* d, pmp_robot_t** out) {
     c.sphere_begin = G.sphere_begin;
     c.sphere_count = G.sphere_count;
     c.only_self = G.only_self_collision ? 1 : 0;
+    if (group_prim_mask) c.prim_mask = group_prim_mask[g];
   }
   P.spheres.assign(d->spheres, d->spheres + (size_t)4 * d->n_spheres);
   P.pairs.assign(d->pairs, d->pairs + (size_t)2 * d->n_pairs);
@@ -537,7 +594,7 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
     }
     std::string err;
     int launches = 0;
-    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_cell, g_num_sms, &s->dev.cloud, &s->cloud[0], &s->cloud_scratch,
+    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_cell, num_sms(), &s->dev.cloud, &s->cloud[0], &s->cloud_scratch,
                     &launches, &err)) {
       pmp_scene_destroy(s);
       return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
@@ -584,7 +641,7 @@ int pmp_scene_update_cloud(pmp_scene_t* s, const float* points, int64_t n, float
   if (n > 0) {
     std::string err;
     int launches = 0;
-    if (cloud_build(points, n, radius, cell, g_num_sms, &fresh, &s->cloud[idle], &s->cloud_scratch, &launches, &err))
+    if (cloud_build(points, n, radius, cell, num_sms(), &fresh, &s->cloud[idle], &s->cloud_scratch, &launches, &err))
       return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
     g_launches += launches;
   } else {
@@ -608,6 +665,7 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
   if (n == 0) return PMP_OK;
   if ((!q_dev && robot->fast.dev.q_dim > 0) || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
   const SceneDev S = scene ? scene->dev : empty_scene();
+  if (!mask_limit_ok(robot->fast, S)) return fail(PMP_ERR_LIMIT, "a robot with per-group scene masks needs a scene of at most 30 primitives");
   const int block = pick_block(robot->fast, S);
   const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
@@ -720,6 +778,7 @@ int pmp_fk_frames(const pmp_robot_t* robot, const float* q_dev, int64_t n, int a
 }
 
 // ---- edges ---------------------------------------------------------------------------------------
+extern "C++" {
 namespace {
 // ompl/generate_sequence.py:11-63: greedy farthest-first permutation, ties -> larger number
 std::vector<int> farthest_sequence(int N) {
@@ -742,57 +801,70 @@ std::vector<int> farthest_sequence(int N) {
   }
   return result;
 }
-uint8_t* g_seq_dev = nullptr;
-std::mutex g_seq_mu;
-int ensure_sequence_table() {
-  std::lock_guard<std::mutex> lk(g_seq_mu);
-  if (g_seq_dev) return PMP_OK;
-  std::vector<uint8_t> t(128 * 128, 0);
-  for (int n = 1; n <= 128; n++) {
-    auto row = farthest_sequence(n);
-    for (int i = 0; i < n; i++) t[(n - 1) * 128 + i] = (uint8_t)row[i];
-  }
-  CUDA_OK(cudaMalloc(&g_seq_dev, t.size()));
-  CUDA_OK(cudaMemcpy(g_seq_dev, t.data(), t.size(), cudaMemcpyHostToDevice));
+const std::vector<uint8_t>& sequence_table_host() {  // SEQUENCE_TABLE rows zero-padded to 128 (generate_sequence.py:76-98)
+  static const std::vector<uint8_t> t = [] {
+    std::vector<uint8_t> v(128 * 128, 0);
+    for (int n = 1; n <= 128; n++) {
+      auto row = farthest_sequence(n);
+      for (int i = 0; i < n; i++) v[(n - 1) * 128 + i] = (uint8_t)row[i];
+    }
+    return v;
+  }();
+  return t;
+}
+int ensure_sequence_table(DeviceState* D) {
+  std::lock_guard<std::mutex> lk(D->seq_mu);
+  if (D->seq_dev) return PMP_OK;
+  const auto& t = sequence_table_host();
+  CUDA_OK(cudaMalloc(&D->seq_dev, t.size()));
+  CUDA_OK(cudaMemcpy(D->seq_dev, t.data(), t.size(), cudaMemcpyHostToDevice));
   return PMP_OK;
 }
 
-struct ValidatorCache {  // device copies of box widths, keyed by content
-  std::vector<double> width;
-  double* dev = nullptr;  // [2][dim]: width, inv_width
-};
-std::mutex g_val_mu;
-std::vector<ValidatorCache> g_val_cache;
+constexpr size_t kMaxValidatorCache = 64;  // distinct box-width vectors kept per device (least recently used goes first)
 
 int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
   if (!v) return fail(PMP_ERR_INVALID, "validator is null");
   if (v->dim != q_dim) return fail(PMP_ERR_INVALID, "box dimension and space dimension mismatch");  // ompl_thin_wrap.hpp:84-86
-  if (int rc = ensure_sequence_table()) return rc;
-  out->seq = g_seq_dev;
+  DeviceState* D;
+  if (int rc = device_state(&D)) return rc;
+  if (int rc = ensure_sequence_table(D)) return rc;
+  out->seq = D->seq_dev;
   out->type = v->type;
   out->resolution = v->resolution;
   out->width = out->inv_width = nullptr;
   if (v->type == PMP_VALIDATOR_BOX) {
     if (!v->box_width) return fail(PMP_ERR_INVALID, "box_width is null");
-    std::lock_guard<std::mutex> lk(g_val_mu);
+    std::lock_guard<std::mutex> lk(D->val_mu);
     std::vector<double> w(v->box_width, v->box_width + q_dim);
-    for (auto& c : g_val_cache)
+    for (auto& c : D->val_cache)
       if (c.width == w) {
+        c.last_use = ++D->val_clock;
         out->width = c.dev;
         out->inv_width = c.dev + q_dim;
         return PMP_OK;
       }
-    ValidatorCache c;
-    c.width = w;
     std::vector<double> both(2 * q_dim);
     for (int i = 0; i < q_dim; i++) {
       if (!(w[i] > 0)) return fail(PMP_ERR_INVALID, "box width must be positive");
       both[i] = w[i];
       both[q_dim + i] = 1.0 / w[i];
     }
+    ValidatorCache c;
+    c.width = w;
+    if (D->val_cache.size() >= kMaxValidatorCache) {
+      // evict the least recently used entry; kernels already queued may still read it, so its memory is
+      // released in stream order behind everything submitted so far (legacy stream = device-wide order)
+      size_t lru = 0;
+      for (size_t i = 1; i < D->val_cache.size(); i++)
+        if (D->val_cache[i].last_use < D->val_cache[lru].last_use) lru = i;
+      CUDA_OK(cudaFreeAsync(D->val_cache[lru].dev, (cudaStream_t)0));
+      D->val_cache.erase(D->val_cache.begin() + (long)lru);
+    }
     CUDA_OK(cudaMalloc(&c.dev, both.size() * 8));
     CUDA_OK(cudaMemcpy(c.dev, both.data(), both.size() * 8, cudaMemcpyHostToDevice));
-    g_val_cache.push_back(c);
+    c.last_use = ++D->val_clock;
+    D->val_cache.push_back(c);
     out->width = c.dev;
     out->inv_width = c.dev + q_dim;
   } else if (v->type == PMP_VALIDATOR_EUCLIDEAN) {
@@ -803,50 +875,23 @@ int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
   return PMP_OK;
 }
 
-// A ring of device counters for the edge kernel's chunk dispenser: one per launch in flight.
-constexpr int kEdgeCounters = 256;
-unsigned long long* g_edge_counters = nullptr;
-std::atomic<unsigned> g_edge_counter_next{0};
-std::mutex g_edge_counter_mu;
-int next_edge_counter(unsigned long long** out) {
-  {
-    std::lock_guard<std::mutex> lk(g_edge_counter_mu);
-    if (!g_edge_counters) CUDA_OK(cudaMalloc(&g_edge_counters, kEdgeCounters * sizeof(unsigned long long)));
-  }
-  *out = g_edge_counters + (g_edge_counter_next++ % kEdgeCounters);
-  return PMP_OK;
-}
-}  // namespace
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
-                    const float* q0_dev, const float* q1_dev, int64_t n, uint32_t* valid_bits_dev,
-                    unsigned long long* n_valid_dev, unsigned long long* n_checked_dev, void* stream) {
-  CHECK_COMMON(robot, n);
-  ValidatorDev V;
-  if (int rc = validator_to_dev(validator, robot->fast.dev.q_dim, &V)) return rc;
-  if (n == 0) return PMP_OK;
-  if (!q0_dev || !q1_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
-  const SceneDev S = scene ? scene->dev : empty_scene();
+// the persistent edge kernel on endpoints, ratios and n_test that are already on the device
+int launch_edges(const pmp_robot_t* robot, const SceneDev& S, const uint8_t* seq, const EdgeArgs& A, cudaStream_t st) {
+  if (!mask_limit_ok(robot->fast, S)) return fail(PMP_ERR_LIMIT, "a robot with per-group scene masks needs a scene of at most 30 primitives");
   const int block = pick_block(robot->fast, S);
   const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
-  const long long n_words = (n + 31) / 32;
+  const long long n_words = (A.n + 31) / 32;
   const long long tiles = (n_words + (block / 32) - 1) / (block / 32);  // one warp per 32 edges at most
   int grid = 0;
   const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
   const bool cloud = S.cloud.enabled != 0;
-  // lane = edge with dynamic refill (k_check_edges_v3); valid edges atomicOr their bit into zeroed words
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned long long* counter = nullptr;
-  if (int rc = next_edge_counter(&counter)) return rc;
-  CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-  CUDA_OK(cudaMemsetAsync(valid_bits_dev, 0, (size_t)n_words * 4, st));
-  {
 #define PMP_E3(BB, AP, CL)                                                                                   \
   do {                                                                                                       \
     if (int rc = grid_for(k_check_edges_v3<BB, AP, CL>, smem, tiles, &grid, block)) return rc;              \
-    k_check_edges_v3<BB, AP, CL><<<grid, block, smem, st>>>(robot->fast.dev, S, V, q0_dev, q1_dev, n, valid_bits_dev, \
-                                                            n_valid_dev, n_checked_dev, counter);           \
+    k_check_edges_v3<BB, AP, CL><<<grid, block, smem, st>>>(robot->fast.dev, S, seq, A);                    \
   } while (0)
 #define PMP_E3_B(BB)                                                                      \
   do {                                                                                    \
@@ -854,31 +899,109 @@ int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pm
     else if (mode == 1) { if (cloud) PMP_E3(BB, 1, true); else PMP_E3(BB, 1, false); }    \
     else { if (cloud) PMP_E3(BB, 0, true); else PMP_E3(BB, 0, false); }                   \
   } while (0)
-      if (block == 128) PMP_E3_B(128); else PMP_E3_B(64);
+  if (block == 128) PMP_E3_B(128); else PMP_E3_B(64);
 #undef PMP_E3_B
 #undef PMP_E3
-  }
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return PMP_OK;
 }
 
+constexpr int64_t kMaxEdgesPerLaunch = (int64_t)1 << 30;  // the kernel indexes edges with 32 bits
+
+// prepare pass + persistent kernel for one launch-sized batch.  Scratch (ratio, n_test, chunk counter and,
+// for FP64 endpoints, their FP32 copies) comes from the stream-ordered pool and goes back to it in stream
+// order, so concurrent callers on different streams never share it and nothing is allocated in steady state.
+template <class T>
+int check_edges_batch(const pmp_robot_t* robot, const SceneDev& S, const ValidatorDev& V, const T* q0, const T* q1, int64_t n,
+                      uint32_t* bits, uint32_t* calls, unsigned long long* n_valid, unsigned long long* n_checked, cudaStream_t st) {
+  constexpr bool f64 = sizeof(T) == 8;
+  const int qd = robot->fast.dev.q_dim;
+  const size_t o_ntest = align256((size_t)n * 8), o_ctr = o_ntest + align256((size_t)n * 4), o_q0 = o_ctr + 256;
+  const size_t qbytes = f64 ? align256((size_t)n * std::max(qd, 1) * 4) : 0;
+  char* scratch = nullptr;
+  CUDA_OK(cudaMallocAsync(&scratch, o_q0 + 2 * qbytes, st));
+  EdgeArgs A{};
+  A.ratio = reinterpret_cast<double*>(scratch);
+  A.ntest = reinterpret_cast<int*>(scratch + o_ntest);
+  A.next_chunk = reinterpret_cast<unsigned long long*>(scratch + o_ctr);
+  float* q0f = f64 ? reinterpret_cast<float*>(scratch + o_q0) : nullptr;
+  float* q1f = f64 ? reinterpret_cast<float*>(scratch + o_q0 + qbytes) : nullptr;
+  A.q0 = f64 ? q0f : reinterpret_cast<const float*>(q0);
+  A.q1 = f64 ? q1f : reinterpret_cast<const float*>(q1);
+  A.n = n;
+  A.bits = bits;
+  A.calls = calls;
+  A.n_valid = n_valid;
+  A.n_checked = n_checked;
+  const int grid = (int)std::min<int64_t>((n * (f64 ? std::max(qd, 1) : 1) + 255) / 256, (int64_t)num_sms() * 8);
+  k_edge_prepare<T><<<grid, 256, 0, st>>>(V, q0, q1, n, qd, q0f, q1f, const_cast<double*>(A.ratio), const_cast<int*>(A.ntest), bits,
+                                          A.next_chunk);
+  g_launches++;
+  int rc = launch_edges(robot, S, V.seq, A, st);
+  cudaError_t e = cudaFreeAsync(scratch, st);
+  if (rc == PMP_OK && e != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("cudaFreeAsync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+template <class T>
+int check_edges_any(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator, const T* q0_dev,
+                    const T* q1_dev, int64_t n, uint32_t* valid_bits_dev, uint32_t* calls_dev, unsigned long long* n_valid_dev,
+                    unsigned long long* n_checked_dev, void* stream) {
+  CHECK_COMMON(robot, n);
+  ValidatorDev V;
+  if (int rc = validator_to_dev(validator, robot->fast.dev.q_dim, &V)) return rc;
+  if (n == 0) return PMP_OK;
+  if (!q0_dev || !q1_dev || !valid_bits_dev) return fail(PMP_ERR_INVALID, "null device pointer");
+  const SceneDev S = scene ? scene->dev : empty_scene();
+  const int qd = robot->fast.dev.q_dim;
+  for (int64_t off = 0; off < n; off += kMaxEdgesPerLaunch) {  // kMaxEdgesPerLaunch is a multiple of 32: words do not straddle
+    const int64_t m = std::min<int64_t>(kMaxEdgesPerLaunch, n - off);
+    if (int rc = check_edges_batch<T>(robot, S, V, q0_dev + off * qd, q1_dev + off * qd, m, valid_bits_dev + off / 32,
+                                      calls_dev ? calls_dev + off : nullptr, n_valid_dev, n_checked_dev, (cudaStream_t)stream))
+      return rc;
+  }
+  return PMP_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int pmp_check_edges(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                    const float* q0_dev, const float* q1_dev, int64_t n, uint32_t* valid_bits_dev,
+                    unsigned long long* n_valid_dev, unsigned long long* n_checked_dev, void* stream) {
+  return check_edges_any<float>(robot, scene, validator, q0_dev, q1_dev, n, valid_bits_dev, nullptr, n_valid_dev, n_checked_dev, stream);
+}
+
+int pmp_check_edges_ex(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                       const void* q0_dev, const void* q1_dev, int endpoints_f64, int64_t n, uint32_t* valid_bits_dev,
+                       uint32_t* calls_per_edge_dev, unsigned long long* n_valid_dev, unsigned long long* n_checked_dev,
+                       void* stream) {
+  if (endpoints_f64)
+    return check_edges_any<double>(robot, scene, validator, (const double*)q0_dev, (const double*)q1_dev, n, valid_bits_dev,
+                                   calls_per_edge_dev, n_valid_dev, n_checked_dev, stream);
+  return check_edges_any<float>(robot, scene, validator, (const float*)q0_dev, (const float*)q1_dev, n, valid_bits_dev,
+                                calls_per_edge_dev, n_valid_dev, n_checked_dev, stream);
+}
+
 // ---- host-buffer entry points ----------------------------------------------------------------------
+extern "C++" {
 namespace {
-struct Workspace {  // grow-only device scratch shared by the *_host calls (serialised by mu)
-  std::mutex mu;
-  cudaStream_t stream[2] = {nullptr, nullptr};
-  void* in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-  size_t in_cap[2][2] = {{0, 0}, {0, 0}};
-  void* outb[2] = {nullptr, nullptr};
-  size_t out_cap[2] = {0, 0};
-  unsigned long long* counters = nullptr;  // [2][2]
-  unsigned long long* counters_host = nullptr;
+// Device scratch + streams of ONE *_host call in flight.  A call checks a workspace out of its device's
+// free list (creating one when none is idle) and hands it back when it returns, so concurrent callers
+// never wait on each other; buffers are grow-only and reused by later calls.
+constexpr int kWsStreams = 3;
+struct HostWorkspace {
+  cudaStream_t stream[kWsStreams] = {};
+  void* in[kWsStreams][2] = {};
+  size_t in_cap[kWsStreams][2] = {};
+  void* outb[kWsStreams] = {};
+  size_t out_cap[kWsStreams] = {};
+  unsigned long long* counters = nullptr;       // device [2]: n_valid, n_checked
+  unsigned long long* counters_host = nullptr;  // pinned [2]
   int init() {
-    if (stream[0]) return PMP_OK;
-    for (int i = 0; i < 2; i++) CUDA_OK(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
-    CUDA_OK(cudaMalloc(&counters, 4 * sizeof(unsigned long long)));
-    CUDA_OK(cudaMallocHost(&counters_host, 4 * sizeof(unsigned long long)));
+    for (int i = 0; i < kWsStreams; i++) CUDA_OK(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc(&counters, 2 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMallocHost(&counters_host, 2 * sizeof(unsigned long long)));
     return PMP_OK;
   }
   int reserve(void** p, size_t* cap, size_t bytes) {
@@ -890,66 +1013,42 @@ struct Workspace {  // grow-only device scratch shared by the *_host calls (seri
     *cap = bytes;
     return PMP_OK;
   }
-} g_ws;
+  int sync_all() {
+    for (int i = 0; i < kWsStreams; i++) CUDA_OK(cudaStreamSynchronize(stream[i]));
+    return PMP_OK;
+  }
+};
+struct WorkspaceLease {  // RAII check-out of a workspace of the current device
+  DeviceState* D = nullptr;
+  HostWorkspace* ws = nullptr;
+  int acquire() {
+    if (int rc = device_state(&D)) return rc;
+    {
+      std::lock_guard<std::mutex> lk(D->ws_mu);
+      if (!D->ws_free.empty()) {
+        ws = D->ws_free.back();
+        D->ws_free.pop_back();
+        return PMP_OK;
+      }
+    }
+    ws = new HostWorkspace();
+    return ws->init();
+  }
+  ~WorkspaceLease() {
+    if (!ws) return;
+    ws->sync_all();  // nothing of this call may still be in flight when another caller takes the buffers
+    std::lock_guard<std::mutex> lk(D->ws_mu);
+    D->ws_free.push_back(ws);
+  }
+};
 constexpr int64_t kHostChunk = 1 << 19;  // items per pipelined chunk (multiple of 32): the tail that cannot overlap is one chunk's kernel
-constexpr int64_t kHostChunkEdges = 1 << 19;  // measured: 128K- and 256K-edge chunks are slower (per-chunk memsets and launches outweigh the better overlap)
-}  // namespace
+// Edge batches: the first chunks are small so that the first kernel starts after a short copy, later ones
+// large so that per-chunk costs (prepare pass, launch, the persistent kernel's tail) stay small.
+inline int64_t edge_chunk_size(int k) { return (int64_t)1 << std::min(19, 16 + k); }
 
-int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n,
-                           uint32_t* valid_bits_host, uint64_t* n_valid) {
-  CHECK_COMMON(robot, n);
-  if (n_valid) *n_valid = 0;
-  if (n == 0) return PMP_OK;
-  if (!q_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
-  std::lock_guard<std::mutex> lk(g_ws.mu);
-  if (int rc = g_ws.init()) return rc;
-  const int qd = robot->full.dev.q_dim;
-  CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
-  int k = 0;
-  for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
-    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
-    if (int rc = g_ws.reserve(&g_ws.in[k][0], &g_ws.in_cap[k][0], (size_t)m * qd * 4)) return rc;
-    if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
-    cudaStream_t st = g_ws.stream[k];
-    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][0], q_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
-    if (int rc = pmp_check_configs(robot, scene, (const float*)g_ws.in[k][0], m, (uint32_t*)g_ws.outb[k], g_ws.counters + k, st)) return rc;
-    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, g_ws.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-  }
-  CUDA_OK(cudaMemcpyAsync(g_ws.counters_host, g_ws.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_ws.stream[0]));
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[1]));
-  // counters copy was queued on stream 0 possibly before stream 1 finished: re-read after both drained
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
-  CUDA_OK(cudaMemcpy(g_ws.counters_host, g_ws.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (n_valid) *n_valid = g_ws.counters_host[0] + g_ws.counters_host[1];
-  return PMP_OK;
-}
-
-int pmp_eval_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n, float* dist_host) {
-  CHECK_COMMON(robot, n);
-  if (n == 0) return PMP_OK;
-  if (!q_host || !dist_host) return fail(PMP_ERR_INVALID, "null host pointer");
-  std::lock_guard<std::mutex> lk(g_ws.mu);
-  if (int rc = g_ws.init()) return rc;
-  const int qd = robot->full.dev.q_dim;
-  int k = 0;
-  for (int64_t off = 0; off < n; off += kHostChunk, k ^= 1) {
-    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
-    if (int rc = g_ws.reserve(&g_ws.in[k][0], &g_ws.in_cap[k][0], (size_t)m * qd * 4)) return rc;
-    if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)m * 8)) return rc;
-    cudaStream_t st = g_ws.stream[k];
-    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][0], q_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
-    if (int rc = pmp_eval_configs(robot, scene, (const float*)g_ws.in[k][0], m, (float*)g_ws.outb[k], st)) return rc;
-    CUDA_OK(cudaMemcpyAsync(dist_host + off * 2, g_ws.outb[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
-  }
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[1]));
-  return PMP_OK;
-}
-
-int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
-                         const float* q0_host, const float* q1_host, int64_t n, uint32_t* valid_bits_host,
-                         uint64_t* n_valid, uint64_t* n_checked) {
+template <class T>
+int check_edges_host_any(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator, const T* q0_host,
+                         const T* q1_host, int64_t n, uint32_t* valid_bits_host, uint64_t* n_valid, uint64_t* n_checked) {
   CHECK_COMMON(robot, n);
   if (n_valid) *n_valid = 0;
   if (n_checked) *n_checked = 0;
@@ -958,31 +1057,98 @@ int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, con
     return validator_to_dev(validator, robot->full.dev.q_dim, &V);
   }
   if (!q0_host || !q1_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
-  std::lock_guard<std::mutex> lk(g_ws.mu);
-  if (int rc = g_ws.init()) return rc;
+  WorkspaceLease L;
+  if (int rc = L.acquire()) return rc;
+  HostWorkspace& W = *L.ws;
   const int qd = robot->full.dev.q_dim;
-  CUDA_OK(cudaMemsetAsync(g_ws.counters, 0, 4 * sizeof(unsigned long long), g_ws.stream[0]));
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
-  int k = 0;
-  for (int64_t off = 0; off < n; off += kHostChunkEdges, k ^= 1) {
-    const int64_t m = std::min<int64_t>(kHostChunkEdges, n - off);
+  CUDA_OK(cudaMemsetAsync(W.counters, 0, 2 * sizeof(unsigned long long), W.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  int64_t off = 0;
+  for (int k = 0; off < n; k++) {
+    const int64_t m = std::min<int64_t>(edge_chunk_size(k), n - off);
+    const int b = k % kWsStreams;
     for (int a = 0; a < 2; a++)
-      if (int rc = g_ws.reserve(&g_ws.in[k][a], &g_ws.in_cap[k][a], (size_t)m * qd * 4)) return rc;
-    if (int rc = g_ws.reserve(&g_ws.outb[k], &g_ws.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
-    cudaStream_t st = g_ws.stream[k];
-    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][0], q0_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(g_ws.in[k][1], q1_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
-    if (int rc = pmp_check_edges(robot, scene, validator, (const float*)g_ws.in[k][0], (const float*)g_ws.in[k][1], m,
-                                 (uint32_t*)g_ws.outb[k], g_ws.counters + k, g_ws.counters + 2 + k, st))
+      if (int rc = W.reserve(&W.in[b][a], &W.in_cap[b][a], (size_t)m * qd * sizeof(T))) return rc;
+    if (int rc = W.reserve(&W.outb[b], &W.out_cap[b], (size_t)((m + 31) / 32) * 4)) return rc;
+    cudaStream_t st = W.stream[b];
+    CUDA_OK(cudaMemcpyAsync(W.in[b][0], q0_host + off * qd, (size_t)m * qd * sizeof(T), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(W.in[b][1], q1_host + off * qd, (size_t)m * qd * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (int rc = check_edges_any<T>(robot, scene, validator, (const T*)W.in[b][0], (const T*)W.in[b][1], m, (uint32_t*)W.outb[b], nullptr,
+                                    W.counters, W.counters + 1, st))
       return rc;
-    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, g_ws.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, W.outb[b], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    off += m;
   }
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[0]));
-  CUDA_OK(cudaStreamSynchronize(g_ws.stream[1]));
-  CUDA_OK(cudaMemcpy(g_ws.counters_host, g_ws.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (n_valid) *n_valid = g_ws.counters_host[0] + g_ws.counters_host[1];
-  if (n_checked) *n_checked = g_ws.counters_host[2] + g_ws.counters_host[3];
+  if (int rc = W.sync_all()) return rc;
+  CUDA_OK(cudaMemcpyAsync(W.counters_host, W.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, W.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  if (n_valid) *n_valid = W.counters_host[0];
+  if (n_checked) *n_checked = W.counters_host[1];
   return PMP_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int pmp_check_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n,
+                           uint32_t* valid_bits_host, uint64_t* n_valid) {
+  CHECK_COMMON(robot, n);
+  if (n_valid) *n_valid = 0;
+  if (n == 0) return PMP_OK;
+  if (!q_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
+  WorkspaceLease L;
+  if (int rc = L.acquire()) return rc;
+  HostWorkspace& W = *L.ws;
+  const int qd = robot->full.dev.q_dim;
+  CUDA_OK(cudaMemsetAsync(W.counters, 0, 2 * sizeof(unsigned long long), W.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  int k = 0;
+  for (int64_t off = 0; off < n; off += kHostChunk, k = (k + 1) % kWsStreams) {
+    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+    if (int rc = W.reserve(&W.in[k][0], &W.in_cap[k][0], (size_t)m * qd * 4)) return rc;
+    if (int rc = W.reserve(&W.outb[k], &W.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
+    cudaStream_t st = W.stream[k];
+    CUDA_OK(cudaMemcpyAsync(W.in[k][0], q_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = pmp_check_configs(robot, scene, (const float*)W.in[k][0], m, (uint32_t*)W.outb[k], W.counters, st)) return rc;
+    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, W.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (int rc = W.sync_all()) return rc;
+  CUDA_OK(cudaMemcpyAsync(W.counters_host, W.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, W.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  if (n_valid) *n_valid = W.counters_host[0];
+  return PMP_OK;
+}
+
+int pmp_eval_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_host, int64_t n, float* dist_host) {
+  CHECK_COMMON(robot, n);
+  if (n == 0) return PMP_OK;
+  if (!q_host || !dist_host) return fail(PMP_ERR_INVALID, "null host pointer");
+  WorkspaceLease L;
+  if (int rc = L.acquire()) return rc;
+  HostWorkspace& W = *L.ws;
+  const int qd = robot->full.dev.q_dim;
+  int k = 0;
+  for (int64_t off = 0; off < n; off += kHostChunk, k = (k + 1) % kWsStreams) {
+    const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+    if (int rc = W.reserve(&W.in[k][0], &W.in_cap[k][0], (size_t)m * qd * 4)) return rc;
+    if (int rc = W.reserve(&W.outb[k], &W.out_cap[k], (size_t)m * 8)) return rc;
+    cudaStream_t st = W.stream[k];
+    CUDA_OK(cudaMemcpyAsync(W.in[k][0], q_host + off * qd, (size_t)m * qd * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = pmp_eval_configs(robot, scene, (const float*)W.in[k][0], m, (float*)W.outb[k], st)) return rc;
+    CUDA_OK(cudaMemcpyAsync(dist_host + off * 2, W.outb[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  }
+  return W.sync_all();
+}
+
+int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                         const float* q0_host, const float* q1_host, int64_t n, uint32_t* valid_bits_host,
+                         uint64_t* n_valid, uint64_t* n_checked) {
+  return check_edges_host_any<float>(robot, scene, validator, q0_host, q1_host, n, valid_bits_host, n_valid, n_checked);
+}
+
+int pmp_check_edges_host_f64(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,
+                             const double* q0_host, const double* q1_host, int64_t n, uint32_t* valid_bits_host,
+                             uint64_t* n_valid, uint64_t* n_checked) {
+  return check_edges_host_any<double>(robot, scene, validator, q0_host, q1_host, n, valid_bits_host, n_valid, n_checked);
 }
 
 // ---- validator sessions (the OMPL-facing adaptor's back end) ----------------------------------------
@@ -1005,7 +1171,7 @@ struct pmp_session {
   char* host_dev = nullptr;  // the device's view of `host`
   char* dev = nullptr;
   size_t arena = 0;
-  unsigned long long* counters = nullptr;       // device [2]: n_valid, n_checked of the early-exit path
+  unsigned long long* counters = nullptr;       // device [3]: n_valid, n_checked and the chunk dispenser of the early-exit path
   unsigned long long* counters_host = nullptr;  // pinned [2]
   std::mutex mu;
 };
@@ -1014,8 +1180,6 @@ namespace {
 constexpr long long kFlatMaxWaypoints = 1 << 17;  // beyond this the early-exit kernel wins
 constexpr long long kZeroCopyWaypoints = 4096;    // flat path: results come back as bytes in mapped memory
 constexpr int64_t kZeroCopyStates = 2048;
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
 // BoxMotionValidator / EuclideanMotionValidator::determine_step_ratio in FP64 on the caller's
 // doubles (ompl/motion_validator.cpp:89-126)
 double host_step_ratio(const pmp_session* s, const double* a, const double* b) {
@@ -1071,12 +1235,12 @@ int pmp_session_create(const pmp_robot_t* robot, const pmp_scene_t* scene, const
   // worst-case compact layout: q0, q1, ratio, off, bits, and the zero-copy result bytes
   const size_t qbytes = align256((size_t)s->cap * std::max(1, s->qd) * 4);
   s->arena = 2 * qbytes + align256((size_t)s->cap * 8) + align256((size_t)(s->cap + 1) * 4) +
-             align256((size_t)(s->cap / 32) * 4) + align256((size_t)kZeroCopyWaypoints);
+             align256(std::max<size_t>((size_t)(s->cap / 32) * 4, (size_t)kFlatMaxWaypoints / 8)) + align256((size_t)kZeroCopyWaypoints);
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaHostAlloc(&s->host, s->arena, cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer(&s->host_dev, s->host, 0);
   if (e == cudaSuccess) e = cudaMalloc(&s->dev, s->arena);
-  if (e == cudaSuccess) e = cudaMalloc(&s->counters, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&s->counters, 3 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&s->counters_host, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     pmp_session_destroy(s);
@@ -1144,68 +1308,77 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
   if (n == 0) return PMP_OK;
   if (((!s1 || !s2) && s->qd > 0) || !valid) return fail(PMP_ERR_INVALID, "null host pointer");
   std::lock_guard<std::mutex> lk(s->mu);
-  if (int rc = ensure_device()) return rc;
+  DeviceState* D;
+  if (int rc = device_state(&D)) return rc;
+  if (int rc = ensure_sequence_table(D)) return rc;
   const pmp_robot_t* robot = s->robot;
   const SceneDev S = s->scene ? s->scene->dev : empty_scene();
+  if (!mask_limit_ok(robot->fast, S)) return fail(PMP_ERR_LIMIT, "a robot with per-group scene masks needs a scene of at most 30 primitives");
   const int block = pick_block(robot->fast, S);
   const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
   const bool cloud = S.cloud.enabled != 0;
+  const uint8_t* seq = sequence_table_host().data();
   uint64_t checked = 0;
   for (int64_t off = 0; off < n; off += s->cap) {
     const int64_t m = std::min<int64_t>(s->cap, n - off);
-    // compact layout for this chunk
+    // compact layout for this chunk: q0 | q1 | ratio | off (flat) or n_test (early exit) | result words | zero-copy bytes
     const size_t qb = align256((size_t)m * std::max(1, s->qd) * 4);
     const size_t o_q1 = qb, o_ratio = 2 * qb, o_off = o_ratio + align256((size_t)m * 8);
     const size_t o_bits = o_off + align256((size_t)(m + 1) * 4);
-    const size_t words = (size_t)((m + 31) / 32);
-    const size_t o_way = o_bits + align256(words * 4);
     float* h0 = reinterpret_cast<float*>(s->host);
     float* h1 = reinterpret_cast<float*>(s->host + o_q1);
     double* hr = reinterpret_cast<double*>(s->host + o_ratio);
     int* ho = reinterpret_cast<int*>(s->host + o_off);
     uint32_t* hbits = reinterpret_cast<uint32_t*>(s->host + o_bits);
-    long long total = 0;
-    ho[0] = 0;
-    for (int64_t e = 0; e < m; e++) {
-      const double* a = s1 + (off + e) * s->qd;
-      const double* b = s2 + (off + e) * s->qd;
-      for (int i = 0; i < s->qd; i++) {
-        h0[e * s->qd + i] = (float)a[i];
-        h1[e * s->qd + i] = (float)b[i];
+    // the host pass: FP64 -> FP32 endpoints, step ratio and waypoint count from the caller's doubles
+    // (motion_validator.cpp:89-126, :45); edges are independent, so large chunks are split over threads
+    auto pack = [&](int64_t lo, int64_t hi) {
+      for (int64_t e = lo; e < hi; e++) {
+        const double* a = s1 + (off + e) * s->qd;
+        const double* b = s2 + (off + e) * s->qd;
+        for (int i = 0; i < s->qd; i++) {
+          h0[e * s->qd + i] = (float)a[i];
+          h1[e * s->qd + i] = (float)b[i];
+        }
+        const double r = host_step_ratio(s, a, b);
+        hr[e] = r;
+        ho[e + 1] = edge_n_test(r);  // n_test; turned into offsets below when the flat path is taken
       }
-      const double r = host_step_ratio(s, a, b);
-      hr[e] = r;
-      if (r != std::numeric_limits<double>::infinity()) {  // motion_validator.cpp:41-45
-        const double nt = std::floor(1.0 / r) + 2.0;
-        total += (nt < 2147483000.0) ? (long long)nt - 1 : 2147483000LL;  // s2 + the n_test - 2 interior points
-      }
-      if (total > 2147483000LL) total = 2147483000LL;
-      ho[e + 1] = (int)total;
+    };
+    const int n_thr = (int)std::min<int64_t>(8, m / 2048);
+    if (n_thr > 1) {
+      std::vector<std::thread> th;
+      for (int t = 0; t < n_thr; t++) th.emplace_back(pack, m * t / n_thr, m * (t + 1) / n_thr);
+      for (auto& t : th) t.join();
+    } else {
+      pack(0, m);
     }
+    long long total = 0;  // s2 + the n_test - 2 interior points per edge
+    for (int64_t e = 0; e < m; e++) total += std::max(0, ho[e + 1] - 1);
     if (total <= kFlatMaxWaypoints) {
       // latency path: every waypoint in one wave
+      ho[0] = 0;
+      for (int64_t e = 0; e < m; e++) ho[e + 1] = ho[e] + std::max(0, ho[e + 1] - 1);
       const bool zero_copy = total <= kZeroCopyWaypoints && m <= kFlatSmemEdges;
+      const size_t way_words = (size_t)((total + 31) / 32);
       char* base = zero_copy ? s->host_dev : s->dev;
-      if (!zero_copy) {
-        for (size_t w = 0; w < words; w++) hbits[w] = 0;
-        CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_bits + words * 4, cudaMemcpyHostToDevice, s->stream));
-      }
       if (total > 0) {
+        if (!zero_copy) CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_bits, cudaMemcpyHostToDevice, s->stream));
         const long long tiles = (total + block - 1) / block;
         int grid = 0;
         const float* d0 = reinterpret_cast<const float*>(base);
         const float* d1 = reinterpret_cast<const float*>(base + o_q1);
         const double* dr = reinterpret_cast<const double*>(base + o_ratio);
         const int* dof = reinterpret_cast<const int*>(base + o_off);
-        uint32_t* db = reinterpret_cast<uint32_t*>(base + o_bits);
-        uint8_t* dway = zero_copy ? reinterpret_cast<uint8_t*>(base + o_way) : nullptr;
+        uint32_t* dwb = zero_copy ? nullptr : reinterpret_cast<uint32_t*>(base + o_bits);
+        uint8_t* dway = zero_copy ? reinterpret_cast<uint8_t*>(base + o_bits) : nullptr;
         const size_t smem_flat = smem;  // the static offset table is accounted for by the occupancy query
 #define PMP_F3(BB, AP, CL)                                                                                      \
   do {                                                                                                          \
     if (int rc = grid_for(k_check_waypoints_flat<BB, AP, CL>, smem_flat, tiles, &grid, block)) return rc;       \
-    k_check_waypoints_flat<BB, AP, CL><<<grid, block, smem_flat, s->stream>>>(robot->fast.dev, S, d0, d1, dr, dof, (int)m, db, dway); \
+    k_check_waypoints_flat<BB, AP, CL><<<grid, block, smem_flat, s->stream>>>(robot->fast.dev, S, d0, d1, dr, dof, (int)m, dwb, dway); \
   } while (0)
 #define PMP_F3_B(BB)                                                                      \
   do {                                                                                    \
@@ -1218,28 +1391,48 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
 #undef PMP_F3
         g_launches++;
         CUDA_OK(cudaGetLastError());
+        if (!zero_copy) CUDA_OK(cudaMemcpyAsync(hbits, s->dev + o_bits, way_words * 4, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
       }
-      if (!zero_copy) CUDA_OK(cudaMemcpyAsync(hbits, s->dev + o_bits, words * 4, cudaMemcpyDeviceToHost, s->stream));
-      if (total > 0 || !zero_copy) CUDA_OK(cudaStreamSynchronize(s->stream));
-      if (zero_copy) {
-        const uint8_t* way = reinterpret_cast<const uint8_t*>(s->host + o_way);
-        for (int64_t e = 0; e < m; e++) {
-          uint8_t ok = 1;
-          for (int t = ho[e]; t < ho[e + 1]; t++) ok &= way[t];
-          valid[off + e] = ok;
+      // per edge: AND over its waypoints, and the reference's call count = position of the first failing
+      // waypoint in ITS visiting order (s2, then sequence[2..] of the farthest-first table; natural order
+      // from n_test = 129 on, motion_validator.cpp:45-78), else the waypoint count
+      const uint8_t* way = reinterpret_cast<const uint8_t*>(hbits);
+      auto ok_at = [&](long long t) -> bool { return zero_copy ? way[t] != 0 : ((hbits[t >> 5] >> (t & 31)) & 1u) != 0; };
+      for (int64_t e = 0; e < m; e++) {
+        const int n_way = ho[e + 1] - ho[e], n_test = n_way + 1;
+        bool ok = true;
+        for (int t = 0; t < n_way && ok; t++) ok = ok_at(ho[e] + t);
+        valid[off + e] = ok ? 1 : 0;
+        if (ok) {
+          checked += (uint64_t)n_way;
+        } else {
+          int k = 0;
+          for (;; k++) {
+            const int j = k == 0 ? 0 : (n_test < 129 ? (int)seq[(n_test - 1) * 128 + (k + 1)] : k);
+            if (!ok_at(ho[e] + j)) break;
+          }
+          checked += (uint64_t)k + 1;
         }
-      } else {
-        for (int64_t e = 0; e < m; e++) valid[off + e] = ((hbits[e >> 5] >> (e & 31)) & 1u) ? 0 : 1;
       }
-      checked += (uint64_t)total;
     } else {
-      // throughput path: lane = edge with early exit (k_check_edges_v3)
-      CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_ratio, cudaMemcpyHostToDevice, s->stream));
-      CUDA_OK(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned long long), s->stream));
-      if (int rc = pmp_check_edges(robot, s->scene, &s->vdesc, reinterpret_cast<const float*>(s->dev),
-                                   reinterpret_cast<const float*>(s->dev + o_q1), m,
-                                   reinterpret_cast<uint32_t*>(s->dev + o_bits), s->counters, s->counters + 1, s->stream))
-        return rc;
+      // throughput path: lane = edge with early exit (k_check_edges_v3) on the host-computed ratios / n_test
+      for (int64_t e = 0; e < m; e++) ho[e] = ho[e + 1];
+      const size_t words = (size_t)((m + 31) / 32);
+      std::memset(hbits, 0, words * 4);
+      CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_bits + words * 4, cudaMemcpyHostToDevice, s->stream));
+      CUDA_OK(cudaMemsetAsync(s->counters, 0, 3 * sizeof(unsigned long long), s->stream));
+      EdgeArgs A{};
+      A.q0 = reinterpret_cast<const float*>(s->dev);
+      A.q1 = reinterpret_cast<const float*>(s->dev + o_q1);
+      A.ratio = reinterpret_cast<const double*>(s->dev + o_ratio);
+      A.ntest = reinterpret_cast<const int*>(s->dev + o_off);
+      A.n = m;
+      A.bits = reinterpret_cast<uint32_t*>(s->dev + o_bits);
+      A.n_valid = s->counters;
+      A.n_checked = s->counters + 1;
+      A.next_chunk = s->counters + 2;
+      if (int rc = launch_edges(robot, S, D->seq_dev, A, s->stream)) return rc;
       CUDA_OK(cudaMemcpyAsync(hbits, s->dev + o_bits, words * 4, cudaMemcpyDeviceToHost, s->stream));
       CUDA_OK(cudaMemcpyAsync(s->counters_host, s->counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
       CUDA_OK(cudaStreamSynchronize(s->stream));
@@ -1258,7 +1451,7 @@ int pmp_sdf_evaluate(const pmp_scene_t* scene, const float* points_dev, int64_t 
   if (int rc = ensure_device()) return rc;
   if (n == 0) return PMP_OK;
   if (!points_dev || !out_dev) return fail(PMP_ERR_INVALID, "null device pointer");
-  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 8);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
   k_sdf_evaluate<<<grid, 256, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, n, out_dev);
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -1272,7 +1465,7 @@ int pmp_sdf_is_outside(const pmp_scene_t* scene, const float* points_dev, const 
   if (int rc = ensure_device()) return rc;
   if (n == 0) return PMP_OK;
   if (!points_dev || !out_dev) return fail(PMP_ERR_INVALID, "null device pointer");
-  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 8);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
   k_sdf_is_outside<<<grid, 256, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, radii_dev, n, out_dev);
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -1287,7 +1480,7 @@ int pmp_cloud_nearest(const pmp_scene_t* scene, const float* points_dev, int64_t
   if (int rc = ensure_device()) return rc;
   if (n == 0) return PMP_OK;
   if (!points_dev || !sqdist_dev) return fail(PMP_ERR_INVALID, "null device pointer");
-  const int grid = (int)std::min<int64_t>((n + 15) / 16, (int64_t)g_num_sms * 16);  // 16 queries per CTA of 128 threads
+  const int grid = (int)std::min<int64_t>((n + 15) / 16, (int64_t)num_sms() * 16);  // 16 queries per CTA of 128 threads
   k_cloud_nearest<<<grid, 128, 0, (cudaStream_t)stream>>>(scene->dev, points_dev, n, sqdist_dev, nearest_index_dev);
   g_launches++;
   CUDA_OK(cudaGetLastError());
@@ -1316,7 +1509,7 @@ __global__ void k_ffma_peak(float* out, int iters, float a, float b) {
 extern "C" int pmp_measure_fp32_peak(double* tflops) {
   if (!tflops) return fail(PMP_ERR_INVALID, "null argument");
   if (int rc = ensure_device()) return rc;
-  const int block = 256, grid = g_num_sms * 8, iters = 4096;
+  const int block = 256, grid = num_sms() * 8, iters = 4096;
   float* out = nullptr;
   CUDA_OK(cudaMalloc(&out, (size_t)grid * block * 4));
   cudaEvent_t e0, e1;

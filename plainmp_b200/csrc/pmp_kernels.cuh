@@ -19,10 +19,11 @@
 namespace pmp {
 
 struct RobotDev {
-  const float4* blob;  // [ops: 5 words][groups: 2 words][spheres: 1 word][pairs: 1 word per 2 pairs][pairs4: 1 word per pair]
+  const float4* blob;  // [ops: 5 words][groups: 2 words][spheres: 1 word][pairs: 1 word per 2 pairs][pairs4: 1 word per pair][gmask: 1 word per 4 groups, optional]
   int blob_words;
   int n_ops, n_groups, n_spheres, n_pairs;
   int off_groups, off_spheres, off_pairs, off_pairs4;  // word offsets into blob
+  int off_gmask;  // per-group scene mask (one unsigned per group), -1 = every group sees every scene entry
   int dof, q_dim, base_type;
   int n_slots;  // frames kept in the stash
   float base_pose[7];
@@ -42,6 +43,7 @@ struct Smem {
   const int2* pairs;
   const float4* pairs4;  // per pair: group a, group b (int bits), (Ra + Rb)^2, -
   const float4* prims;
+  const unsigned* gmask;  // nullptr unless the robot was created with per-group scene masks
   float* stash;
 };
 
@@ -58,6 +60,7 @@ __device__ __forceinline__ Smem stage_tables(const RobotDev& R, const SceneDev& 
   t.spheres = sm + R.off_spheres;
   t.pairs = reinterpret_cast<const int2*>(sm + R.off_pairs);
   t.pairs4 = sm + R.off_pairs4;
+  t.gmask = R.off_gmask >= 0 ? reinterpret_cast<const unsigned*>(sm + R.off_gmask) : nullptr;
   t.prims = pr;
   t.stash = reinterpret_cast<float*>(pr + S.n_prims * kPrimWords);
   return t;
@@ -458,8 +461,11 @@ struct ValidatorDev {
   const uint8_t* seq;       // [128][128] SEQUENCE_TABLE (generate_sequence.py), device
 };
 
-// determine_step_ratio in FP64 (the waypoint count must not depend on FP32 rounding)
-__device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const float* a, const float* b, int dim) {
+// determine_step_ratio in FP64 (the waypoint count must not depend on FP32 rounding).  T = float for
+// FP32 endpoints (every float is a double, so this is what the reference computes for those states) or
+// double for the reference's own state type.
+template <class T>
+__device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const T* a, const T* b, int dim) {
   if (V.type == PMP_VALIDATOR_BOX) {  // motion_validator.cpp:89-111
     double diff_longest = 0.0, max_diff = -INFINITY;
     int longest = 0;
@@ -483,6 +489,42 @@ __device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const f
   return V.resolution / sqrt(d2);
 }
 
+// n_test of motion_validator.cpp:45 from the step ratio: 0 = "no check at all" (ratio == inf, :41-43).
+// The reference converts floor(1 / ratio) + 2 to size_t; anything beyond 2^31 waypoints is clamped (such
+// an edge never finishes there either), NaN (non-finite endpoints) becomes 2 = "s2 only".
+__host__ __device__ __forceinline__ int edge_n_test(const double ratio) {
+  if (ratio == INFINITY) return 0;
+  const double nt = floor(1.0 / ratio) + 2.0;
+  if (!(nt == nt)) return 2;
+  return nt > 2147483000.0 ? 2147483000 : (nt < 2.0 ? 2 : (int)nt);
+}
+
+// Pre-pass of the edge kernel: everything FP64 about an edge happens here, once, instead of inside
+// the persistent loop below (where it cost registers for the whole kernel): step ratio and n_test per
+// edge, the FP64 -> FP32 conversion of the endpoints when the caller holds doubles, and the zeroing
+// of the result words and of the chunk dispenser.
+template <class T>
+__global__ void __launch_bounds__(256)
+k_edge_prepare(const ValidatorDev V, const T* __restrict__ q0, const T* __restrict__ q1, const long long n, const int dim,
+               float* __restrict__ q0f, float* __restrict__ q1f, double* __restrict__ ratio, int* __restrict__ ntest,
+               uint32_t* __restrict__ bits, unsigned long long* __restrict__ next_chunk) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 == 0) *next_chunk = 0ull;
+  for (long long w = t0; w < (n + 31) / 32; w += stride) bits[w] = 0u;
+  if (q0f) {  // T = double: the kernels read FP32 endpoints
+    for (long long i = t0; i < n * dim; i += stride) {
+      q0f[i] = (float)q0[i];
+      q1f[i] = (float)q1[i];
+    }
+  }
+  for (long long e = t0; e < n; e += stride) {
+    const double r = edge_step_ratio<T>(V, q0 + e * dim, q1 + e * dim, dim);
+    ratio[e] = r;
+    ntest[e] = edge_n_test(r);
+  }
+}
+
 // ---- motion edges: lane = edge with dynamic refill ------------------------------------------------
 // Every lane walks ITS OWN edge through the reference's visiting order (s2 first, then the
 // farthest-first table order, motion_validator.cpp:45-78) one waypoint per round, exactly like the
@@ -491,28 +533,44 @@ __device__ __forceinline__ double edge_step_ratio(const ValidatorDev& V, const f
 // immediately takes the next edge of the warp's chunk, and the warp takes a new chunk of
 // kEdgeChunk edges from a global counter when its chunk runs dry, so no check is ever spent on a
 // waypoint the reference would not have tested and the lanes stay full until the batch ends.
-// Valid edges set their bit with one atomicOr (the host wrapper zeroes the words first).
+// Valid edges set their bit with one atomicOr (k_edge_prepare zeroes the words first).
+// calls (optional): per edge, the number of is_valid calls = the reference's own count for that edge.
 constexpr int kEdgeChunk = 256;
 
+struct EdgeArgs {
+  const float* q0;
+  const float* q1;
+  const double* ratio;  // [n] k_edge_prepare / the session's host pass
+  const int* ntest;     // [n]
+  long long n;
+  uint32_t* bits;
+  uint32_t* calls;  // optional
+  unsigned long long* n_valid;
+  unsigned long long* n_checked;
+  unsigned long long* next_chunk;
+};
+
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 512 / B)  // (capping it at 96 registers for a 5th CTA was measured: 7 % slower)
-k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const float* __restrict__ q0,
-                 const float* __restrict__ q1, const long long n, uint32_t* __restrict__ bits,
-                 unsigned long long* __restrict__ n_valid, unsigned long long* __restrict__ n_checked,
-                 unsigned long long* __restrict__ next_chunk) {
+__global__ void __launch_bounds__(B, 512 / B)
+k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__ seq, const EdgeArgs A) {
   extern __shared__ float4 sm[];
   const Smem T = stage_tables(R, S, sm);
   constexpr unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  long long next = 0, chunk_end = 0;  // warp-uniform: the unassigned part of the warp's chunk
-  bool more_chunks = true;            // warp-uniform
-  // per-lane edge state
-  long long e = -1;
-  long long w = 0, n_way = 0, n_test = 0;
-  double ratio = 0.0;
-  unsigned cnt_valid = 0;
-  unsigned long long cnt_checked = 0;
+  int next = 0, chunk_end = 0;  // warp-uniform: the unassigned part of the warp's chunk
+  bool more_chunks = true;      // warp-uniform
+  // per-lane edge state: edge index within this launch (the host splits batches of 2^31 edges or more), -1 = none
+  int e = -1, w = 0, n_test = 0;
+  unsigned cnt_valid = 0, cnt_checked = 0;
+  auto decide = [&](const bool valid) {
+    if (valid) {
+      atomicOr(A.bits + (e >> 5), 1u << (e & 31));
+      cnt_valid++;
+    }
+    if (A.calls) A.calls[e] = (unsigned)w;
+    e = -1;
+  };
   for (;;) {
     // ---- refill: every lane without an edge takes the next one ----
     for (;;) {
@@ -520,63 +578,55 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const
       if (!need) break;
       if (next >= chunk_end) {
         if (!more_chunks) break;
-        long long c = 0;
-        if (lane == 0) c = (long long)atomicAdd(next_chunk, (unsigned long long)kEdgeChunk);
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(A.next_chunk, (unsigned long long)kEdgeChunk);
         c = __shfl_sync(full, c, 0);
-        if (c >= n) {
+        if (c >= (unsigned long long)A.n) {
           more_chunks = false;
           break;
         }
-        next = c;
-        chunk_end = min(c + (long long)kEdgeChunk, n);
+        next = (int)c;
+        chunk_end = (int)min((long long)c + kEdgeChunk, A.n);
+        if (cnt_checked > (1u << 30)) {  // keep the 32-bit per-lane counter far from wrapping
+          if (A.n_checked) atomicAdd(A.n_checked, (unsigned long long)cnt_checked);
+          cnt_checked = 0;
+        }
       }
-      const long long cand = next + __popc(need & lt);
-      next = min(next + (long long)__popc(need), chunk_end);
+      const int cand = next + __popc(need & lt);
+      next = min(next + __popc(need), chunk_end);
       if (e < 0 && cand < chunk_end) {
         e = cand;
-        ratio = edge_step_ratio(V, q0 + e * R.q_dim, q1 + e * R.q_dim, R.q_dim);
-        if (ratio == INFINITY) {  // zero-length edge: valid without any check (motion_validator.cpp:41-43)
-          atomicOr(bits + (e >> 5), 1u << (e & 31));
-          cnt_valid++;
-          e = -1;
-        } else {
-          n_test = (long long)floor(1.0 / ratio) + 2;  // :45
-          n_way = n_test - 1;                           // s2, then the interior points 1 .. n_test-2
-          w = 0;
-        }
+        w = 0;
+        n_test = __ldg(A.ntest + e);
+        if (n_test == 0) decide(true);  // zero-length edge: valid without any check (motion_validator.cpp:41-43)
       }
     }
     const bool work = e >= 0;
     if (!__any_sync(full, work)) break;
-    // ---- one waypoint per lane ----
+    // ---- one waypoint per lane: s2 (w = 0), then the interior points 1 .. n_test-2 ----
+    const long long ge = work ? e : 0;
     float t = 1.f;
     if (work && w > 0) {
-      if (n_test < 129)
-        t = (float)((double)V.seq[(n_test - 1) * 128 + (w + 1)] * ratio);  // sequence[i], i = w + 1
-      else
-        t = (float)((double)w * ratio);
+      const int idx = (n_test < 129) ? (int)seq[(n_test - 1) * 128 + (w + 1)] : w;  // sequence[i], i = w + 1
+      t = (float)((double)idx * __ldg(A.ratio + ge));
     }
-    const long long ee = work ? e : 0;
-    QEdge acc{q0 + ee * R.q_dim, q1 + ee * R.q_dim, t, w == 0};
+    QEdge acc{A.q0 + ge * R.q_dim, A.q1 + ge * R.q_dim, t, w == 0};
     const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, work);
     if (work) {
       cnt_checked++;
-      if (!ok) {
-        e = -1;  // first invalid waypoint decides the edge
-      } else if (++w >= n_way) {
-        atomicOr(bits + (e >> 5), 1u << (e & 31));
-        cnt_valid++;
-        e = -1;
-      }
+      w++;
+      if (!ok) decide(false);  // first invalid waypoint decides the edge
+      else if (w >= n_test - 1) decide(true);
     }
   }
+  unsigned long long tot_valid = cnt_valid, tot_checked = cnt_checked;
   for (int off = 16; off; off >>= 1) {
-    cnt_valid += __shfl_down_sync(full, cnt_valid, off);
-    cnt_checked += __shfl_down_sync(full, cnt_checked, off);
+    tot_valid += __shfl_down_sync(full, tot_valid, off);
+    tot_checked += __shfl_down_sync(full, tot_checked, off);
   }
   if (lane == 0) {
-    if (n_valid && cnt_valid) atomicAdd(n_valid, (unsigned long long)cnt_valid);
-    if (n_checked && cnt_checked) atomicAdd(n_checked, cnt_checked);
+    if (A.n_valid && tot_valid) atomicAdd(A.n_valid, tot_valid);
+    if (A.n_checked && tot_checked) atomicAdd(A.n_checked, tot_checked);
   }
 }
 
@@ -589,17 +639,19 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const ValidatorDev V, const
 // checkMotion's result is an AND, so the answer is the reference's.  The step ratio and the waypoint
 // counts come from the host in FP64 (computed from the caller's doubles exactly as
 // determine_step_ratio does); off[e] .. off[e + 1] are edge e's waypoints.
-// way_ok != nullptr (zero-copy mode, tiny batches): every waypoint writes one byte into host-mapped
-// memory with a plain store and the host ANDs them per edge — no atomics on system memory, no D2H
-// copy.  n_edges <= kFlatSmemEdges: the offset table is staged in shared memory so the search does
-// not walk host memory.
+// Results are per WAYPOINT, so that the host can also report the reference's own is_valid call count
+// (the position of the first failing waypoint in the reference's visiting order):
+//   way_ok   (zero-copy mode, tiny batches): one byte per waypoint in host-mapped memory, plain stores;
+//   way_bits (staged mode): one bit per waypoint, one word per warp (ballot), copied back by the host.
+// n_edges <= kFlatSmemEdges: the offset table is staged in shared memory so the search does not walk
+// host memory.
 constexpr int kFlatSmemEdges = 1024;
 
 template <int B, int MODE, bool CLOUD>
 __global__ void __launch_bounds__(B, 512 / B)
 k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restrict__ q0, const float* __restrict__ q1,
                        const double* __restrict__ ratio, const int* __restrict__ off, const int n_edges,
-                       uint32_t* __restrict__ bad_bits, uint8_t* __restrict__ way_ok) {
+                       uint32_t* __restrict__ way_bits, uint8_t* __restrict__ way_ok) {
   extern __shared__ float4 sm[];
   __shared__ int s_off[kFlatSmemEdges + 1];
   const bool off_in_smem = n_edges <= kFlatSmemEdges;
@@ -625,9 +677,11 @@ k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restri
     const float rate = j == 0 ? 1.f : (float)((double)j * __ldg(ratio + e));
     QEdge acc{q0 + (long long)e * R.q_dim, q1 + (long long)e * R.q_dim, rate, j == 0};
     const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, active);
-    if (active) {
-      if (way_ok) way_ok[t] = ok ? 1 : 0;
-      else if (!ok) atomicOr(bad_bits + (e >> 5), 1u << (e & 31));
+    if (way_ok) {
+      if (active) way_ok[t] = ok ? 1 : 0;
+    } else {
+      const unsigned b = __ballot_sync(0xffffffffu, ok);
+      if ((threadIdx.x & 31) == 0 && active) way_bits[t >> 5] = b;
     }
     __syncwarp();
   }

@@ -443,6 +443,7 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
           const float3 gc = place(cur, g.x, g.y, g.z);
           far |= v3_store_gc<B, GC16>(X, base, gi, gc);
           pm = (ext && !(gw.w & 1)) ? v3_cull_mask<CLOUD>(S, T, gc, g.w) : 0u;
+          if (T.gmask) pm &= T.gmask[gi];  // composite constraints: a group sees its own member's scene entries only
         }
         if (!v3_push_env(X, gi, pm)) {
           // After the drain the group is normally restarted from its full mask.  A group that yields

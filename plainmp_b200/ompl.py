@@ -49,12 +49,13 @@ class MotionValidator:
             self._v, self._keep = tables.make_validator(int(self._type), self._dim, None, vconfig.resolution)
 
     def check_motion(self, s1: Sequence[float], s2: Sequence[float]) -> bool:
-        v, _ = self.check_motion_batch(np.asarray(s1).reshape(1, -1), np.asarray(s2).reshape(1, -1))
+        v, _ = self.check_motion_batch(np.asarray(s1, dtype=np.float64).reshape(1, -1), np.asarray(s2, dtype=np.float64).reshape(1, -1))
         return bool(v[0])
 
-    def check_motion_batch(self, S1, S2):
-        """(valid bool[n], number of waypoint validity checks executed)."""
-        return tables.check_edges(self._cst._robot(), self._cst._scene(), self._v, S1, S2)
+    def check_motion_batch(self, S1, S2, with_calls: bool = False):
+        """(valid bool[n], number of waypoint validity checks executed[, is_valid calls per edge]).
+        float64 inputs are taken as they are (the step ratio is computed from the doubles)."""
+        return tables.check_edges(self._cst._robot(), self._cst._scene(), self._v, S1, S2, with_calls)
 
 
 class ValidatorSession:

@@ -32,6 +32,10 @@ def _inverse3(a: np.ndarray) -> np.ndarray:
     return r
 
 
+import itertools
+
+_UIDS = itertools.count(1)  # see PrimitiveSDFBase.__init__
+
 class Pose:
     """primitive_sdf.hpp:30-75; binding primitive.cpp:20-32."""
 
@@ -193,6 +197,9 @@ class PrimitiveSDFBase(SDFBase):
         self._lb = np.zeros(3)
         self._ub = np.zeros(3)
         self._version = 0
+        # a process-unique id: CPython reuses addresses of freed objects, so id(self) cannot key a cache
+        # (a new SDF could inherit the id of a dead one and be mistaken for it, unmoved)
+        self._uid = next(_UIDS)
 
     @property
     def lb(self) -> np.ndarray:
@@ -206,7 +213,7 @@ class PrimitiveSDFBase(SDFBase):
         return [self]
 
     def _state_key(self):
-        return (id(self), self._version)
+        return (self._uid, self._version)
 
 
 class GroundSDF(PrimitiveSDFBase):

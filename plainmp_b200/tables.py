@@ -127,7 +127,10 @@ class RobotTable:
         group_only_self: Sequence[bool],
         pairs: Sequence[Tuple[int, int]],
         extra_links: Sequence[int] = (),
+        group_prim_mask: Optional[Sequence[int]] = None,
     ):
+        """group_prim_mask (optional, one uint32 per group): which scene entries the group is tested
+        against (bit k < 30 = primitive k, bit 30 = the cloud) — pmp_robot_create_ex."""
         arrays = RobotTable.build_arrays(kin, control_joint_ids, base_type, group_links, group_spheres, group_only_self, pairs, extra_links)
         self.program = arrays["program"]
         self.groups = arrays["groups"]
@@ -157,7 +160,14 @@ class RobotTable:
         desc.pairs = self.pairs.ctypes.data
         h = C.c_void_p()
         _device()  # tables are uploaded to torch's current device
-        _capi.check(lib.pmp_robot_create(C.byref(desc), C.byref(h)))
+        self.group_prim_mask = None
+        if group_prim_mask is not None:
+            self.group_prim_mask = np.ascontiguousarray(group_prim_mask, dtype=np.uint32)
+            if self.group_prim_mask.shape != (n_groups,):
+                raise ValueError("group_prim_mask needs one entry per group")
+            _capi.check(lib.pmp_robot_create_ex(C.byref(desc), self.group_prim_mask.ctypes.data, C.byref(h)))
+        else:
+            _capi.check(lib.pmp_robot_create(C.byref(desc), C.byref(h)))
         self._h = h
         self._lib = lib
 
@@ -361,7 +371,7 @@ class SceneTable:
         _capi.check(lib.pmp_scene_create(C.byref(desc), C.byref(h)))
         self._h = h
         self._lib = lib
-        self._cloud_id = id(cloud) if cloud is not None else None
+        self._cloud_id = cloud._state_key() if cloud is not None else None
         self._cloud_cell = cloud_cell
         self.n_updates = 0
 
@@ -377,7 +387,7 @@ class SceneTable:
             _torch().cuda.current_stream().synchronize()  # other streams (sessions) may read the records next
             self.prims = prims
             self.n_updates += 1
-        new_id = id(cloud) if cloud is not None else None
+        new_id = cloud._state_key() if cloud is not None else None
         if new_id != self._cloud_id:
             if cloud is None:
                 _capi.check(self._lib.pmp_scene_update_cloud(self._h, None, 0, 0.0, 0.0))
@@ -545,29 +555,60 @@ def make_validator(vtype: int, dim: int, box_width: Optional[Sequence[float]], r
     return v, keep
 
 
-def check_edges(table: RobotTable, scene: Optional[SceneTable], validator, q0, q1):
-    """Returns (valid bool[n], n_waypoint_checks)."""
+def _as_q64(table: RobotTable, q) -> "object":
+    """q as a contiguous float64 CUDA tensor [n, q_dim]: the reference's own state type."""
     torch = _torch()
-    a = _as_q(table, q0)
-    b = _as_q(table, q1)
+    dev = _device()
+    if isinstance(q, torch.Tensor):
+        t = q if q.device.type == "cuda" else q.to(dev)
+        t = t.to(torch.float64).contiguous()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64)).to(dev)
+    if t.ndim != 2 or t.shape[1] != table.q_dim:
+        raise ValueError(f"q must have shape [n, {table.q_dim}], got {tuple(t.shape)}")
+    return t
+
+
+def _is_f64(q) -> bool:
+    torch = _torch()
+    if isinstance(q, torch.Tensor):
+        return q.dtype == torch.float64
+    return np.asarray(q).dtype == np.float64
+
+
+def check_edges(table: RobotTable, scene: Optional[SceneTable], validator, q0, q1, with_calls: bool = False):
+    """Returns (valid bool[n], n_waypoint_checks) — and, with ``with_calls``, the number of is_valid
+    calls per edge (uint32[n]) as a third element.  float64 endpoints (what the reference's callers
+    hold) keep their precision for the step ratio and the waypoint count (determine_step_ratio works on
+    the caller's doubles, motion_validator.cpp:89-126); float32 endpoints are exact as they are."""
+    torch = _torch()
+    f64 = _is_f64(q0) or _is_f64(q1)
+    a = _as_q64(table, q0) if f64 else _as_q(table, q0)
+    b = _as_q64(table, q1) if f64 else _as_q(table, q1)
     if a.shape != b.shape:
         raise ValueError("q0 and q1 must have the same shape")
     n = a.shape[0]
     bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=a.device)
     counters = torch.zeros(2, dtype=torch.int64, device=a.device)
+    calls = torch.empty(n, dtype=torch.int32, device=a.device) if with_calls else None
     _capi.check(
-        table._lib.pmp_check_edges(
+        table._lib.pmp_check_edges_ex(
             table.handle,
             scene.handle if scene is not None else None,
             C.byref(validator),
             a.data_ptr(),
             b.data_ptr(),
+            1 if f64 else 0,
             n,
             bits.data_ptr(),
+            calls.data_ptr() if with_calls else None,
             counters.data_ptr(),
             counters.data_ptr() + 8,
             _stream_ptr(),
         )
     )
     c = counters.cpu().numpy()
-    return unpack_bits(bits.cpu().numpy(), n), int(c[1])
+    valid = unpack_bits(bits.cpu().numpy(), n)
+    if with_calls:
+        return valid, int(c[1]), calls.cpu().numpy().view(np.uint32)
+    return valid, int(c[1])

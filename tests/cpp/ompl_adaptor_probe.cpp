@@ -17,7 +17,7 @@ extern "C" int probe_validators(pmp_session_t* session, int dim, const double* s
     auto si = std::make_shared<ob::SpaceInformation>(space);
     std::size_t calls = 0;
     si->setStateValidityChecker(plainmp_b200::state_validity_fn(session, (unsigned)dim, &calls));
-    auto mv = std::make_shared<plainmp_b200::SessionMotionValidator>(si, session);
+    auto mv = std::make_shared<plainmp_b200::SessionMotionValidator>(si, session, &calls);  // one counter, as in the reference
     std::vector<ob::State*> A(n), B(n);
     std::vector<std::pair<const ob::State*, const ob::State*>> edges;
     for (int i = 0; i < n; i++) {
@@ -34,9 +34,9 @@ extern "C" int probe_validators(pmp_session_t* session, int dim, const double* s
       out_single[i] = base.checkMotion(A[i], B[i]) ? 1 : 0;
       out_s2_valid[i] = si->isValid(B[i]) ? 1 : 0;
     }
+    *n_is_valid_calls = calls;  // n isValid(s2) calls + every waypoint check of the n single checkMotion calls
     auto batch = mv->checkMotions(edges);
     for (int i = 0; i < n; i++) out_batch[i] = batch[i];
-    *n_is_valid_calls = calls;
     for (int i = 0; i < n; i++) {
       si->freeState(A[i]);
       si->freeState(B[i]);

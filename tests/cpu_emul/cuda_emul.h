@@ -286,6 +286,13 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { void* q = nu
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 #endif
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+// stream-ordered allocation: everything is synchronous here, so these are plain malloc / free
+template <class T> inline cudaError_t cudaMallocAsync(T** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+typedef void* cudaMemPool_t;
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc(p, n); }
 template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }

@@ -8,6 +8,7 @@ import pytest
 
 from oracle import bridge, ref_bridge
 from fuzz_util import random_case, sample_q
+from parity_util import assert_edge_parity
 from plainmp_b200.kinematics import BaseType
 from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorSession, ValidatorType
 
@@ -65,13 +66,12 @@ def test_edges_and_session_on_random_robot(cuda_lib, seed):
     q0 = sample_q(lb, ub, 1500, seed + 1)
     q1 = np.clip(q0.astype(np.float64) + rng.uniform(-0.6, 0.6, q0.shape), lb, ub).astype(np.float32)
     for vtype, res in ((ValidatorType.BOX, 0.0), (ValidatorType.EUCLIDEAN, 0.07)):
-        want, _ = bridge.OracleValidator(int(vtype), dim, widths, res).check_motion_batch(o, q0.astype(np.float64), q1.astype(np.float64), n_threads=4)
         cfg = ValidatorConfig(vtype, res, list(widths))
-        got, _ = MotionValidator(cst, cfg).check_motion_batch(q0, q1)
-        assert (got != want).mean() < 0.006, desc
+        got, n_checked, calls = MotionValidator(cst, cfg).check_motion_batch(q0, q1, with_calls=True)
+        assert_edge_parity(cst, int(vtype), widths, res, q0, q1, got, n_checked, calls, f"{desc} {vtype.name}")
         ses = ValidatorSession(cst, cfg, capacity=512)
         got_s = ses.check_motion(q0.astype(np.float64), q1.astype(np.float64))
-        assert (got_s != want).mean() < 0.006, desc
+        assert_edge_parity(cst, int(vtype), widths, res, q0, q1, got_s, ses.is_valid_call_count, None, f"{desc} {vtype.name} (session)")
         ses.close()
 
 
@@ -125,9 +125,9 @@ def test_queue_overflow_stress_on_random_robots(cuda_lib, mode):
                 rng = np.random.default_rng(seed)
                 widths = rng.uniform(0.02, 0.2, len(lb))
                 q1 = np.clip(Qd[:1024] + rng.uniform(-0.5, 0.5, (1024, len(lb))), lb, ub).astype(np.float32)
-                e_want, _ = bridge.OracleValidator(0, len(lb), widths, 0.0).check_motion_batch(o, Qd[:1024], q1.astype(np.float64), n_threads=4)
-                e_got, _ = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, list(widths))).check_motion_batch(Q[:1024], q1)
-                assert (e_got != e_want).mean() < 0.006, desc
+                from parity_util import assert_edge_parity
+                e_got, e_n, e_calls = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, list(widths))).check_motion_batch(Q[:1024], q1, with_calls=True)
+                assert_edge_parity(cst, 0, widths, 0.0, Q[:1024], q1, e_got, e_n, e_calls, desc)
         print("OK")
         """
     )

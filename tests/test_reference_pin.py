@@ -356,3 +356,72 @@ def test_reference_side_flatten_equals_host_mirror_tables(name):
         np.testing.assert_allclose(np.sort(flat["cloud_points"], axis=0), np.sort(cloud.points.astype(np.float32), axis=0), atol=0)
     else:
         assert len(flat["cloud_points"]) == 0
+
+
+# ---- IneqCompositeCst and the per-edge call counts --------------------------------------------------
+def _composite_case(moving_base=False):
+    from plainmp_b200.constraint import IneqCompositeCst
+
+    if moving_base:
+        spec = PR2RarmSpec(base_type=BaseType.PLANAR)
+        a = spec.create_collision_const(self_collision=True, use_cache=False)
+        b = spec.create_collision_const(self_collision=False, use_cache=False)
+        a.set_sdf(psdf.BoxSDF([1, 1, 1], psdf.Pose([0.9, 0.5, 0.5])))
+        b.set_sdf(psdf.UnionSDF([psdf.CylinderSDF(0.2, 1.0, psdf.Pose([-0.6, 0.2, 0.6])), psdf.GroundSDF(0.0)]))
+    else:
+        spec, a = workloads.make_panda()
+        b = spec.create_collision_const(self_collision=False, use_cache=False)
+        b.set_sdf(psdf.UnionSDF([psdf.SphereSDF(0.25, psdf.Pose([0.45, 0.1, 0.55])),
+                                 psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([-0.5, 0.3, 0.4], rpy_matrix(0.3, 0.2, 0.1)))]))
+    c = spec.create_collision_const(self_collision=True, use_cache=False)  # self-collision only: no scene at all
+    return spec, IneqCompositeCst([a, b, c])
+
+
+@pytest.mark.parametrize("moving_base", [False, True])
+def test_composite_constraint_matches_reference(moving_base):
+    """IneqCompositeCst::is_valid / evaluate (constraints/composite_constraint.hpp:39-61, 98-105): ONE
+    update_kintree through the first member, AND of is_valid_dirty, rows stacked in member order."""
+    spec, comp = _composite_case(moving_base)
+    rc, oc = ref_bridge.RefComposite(comp), bridge.OracleComposite(comp, n_threads=4)
+    rng = np.random.default_rng(31)
+    if moving_base:
+        Q = rng.standard_normal((3000, oc.q_dim))
+        Q[:, 7:] *= 0.4
+    else:
+        Q = workloads.random_configs(spec, 3000, 31).astype(np.float64)
+    v_r, v_o = rc.is_valid_batch(Q), oc.is_valid_batch(Q)
+    assert (v_r == v_o).all() and 0.05 < v_r.mean() < 0.95
+    # the composite is the AND of its members (each driven by the same q)
+    members = np.all([ref_bridge.RefCst(c).is_valid_batch(Q) for c in comp.constraints], axis=0)
+    assert (v_r == members).all()
+    vals_r, jac_r = rc.evaluate_batch(Q[:400], with_jac=True)
+    vals_o = oc.evaluate_batch(Q[:400]).reshape(400, -1)
+    on = ~np.isnan(vals_o[0])
+    assert on.sum() == rc.dim == comp.cst_dim()
+    np.testing.assert_allclose(vals_o[:, on], vals_r, atol=TOL, rtol=0)
+    # ctor :27-37: members on different kinematic models are refused (a second spec owns a second model)
+    from plainmp_b200.constraint import IneqCompositeCst
+
+    other_spec = type(spec)(base_type=spec.base_type) if moving_base else type(spec)()
+    other = other_spec.create_collision_const(use_cache=False)
+    assert other.get_kin() is not comp.constraints[0].get_kin()
+    with pytest.raises(RuntimeError):
+        IneqCompositeCst([comp.constraints[0], other])
+
+
+@pytest.mark.parametrize("vtype", [0, 1])
+def test_per_edge_call_counts_match_reference(vtype):
+    """checkMotion's is_valid call count PER EDGE (the position of the first failing waypoint in the
+    visiting order of motion_validator.cpp:45-78): restatement == compiled reference, edge for edge."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    o = bridge.OracleCst(cst, n_threads=4)
+    w = np.array([0.05, 0.07, 0.05, 0.1, 0.05, 0.2, 0.05])
+    for planner_like in (False, True):
+        q0, q1 = workloads.random_edges(spec, 3000, 77, planner_like, (lambda q: o.is_valid_batch(q.astype(np.float64))) if planner_like else None)
+        q0, q1 = q0.astype(np.float64), q1.astype(np.float64)
+        v_r, c_r = ref_bridge.RefCst(cst).check_motion_batch_ex(vtype, w, 0.08, q0, q1)
+        v_o, c_o, m = bridge.OracleValidator(vtype, 7, w, 0.08).check_motion_batch_ex(o, q0, q1, 4)
+        assert (v_r == v_o).all() and (c_r == c_o).all()
+        assert (c_r >= 1).all() and np.isfinite(m).all() and (m >= 0).all()
+        v_t, c_t = ref_bridge.check_motion_batch_threads(cst, vtype, w, 0.08, q0, q1, 3)
+        assert (v_t == v_r).all() and (c_t == c_r).all()

@@ -1,10 +1,16 @@
 #!/usr/bin/env python3
-"""Per-source-line instruction counts from an .ncu-rep captured with --import-source on.
+"""Per-source-line instruction counts from an .ncu-rep captured with --import-source on (or its exported source page, .csv / .csv.gz).
   python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top_n]
 """
 import csv, io, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+if rep.endswith(".csv.gz"):  # exported on the GPU box: ncu -i rep --page source --csv --print-source cuda,sass | gzip
+    import gzip
+    raw = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 fname = "?"; hdr = None; out = []
 for r in rows:

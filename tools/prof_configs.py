@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small driver for ncu: a few launches of the validity kernel on a resident batch.
-  python tools/prof_configs.py [workload] [n] [launches]      (workload: panda | panda_ceiled | fetch | pr2cloud | pr2cloud100k | edgesA | edgesB)
+  python tools/prof_configs.py [workload] [n] [launches]      (workload: panda | panda_ceiled | fetch | pr2cloud | pr2cloud100k | edgesA | edgesB | eval_<panda|fetch|pr2cloud|pr2cloud100k>)
 """
 import ctypes as C
 import sys
@@ -32,6 +32,18 @@ if wl.startswith("edges"):
         _capi.check(lib.pmp_check_edges(robot.handle, scene.handle, C.byref(mv._v), a.data_ptr(), b.data_ptr(), n, bits.data_ptr(), ctr.data_ptr(), ctr.data_ptr() + 8, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     print(wl, n, "valid", ctr[0].item() / reps / n, "checks/edge", ctr[1].item() / reps / n)
+elif wl.startswith("eval_"):
+    # evaluate(): min signed distances (exact FK), e.g. eval_panda, eval_pr2cloud, evalgrad_pr2cloud100k
+    base = wl.split("_", 1)[1]
+    spec, cst = {"panda": workloads.make_panda, "fetch": workloads.make_fetch, "pr2cloud": lambda: workloads.make_pr2_cloud(1_000_000),
+                 "pr2cloud100k": lambda: workloads.make_pr2_cloud(100_000)}[base]()
+    robot, scene = cst._robot(), cst._scene()
+    q = torch.from_numpy(workloads.random_configs(spec, n, 5)).to(dev)
+    dist = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    for _ in range(reps):
+        _capi.check(lib.pmp_eval_configs(robot.handle, scene.handle, q.data_ptr(), n, dist.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    print(wl, n, "mean ext", float(dist[:, 0].mean()))
 else:
     spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch,
                  "pr2cloud": lambda: workloads.make_pr2_cloud(1_000_000), "pr2cloud100k": lambda: workloads.make_pr2_cloud(100_000)}[wl]()

@@ -51,7 +51,7 @@ class EmuTables:
                 cst.get_kin(), cst._control_joint_ids, cst._base_type, cst._group_links, cst._group_spheres, cst._group_only_self, cst._pairs
             )
             leaves = cst._leaves()
-        self._keep = (a, masks)
+        self._keep, self._masks = a, masks
         d = _capi.RobotDesc()
         d.dof, d.base_type = a["dof"], int(a["base_type"])
         for i in range(7):
@@ -110,7 +110,7 @@ class EmuTables:
 
     def fk_spheres(self, Q, accurate):
         Q = np.ascontiguousarray(Q, dtype=np.float32)
-        out = np.zeros((Q.shape[0], len(self._keep[0]["spheres"]), 4), dtype=np.float32)
+        out = np.zeros((Q.shape[0], len(self._keep["spheres"]), 4), dtype=np.float32)
         rc = self.lib.pmp_fk_spheres(self.robot, Q.ctypes.data, Q.shape[0], int(accurate), out.ctypes.data, None)
         assert rc == 0, self.lib.pmp_last_error()
         return out

@@ -938,7 +938,7 @@ def test_composite_constraint_single_fk(cuda_lib, moving_base):
         e_sep = np.all([MotionValidator(c, ValidatorConfig(ValidatorType.BOX, 0.0, list(w))).check_motion_batch(q0, q1)[0] for c in comp.constraints], axis=0)
         assert (e_got == e_sep).all() and 0.1 < e_got.mean() < 0.95
     # a moved primitive of one member is followed in place; a composite too large for one table falls back
-    comp.constraints[1].get_sdf().translate([0.05, 0.0, 0.1])
+    comp.constraints[0].get_sdf().translate([0.05, 0.0, 0.1])  # (member 0's scene has no ground plane: translate is defined)
     got2 = comp.is_valid_batch(Q)
     oc2 = bridge.OracleComposite(comp, n_threads=4)
     assert_validity_parity(got2, oc2.is_valid_batch(Qd), oc2.margin_batch(Qd), "composite after translate")

@@ -32,13 +32,29 @@ sys.path.insert(0, str(ROOT))
 _REAL_STDOUT = None
 METRIC = "collision_checked_configs_per_sec"
 UNIT = "configs/s"
-# dense algorithmic work of one panda dual-bars configuration
-F_CFG_DENSE = 14.7e3          # flop/config (no culling, no early exit)
-BYTES_PER_CFG = 7 * 4 + 1 / 8  # q in + 1 validity bit out
-# measured once with ncu --set full on the same kernel (profiles/r01_s34_panda_ncu.md): percentages of peak
-NCU_PIPE_FIGURES = {"source": "profiles/r01_s34_panda_ncu.md", "issue_active_pct": 68.7, "fma_pipe_pct": 25.5, "alu_pipe_pct": 42.4, "lsu_pipe_pct": 25.4,
-                    "warp_inst_per_config": 183.3, "lanes_active_per_inst": 24.29, "warps_active_pct": 28.8}
-DRAM_BYTES_PER_CFG_NCU = 29.4   # measured once with ncu --set full (profiles/r01_s34_panda_ncu.md), per configuration
+# dense algorithmic work of one configuration (flop, no culling, no early exit) and bytes
+F_CFG_DENSE = {"panda_dual_bars": 14.7e3, "panda_ceiled": 16.4e3, "fetch_table": 17.3e3}
+# the SAME text in both arms (the driver compares config.workload of the two lines)
+WORKLOAD_TEXT = {
+    "panda_dual_bars": "panda_dual_bars: uniform random 7-DOF panda configs, FK + SphereCollisionCst env (box + 2 cylinders) + 11 self pairs, validity bits + count",
+    "panda_ceiled": "panda_ceiled: uniform random 7-DOF panda configs, FK + SphereCollisionCst env (2 boxes + 2 cylinders) + 11 self pairs, validity bits + count",
+    "fetch_table": "fetch_table: uniform random 8-DOF fetch configs, FK + SphereCollisionCst env (table box + ground + 4 anchor primitives) + 14 self pairs, validity bits + count",
+}
+# ncu figures are READ from the file tools/ncu_head_json.py writes out of one `ncu --set full` pass at the
+# commit named inside it (never pasted): per-item warp instructions, DRAM bytes, pipe / issue / occupancy
+NCU_HEAD = ROOT / "profiles" / "r02_ncu_head.json"
+NCU_KEY = {"panda_dual_bars": "panda", "panda_ceiled": "panda_ceiled", "fetch_table": "fetch"}
+
+
+def ncu_record(workload):
+    try:
+        d = json.loads(NCU_HEAD.read_text())
+        rec = dict(d["workloads"][NCU_KEY[workload]])
+        rec["commit"] = d.get("commit")
+        rec["source"] = str(NCU_HEAD.relative_to(ROOT))
+        return rec
+    except Exception:
+        return None
 
 
 def parse_args():
@@ -51,6 +67,9 @@ def parse_args():
     p.add_argument("--workload", default="panda_dual_bars", choices=["panda_dual_bars", "panda_ceiled", "fetch_table"])
     p.add_argument("--extras", type=int, default=1, help="also measure edges/s, fetch and cloud side metrics (N=1)")
     p.add_argument("--cpu-sample", type=int, default=1 << 24, help="configurations per CPU-baseline pass (about 10 s of CPU work on 16 cores)")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --per-gpu configs on every rank; strong: --total configs split over the ranks")
+    p.add_argument("--total", type=int, default=1 << 24, help="global configurations per step with --scaling strong")
+    p.add_argument("--sweep-out", default="", help="also run BASELINE config 5's sweep (strong scaling of 1M / 16M / 256M total, weak at the same per-GPU sizes) in this process and append one JSON line per point to this file")
     return p.parse_args()
 
 
@@ -301,7 +320,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "robot": "panda", "per_step_configs": n, "note": note + "; all host threads, one kin+cst per thread"},
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "per_step_configs": n, "note": note + "; all host threads, one kin+cst per thread"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": f"{n} uniform random panda configs per step", "single_thread_value": single},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -310,6 +329,95 @@ def run_reference(args):
 
 
 # ---- B200 arm --------------------------------------------------------------------------------------
+class ShardedStep:
+    """One step of the sharded hot path on this rank: the validity kernel over the rank's resident
+    configurations and, for N > 1, ONE NCCL collective that delivers every rank's packed words AND its
+    64-bit valid count (the kernel writes the count straight behind the words, parallel.gather_validity_fused).
+    The collective of step i runs on a side stream and overlaps the kernel of step i + 1 (two send /
+    receive buffer pairs)."""
+
+    def __init__(self, torch, dist, tables, parallel, robot, scene, q_dev, world, dev):
+        self.torch, self.dist, self.tables, self.parallel = torch, dist, tables, parallel
+        self.robot, self.scene, self.q, self.world = robot, scene, q_dev, world
+        n = q_dev.shape[0]
+        self.n, self.n_words = n, (n + 31) // 32
+        self.per = parallel.fused_words(self.n_words)
+        self.send = [torch.zeros(self.per, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.recv = [torch.empty(self.per * world, dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
+        self.comm = torch.cuda.Stream(device=dev) if world > 1 else None
+        self.kernel_done = [torch.cuda.Event() for _ in range(2)]
+        self.comm_done = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def bits(self, b):
+        return self.send[b][: self.n_words]
+
+    def count(self, b):
+        return self.send[b][self.per - 2 :].view(self.torch.int64)
+
+    def __call__(self, kev=None):
+        torch = self.torch
+        b = self.i & 1
+        self.i += 1
+        cur = torch.cuda.current_stream()
+        if self.world > 1:
+            cur.wait_event(self.comm_done[b])  # the gather of step i - 2 has read this send buffer
+        self.count(b).zero_()
+        if kev:
+            kev[0].record()
+        self.tables.check_configs_device(self.robot, self.scene, self.q, self.bits(b), self.count(b))
+        if kev:
+            kev[1].record()
+        if self.world > 1:
+            self.kernel_done[b].record(cur)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.kernel_done[b])
+                self.dist.all_gather_into_tensor(self.recv[b], self.send[b])
+                self.comm_done[b].record(self.comm)
+        return b
+
+    def join(self):
+        if self.world > 1:
+            cur = self.torch.cuda.current_stream()
+            for e in self.comm_done:
+                cur.wait_event(e)
+
+
+def timed_steps(torch, dist, step, steps, warmup, world, dev, with_kernel_events=False):
+    """W warm-up steps, then exactly K steps between a barrier + synchronise on both sides; device time
+    (CUDA events on the launching stream), max over ranks.  Returns (ms per step, mean kernel ms, last buffer)."""
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    step.join()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)] if with_kernel_events else None
+    e0.record()
+    last = 0
+    for i in range(steps):
+        last = step(kev[i] if kev else None)
+    step.join()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev])) if kev else None
+    return float(ms.item()) / steps, kernel_ms, last
+
+
+def popcount_words(torch, words):
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=words.device)
+    return int(lut[words.contiguous().view(torch.uint8).long()].sum().item())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -340,71 +448,60 @@ def run_b200(args):
 
     spec, cst = make_workload(args.workload)
     robot, scene = cst._robot(), cst._scene()
-    n_local = args.per_gpu
-    n_global = n_local * world
+    if args.scaling == "strong":
+        lo, hi = parallel.shard_bounds(args.total, rank, world)
+        n_local, n_global = hi - lo, args.total
+    else:
+        n_local = args.per_gpu
+        n_global = n_local * world
     # synthetic inputs: uniform in the joint limits, generated on the host with a fixed seed per rank
     lb, ub = spec.angle_bounds()
+    dof = lb.shape[0]
     rng = np.random.default_rng(5 + rank)
-    q_host = torch.empty((n_local, lb.shape[0]), dtype=torch.float32, pin_memory=True)
+    q_host = torch.empty((n_local, dof), dtype=torch.float32, pin_memory=True)
     chunk = 1 << 20
     for i in range(0, n_local, chunk):
         m = min(chunk, n_local - i)
-        q_host[i : i + m] = torch.from_numpy(rng.uniform(lb, ub, size=(m, lb.shape[0])).astype(np.float32))
+        q_host[i : i + m] = torch.from_numpy(rng.uniform(lb, ub, size=(m, dof)).astype(np.float32))
     q_dev = q_host.to(dev, non_blocking=True)
-    bits = torch.empty((n_local + 31) // 32, dtype=torch.int32, device=dev)
-    count = torch.zeros(1, dtype=torch.int64, device=dev)
-    n_words = parallel.shard_words(n_global, world)
-    gathered = torch.empty(n_words * world, dtype=torch.int32, device=dev) if world > 1 else None
-    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    step = ShardedStep(torch, dist, tables, parallel, robot, scene, q_dev, world, dev)
 
-    def step():
-        count.zero_()
-        tables.check_configs_device(robot, scene, q_dev, bits, count)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, bits)
-            total.copy_(count)
-            dist.all_reduce(total)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
     try:
         gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:
         gpu_uuid = None
+    # warm-up outside the sampled region, then clocks sampled DURING the timed steps
+    for _ in range(max(args.warmup, 3)):
+        step()
+    step.join()
+    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank, gpu_uuid)
     if rank == 0:
         sampler.start()
     launches0 = lib.pmp_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    ev[0].record()
-    for i in range(args.steps):
-        count.zero_()
-        kev[i][0].record()
-        tables.check_configs_device(robot, scene, q_dev, bits, count)
-        kev[i][1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, bits)
-            total.copy_(count)
-            dist.all_reduce(total)
-        ev[i + 1].record()
-    sync_all()
+    ms_per_step, kernel_ms, last = timed_steps(torch, dist, step, args.steps, 0, world, dev, with_kernel_events=True)
     launches = lib.pmp_launch_count() - launches0
-    elapsed_ms = torch.tensor([ev[0].elapsed_time(ev[-1])], device=dev)
+    count_local = int(step.count(last).item())
+    valid_frac = count_local / max(n_local, 1)
+    value = n_global / (ms_per_step * 1e-3)
+
+    # ---- N > 1: the gathered words and counts are CHECKED, not just moved ----
+    gather_check = None
     if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed_ms.item())
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    valid_frac = float(count.item()) / n_local
-    value = n_global * args.steps / (elapsed_ms * 1e-3)
+        words_all, counts = parallel.gather_validity_fused(step.send[last], step.recv[last], n_global)
+        table = step.recv[last].view(world, step.per)
+        ok_counts = all(int(counts[r].item()) == popcount_words(torch, table[r, : step.n_words]) for r in range(world))
+        # rank 0 recomputes the head of EVERY rank's shard (same seeded generator) on its own GPU
+        head = min(chunk, n_local)
+        ok_words = True
+        if rank == 0:
+            for r in range(world):
+                qr = torch.from_numpy(np.random.default_rng(5 + r).uniform(lb, ub, size=(head, dof)).astype(np.float32)).to(dev)
+                br, _ = tables.check_configs_device(robot, scene, qr)
+                ok_words &= bool(torch.equal(br[: head // 32], table[r, : head // 32]))
+        gather_check = {"counts_equal_popcount_of_gathered_words": ok_counts, "rank0_recomputed_head_of_every_shard": ok_words, "head_configs_per_rank": head,
+                        "global_valid": int(counts.sum().item())}
+        assert ok_counts and ok_words, f"gathered validity words / counts are wrong: {gather_check}"
 
     # ---- e2e through the host-buffer C ABI (pinned host in, bits + count out) ----
     words_host = torch.empty((n_local + 31) // 32, dtype=torch.int32, pin_memory=True)
@@ -416,6 +513,12 @@ def run_b200(args):
             lib.pmp_check_configs_host(robot.handle, scene.handle, q_host.data_ptr(), n_local, words_host.data_ptr(), C.byref(nv))
         )
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     for _ in range(2):
         e2e_step()
     sync_all()
@@ -426,23 +529,34 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_global * e2e_steps / float(e2e_s.item())
-    assert torch.equal(words_host.to(dev), bits), "host-buffer path and device path disagree"
+    assert torch.equal(words_host.to(dev), step.bits(last)), "host-buffer path and device path disagree"
+    assert nv.value == count_local
     # the bound of the e2e path: a bare pinned H2D copy of the same input bytes on this box
     scratch = torch.empty_like(q_dev)
     h2d_s = time_cuda(torch, lambda: scratch.copy_(q_host, non_blocking=True), steps=5, warmup=2)
     h2d_gbs = q_host.numel() * 4 / h2d_s / 1e9
     del scratch
+    # what the reference's binding really holds: PAGEABLE FP64 numpy (bindings/constraint.cpp:82) — packed to
+    # FP32 by host threads while staged (pmp_check_configs_host_f64)
+    n64 = min(n_local, 1 << 22)
+    q64 = q_host[:n64].numpy().astype(np.float64)  # pageable
+    w64 = np.zeros((n64 + 31) // 32, dtype=np.uint32)
+    f64_step = lambda: _capi.check(lib.pmp_check_configs_host_f64(robot.handle, scene.handle, q64.ctypes.data, n64, w64.ctypes.data, C.byref(nv)))  # noqa: E731
+    f64_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        f64_step()
+    f64_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(f64_s, op=dist.ReduceOp.MAX)
+    e2e_f64_value = n64 * world * 3 / float(f64_s.item())
+    assert (torch.from_numpy(w64.view(np.int32)).to(dev) == step.bits(last)[: (n64 + 31) // 32]).all()
     clocks = sampler.stop() if rank == 0 else None
 
     extras = {}
     cpu_baseline = None
     if rank == 0 and world == 1:
-        peaks = {}
-        try:
-            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        except Exception:
-            pass
-        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         tf = C.c_double(0.0)
         if lib.pmp_measure_fp32_peak(C.byref(tf)) == 0:
             extras["fp32_ffma_tflops_measured"] = tf.value
@@ -451,16 +565,49 @@ def run_b200(args):
         # CPU baseline: the reference's own CPU path (oracle/_ref, else the restatement), bounded sample
         cpu_baseline, _ = cpu_baseline_block(cst, spec, args.cpu_sample, os.cpu_count() or 1)
         extras["work_model"] = work_model(cst, spec)
+    if args.sweep_out:
+        sweep(torch, dist, tables, parallel, robot, scene, lb, ub, world, rank, dev, args.sweep_out)
     if rank == 0:
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
-        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         per_gpu_rate = n_local / (kernel_ms * 1e-3)
-        achieved_gbs = per_gpu_rate * BYTES_PER_CFG / 1e9
+        bytes_per_cfg = dof * 4 + 1 / 8
+        f_dense = F_CFG_DENSE[args.workload]
         fp32_peak = extras.get("fp32_ffma_tflops_measured") or 74.4
+        ncu = ncu_record(args.workload)
+        wm = extras.get("work_model") or {}
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6
+        roofline = {
+            # the resource that bounds this path: FP32 SIMT instruction issue, not HBM and not tensor cores
+            "bound": "fp32_simt", "unit": "TFLOP/s",
+            "achieved": per_gpu_rate * f_dense / 1e12, "peak": fp32_peak, "frac": per_gpu_rate * f_dense / 1e12 / fp32_peak,
+            "peak_source": "FFMA micro-benchmark on this GPU in this run (pmp_measure_fp32_peak)" if extras.get("fp32_ffma_tflops_measured") else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+            "algorithmic_flop_per_config": f_dense,
+            "note": "achieved = dense-equivalent flop (SURVEY 8d: no culling, no early exit) x configs/s of the kernel alone (CUDA events around each launch, mean of the timed steps); "
+                    "the kernel legitimately skips most of the dense work, so `frac` says how the rate compares with a dense FP32 implementation at peak, `executed_frac` what the "
+                    "reference's own algorithm executes, and `ncu` what the pipes and the issue slots really did",
+            "executed_flop_per_config": wm.get("executed_flop_per_config"),
+            "executed_frac": (per_gpu_rate * wm["executed_flop_per_config"] / 1e12 / fp32_peak) if wm.get("executed_flop_per_config") else None,
+            "kernel_ms": kernel_ms, "configs_per_launch": n_local,
+            # HBM, the secondary roof: algorithmic bytes vs measured traffic of the same kernel
+            "hbm": {"achieved_gbs": per_gpu_rate * bytes_per_cfg / 1e9, "peak_gbs": hbm_peak, "frac": per_gpu_rate * bytes_per_cfg / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_config": bytes_per_cfg, "algorithmic_gb_per_launch": bytes_per_cfg * n_local / 1e9},
+            "traffic": (ncu["dram_bytes_per_item"] * n_local / 1e9) if ncu and ncu.get("dram_bytes_per_item") else None,
+            "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per configuration x configs per launch)",
+        }
+        if ncu:
+            roofline["ncu"] = {k: ncu.get(k) for k in ("commit", "source", "kernel", "registers_per_thread", "occupancy_limit_registers", "occupancy_limit_shared_mem",
+                                                       "warps_active_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct", "lsu_pipe_pct", "lanes_active_per_inst",
+                                                       "warp_inst_per_item", "dram_bytes_per_item")}
+            if ncu.get("warp_inst_per_item"):
+                roofline["issue_slots"] = {"achieved_gwarp_inst_s": per_gpu_rate * ncu["warp_inst_per_item"] / 1e9, "peak_gwarp_inst_s": issue_peak / 1e9,
+                                           "frac": per_gpu_rate * ncu["warp_inst_per_item"] / issue_peak,
+                                           "note": "warp instructions per configuration (ncu, same kernel at the commit above) x this run's rate / (148 SMs x 4 schedulers x sampled SM clock)"}
         line = {
             "metric": METRIC,
             "value": value,
@@ -468,53 +615,30 @@ def run_b200(args):
             "n_gpus": world,
             "steps": args.steps,
             "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps,
+            "ms_per_step": ms_per_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: uniform random 7-DOF panda configs, FK + SphereCollisionCst env (box + 2 cylinders) + 11 self pairs, validity bits + count",
-                "robot": "panda", "per_gpu_configs": n_local, "global_configs": n_global,
-                "l2": "inputs (28 B/config x per_gpu_configs) exceed the 126 MB L2; no flush needed",
-                "parallelism": f"item-sharded x{world}, tables replicated" + (", NCCL all_gather(bits)+all_reduce(count) per step" if world > 1 else ""),
+                "workload": WORKLOAD_TEXT[args.workload],
+                "robot": spec.__class__.__name__, "per_gpu_configs": n_local, "global_configs": n_global,
+                "l2": "inputs (28 B/config x per_gpu_configs) exceed the 126 MB L2; no flush needed" if n_local * dof * 4 > 126e6 else "inputs fit the L2 at this size (sweep point)",
+                "parallelism": f"item-sharded x{world}, tables replicated" + (", ONE NCCL all_gather per step (words + 64-bit count), overlapped with the next step's kernel" if world > 1 else ""),
                 "numa_node_rank0": numa_node, "valid_fraction": valid_frac,
             },
-            "roofline": {
-                "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "traffic": DRAM_BYTES_PER_CFG_NCU * n_local / 1e9, "traffic_unit": "GB per launch",
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 29.4 B/config (profiles/r01_s34_panda_ncu.md), scaled to this launch",
-                "algorithmic_gb_per_launch": BYTES_PER_CFG * n_local / 1e9,
-                "peak_source": hbm_src, "kernel_ms": kernel_ms,
-                "note": "algorithmic bytes = 28.125 B/config; the kernel is FP32-SIMT issue bound, see roofline_fp32",
-            },
-            "roofline_fp32": {
-                "bound": "fp32_simt", "achieved": per_gpu_rate * F_CFG_DENSE / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": per_gpu_rate * F_CFG_DENSE / 1e12 / fp32_peak,
-                "note": "dense-equivalent: 14.7 kflop/config (SURVEY 8d, no culling) x configs/s; peak = FFMA micro-benchmark on this GPU" if extras.get("fp32_ffma_tflops_measured") else "dense-equivalent; nominal peak",
-                # the other two readings of the same rate: arithmetic the reference's algorithm executes
-                # (oracle counters, culling and early exit included), and what the pipes did (ncu)
-                "executed_flop_per_config": (extras.get("work_model") or {}).get("executed_flop_per_config"),
-                "executed_frac": (per_gpu_rate * extras["work_model"]["executed_flop_per_config"] / 1e12 / fp32_peak) if extras.get("work_model") else None,
-                "ncu": NCU_PIPE_FIGURES,
-            },
-            # the resource that actually binds the kernel: warp-instruction issue slots (4 schedulers per SM,
-            # one warp instruction per cycle each).  achieved = ncu's warp instructions per configuration for
-            # this kernel x the configurations/s measured in this run; peak at the sampled SM clock.
-            "roofline_issue": {
-                "bound": "issue_slots", "unit": "Gwarp-inst/s",
-                "achieved": per_gpu_rate * NCU_PIPE_FIGURES["warp_inst_per_config"] / 1e9,
-                "peak": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                "frac": per_gpu_rate * NCU_PIPE_FIGURES["warp_inst_per_config"] / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
-                "note": "warp_inst_per_config from " + NCU_PIPE_FIGURES["source"] + "; ncu's own smsp__issue_active for the same kernel: %.1f %%" % NCU_PIPE_FIGURES["issue_active_pct"],
-            },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * lb.shape[0] * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 16) * world, "steps": e2e_steps,
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * dof * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 8) * world, "steps": e2e_steps,
                     "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs,
-                    "frac_of_h2d_copy": (e2e_value / world) * lb.shape[0] * 4 / 1e9 / h2d_gbs},
+                    "frac_of_h2d_copy": (e2e_value / world) * dof * 4 / 1e9 / h2d_gbs,
+                    "from_pageable_fp64": {"value": e2e_f64_value, "unit": UNIT, "configs_per_call": n64,
+                                           "note": "pmp_check_configs_host_f64: pageable float64 numpy in (what the reference's binding holds), packed to FP32 by host threads into pinned staging"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if gather_check:
+            line["gather_check"] = gather_check
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if extras:
@@ -523,6 +647,35 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sweep(torch, dist, tables, parallel, robot, scene, lb, ub, world, rank, dev, out_path):
+    """BASELINE config 5: 1 M - 256 M configurations sharded over the ranks with the NCCL gather of the
+    validity words, STRONG scaling (fixed total split over N) next to WEAK scaling (fixed per-GPU size);
+    inputs generated on the device (uniform in the joint limits).  One JSON line per point."""
+    dof = lb.shape[0]
+    lo_t = torch.tensor(lb, dtype=torch.float32, device=dev)
+    span = torch.tensor(ub - lb, dtype=torch.float32, device=dev)
+    points = [("strong", t) for t in (1 << 20, 1 << 22, 1 << 24, 1 << 26, 1 << 28)] + [("weak", t) for t in (1 << 20, 1 << 24)]
+    for kind, size in points:
+        if kind == "strong":
+            a, b = parallel.shard_bounds(size, rank, world)
+            n_local, n_global = b - a, size
+        else:
+            n_local, n_global = size, size * world
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1000 + rank)
+        q = torch.rand((n_local, dof), generator=gen, device=dev, dtype=torch.float32) * span + lo_t
+        step = ShardedStep(torch, dist, tables, parallel, robot, scene, q, world, dev)
+        steps = int(max(5, min(200, 4e8 // max(n_local, 1))))
+        ms, _, last = timed_steps(torch, dist, step, steps, 3, world, dev)
+        if rank == 0:
+            rec = {"scaling": kind, "n_gpus": world, "global_configs": n_global, "per_gpu_configs": n_local, "steps": steps, "ms_per_step": ms,
+                   "configs_per_s": n_global / (ms * 1e-3), "collective": "one all_gather (words + count) per step, overlapped" if world > 1 else "none"}
+            with open(out_path, "a") as f:
+                f.write(json.dumps(rec) + "\n")
+        del step, q
+        torch.cuda.empty_cache()
 
 
 def time_cuda(torch, fn, steps=5, warmup=2):

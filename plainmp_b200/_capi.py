@@ -14,7 +14,8 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "libplainmp_b200.so"
+# PMP_B200_LIB: another build of the same sources (kernel A/B runs on the GPU box, tools/gpu_ab.sh); never a fallback
+LIB_PATH = Path(os.environ["PMP_B200_LIB"]) if os.environ.get("PMP_B200_LIB") else PKG_DIR / "libplainmp_b200.so"
 SRC_DIR = PKG_DIR / "csrc"
 
 NVCC_FLAGS = [
@@ -138,6 +139,7 @@ SYMBOLS = {
     "pmp_check_edges": (_i32, [_p, _p, C.POINTER(Validator), _p, _p, _i64, _p, _p, _p, _p]),
     "pmp_check_edges_ex": (_i32, [_p, _p, C.POINTER(Validator), _p, _p, _i32, _i64, _p, _p, _p, _p, _p]),
     "pmp_check_configs_host": (_i32, [_p, _p, _p, _i64, _p, C.POINTER(C.c_uint64)]),
+    "pmp_check_configs_host_f64": (_i32, [_p, _p, _p, _i64, _p, C.POINTER(C.c_uint64)]),
     "pmp_eval_configs_host": (_i32, [_p, _p, _p, _i64, _p]),
     "pmp_check_edges_host": (
         _i32,

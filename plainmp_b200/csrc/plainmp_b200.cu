@@ -4,8 +4,10 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -413,7 +415,8 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   if (v3) {
     // FP16 group centres (MODE 2) cost a few instructions per pair; they are used only where the
     // bytes they save buy another resident CTA per SM (estimated with a 4-primitive scene and the
-    // register limit of these kernels: 5 CTAs of 128 threads at 85-86 registers)
+    // register bound of these kernels: 5 CTAs of 128 threads, at most 96 registers; a 6-CTA variant at 80
+    // registers was measured in round 2 and lost, profiles/r02_s3_ab_flat_drain_6cta.txt)
     const bool fixed = d->base_type == PMP_BASE_FIXED;
     auto ctas = [&](bool gc16) {
       const size_t stash = (size_t)n_slots * 7 + (size_t)v3_gc_floats(n_groups, gc16) + (size_t)kV3WordsPerThread;
@@ -1137,6 +1140,148 @@ int pmp_eval_configs_host(const pmp_robot_t* robot, const pmp_scene_t* scene, co
     CUDA_OK(cudaMemcpyAsync(dist_host + off * 2, W.outb[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st));
   }
   return W.sync_all();
+}
+
+// ---- FP64 host states (what the reference's bindings hold: numpy float64 -> Eigen::VectorXd) ---------------
+extern "C++" {
+namespace {
+// A few persistent host threads for the FP64 -> FP32 packing of large host batches (a pageable double
+// array cannot be DMA'd as it is: the bytes have to be touched once anyway, so they are converted while
+// being staged, which also halves what crosses PCIe).
+class PackPool {
+ public:
+  static PackPool& get() {
+    // never destroyed: its detached threads wait on the condition variable for the life of the process
+    // (destroying a condition variable that has waiters blocks at exit)
+    static PackPool* p = new PackPool();
+    return *p;
+  }
+  int size() const { return (int)th_.size() + 1; }
+  // runs fn(t) for t in [0, n_tasks) on the pool's threads and the caller
+  void run(int n_tasks, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> serial(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_tasks_ = n_tasks;
+      next_ = 0;
+      pending_ = n_tasks;
+      gen_++;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  PackPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n = (int)std::min<unsigned>(hw ? hw : 4u, 16u) / 2;  // half of the cores, at most 8
+    for (int i = 0; i + 1 < std::max(n, 1); i++) th_.emplace_back([this] { loop(); });
+    for (auto& t : th_) t.detach();
+  }
+  void work() {
+    for (;;) {
+      int t;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!fn_ || next_ >= n_tasks_) return;
+        t = next_++;
+      }
+      (*fn_)(t);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+      }
+      work();
+    }
+  }
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> th_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_tasks_ = 0, next_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+};
+
+struct PinnedRing {  // pinned FP32 staging of the FP64 entry points: grow-only, one ring per workspace stream
+  float* buf[kWsStreams] = {};
+  size_t cap[kWsStreams] = {};
+  cudaEvent_t copied[kWsStreams] = {};
+  int reserve(int k, size_t bytes) {
+    if (!copied[k]) CUDA_OK(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+    if (cap[k] >= bytes) return PMP_OK;
+    if (buf[k]) cudaFreeHost(buf[k]);
+    buf[k] = nullptr;
+    cap[k] = 0;
+    CUDA_OK(cudaMallocHost(&buf[k], bytes));
+    cap[k] = bytes;
+    return PMP_OK;
+  }
+};
+std::mutex g_ring_mu;
+std::unordered_map<HostWorkspace*, PinnedRing*> g_rings;
+PinnedRing* ring_of(HostWorkspace* w) {
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  PinnedRing*& r = g_rings[w];
+  if (!r) r = new PinnedRing();
+  return r;
+}
+}  // namespace
+}  // extern "C++"
+
+int pmp_check_configs_host_f64(const pmp_robot_t* robot, const pmp_scene_t* scene, const double* q_host, int64_t n,
+                               uint32_t* valid_bits_host, uint64_t* n_valid) {
+  CHECK_COMMON(robot, n);
+  if (n_valid) *n_valid = 0;
+  if (n == 0) return PMP_OK;
+  if (!q_host || !valid_bits_host) return fail(PMP_ERR_INVALID, "null host pointer");
+  WorkspaceLease L;
+  if (int rc = L.acquire()) return rc;
+  HostWorkspace& W = *L.ws;
+  PinnedRing& R = *ring_of(L.ws);
+  const int qd = robot->full.dev.q_dim;
+  CUDA_OK(cudaMemsetAsync(W.counters, 0, 2 * sizeof(unsigned long long), W.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  constexpr int64_t kChunk = 1 << 18;  // small enough that packing chunk k + 1 overlaps the copy and kernel of chunk k
+  PackPool& pool = PackPool::get();
+  int k = 0;
+  for (int64_t off = 0; off < n; off += kChunk, k = (k + 1) % kWsStreams) {
+    const int64_t m = std::min<int64_t>(kChunk, n - off);
+    const size_t bytes = (size_t)m * qd * 4;
+    if (int rc = R.reserve(k, bytes)) return rc;
+    if (int rc = W.reserve(&W.in[k][0], &W.in_cap[k][0], bytes)) return rc;
+    if (int rc = W.reserve(&W.outb[k], &W.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
+    CUDA_OK(cudaEventSynchronize(R.copied[k]));  // the previous copy out of this staging buffer is done
+    const double* src = q_host + off * qd;
+    float* dst = R.buf[k];
+    const int64_t total = m * qd;
+    const int tasks = (int)std::min<int64_t>(pool.size(), std::max<int64_t>(1, total / 16384));
+    pool.run(tasks, [&](int t) {
+      const int64_t lo = total * t / tasks, hi = total * (t + 1) / tasks;
+      for (int64_t i = lo; i < hi; i++) dst[i] = (float)src[i];
+    });
+    cudaStream_t st = W.stream[k];
+    CUDA_OK(cudaMemcpyAsync(W.in[k][0], dst, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(R.copied[k], st));
+    if (int rc = pmp_check_configs(robot, scene, (const float*)W.in[k][0], m, (uint32_t*)W.outb[k], W.counters, st)) return rc;
+    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, W.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (int rc = W.sync_all()) return rc;
+  CUDA_OK(cudaMemcpyAsync(W.counters_host, W.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, W.stream[0]));
+  CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  if (n_valid) *n_valid = W.counters_host[0];
+  return PMP_OK;
 }
 
 int pmp_check_edges_host(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator,

@@ -157,7 +157,7 @@ struct QEdge {
 // stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
 // out of the primitives-only kernel).
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 512 / B)
+__global__ void __launch_bounds__(B, 640 / B)  // 5 CTAs of 128 threads per SM: at most 96 registers
 k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
                    uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
   extern __shared__ float4 sm[];
@@ -535,7 +535,7 @@ k_edge_prepare(const ValidatorDev V, const T* __restrict__ q0, const T* __restri
 // waypoint the reference would not have tested and the lanes stay full until the batch ends.
 // Valid edges set their bit with one atomicOr (k_edge_prepare zeroes the words first).
 // calls (optional): per edge, the number of is_valid calls = the reference's own count for that edge.
-constexpr int kEdgeChunk = 256;
+constexpr int kEdgeChunk = 32;  // one dispenser atomic per 32 edges: with 2960 resident warps, 256-edge chunks left a 1 M-edge batch with 1-2 chunks per warp (no balancing at all)
 
 struct EdgeArgs {
   const float* q0;
@@ -551,7 +551,7 @@ struct EdgeArgs {
 };
 
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 512 / B)
+__global__ void __launch_bounds__(B, 640 / B)  // 5 CTAs of 128 threads per SM: at most 96 registers
 k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__ seq, const EdgeArgs A) {
   extern __shared__ float4 sm[];
   const Smem T = stage_tables(R, S, sm);
@@ -648,7 +648,7 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__
 constexpr int kFlatSmemEdges = 1024;
 
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 512 / B)
+__global__ void __launch_bounds__(B, 640 / B)
 k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restrict__ q0, const float* __restrict__ q1,
                        const double* __restrict__ ratio, const int* __restrict__ off, const int n_edges,
                        uint32_t* __restrict__ way_bits, uint8_t* __restrict__ way_ok) {

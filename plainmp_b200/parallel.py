@@ -77,6 +77,30 @@ def gather_validity(
     return out[: (n + 31) // 32], int(total.item())
 
 
+def fused_words(n_local_words: int) -> int:
+    """Length (int32 elements) of a rank's send buffer for ``gather_validity_fused``: the packed words,
+    padded to an even count so that the 64-bit counter behind them is 8-byte aligned, plus that counter."""
+    return (n_local_words + 1) // 2 * 2 + 2
+
+
+def gather_validity_fused(
+    send: torch.Tensor, out: torch.Tensor, n: int, group: Optional[dist.ProcessGroup] = None
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ONE collective per step: every rank's send buffer holds its packed validity words followed by
+    its 64-bit valid count (``fused_words`` int32 elements; the kernel writes the count straight behind
+    the words), so a single all-gather delivers words and counts to every rank — no separate
+    all-reduce.  ``out`` is the [world * len(send)] receive buffer.  Returns (views of) the words of
+    all n items in rank order and the per-rank counts (int64[world]); no host synchronisation."""
+    world = dist.get_world_size(group)
+    dist.all_gather_into_tensor(out, send, group=group)
+    per = send.numel()
+    table = out.view(world, per)
+    w = shard_words(n, world)
+    words = table[:, :w].reshape(-1)[: (n + 31) // 32]
+    counts = table[:, per - 2 :].contiguous().view(torch.int64).reshape(world)
+    return words, counts
+
+
 def reduce_min(local_min: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     out = local_min.clone()
     dist.all_reduce(out, op=dist.ReduceOp.MIN, group=group)

@@ -44,8 +44,16 @@ def _worker(rank, world, port, n, seed, result_path):
 
     words, total = parallel.check_configs_sharded(compute, torch.from_numpy(Q[lo:hi]), n)
     mn = parallel.reduce_min(torch.tensor([float(rank) - 0.5]))
+    # the one-collective form: words and the 64-bit count in ONE send buffer (what bench.py's step does)
+    w_local, cnt = compute(torch.from_numpy(Q[lo:hi]))
+    per = parallel.fused_words(parallel.shard_words(n, world))
+    send = torch.zeros(per, dtype=torch.int32)
+    send[: w_local.numel()] = w_local
+    send[per - 2 :] = cnt.to(torch.int64).view(torch.int32)
+    recv = torch.empty(per * world, dtype=torch.int32)
+    f_words, f_counts = parallel.gather_validity_fused(send, recv, n)
     if rank == 0:
-        np.savez(result_path, words=words.numpy(), total=total, mn=mn.numpy())
+        np.savez(result_path, words=words.numpy(), total=total, mn=mn.numpy(), f_words=f_words.numpy(), f_counts=f_counts.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,3 +76,4 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     assert (got == want).all()
     assert int(r["total"]) == int(want.sum())
     assert float(r["mn"][0]) == -0.5
+    assert (r["f_words"] == r["words"]).all() and int(r["f_counts"].sum()) == int(want.sum()) and len(r["f_counts"]) == 2

@@ -817,3 +817,50 @@ def test_emulated_composite_constraint_single_fk(emu):
     e_got, _ = t.check_edges(0, np.full(7, 0.05), 0.0, q0, q1)
     e_sep = EmuTables(emu, a).check_edges(0, np.full(7, 0.05), 0.0, q0, q1)[0] & EmuTables(emu, b).check_edges(0, np.full(7, 0.05), 0.0, q0, q1)[0]
     assert (e_got == e_sep).all()
+
+
+@pytest.mark.parametrize("n_side", [10, 11])
+def test_emulated_huge_sphere_group_unit_offsets(emu, n_side):
+    """create_attached_box_collision_const-style grids (robot_spec.py:561-595: 10 x 10 x 10 zero-radius
+    spheres on the hand).  1000 spheres per group stay on the flat work-unit list, whose 16-bit unit offsets
+    then force early drains (32 lanes x 1000 units > 60000 would not fit: the push is split); 1331 spheres
+    exceed kBigGroup and take the 8-lane path instead."""
+    spec = PandaSpec()
+    g = np.linspace(-0.06, 0.06, n_side)
+    pts = np.array([[x, y, z + 0.18] for x in g for y in g for z in g]).T
+    att = SphereAttachmentSpec("panda_link8", pts, np.zeros(pts.shape[1]), False)
+    cst = spec.create_collision_const(attachments=[att], use_cache=False, reorder_spheres=False)
+    # plates whose AABBs cover the whole workspace: every lane queues the big group against every plate
+    plates = [psdf.BoxSDF([0.02, 4.0, 4.0], psdf.Pose([1.6 + 0.1 * k, 0.0, 0.5])) for k in range(3)]
+    for k, pl in enumerate(plates):
+        pl.rotate_z(0.3 + 0.9 * k)
+    cst.set_sdf(psdf.UnionSDF(plates + [psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.45, 0.0, 0.5]))]))
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    Q = workloads.random_configs(spec, 96, 7)
+    Qd = Q.astype(np.float64)
+    want = o.is_valid_batch(Qd)
+    assert 0.1 < want.mean() < 0.9
+    _parity(t.check(Q), want, o.margin_batch(Qd), f"{n_side ** 3}-sphere group")
+
+
+def test_emulated_fp64_host_entry_points(emu):
+    """pmp_check_configs_host_f64 / pmp_check_edges_host_f64: the reference's callers hold FP64 states; the
+    packing threads + staged copies must give the words of the FP32 entry points on the same values."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    Q = workloads.random_configs(spec, 300, 23)
+    Qd = np.ascontiguousarray(Q, dtype=np.float64)
+    want = t.check(Q)
+    bits = np.zeros((300 + 31) // 32, dtype=np.uint32)
+    nv = C.c_uint64(0)
+    assert emu.pmp_check_configs_host_f64(t.robot, t.scene, Qd.ctypes.data, 300, bits.ctypes.data, C.byref(nv)) == 0, emu.pmp_last_error()
+    assert (tables.unpack_bits(bits, 300) == want).all() and nv.value == int(want.sum())
+    q0, q1 = workloads.random_edges(spec, 96, 4, True, lambda q: t.check(q))
+    e32, nc32 = t.check_edges(0, np.full(7, 0.05), 0.0, q0, q1)
+    v, keep = tables.make_validator(0, 7, np.full(7, 0.05), 0.0)
+    a, b = np.ascontiguousarray(q0, dtype=np.float64), np.ascontiguousarray(q1, dtype=np.float64)
+    ebits = np.zeros(3, dtype=np.uint32)
+    nv, nc = C.c_uint64(0), C.c_uint64(0)
+    assert emu.pmp_check_edges_host_f64(t.robot, t.scene, C.byref(v), a.ctypes.data, b.ctypes.data, 96, ebits.ctypes.data, C.byref(nv), C.byref(nc)) == 0
+    assert (tables.unpack_bits(ebits, 96) == e32).all() and nc.value == nc32 and nv.value == int(e32.sum())

@@ -16,6 +16,6 @@ for wl in $wls; do
   gzip -f ${rep}_source.csv ${rep}_sass.csv
   if [ "$wl" != "panda" ]; then rm -f $rep.ncu-rep; fi
 done
-timeout 600 python tools/time_workloads.py > gpurun_out/${tag}_times.txt 2>&1
-timeout 900 python tools/probe_parity_fullsize.py edges fetch cloud100k cloud1m > gpurun_out/${tag}_probe.txt 2>&1
+[ -n "$SKIP_TIMES" ] || timeout 600 python tools/time_workloads.py > gpurun_out/${tag}_times.txt 2>&1
+[ -n "$SKIP_TIMES" ] || timeout 900 python tools/probe_parity_fullsize.py edges fetch cloud100k cloud1m > gpurun_out/${tag}_probe.txt 2>&1
 du -sh gpurun_out

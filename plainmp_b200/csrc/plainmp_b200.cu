@@ -14,6 +14,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "pmp_cloud_build.h"
 #include "pmp_kernels.cuh"
 
@@ -139,6 +141,7 @@ struct RobotTables {
   int v3_mode = 0;                          // MODE of the validity kernels (pmp_v3.cuh: warp_check_interp)
   size_t stash_floats_per_thread = 0;       // validity kernels (v3 layout) / FK kernels
   size_t stash_floats_per_thread_eval = 0;  // evaluate kernel: one word per group (+1) after the group centres
+  int n_env_spheres = 0;                    // spheres of the groups that take part in environment checks
 };
 
 struct pmp_robot {
@@ -403,6 +406,9 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   D.off_pairs = off_pairs;
   D.off_pairs4 = off_pairs4;
   D.off_gmask = has_gmask ? off_gmask : -1;
+  out->n_env_spheres = 0;
+  for (const GroupD& G : P.groups)
+    if (!G.only_self) out->n_env_spheres += G.sphere_count;
   D.dof = d->dof;
   D.q_dim = q_dim;
   D.base_type = d->base_type;
@@ -701,6 +707,12 @@ int pmp_check_configs(const pmp_robot_t* robot, const pmp_scene_t* scene, const 
   return PMP_OK;
 }
 
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// evaluate(): one kernel, or — when the scene has a CloudSDF — three: pass 1 without the cloud (candidate
+// spheres written to stream-ordered scratch), the warp-per-configuration cloud stage, and the Jacobian rows.
+constexpr int64_t kEvalCoopChunk = 1 << 17;  // configurations per pass of the cooperative path (bounds the scratch)
+
 static int eval_launch(const pmp_robot_t* robot, const pmp_scene_t* scene, const float* q_dev, int64_t n, float* dist_dev,
                        float* jac_dev, void* stream) {
   CHECK_COMMON(robot, n);
@@ -710,16 +722,63 @@ static int eval_launch(const pmp_robot_t* robot, const pmp_scene_t* scene, const
   const int block = pick_block_per_thread(robot->fast, S, true);
   if (!block) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const size_t smem = smem_bytes(robot->fast, S, block, true);
+  cudaStream_t st = (cudaStream_t)stream;
   int grid = 0;
-  if (jac_dev) {
-    if (int rc = grid_for(k_eval_configs<true>, smem, (n + block - 1) / block, &grid, block)) return rc;
-    k_eval_configs<true><<<grid, block, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, jac_dev);
-  } else {
-    if (int rc = grid_for(k_eval_configs<false>, smem, (n + block - 1) / block, &grid, block)) return rc;
-    k_eval_configs<false><<<grid, block, smem, (cudaStream_t)stream>>>(robot->fast.dev, S, q_dev, n, dist_dev, nullptr);
+  const bool coop = S.cloud.enabled != 0 && robot->fast.n_env_spheres > 0;
+  if (!coop) {
+    CloudCand none{};
+    if (jac_dev) {
+      if (int rc = grid_for(k_eval_configs<true, false>, smem, (n + block - 1) / block, &grid, block)) return rc;
+      k_eval_configs<true, false><<<grid, block, smem, st>>>(robot->fast.dev, S, q_dev, n, dist_dev, jac_dev, none);
+    } else {
+      if (int rc = grid_for(k_eval_configs<false, false>, smem, (n + block - 1) / block, &grid, block)) return rc;
+      k_eval_configs<false, false><<<grid, block, smem, st>>>(robot->fast.dev, S, q_dev, n, dist_dev, nullptr, none);
+    }
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return PMP_OK;
   }
-  g_launches++;
-  CUDA_OK(cudaGetLastError());
+  const int qd = robot->fast.dev.q_dim;
+  const int stride = robot->fast.n_env_spheres;
+  for (int64_t off = 0; off < n; off += kEvalCoopChunk) {
+    const int64_t m = std::min<int64_t>(kEvalCoopChunk, n - off);
+    const size_t o_op = align256((size_t)m * stride * 16), o_cnt = o_op + (jac_dev ? align256((size_t)m * stride * 4) : 0);
+    const size_t o_arg = o_cnt + align256((size_t)m * 4), total = o_arg + (jac_dev ? align256((size_t)m * sizeof(EvalArgmin)) : 0);
+    char* scratch = nullptr;
+    CUDA_OK(cudaMallocAsync(&scratch, total, st));
+    CloudCand CC{};
+    CC.sph = reinterpret_cast<float4*>(scratch);
+    CC.op = jac_dev ? reinterpret_cast<int*>(scratch + o_op) : nullptr;
+    CC.count = reinterpret_cast<int*>(scratch + o_cnt);
+    CC.argmin = jac_dev ? reinterpret_cast<EvalArgmin*>(scratch + o_arg) : nullptr;
+    CC.stride = stride;
+    const float* qc = q_dev + off * qd;
+    float* dc = dist_dev + off * 2;
+    int rc = PMP_OK;
+    const int warps_grid = (int)std::min<int64_t>((m + 3) / 4, (int64_t)num_sms() * 16);  // 4 warps (configurations) per CTA
+    if (jac_dev) {
+      float* jc = jac_dev + off * 2 * qd;
+      rc = grid_for(k_eval_configs<true, true>, smem, (m + block - 1) / block, &grid, block);
+      if (rc == PMP_OK) {
+        k_eval_configs<true, true><<<grid, block, smem, st>>>(robot->fast.dev, S, qc, m, dc, jc, CC);
+        k_eval_cloud_coop<true><<<warps_grid, 128, 0, st>>>(S, CC, m, dc);
+        rc = grid_for(k_eval_jacobian, smem, (m + block - 1) / block, &grid, block);
+      }
+      if (rc == PMP_OK) k_eval_jacobian<<<grid, block, smem, st>>>(robot->fast.dev, S, qc, m, CC, jc);
+      g_launches += 3;
+    } else {
+      rc = grid_for(k_eval_configs<false, true>, smem, (m + block - 1) / block, &grid, block);
+      if (rc == PMP_OK) {
+        k_eval_configs<false, true><<<grid, block, smem, st>>>(robot->fast.dev, S, qc, m, dc, nullptr, CC);
+        k_eval_cloud_coop<false><<<warps_grid, 128, 0, st>>>(S, CC, m, dc);
+      }
+      g_launches += 2;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (rc != PMP_OK) return rc;
+    if (e != cudaSuccess) return fail(PMP_ERR_CUDA, cudaGetErrorString(e));
+  }
   return PMP_OK;
 }
 
@@ -878,8 +937,6 @@ int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
   return PMP_OK;
 }
 
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
 // the persistent edge kernel on endpoints, ratios and n_test that are already on the device
 int launch_edges(const pmp_robot_t* robot, const SceneDev& S, const uint8_t* seq, const EdgeArgs& A, cudaStream_t st) {
   if (!mask_limit_ok(robot->fast, S)) return fail(PMP_ERR_LIMIT, "a robot with per-group scene masks needs a scene of at most 30 primitives");
@@ -911,6 +968,7 @@ int launch_edges(const pmp_robot_t* robot, const SceneDev& S, const uint8_t* seq
 }
 
 constexpr int64_t kMaxEdgesPerLaunch = (int64_t)1 << 30;  // the kernel indexes edges with 32 bits
+constexpr int64_t kSortEdgesFrom = 4096;                   // smaller batches are not worth the radix pass
 
 // prepare pass + persistent kernel for one launch-sized batch.  Scratch (ratio, n_test, chunk counter and,
 // for FP64 endpoints, their FP32 copies) comes from the stream-ordered pool and goes back to it in stream
@@ -920,16 +978,26 @@ int check_edges_batch(const pmp_robot_t* robot, const SceneDev& S, const Validat
                       uint32_t* bits, uint32_t* calls, unsigned long long* n_valid, unsigned long long* n_checked, cudaStream_t st) {
   constexpr bool f64 = sizeof(T) == 8;
   const int qd = robot->fast.dev.q_dim;
+  const bool sorted = n >= kSortEdgesFrom;
+  size_t sort_tmp = 0;
+  if (sorted)
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint8_t*)nullptr, (uint8_t*)nullptr, (const uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)n, 0, 8, st));
   const size_t o_ntest = align256((size_t)n * 8), o_ctr = o_ntest + align256((size_t)n * 4), o_q0 = o_ctr + 256;
   const size_t qbytes = f64 ? align256((size_t)n * std::max(qd, 1) * 4) : 0;
+  // longest-first order: keys in / out (u8), indices in / out (u32), CUB's temporary storage
+  const size_t o_key = o_q0 + 2 * qbytes, o_idx = o_key + (sorted ? 2 * align256((size_t)n) : 0);
+  const size_t o_tmp = o_idx + (sorted ? 2 * align256((size_t)n * 4) : 0), total = o_tmp + (sorted ? align256(sort_tmp) : 0);
   char* scratch = nullptr;
-  CUDA_OK(cudaMallocAsync(&scratch, o_q0 + 2 * qbytes, st));
+  CUDA_OK(cudaMallocAsync(&scratch, total, st));
   EdgeArgs A{};
   A.ratio = reinterpret_cast<double*>(scratch);
   A.ntest = reinterpret_cast<int*>(scratch + o_ntest);
   A.next_chunk = reinterpret_cast<unsigned long long*>(scratch + o_ctr);
   float* q0f = f64 ? reinterpret_cast<float*>(scratch + o_q0) : nullptr;
   float* q1f = f64 ? reinterpret_cast<float*>(scratch + o_q0 + qbytes) : nullptr;
+  uint8_t* key = sorted ? reinterpret_cast<uint8_t*>(scratch + o_key) : nullptr;
+  uint32_t* idx = sorted ? reinterpret_cast<uint32_t*>(scratch + o_idx) : nullptr;
   A.q0 = f64 ? q0f : reinterpret_cast<const float*>(q0);
   A.q1 = f64 ? q1f : reinterpret_cast<const float*>(q1);
   A.n = n;
@@ -939,9 +1007,18 @@ int check_edges_batch(const pmp_robot_t* robot, const SceneDev& S, const Validat
   A.n_checked = n_checked;
   const int grid = (int)std::min<int64_t>((n * (f64 ? std::max(qd, 1) : 1) + 255) / 256, (int64_t)num_sms() * 8);
   k_edge_prepare<T><<<grid, 256, 0, st>>>(V, q0, q1, n, qd, q0f, q1f, const_cast<double*>(A.ratio), const_cast<int*>(A.ntest), bits,
-                                          A.next_chunk);
+                                          A.next_chunk, key, idx);
   g_launches++;
-  int rc = launch_edges(robot, S, V.seq, A, st);
+  int rc = PMP_OK;
+  if (sorted) {
+    uint32_t* order = idx + align256((size_t)n * 4) / 4;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(scratch + o_tmp, sort_tmp, (const uint8_t*)key, key + align256((size_t)n),
+                                                    (const uint32_t*)idx, order, (int)n, 0, 8, st);
+    if (e != cudaSuccess) rc = fail(PMP_ERR_CUDA, std::string("edge order sort: ") + cudaGetErrorString(e));
+    A.order = order;
+    g_launches++;
+  }
+  if (rc == PMP_OK) rc = launch_edges(robot, S, V.seq, A, st);
   cudaError_t e = cudaFreeAsync(scratch, st);
   if (rc == PMP_OK && e != cudaSuccess) return fail(PMP_ERR_CUDA, std::string("cudaFreeAsync: ") + cudaGetErrorString(e));
   return rc;

@@ -254,9 +254,9 @@ __device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, cons
 // uniform throughout.  Returns the squared NN distance (or the bound if nothing beat it) and the
 // original index of the nearest point through *idx (-1 if none).
 __device__ inline float cloud_nn8(const CloudDev& C, const float3 p, float best, const unsigned smask, const int sub,
-                                  const int kshift, int* idx) {
+                                  const int kshift, int* idx, int* pos = nullptr) {
   const int top = C.n_levels - 1;
-  int best_i = -1;
+  int best_i = -1, best_pos = -1;
   int l = top, n = 0;
   unsigned long long masks = 0;
   auto child_mask = [&](const int level, const int first) -> unsigned {
@@ -287,18 +287,22 @@ __device__ inline float cloud_nn8(const CloudDev& C, const float3 p, float best,
       const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
       float d2 = dx * dx + dy * dy + dz * dz;
       int di = __float_as_int(x.w);
+      int dp = 8 * child + sub;  // position in the Morton-sorted array
 #pragma unroll
       for (int off = 4; off; off >>= 1) {
         const float od = __shfl_xor_sync(smask, d2, off);
         const int oi = __shfl_xor_sync(smask, di, off);
+        const int op = __shfl_xor_sync(smask, dp, off);
         if (od < d2 || (od == d2 && oi < di)) {  // ties -> smaller original index, the same on every lane
           d2 = od;
           di = oi;
+          dp = op;
         }
       }
       if (d2 < best) {
         best = d2;
         best_i = di;
+        best_pos = dp;
       }
     } else {
       l--;
@@ -307,6 +311,7 @@ __device__ inline float cloud_nn8(const CloudDev& C, const float3 p, float best,
     }
   }
   *idx = best_i;
+  if (pos) *pos = best_pos;
   return best;
 }
 

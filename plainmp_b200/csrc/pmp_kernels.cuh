@@ -203,10 +203,107 @@ __device__ __forceinline__ bool op_is_ancestor(const Smem& T, const int anc, int
   return x == anc;
 }
 
-template <bool GRAD>
+// Pass 2 of evaluate(): the Jacobian rows at the arg-min sphere / sphere pair recorded in A.
+template <class QAcc>
+__device__ __forceinline__ void eval_jacobian_rows(const RobotDev& R, const SceneDev& S, const Smem& T, const QAcc& acc, const EvalArgmin& A,
+                                                   const bool ext, float* __restrict__ je, float* __restrict__ js) {
+  const float nanv = __int_as_float(0x7fc00000);
+  for (int c = 0; c < R.q_dim; c++) {
+    je[c] = ext ? 0.f : nanv;
+    js[c] = (R.n_pairs > 0) ? 0.f : nanv;
+  }
+  float3 ge = make3(0.f, 0.f, 0.f);  // d(sdf)/d(centre) at the arg-min sphere
+  if (A.ext_op >= 0) {
+    if (A.ext_prim >= 0) {
+      ge = prim_gradient(load_prim(T.prims, A.ext_prim), A.ext_c);
+    } else {
+      const float dx = A.ext_c.x - A.ext_nn.x, dy = A.ext_c.y - A.ext_nn.y, dz = A.ext_c.z - A.ext_nn.z;
+      const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
+      ge = make3(dx * inv, dy * inv, dz * inv);
+    }
+  }
+  float3 ns = make3(0.f, 0.f, 0.f);  // (c1 - c2) / |c1 - c2|
+  if (A.self_op_a >= 0) {
+    const float dx = A.self_ca.x - A.self_cb.x, dy = A.self_ca.y - A.self_cb.y, dz = A.self_ca.z - A.self_cb.z;
+    const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
+    ns = make3(dx * inv, dy * inv, dz * inv);
+  }
+  if (A.ext_op < 0 && A.self_op_a < 0) return;
+  walk_links<false>(R, T, acc, [&](int op, const Frame& f) -> bool {
+    const int kind = __float_as_int(T.ops[kOpWords * op + 1].w);
+    if (kind == PMP_OP_FIXED) return true;
+    const float4 w2 = T.ops[kOpWords * op + 2];
+    const int qi = __float_as_int(w2.w);
+    // joint axis in the op's own frame: word 2 for a revolute joint; a prismatic op keeps it in word 4
+    // (word 2 holds the axis folded into the parent's frame, which is what the translation needs)
+    const float4 wj = (kind == PMP_OP_PRISMATIC) ? T.ops[kOpWords * op + 4] : w2;
+    const float3 wa = quat_rot(f.qx, f.qy, f.qz, f.qw, make3(wj.x, wj.y, wj.z));  // axis w.r.t. the root
+    auto column = [&](const float3 c) -> float3 {
+      if (kind == PMP_OP_PRISMATIC) return wa;
+      const float rx = c.x - f.tx, ry = c.y - f.ty, rz = c.z - f.tz;
+      return make3(wa.y * rz - wa.z * ry, wa.z * rx - wa.x * rz, wa.x * ry - wa.y * rx);
+    };
+    if (A.ext_op >= 0 && op_is_ancestor(T, op, A.ext_op)) {
+      const float3 col = column(A.ext_c);
+      je[qi] = col.x * ge.x + col.y * ge.y + col.z * ge.z;
+    }
+    if (A.self_op_a >= 0) {
+      float v = 0.f;
+      if (op_is_ancestor(T, op, A.self_op_a)) {
+        const float3 col = column(A.self_ca);
+        v += col.x * ns.x + col.y * ns.y + col.z * ns.z;
+      }
+      if (op_is_ancestor(T, op, A.self_op_b)) {
+        const float3 col = column(A.self_cb);
+        v -= col.x * ns.x + col.y * ns.y + col.z * ns.z;
+      }
+      js[qi] = v;
+    }
+    return true;
+  });
+  // moving base (algorithm.cpp:378-430): translation columns are unit vectors, rotation columns
+  // axis_k x (c - t_base) with the roll / pitch / yaw axes of R = Rz(yaw) Ry(pitch) Rx(roll).
+  // For the self row every base column cancels (both points move rigidly with the base).
+  if (R.base_type != PMP_BASE_FIXED && A.ext_op >= 0) {
+    const Frame b = base_frame(R, acc);
+    const float rx = A.ext_c.x - b.tx, ry = A.ext_c.y - b.ty, rz = A.ext_c.z - b.tz;
+    auto rot_col = [&](const float ax, const float ay, const float az) -> float {
+      return (ay * rz - az * ry) * ge.x + (az * rx - ax * rz) * ge.y + (ax * ry - ay * rx) * ge.z;
+    };
+    je[R.dof] = ge.x;
+    je[R.dof + 1] = ge.y;
+    if (R.base_type == PMP_BASE_PLANAR) {
+      je[R.dof + 2] = rot_col(0.f, 0.f, 1.f);
+    } else {
+      je[R.dof + 2] = ge.z;
+      float sy, cy, sp, cp;
+      sincosf(acc(R.dof + 5), &sy, &cy);
+      sincosf(acc(R.dof + 4), &sp, &cp);
+      je[R.dof + 3] = rot_col(cy * cp, sy * cp, -sp);
+      je[R.dof + 4] = rot_col(-sy, cy, 0.f);
+      je[R.dof + 5] = rot_col(0.f, 0.f, 1.f);
+    }
+  }
+}
+
+// Scratch of the cooperative cloud stage of evaluate() (COOP): for every configuration the env spheres
+// whose group passes the cloud's group-level cull, placed with exact FK — [config][slot] float4 (x, y, z, r)
+// and, for the Jacobian rows, the op that carries each of them.
+struct CloudCand {
+  float4* sph;         // [n][stride]
+  int* op;             // [n][stride] (GRAD only)
+  int* count;          // [n]
+  EvalArgmin* argmin;  // [n] (GRAD only): pass 1's arg-min record, completed by the cloud stage
+  int stride;          // env spheres of the robot
+};
+
+// COOP: the scene's CloudSDF is NOT queried here; the candidate spheres are handed to k_eval_cloud_coop,
+// which works each configuration with a whole warp (8 lanes per nearest-point query), and for GRAD the
+// Jacobian rows are left to k_eval_jacobian.  Without a cloud the kernel does everything itself.
+template <bool GRAD, bool COOP>
 __global__ void __launch_bounds__(128)
 k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
-               float* __restrict__ out, float* __restrict__ jac) {
+               float* __restrict__ out, float* __restrict__ jac, const CloudCand CC) {
   extern __shared__ float4 sm[];
   const Smem T = stage_tables(R, S, sm);
   const float cutoff = 0.1f;  // primitive_sphere_collision.hpp:115
@@ -221,7 +318,7 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
     EvalArgmin A;
     A.ext_op = -1; A.ext_prim = -1; A.self_op_a = -1; A.self_op_b = -1;
     A.ext_c = A.ext_nn = A.self_ca = A.self_cb = make3(0.f, 0.f, 0.f);
-    int gi = 0;
+    int gi = 0, n_cand = 0;
     auto visit = [&](int op, const Frame& f) -> bool {
       while (gi < R.n_groups) {
         const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
@@ -260,6 +357,13 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
               if (c.x < S.cloud.lbx - rr || c.x > S.cloud.ubx + rr || c.y < S.cloud.lby - rr ||
                   c.y > S.cloud.uby + rr || c.z < S.cloud.lbz - rr || c.z > S.cloud.ubz + rr)
                 continue;
+              if (COOP) {
+                const long long slot = item * CC.stride + n_cand;
+                CC.sph[slot] = make_float4(c.x, c.y, c.z, sp.w);
+                if (GRAD) CC.op[slot] = op;
+                n_cand++;
+                continue;
+              }
               float lo, hi;
               cloud_bounds(S.cloud, c, lo, hi);
               const float need = min_ext + sp.w + S.cloud.rho;  // only NN below this can lower the min
@@ -318,87 +422,123 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
     const float nanv = __int_as_float(0x7fc00000);
     out[2 * item] = ext ? min_ext : nanv;
     out[2 * item + 1] = (R.n_pairs > 0) ? min_self : nanv;
+    if (COOP) {
+      CC.count[item] = n_cand;
+      if (GRAD) CC.argmin[item] = A;
+      continue;  // k_eval_cloud_coop finishes the ext value, k_eval_jacobian writes the rows
+    }
     if (!GRAD) continue;
+    eval_jacobian_rows(R, S, T, acc, A, ext, jac + (2 * item) * R.q_dim, jac + (2 * item + 1) * R.q_dim);
+  }
+}
 
-    // ---- pass 2: Jacobian rows ----
-    float* je = jac + (2 * item) * R.q_dim;
-    float* js = je + R.q_dim;
-    for (int c = 0; c < R.q_dim; c++) {
-      je[c] = ext ? 0.f : nanv;
-      js[c] = (R.n_pairs > 0) ? 0.f : nanv;
-    }
-    float3 ge = make3(0.f, 0.f, 0.f);  // d(sdf)/d(centre) at the arg-min sphere
-    if (A.ext_op >= 0) {
-      if (A.ext_prim >= 0) {
-        ge = prim_gradient(load_prim(T.prims, A.ext_prim), A.ext_c);
-      } else {
-        const float dx = A.ext_c.x - A.ext_nn.x, dy = A.ext_c.y - A.ext_nn.y, dz = A.ext_c.z - A.ext_nn.z;
-        const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
-        ge = make3(dx * inv, dy * inv, dz * inv);
+// The cloud stage of evaluate(), one WARP per configuration: the candidate spheres (those of the groups
+// that passed the group-level cull in k_eval_configs<., true>) are taken 32 at a time — every lane reads
+// the distance field's lower / upper bound for one of them (the upper bounds tighten the running minimum
+// before any tree is touched), then the candidates the field cannot rule out go to the tree four at a
+// time, 8 lanes per exact nearest-point query (cloud_nn8) bounded by the running minimum, which every
+// answered query tightens for the ones that follow.  Same value as evaluate_ext_collision's loop
+// (primitive_sphere_collision.cpp:256-295): min over env spheres of sqrt(NN^2) - rho - r, cut off at 0.1.
+template <bool GRAD>
+__global__ void __launch_bounds__(128)
+k_eval_cloud_coop(const SceneDev S, const CloudCand CC, const long long n, float* __restrict__ out) {
+  const CloudDev& C = S.cloud;
+  constexpr unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, sub = lane & 7, k = lane >> 3;
+  const unsigned smask = 0xffu << (8 * k);
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long cfg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cfg < n; cfg += n_warps) {
+    const int m = CC.count[cfg];
+    if (m == 0) continue;
+    float cur = out[2 * cfg];  // min over the primitives (or the cutoff); warp-uniform from here on
+    int best_slot = -1, best_pos = -1;
+    for (int c0 = 0; c0 < m; c0 += 32) {
+      const int slot = c0 + lane;
+      float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+      float lo = INFINITY, hi = INFINITY;
+      if (slot < m) {
+        sp = CC.sph[cfg * CC.stride + slot];
+        cloud_bounds(C, make3(sp.x, sp.y, sp.z), lo, hi);
       }
-    }
-    float3 ns = make3(0.f, 0.f, 0.f);  // (c1 - c2) / |c1 - c2|
-    if (A.self_op_a >= 0) {
-      const float dx = A.self_ca.x - A.self_cb.x, dy = A.self_ca.y - A.self_cb.y, dz = A.self_ca.z - A.self_cb.z;
-      const float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f));
-      ns = make3(dx * inv, dy * inv, dz * inv);
-    }
-    if (A.ext_op < 0 && A.self_op_a < 0) continue;
-    walk_links<false>(R, T, acc, [&](int op, const Frame& f) -> bool {
-      const int kind = __float_as_int(T.ops[kOpWords * op + 1].w);
-      if (kind == PMP_OP_FIXED) return true;
-      const float4 w2 = T.ops[kOpWords * op + 2];
-      const int qi = __float_as_int(w2.w);
-      // joint axis in the op's own frame: word 2 for a revolute joint; a prismatic op keeps it in word 4
-      // (word 2 holds the axis folded into the parent's frame, which is what the translation needs)
-      const float4 wj = (kind == PMP_OP_PRISMATIC) ? T.ops[kOpWords * op + 4] : w2;
-      const float3 wa = quat_rot(f.qx, f.qy, f.qz, f.qw, make3(wj.x, wj.y, wj.z));  // axis w.r.t. the root
-      auto column = [&](const float3 c) -> float3 {
-        if (kind == PMP_OP_PRISMATIC) return wa;
-        const float rx = c.x - f.tx, ry = c.y - f.ty, rz = c.z - f.tz;
-        return make3(wa.y * rz - wa.z * ry, wa.z * rx - wa.x * rz, wa.x * ry - wa.y * rx);
-      };
-      if (A.ext_op >= 0 && op_is_ancestor(T, op, A.ext_op)) {
-        const float3 col = column(A.ext_c);
-        je[qi] = col.x * ge.x + col.y * ge.y + col.z * ge.z;
-      }
-      if (A.self_op_a >= 0) {
-        float v = 0.f;
-        if (op_is_ancestor(T, op, A.self_op_a)) {
-          const float3 col = column(A.self_ca);
-          v += col.x * ns.x + col.y * ns.y + col.z * ns.z;
+      // the field's upper bounds: an upper bound of the answer (used only to prune, never reported)
+      float ub = (slot < m && hi < INFINITY) ? (hi * (1.f + 1e-6f) + 1e-6f) - C.rho - sp.w : INFINITY;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) ub = fminf(ub, __shfl_xor_sync(full, ub, off));
+      const float prune = fminf(cur, ub + 2e-6f);
+      unsigned cand = __ballot_sync(full, slot < m && lo - C.rho - sp.w < prune);
+      while (cand) {
+        // the next four candidates, one per 8-lane sub-warp
+        int owner = -1;
+        unsigned rest = cand;
+        for (int j = 0; j <= k && rest; j++) {
+          owner = __ffs(rest) - 1;
+          rest &= rest - 1u;
+          if (j < k) owner = -1;
         }
-        if (op_is_ancestor(T, op, A.self_op_b)) {
-          const float3 col = column(A.self_cb);
-          v -= col.x * ns.x + col.y * ns.y + col.z * ns.z;
+        for (int j = 0; j < 4 && cand; j++) cand &= cand - 1u;
+        const int src = owner < 0 ? 0 : owner;
+        const float4 qs = make_float4(__shfl_sync(full, sp.x, src), __shfl_sync(full, sp.y, src), __shfl_sync(full, sp.z, src), __shfl_sync(full, sp.w, src));
+        const float qlo = __shfl_sync(full, lo, src);
+        float val = INFINITY;
+        int pos = -1;
+        const float need = fminf(cur, prune) + qs.w + C.rho;  // only a nearest point closer than this lowers the minimum
+        if (owner >= 0 && qlo < need && need > 0.f) {
+          // strict search against a bound nudged up by one ulp, so that a point AT the bound is found
+          const float b2 = __uint_as_float(__float_as_uint(need * need) + 1u);
+          int idx;
+          const float d2 = cloud_nn8(C, make3(qs.x, qs.y, qs.z), b2, smask, sub, 8 * k, &idx, &pos);
+          if (idx >= 0) val = sqrtf(d2) - C.rho - qs.w;
         }
-        js[qi] = v;
-      }
-      return true;
-    });
-    // moving base (algorithm.cpp:378-430): translation columns are unit vectors, rotation columns
-    // axis_k x (c - t_base) with the roll / pitch / yaw axes of R = Rz(yaw) Ry(pitch) Rx(roll).
-    // For the self row every base column cancels (both points move rigidly with the base).
-    if (R.base_type != PMP_BASE_FIXED && A.ext_op >= 0) {
-      const Frame b = base_frame(R, acc);
-      const float rx = A.ext_c.x - b.tx, ry = A.ext_c.y - b.ty, rz = A.ext_c.z - b.tz;
-      auto rot_col = [&](const float ax, const float ay, const float az) -> float {
-        return (ay * rz - az * ry) * ge.x + (az * rx - ax * rz) * ge.y + (ax * ry - ay * rx) * ge.z;
-      };
-      je[R.dof] = ge.x;
-      je[R.dof + 1] = ge.y;
-      if (R.base_type == PMP_BASE_PLANAR) {
-        je[R.dof + 2] = rot_col(0.f, 0.f, 1.f);
-      } else {
-        je[R.dof + 2] = ge.z;
-        float sy, cy, sp, cp;
-        sincosf(acc(R.dof + 5), &sy, &cy);
-        sincosf(acc(R.dof + 4), &sp, &cp);
-        je[R.dof + 3] = rot_col(cy * cp, sy * cp, -sp);
-        je[R.dof + 4] = rot_col(-sy, cy, 0.f);
-        je[R.dof + 5] = rot_col(0.f, 0.f, 1.f);
+        // warp-wide minimum over the four answers (ties -> the lower sub-warp, deterministic)
+        float bv = val;
+        int bk = k;
+#pragma unroll
+        for (int off = 16; off >= 8; off >>= 1) {
+          const float ov = __shfl_xor_sync(full, bv, off);
+          const int ok = __shfl_xor_sync(full, bk, off);
+          if (ov < bv || (ov == bv && ok < bk)) {
+            bv = ov;
+            bk = ok;
+          }
+        }
+        if (bv < cur) {
+          cur = bv;
+          if (GRAD) {
+            best_slot = c0 + __shfl_sync(full, src, bk * 8);
+            best_pos = __shfl_sync(full, pos, bk * 8);
+          }
+        }
       }
     }
+    if (lane == 0) {
+      out[2 * cfg] = cur;
+      if (GRAD && best_slot >= 0) {
+        EvalArgmin& A = CC.argmin[cfg];
+        const float4 sp = CC.sph[cfg * CC.stride + best_slot];
+        const float4 x = C.pts[best_pos];
+        A.ext_op = CC.op[cfg * CC.stride + best_slot];
+        A.ext_prim = -1;
+        A.ext_c = make3(sp.x, sp.y, sp.z);
+        A.ext_nn = make3(x.x, x.y, x.z);
+      }
+    }
+  }
+}
+
+// Pass 2 of evaluate() as its own kernel (COOP scenes): Jacobian rows from the completed arg-min records.
+__global__ void __launch_bounds__(128)
+k_eval_jacobian(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n, const CloudCand CC,
+                float* __restrict__ jac) {
+  extern __shared__ float4 sm[];
+  const Smem T = stage_tables(R, S, sm);
+  const bool ext = (S.n_prims > 0) || S.cloud.enabled;
+  const long long n_tiles = (n + blockDim.x - 1) / blockDim.x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long item = tile * blockDim.x + threadIdx.x;
+    if (item >= n) continue;
+    QDirect acc{q + item * R.q_dim};
+    const EvalArgmin A = CC.argmin[item];
+    eval_jacobian_rows(R, S, T, acc, A, ext, jac + (2 * item) * R.q_dim, jac + (2 * item + 1) * R.q_dim);
   }
 }
 
@@ -502,12 +642,13 @@ __host__ __device__ __forceinline__ int edge_n_test(const double ratio) {
 // Pre-pass of the edge kernel: everything FP64 about an edge happens here, once, instead of inside
 // the persistent loop below (where it cost registers for the whole kernel): step ratio and n_test per
 // edge, the FP64 -> FP32 conversion of the endpoints when the caller holds doubles, and the zeroing
-// of the result words and of the chunk dispenser.
+// of the result words and of the chunk dispenser, and the keys of the longest-first order.
 template <class T>
 __global__ void __launch_bounds__(256)
 k_edge_prepare(const ValidatorDev V, const T* __restrict__ q0, const T* __restrict__ q1, const long long n, const int dim,
                float* __restrict__ q0f, float* __restrict__ q1f, double* __restrict__ ratio, int* __restrict__ ntest,
-               uint32_t* __restrict__ bits, unsigned long long* __restrict__ next_chunk) {
+               uint32_t* __restrict__ bits, unsigned long long* __restrict__ next_chunk, uint8_t* __restrict__ sort_key,
+               uint32_t* __restrict__ sort_idx) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t0 == 0) *next_chunk = 0ull;
@@ -521,7 +662,12 @@ k_edge_prepare(const ValidatorDev V, const T* __restrict__ q0, const T* __restri
   for (long long e = t0; e < n; e += stride) {
     const double r = edge_step_ratio<T>(V, q0 + e * dim, q1 + e * dim, dim);
     ratio[e] = r;
-    ntest[e] = edge_n_test(r);
+    const int nt = edge_n_test(r);
+    ntest[e] = nt;
+    if (sort_key) {  // longest edges first (see EdgeArgs::order)
+      sort_key[e] = (uint8_t)(255 - min(nt, 255));
+      sort_idx[e] = (uint32_t)e;
+    }
   }
 }
 
@@ -542,6 +688,11 @@ struct EdgeArgs {
   const float* q1;
   const double* ratio;  // [n] k_edge_prepare / the session's host pass
   const int* ntest;     // [n]
+  // [n] or nullptr: the order in which the dispenser hands the edges out — by decreasing waypoint count
+  // (one 8-bit radix pass over n_test).  A lane walks its edge serially, one waypoint per round, so a
+  // 64-waypoint edge taken last would keep its warp (and the kernel) alive for 64 more rounds with
+  // nothing left to overlap; taken first, it finishes while the short edges fill the other lanes.
+  const uint32_t* order;
   long long n;
   uint32_t* bits;
   uint32_t* calls;  // optional
@@ -595,7 +746,7 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__
       const int cand = next + __popc(need & lt);
       next = min(next + __popc(need), chunk_end);
       if (e < 0 && cand < chunk_end) {
-        e = cand;
+        e = A.order ? (int)__ldg(A.order + cand) : cand;
         w = 0;
         n_test = __ldg(A.ntest + e);
         if (n_test == 0) decide(true);  // zero-length edge: valid without any check (motion_validator.cpp:41-43)

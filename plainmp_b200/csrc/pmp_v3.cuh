@@ -13,15 +13,13 @@
 //            centre / half-extent form) -> every surviving (configuration, group, primitive)
 //            triple is PUSHED into a warp-local queue in shared memory (the warp is converged, so
 //            the queue tail is a warp-uniform register: ballot + popc + one STS, no atomics);
-//   drain    env items (one group against ONE primitive, the primitive's test variant resolved at
-//            scene build) are walked as ONE flat list of (item, sphere) work units, 32 units per round,
-//            one per lane: the warp stays full whatever the group sizes (round 2; the 8-lane-per-item
-//            version ran at 18.7 of 32 lanes and cost 60 of the kernel's 183 warp-instructions per
-//            configuration).  Cloud / overflow items and self items (one listed group pair) keep four
-//            independent 8-lane sub-warps per round.  A warp-uniform `bad` mask retires configurations
-//            (REDUX.OR); later work of a retired configuration is skipped.  If a push would overflow a
-//            queue, phase 1 stops, the queue is drained and phase 1 resumes where it stopped, so any
-//            table size works with fixed 512 + 128 byte queues.
+//   drain    one flat loop over the queue, four independent 8-lane sub-warps per round: an env
+//            item is one group against ONE primitive (one sphere per lane, the primitive's test
+//            variant resolved at scene build), a self item is one listed group pair.  A
+//            warp-uniform `bad` mask retires configurations (REDUX.OR); later items of a retired
+//            configuration are skipped.  If a push would overflow a queue, phase 1 stops, the
+//            queue is drained and phase 1 resumes where it stopped, so any table size works with
+//            fixed 512 + 128 byte queues.
 //
 // The result is unchanged: validity depends neither on the broad-phase hierarchy nor on the order
 // of the tests (SURVEY finding 7, App. A.4; reference: check_ext_collision / check_self_collision,
@@ -30,20 +28,12 @@
 
 namespace pmp {
 
-constexpr int kQE = 84;   // env items per warp:  lane | group << 5 | primitive << 16
+constexpr int kQE = 128;  // env items per warp:  lane | group << 5 | primitive << 16
 constexpr int kQS = 32;   // self items per warp: lane | pair << 5
-// Per-warp queue bytes: [env items u32 x kQE = 336][unit offsets u16 x (kQE + 1), padded = 176][self items u32 x kQS = 128].
-// Direct-primitive items fill the env array from the bottom and carry a running offset into the flat
-// list of (item, sphere) work units the drain walks; cloud / overflow items fill it from the top and are
-// drained by 8-lane sub-warps.  The self drain's scratch row (float4[32] per warp) lives in the bytes of
-// the env items + offsets: every env item has been drained before the first self item is looked at.
-constexpr int kQOffBytes = 176;
-static_assert(kQE * 4 + kQOffBytes == 32 * 16, "the env queue and the scratch row share their bytes");
-static_assert((kQE + 1) * 2 <= kQOffBytes, "unit offsets");
-constexpr int kV3WordsPerThread = (kQE * 4 + kQOffBytes + kQS * 4) / 128;  // = 5 floats per thread
-static_assert(kV3WordsPerThread * 128 == kQE * 4 + kQOffBytes + kQS * 4, "queue bytes per warp");
-constexpr int kMaxUnits = 60000;  // unit offsets are 16-bit
-constexpr int kBigGroup = 1024;   // groups with more spheres go through the 8-lane path (32 lanes x kBigGroup units always fit)
+// The self drain's scratch row (float4[32] per warp) lives in the bytes of the env queue: every env
+// item has been drained before the first self item is looked at, so the two are never live together.
+static_assert(kQE * 4 == 32 * 16, "the env queue and the scratch row share their bytes");
+constexpr int kV3WordsPerThread = (kQE + kQS) / 32;  // env queue (= scratch row) + self queue, per warp
 // (kSlotBase, pmp_kernels.cuh: the root frame of a FIXED-base robot is taken from the handle)
 //
 // Group centres in the stash.  They are read back only by the SELF broad phase (bounding spheres of a
@@ -71,7 +61,9 @@ template <int B>
 struct V3View {
   float* frames;    // [slot][7][B]
   float* gc;        // [group][3][B] floats, or (GC16) the same shape in halves
-  char* queues;  // [warp][kV3WordsPerThread * 128 bytes]: env items | unit offsets | self items (scratch row aliases the first 512)
+  float4* scratch;  // [warp][32]   (aliases qenv)
+  unsigned* qenv;   // [warp][kQE]
+  unsigned* qself;  // [warp][kQS]
 };
 
 // floats per thread taken by the group centres
@@ -82,7 +74,9 @@ __device__ __forceinline__ V3View<B> v3_view(const RobotDev& R, const Smem& T, c
   V3View<B> v;
   v.frames = T.stash;
   v.gc = T.stash + R.n_slots * 7 * B;
-  v.queues = reinterpret_cast<char*>(v.gc + v3_gc_floats(R.n_groups, gc16) * B);
+  v.scratch = reinterpret_cast<float4*>(v.gc + v3_gc_floats(R.n_groups, gc16) * B);
+  v.qenv = reinterpret_cast<unsigned*>(v.scratch);
+  v.qself = v.qenv + kQE * (B / 32);
   return v;
 }
 
@@ -156,70 +150,26 @@ __device__ __forceinline__ Frame apply_op_v3(const Frame& p, const float4 wB, co
 }
 
 // ---- drains ---------------------------------------------------------------------------------------
-// Direct-primitive env items: ONE flat list of (item, sphere) work units, 32 units per round, one unit
-// per lane.  Item k owns the units [off[k], off[k + 1]); the lanes of a round find their item from the
-// starts that fall inside the round (one 16-bit load per lane, a REDUX.OR and a POPC — no search).  Every
-// lane then places ONE sphere of its item's group and tests it against the item's primitive, so the warp
-// stays full whatever the group sizes are (the 8-lane-per-item version of round 1 ran at 18.7 of 32
-// lanes).  A warp-uniform `bad` mask retires configurations (REDUX.OR); units of a retired configuration
-// are skipped.
-template <int B>
-__device__ __forceinline__ unsigned drain_env_flat(const Smem& T, const V3View<B>& V, const Frame& basef, const unsigned* qenv,
-                                                   const unsigned short* qoff, const int n_env, const int n_units, unsigned bad,
-                                                   const int lane, const int wbase) {
-  constexpr unsigned full = 0xffffffffu;
-  int k0 = 0;  // the item that owns unit `base`: off[k0] <= base < off[k0 + 1]
-  for (int base = 0; base < n_units; base += 32) {
-    // starts of later items inside (base, base + 32]: bit j = an item starts at unit base + 1 + j
-    const int kj = k0 + 1 + lane;
-    unsigned bit = 0u;
-    if (kj < n_env) {
-      const int sj = (int)qoff[kj] - base - 1;
-      if (sj < 32) bit = 1u << sj;
-    }
-    const unsigned starts = __reduce_or_sync(full, bit);
-    const int item = k0 + __popc(starts & ((1u << lane) - 1u));
-    const int u = base + lane;
-    unsigned hitbit = 0u;
-    if (u < n_units) {
-      const unsigned h = qenv[item];
-      const int src = h & 31;
-      if (!((bad >> src) & 1u)) {
-        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * ((h >> 5) & (kMaxGroupsV3 - 1)) + 1]);
-        const Frame f = v3_group_frame(V, basef, gw.w >> 8, wbase + src);
-        const float4 sp = T.spheres[gw.y + (u - (int)qoff[item])];
-        const Prim P = load_prim(T.prims, h >> 16);
-        if (!prim_is_outside(P, place(f, sp.x, sp.y, sp.z), sp.w)) hitbit = 1u << src;
-      }
-    }
-    bad |= __reduce_or_sync(full, hitbit);
-    k0 += __popc(starts);
-  }
-  return bad;
-}
-
-// Cloud and overflow (primitive index >= 30) env items, and the items of groups with more than kBigGroup
-// spheres, queued from the top of the env array downwards:
-// 8 lanes per (configuration, group) item, one sphere per lane per round.  Sub-warps are independent;
-// they meet again at the REDUX that retires configurations.
+// env items: 8 lanes per (configuration, group, primitive) item, one sphere per lane per round.
+// Sub-warps are independent; they meet again at the REDUX that retires configurations.
 template <int B, bool CLOUD>
-__device__ __forceinline__ unsigned drain_env_special(const SceneDev& S, const Smem& T, const V3View<B>& V, const Frame& basef,
-                                                      const unsigned* qtop, const int n_spc, unsigned bad, const int lane,
-                                                      const int wbase) {
+__device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const Frame& basef,
+                                              const unsigned* qenv, const int n_env, unsigned bad, const int lane,
+                                              const int wbase) {
   constexpr unsigned full = 0xffffffffu;
   const int sub = lane & 7, k = lane >> 3;
-  for (int b0 = 0; b0 < n_spc; b0 += 4) {
+  for (int b0 = 0; b0 < n_env; b0 += 4) {
     const int it = b0 + k;
     unsigned hitbit = 0;
-    if (it < n_spc) {
-      const unsigned h = qtop[-it];
+    if (it < n_env) {
+      const unsigned h = qenv[it];
       const int src = h & 31;
       if (!((bad >> src) & 1u)) {
         const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * ((h >> 5) & (kMaxGroupsV3 - 1)) + 1]);
         const Frame f = v3_group_frame(V, basef, gw.w >> 8, wbase + src);
         const unsigned kp = h >> 16;
         bool hit = false;
-        if (kp < 30u) {  // a direct primitive of a group too large for the flat list
+        if (kp < 30u) {
           const Prim P = load_prim(T.prims, kp);
           for (int s = sub; s < gw.z; s += 8) {
             const float4 sp = T.spheres[gw.y + s];
@@ -342,14 +292,13 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
 template <int B>
 struct V3Ctx {
   V3View<B> V;
-  unsigned* qenv;        // [kQE]: direct-primitive items from index 0 up, cloud / overflow items from kQE - 1 down
-  unsigned short* qoff;  // [kQE + 1]: first work unit of every direct item, off[n_env] = n_units
-  unsigned* qself;       // [kQS]
-  float4* scratch;       // [32], the self drain's row (aliases qenv + qoff)
+  unsigned* qenv;
+  unsigned* qself;
+  float4* scratch;
   int tid, lane, wbase;
   unsigned lt;        // lanes below this one
   unsigned bad;       // warp-uniform: bit l set = lane l's configuration is known to be invalid
-  int n_env, n_spc, n_units, n_self;  // warp-uniform queue fills
+  int n_env, n_self;  // warp-uniform queue fills
   bool active;
 };
 
@@ -361,15 +310,12 @@ __device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, c
   X.wbase = X.tid & ~31;
   X.lt = (1u << X.lane) - 1u;
   X.V = v3_view<B>(R, T, gc16);
-  char* q = X.V.queues + (X.tid >> 5) * (kV3WordsPerThread * 128);
-  X.qenv = reinterpret_cast<unsigned*>(q);
-  X.qoff = reinterpret_cast<unsigned short*>(q + kQE * 4);
-  X.qself = reinterpret_cast<unsigned*>(q + kQE * 4 + kQOffBytes);
-  X.scratch = reinterpret_cast<float4*>(q);
+  const int warp = X.tid >> 5;
+  X.qenv = X.V.qenv + warp * kQE;
+  X.qself = X.V.qself + warp * kQS;
+  X.scratch = X.V.scratch + warp * 32;
   X.bad = 0;
   X.n_env = 0;
-  X.n_spc = 0;
-  X.n_units = 0;
   X.n_self = 0;
   X.active = active;
   return X;
@@ -415,39 +361,26 @@ __device__ __forceinline__ unsigned v3_cull_mask(const SceneDev& S, const Smem& 
   return pm;
 }
 
-// Push one queue item per set bit of this lane's cull mask `pm` for group gi (n_sph spheres), consuming
-// the bits as they are queued: direct primitives (bits 0..29) at the bottom of the env array together
-// with their unit offset, the cloud / overflow bits at its top.  Returns false when the items of the
-// next round do not fit; `pm` then holds what is still to be queued.  The caller drains and either
-// restarts the group from its full mask (items queued before are then only re-tested) or, for a group
-// that cannot fit even into an empty queue, calls again with the remaining bits.
+// Push one queue item per set bit of this lane's cull mask `pm` for group gi, consuming the bits as
+// they are queued.  Returns false when the items of the next round do not fit; `pm` then holds what
+// is still to be queued.  The caller drains and either restarts the group from its full mask (items
+// queued before are then only re-tested) or, for a group that cannot fit even into an empty queue,
+// calls again with the remaining bits.
 template <int B>
-__device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, const int n_sph, unsigned& pm) {
+__device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, unsigned& pm) {
   constexpr unsigned full = 0xffffffffu;
   if (!(X.active && !((X.bad >> X.lane) & 1u))) pm = 0u;
   unsigned ball = __ballot_sync(full, pm != 0u);
   while (ball) {
     const int cnt = __popc(ball);
-    if (X.n_env + X.n_spc + cnt > kQE || X.n_units + cnt * n_sph > kMaxUnits) return false;
-    unsigned b = 32u;
+    if (X.n_env + cnt > kQE) return false;
     if (pm) {
-      b = __ffs(pm) - 1;
+      const unsigned b = __ffs(pm) - 1;
       pm &= pm - 1u;
+      const unsigned kp = (b < 30u) ? b : (b == 30u ? kItemCloud : kItemOverflow);
+      X.qenv[X.n_env + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)gi << 5) | (kp << 16);
     }
-    const bool direct = (b < 30u) & (n_sph <= kBigGroup);
-    const unsigned dball = __ballot_sync(full, direct);  // lanes that queue a flat-list item this round
-    if (direct) {
-      const int r = __popc(dball & X.lt);
-      X.qenv[X.n_env + r] = (unsigned)X.lane | ((unsigned)gi << 5) | (b << 16);
-      X.qoff[X.n_env + r + 1] = (unsigned short)(X.n_units + (r + 1) * n_sph);
-    } else if (b < 32u) {
-      const int r = __popc(ball & ~dball & X.lt);
-      X.qenv[kQE - 1 - X.n_spc - r] = (unsigned)X.lane | ((unsigned)gi << 5) | ((b < 30u ? b : (b == 30u ? kItemCloud : kItemOverflow)) << 16);
-    }
-    const int nd = __popc(dball);
-    X.n_env += nd;
-    X.n_units += nd * n_sph;
-    X.n_spc += cnt - nd;
+    X.n_env += cnt;
     ball = __ballot_sync(full, pm != 0u);
   }
   return true;
@@ -478,7 +411,6 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
   constexpr bool APPROX = MODE != 0;  // FIXED base (constraints/primitive.hpp:39-60)
   constexpr bool GC16 = MODE == 2;
   V3Ctx<B> X = v3_begin<B>(R, T, active, GC16);
-  if (X.lane == 0) X.qoff[0] = 0;  // (never overwritten: pushes write off[k + 1])
   const bool ext = (S.n_prims > 0) || CLOUD;
   const Frame base = base_frame(R, q);
   bool far = false;
@@ -512,9 +444,8 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
           far |= v3_store_gc<B, GC16>(X, base, gi, gc);
           pm = (ext && !(gw.w & 1)) ? v3_cull_mask<CLOUD>(S, T, gc, g.w) : 0u;
           if (T.gmask) pm &= T.gmask[gi];  // composite constraints: a group sees its own member's scene entries only
-          if (gw.z == 0) pm = 0u;          // a group without spheres cannot collide (and a flat-list item needs >= 1 unit)
         }
-        if (!v3_push_env(X, gi, gw.z, pm)) {
+        if (!v3_push_env(X, gi, pm)) {
           // After the drain the group is normally restarted from its full mask.  A group that yields
           // more items than the whole queue holds (e.g. 5+ primitives passing the cull on all 32
           // lanes) would stall again in exactly the same place for ever if no lane died in between:
@@ -531,9 +462,8 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
       ready = false;
     }
     __syncwarp();
-    X.bad = drain_env_flat<B>(T, X.V, base, X.qenv, X.qoff, X.n_env, X.n_units, X.bad, X.lane, X.wbase);
-    if (X.n_spc) X.bad = drain_env_special<B, CLOUD>(S, T, X.V, base, X.qenv + (kQE - 1), X.n_spc, X.bad, X.lane, X.wbase);
-    X.n_env = X.n_spc = X.n_units = 0;
+    X.bad = drain_env<B, CLOUD>(S, T, X.V, base, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
+    X.n_env = 0;
     if (!stalled) break;
     __syncwarp();
   }

@@ -213,8 +213,11 @@ struct Flatten {
     for (const auto& s : cst.all_sdfs_cache_) {
       const col::SDFType t = s->get_type();
       if (t == col::SDFType::CLOUD) {
-        if (!out->cloud_points.empty()) throw std::runtime_error("plainmp_b200: at most one CloudSDF per scene");
+        // CloudSDFs of equal radius are merged into one point set: min_k (sqrt(NN_k^2) - rho) =
+        // sqrt(min_k NN_k^2) - rho, and each leaf's AABB pre-test is implied by the distance test
         const auto& c = static_cast<const col::CloudSDF&>(*s);
+        if (!out->cloud_points.empty() && out->cloud_radius != (float)c.radius_)
+          throw std::runtime_error("plainmp_b200: CloudSDFs of different radii in one scene are not supported");
         for (const auto& node : c.kdtree_->nodes_)
           for (int a = 0; a < 3; a++) out->cloud_points.push_back((float)node.point(a));
         out->cloud_radius = (float)c.radius_;

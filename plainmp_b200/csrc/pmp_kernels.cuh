@@ -153,11 +153,15 @@ struct QEdge {
 };
 
 // ---- kernels ------------------------------------------------------------------------------------
+// Resident threads per SM the register allocation of the validity kernel is bounded for (A/B knob of the build).
+#ifndef PMP_CFG_MIN_THREADS
+#define PMP_CFG_MIN_THREADS 512  // 88 registers; bounding for 640 (85 registers) measured 4 % slower on every workload (profiles/r02_s5_ab_register_bound.txt)
+#endif
 // v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  MODE: see warp_check_interp.  B = blockDim.x (compile-time so that the
 // stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
 // out of the primitives-only kernel).
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 640 / B)  // 5 CTAs of 128 threads per SM: at most 96 registers
+__global__ void __launch_bounds__(B, PMP_CFG_MIN_THREADS / B)
 k_check_configs_v3(const RobotDev R, const SceneDev S, const float* __restrict__ q, const long long n,
                    uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid) {
   extern __shared__ float4 sm[];

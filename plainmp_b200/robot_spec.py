@@ -199,6 +199,38 @@ class RobotSpec:
             self._csts[self_collision] = cst
         return cst
 
+    def create_attached_box_collision_const(
+        self,
+        box,
+        parent_link_name: str,
+        relative_position: np.ndarray,
+        n_grid: int = 6,
+        reorder_spheres: bool = True,
+    ) -> SphereCollisionCst:
+        """robot_spec.py:561-595 (deprecated there, kept for drop-in use): a grasped box as an n_grid^3
+        lattice of ZERO-radius spheres, keeping the lattice points within 1 cm of the box surface,
+        attached to ``parent_link_name`` at ``relative_position`` + (point - box centre); one group,
+        no self-collision pairs, no anchor.  ``box`` is a psdf BoxSDF (the reference takes a skrobot
+        Box and converts it with primitive_to_plainmp_sdf, utils.py:25-57; anything with
+        ``_extents``, ``worldpos()`` and ``worldrot()`` is accepted the same way)."""
+        if isinstance(box, BoxSDF):
+            extent, center, rot = box.width, box.pose.position, box.pose.rotation
+        else:
+            extent = np.asarray(box._extents, dtype=np.float64)
+            center = np.asarray(box.worldpos(), dtype=np.float64)
+            rot = np.asarray(box.worldrot(), dtype=np.float64)
+        axes = [np.linspace(-0.5 * e, 0.5 * e, n_grid) for e in extent]
+        grid = np.meshgrid(*axes)  # default 'xy' indexing, as the reference calls it
+        local = np.stack([g.flatten() for g in grid], axis=1)
+        # signed distance of a point inside the box: minus the distance to the nearest face
+        # (BoxSDF::evaluate, primitive_sdf.hpp:300-312, for points with every |p_k| <= half_k)
+        sd = -np.min(0.5 * extent[None, :] - np.abs(local), axis=1)
+        local = local[sd > -1e-2]
+        points_from_center = local @ rot.T  # transform_vector(p) - worldpos()
+        points_from_link = points_from_center + np.asarray(relative_position, dtype=np.float64).reshape(1, 3)
+        spec = SphereAttachmentSpec(parent_link_name, points_from_link.T, np.zeros(len(points_from_link)), False)
+        return SphereCollisionCst(self.get_kin(), self.control_joint_names, self.base_type, [spec], [], None, reorder_spheres)
+
 
 class PandaSpec(RobotSpec):
     conf_name = "panda"
@@ -214,21 +246,79 @@ class FetchSpec(RobotSpec):
         return np.array([d[n] for n in self.control_joint_names])
 
 
-class PR2DualarmSpec(RobotSpec):
-    conf_name = "pr2_dualarm"
+class PR2SpecBase(RobotSpec):
+    """robot_spec.py:691-717."""
+
     urdf_name = "pr2"
+
+    @property
+    def default_joint_positions(self) -> Dict[str, float]:
+        return dict(self.conf_dict["default_joint_positions"])
+
+    @property
+    def q_default(self) -> np.ndarray:
+        d = self.conf_dict["default_joint_positions"]
+        return np.array([d[n] for n in self.control_joint_names])
 
     def reflect_default_joint_positions(self) -> None:
         """example/pr2_dualarm_ik_and_plan.py:27-29: non-controlled joints at the aux.yaml values."""
         self.reflect_joint_positions(self.conf_dict["default_joint_positions"])
 
 
-class PR2RarmSpec(PR2DualarmSpec):
+class PR2BaseOnlySpec(PR2SpecBase):
+    """robot_spec.py:720-732: no controlled joint, PLANAR base — q = (x, y, yaw)."""
+
+    conf_name = "pr2_base_only"
+
+    def __init__(self, conf_file: Optional[Path] = None, urdf_file: Optional[Path] = None):
+        super().__init__(BaseType.PLANAR, conf_file, urdf_file)
+
+
+class PR2DualarmSpec(PR2SpecBase):
+    conf_name = "pr2_dualarm"
+
+
+class PR2RarmSpec(PR2SpecBase):
     conf_name = "pr2_rarm"
 
 
-class PR2LarmSpec(PR2DualarmSpec):
+class PR2LarmSpec(PR2SpecBase):
     conf_name = "pr2_larm"
+
+
+class JaxonSpec(RobotSpec):
+    """robot_spec.py:841-933: FLOATING-base humanoid, 31 controlled joints + 6 base entries; the foot
+    links (on the ground) and optionally the grippers carry no spheres.  The URDF under data/ is a
+    jaxon-LIKE skeleton (tools/make_jaxon_skeleton.py), the sphere table is the reference's."""
+
+    conf_name = "jaxon"
+    urdf_name = "jaxon"
+
+    def __init__(self, gripper_collision: bool = True, conf_file: Optional[Path] = None, urdf_file: Optional[Path] = None):
+        super().__init__(BaseType.FLOATING, conf_file, urdf_file)
+        self.gripper_collision = bool(gripper_collision)
+
+    def parse_sphere_specs(self) -> List[SphereAttachmentSpec]:
+        ignore = ["RLEG_LINK5", "LLEG_LINK5"]
+        if not self.gripper_collision:
+            ignore += ["RARM_FINGER0", "RARM_FINGER1", "RARM_LINK7", "LARM_FINGER0", "LARM_FINGER1", "LARM_LINK7"]
+        return [s for s in super().parse_sphere_specs() if s.parent_link_name not in ignore]
+
+    @property
+    def reset_manip_pose_q(self) -> np.ndarray:
+        table = {
+            "RLEG": [0.0, 0.0, -0.349066, 0.698132, -0.349066, 0.0],
+            "LLEG": [0.0, 0.0, -0.349066, 0.698132, -0.349066, 0.0],
+            "CHEST": [0.0, 0.0, 0.0],
+            "RARM": [0.0, 0.959931, -0.349066, -0.261799, -1.74533, -0.436332, 0.0, -0.785398],
+            "LARM": [0.0, 0.959931, 0.349066, 0.261799, -1.74533, 0.436332, 0.0, -0.785398],
+        }
+        d = {f"{k}_JOINT{i}": a for k, v in table.items() for i, a in enumerate(v)}
+        return np.hstack([[d[j] for j in self.control_joint_names], [0, 0, 1.0, 0, 0, 0]])
+
+    def angle_bounds(self) -> Tuple[np.ndarray, np.ndarray]:
+        lb, ub = super().angle_bounds()
+        return (np.hstack([lb, [-1.0, -1.0, 0.0, -1.0, -1.0, -1.0]]), np.hstack([ub, [2.0, 1.0, 3.0, 1.0, 1.0, 1.0]]))
 
 
 class OpenArmV10DualSpec(RobotSpec):

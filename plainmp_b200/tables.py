@@ -76,8 +76,9 @@ class LinkProgram:
         for k, lid in enumerate(order):
             L = links[lid]
             if not L.consider_rotation:
+                # (sphere groups AT such a link were moved to its parent by RobotTable.build_arrays)
                 raise NotImplementedError(
-                    f"link {L.name}: consider_rotation=False links cannot carry spheres or children on the CUDA path"
+                    f"link {L.name}: a consider_rotation=False link cannot have children or be queried for a full pose on the CUDA path"
                 )
             op = ops[k]
             op["parent"] = -1 if L.parent < 0 else self.op_of_link[L.parent]
@@ -175,6 +176,26 @@ class RobotTable:
     def build_arrays(kin, control_joint_ids, base_type, group_links, group_spheres, group_only_self, pairs, extra_links=()):
         """The C-ABI tables of a robot as numpy arrays (no device needed): link program, groups with
         their bounding spheres, spheres, pairs."""
+        group_links = list(group_links)
+        group_spheres = [np.asarray(sp, dtype=np.float64).reshape(-1, 4) for sp in group_spheres]
+        for g, lid in enumerate(group_links):
+            L = kin.links[lid]
+            if L.consider_rotation:
+                continue
+            # A link added with consider_rotation=False gets only its POSITION from FK (parent position +
+            # parent rotation * local offset, algorithm.cpp:164-178); its quaternion is never written.  Spheres
+            # AT the link origin are therefore well defined — and identical to spheres of the parent link at
+            # the link's local offset, which is how they are flattened.  Offsets from such a link would be
+            # rotated by whatever the reference's cache holds (uninitialised memory): refused.
+            if np.any(group_spheres[g][:, :3] != 0.0):
+                raise NotImplementedError(
+                    f"link {L.name}: spheres offset from a consider_rotation=False link are rotated by an unset quaternion in the reference"
+                )
+            _, trans, _ = kin.local_transform(lid)
+            sp = group_spheres[g].copy()
+            sp[:, :3] = np.asarray(trans, dtype=np.float64).reshape(1, 3)
+            group_spheres[g] = sp
+            group_links[g] = L.parent
         program = LinkProgram(kin, control_joint_ids, list(group_links) + list(extra_links))
         n_groups = len(group_links)
         groups = np.zeros(n_groups, dtype=_capi.GROUP_DTYPE)
@@ -294,17 +315,21 @@ def link_pose_via_cuda(kin: KinematicModel, link_name: str) -> np.ndarray:
 # scene
 # ---------------------------------------------------------------------------------------------
 def flatten_primitives(leaves) -> Tuple[np.ndarray, Optional[object]]:
-    """[anchor primitives..., user primitives...] -> pmp_prim_t array (+ the CloudSDF if any)."""
+    """[anchor primitives..., user primitives...] -> pmp_prim_t array (+ the scene's cloud, if any).
+
+    The reference keeps every CloudSDF leaf as its own entry (primitive_sphere_collision.cpp:436-448).
+    CloudSDFs of EQUAL radius are merged here into one point set: min over the leaves of
+    sqrt(NN_k^2) - rho equals sqrt(min_k NN_k^2) - rho, and a leaf's AABB pre-test
+    (primitive_sdf.hpp:573-582) is implied by the distance test, so validity and values are unchanged;
+    one device index then serves all of them."""
     from . import psdf
 
     prims = []
-    cloud = None
+    clouds = []
     for leaf in leaves:
         t = leaf.get_type()
         if t == psdf.T_CLOUD:
-            if cloud is not None:
-                raise NotImplementedError("at most one CloudSDF per scene is supported on the CUDA path")
-            cloud = leaf
+            clouds.append(leaf)
             continue
         rec = np.zeros((), dtype=_capi.PRIM_DTYPE)
         rec["lb"] = np.maximum(leaf._lb, -3.0e38)
@@ -345,7 +370,32 @@ def flatten_primitives(leaves) -> Tuple[np.ndarray, Optional[object]]:
             rec["rot_col0"], rec["rot_col1"], rec["rot_col2"] = cols[:, 0], cols[:, 1], cols[:, 2]
         prims.append(rec)
     arr = np.array(prims, dtype=_capi.PRIM_DTYPE) if prims else np.zeros(0, dtype=_capi.PRIM_DTYPE)
+    cloud = None
+    if len(clouds) == 1:
+        cloud = clouds[0]
+    elif clouds:
+        if len({c.radius for c in clouds}) > 1:
+            raise NotImplementedError("CloudSDFs of different radii in one scene are not supported on the CUDA path")
+        cloud = _MergedCloud(clouds)
     return arr, cloud
+
+
+class _MergedCloud:
+    """Several CloudSDF leaves of one radius as one point set (see flatten_primitives)."""
+
+    def __init__(self, clouds):
+        self._members = list(clouds)  # keeps the leaves (and with them their uids) alive
+        self.radius = clouds[0].radius
+        self._points = None
+
+    @property
+    def points(self) -> np.ndarray:
+        if self._points is None:
+            self._points = np.ascontiguousarray(np.vstack([c.points for c in self._members]))
+        return self._points
+
+    def _state_key(self):
+        return tuple(c._state_key() for c in self._members)
 
 
 class SceneTable:

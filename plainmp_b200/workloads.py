@@ -116,3 +116,75 @@ def random_edges(spec, n: int, seed: int, planner_like: bool, valid_fn=None):
     else:
         q1 = rng.uniform(lb, ub, size=q0.shape).astype(np.float32)
     return q0, q1
+
+
+def make_jaxon(gripper_collision: bool = True):
+    """JaxonSpec (FLOATING base, 31 joints + 6 base entries, the largest sphere table of conf/) standing
+    next to a table and under a beam, on the ground."""
+    from .robot_spec import JaxonSpec
+
+    spec = JaxonSpec(gripper_collision=gripper_collision)
+    cst = spec.create_collision_const(use_cache=False)
+    cst.set_sdf(
+        psdf.UnionSDF(
+            [
+                psdf.BoxSDF([0.8, 1.6, 0.05], psdf.Pose([0.9, 0.0, 0.8])),
+                psdf.BoxSDF([0.2, 3.0, 0.2], psdf.Pose([0.3, 0.0, 2.3])),
+                psdf.CylinderSDF(0.1, 1.2, psdf.Pose([0.6, -0.9, 0.6])),
+                psdf.GroundSDF(0.0),
+            ]
+        )
+    )
+    return spec, cst
+
+
+def make_pr2_base_only():
+    """PR2BaseOnlySpec (no controlled joint, PLANAR base: q = x, y, yaw) between furniture-sized boxes."""
+    from .robot_spec import PR2BaseOnlySpec
+
+    spec = PR2BaseOnlySpec()
+    spec.reflect_default_joint_positions()
+    cst = spec.create_collision_const(use_cache=False)
+    rot = np.array([[np.cos(0.4), -np.sin(0.4), 0], [np.sin(0.4), np.cos(0.4), 0], [0, 0, 1.0]])
+    cst.set_sdf(
+        psdf.UnionSDF(
+            [
+                psdf.BoxSDF([1.0, 2.0, 0.8], psdf.Pose([1.6, 0.0, 0.4])),
+                psdf.BoxSDF([0.6, 0.6, 1.8], psdf.Pose([-0.5, 1.4, 0.9], rot)),
+                psdf.CylinderSDF(0.25, 1.0, psdf.Pose([0.2, -1.5, 0.5])),
+            ]
+        )
+    )
+    return spec, cst
+
+
+def random_configs_moving_base(spec, n: int, seed: int, base_lb, base_ub) -> np.ndarray:
+    """Joints uniform in their limits, base entries uniform in [base_lb, base_ub] (3 entries for a PLANAR
+    base, 6 for a FLOATING one), rounded to float32 like random_configs."""
+    kin = spec.get_kin()
+    limits = kin.get_joint_position_limits(kin.get_joint_ids(spec.control_joint_names))
+    lb = np.array([l[0] for l in limits] + list(base_lb), dtype=np.float64)
+    ub = np.array([l[1] for l in limits] + list(base_ub), dtype=np.float64)
+    lb[lb == -np.inf] = -2 * np.pi
+    ub[ub == np.inf] = 2 * np.pi
+    rng = np.random.default_rng(seed)
+    return rng.uniform(lb, ub, size=(n, lb.shape[0])).astype(np.float32)
+
+
+def make_panda_position_only_link(offset_spheres: bool = False):
+    """Panda with a link added with consider_rotation=False (kinematics.cpp:300-337: FK gives such a link
+    its position only) that carries spheres at its origin and a self-collision pair with the forearm."""
+    from .constraint import SphereAttachmentSpec, SphereCollisionCst
+    from .kinematics import BaseType, KinematicModel
+
+    spec = PandaSpec()
+    kin = KinematicModel(spec.get_kin()._urdf_xml)
+    kin.add_new_link("tool_tip", "panda_hand", np.array([0.02, -0.01, 0.22]), np.array([0.3, -0.2, 0.5]), False)
+    pos = np.array([[0.01, 0, 0]] if offset_spheres else [[0.0, 0, 0], [0.0, 0, 0]]).T
+    specs = [
+        SphereAttachmentSpec("tool_tip", pos, np.array([0.06] if offset_spheres else [0.06, 0.0]), False),
+        SphereAttachmentSpec("panda_link5", np.array([[0.0, 0.05, -0.1], [0.0, 0.0, 0.0]]).T, np.array([0.07, 0.05]), False),
+    ]
+    cst = SphereCollisionCst(kin, spec.control_joint_names, BaseType.FIXED, specs, [("tool_tip", "panda_link5")], None)
+    cst.set_sdf(panda_dual_bars_sdf())
+    return spec, cst

@@ -62,3 +62,50 @@ def assert_edge_parity(cst, vtype, widths, res, q0, q1, got, n_checked, calls, w
         if clear.all():
             assert int(n_checked) == int(calls_ref.astype(np.int64).sum()), f"{what}: {n_checked} is_valid calls, the reference makes {int(calls_ref.sum())}"
     return want
+
+
+JAC_TOL = 1e-4  # the reference's own Jacobian check passes at 4 decimals (tests/test_constraints.py:36-44)
+
+
+def assert_jacobian_parity(o, Q, jac, want_j, what, tol=JAC_TOL, delta=EPS_BAND, samples=16, max_fraction=0.03):
+    """Rows of evaluate()'s Jacobian against the reference's (o: FP64 oracle of the same constraint).
+
+    Every row that differs from the reference's row by more than `tol` is looked at and must be explained
+    by one of two things, both properties of the REFERENCE's rows rather than of the CUDA path:
+      (1) the reference differentiates the SDF by a forward difference with step 1e-6
+          (primitive_sphere_collision.cpp:305-312); where a sphere centre lies within millimetres of the
+          nearest feature the distance field's curvature (1 / distance) makes that difference itself
+          wrong by > 1e-4.  The CUDA row (analytic gradient) must then match the derivative of the
+          reference's own VALUE function, taken by central differences in FP64, within `tol`;
+      (2) the rows are piecewise smooth in q and jump where the arg-min sphere / primitive face changes:
+          the CUDA row must match the reference's row at some point within `delta` of q (per coordinate;
+          the 1e-5 band of the validity rule, here in configuration space).
+    Unexplained rows fail; so does an implausible number of explained ones."""
+    Qd = np.asarray(Q, dtype=np.float64)
+    assert jac.shape == want_j.shape, what
+    assert (np.isnan(jac) == np.isnan(want_j)).all(), f"{what}: NaN pattern of disabled terms differs"
+    err = np.abs(np.nan_to_num(jac) - np.nan_to_num(want_j)).max(axis=2)  # [n, terms]
+    bad = np.argwhere(err > tol)
+    rng = np.random.default_rng(1)
+    d = Qd.shape[1]
+    h = 1e-6
+    n_fd, n_kink, unexplained = 0, 0, []
+    for i, t in bad:
+        P = np.concatenate([Qd[i][None] + h * np.eye(d), Qd[i][None] - h * np.eye(d)])
+        v = o.evaluate_batch(P)[:, t]
+        e_cd = float(np.abs((v[:d] - v[d:]) / (2 * h) - jac[i, t]).max())
+        if e_cd <= tol:
+            n_fd += 1
+            continue
+        near = Qd[i][None] + rng.uniform(-delta, delta, size=(samples, d))
+        _, jn = o.evaluate_grad_batch(near)
+        e = np.abs(np.nan_to_num(jn[:, t]) - np.nan_to_num(jac[i, t])[None]).max(axis=1)
+        if e.min() <= tol:
+            n_kink += 1
+            continue
+        unexplained.append((int(i), int(t), float(err[i, t]), e_cd, float(e.min())))
+    print(f"[parity] {what}: {err.size} Jacobian rows, max error {err.max() if err.size else 0:.2e}, {len(bad)} differ by more than {tol}: "
+          f"{n_fd} match the central-difference derivative of the reference's values, {n_kink} sit on a tie / kink, {len(unexplained)} unexplained")
+    assert not unexplained, f"{what}: unexplained Jacobian rows (item, term, error vs reference, vs central difference, best nearby): {unexplained[:5]}"
+    assert len(bad) <= max_fraction * max(err.size, 1), f"{what}: {len(bad)} of {err.size} rows differ — too many to be special points"
+    return err

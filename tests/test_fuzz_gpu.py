@@ -8,7 +8,7 @@ import pytest
 
 from oracle import bridge, ref_bridge
 from fuzz_util import random_case, sample_q
-from parity_util import assert_edge_parity
+from parity_util import assert_edge_parity, assert_jacobian_parity
 from plainmp_b200.kinematics import BaseType
 from plainmp_b200.ompl import MotionValidator, ValidatorConfig, ValidatorSession, ValidatorType
 
@@ -48,10 +48,9 @@ def test_cuda_equals_reference_on_random_robot(cuda_lib, seed):
     vals, jac = cst.evaluate_grad_batch(Q[:600])
     want_v, want_j = o.evaluate_grad_batch(Qd[:600])
     np.testing.assert_allclose(vals, want_v, atol=TOL, rtol=0, equal_nan=True, err_msg=desc)
-    assert (np.isnan(jac) == np.isnan(want_j)).all(), desc
     if jac.size:
-        err = np.abs(np.nan_to_num(jac) - np.nan_to_num(want_j)).max(axis=2)
-        assert (err > 1e-3).mean() < 0.03, f"{desc}: {(err > 1e-3).mean():.2%} Jacobian rows differ (max {err.max():.3e})"
+        # 1e-4 (the reference's own 4-decimal check); a row that differs must sit on a tie / kink (parity_util)
+        assert_jacobian_parity(o, Q[:600], jac, want_j, desc, max_fraction=0.05)
 
 
 @pytest.mark.parametrize("seed", range(1000, 1012))

@@ -425,3 +425,148 @@ def test_per_edge_call_counts_match_reference(vtype):
         assert (c_r >= 1).all() and np.isfinite(m).all() and (m >= 0).all()
         v_t, c_t = ref_bridge.check_motion_batch_threads(cst, vtype, w, 0.08, q0, q1, 3)
         assert (v_t == v_r).all() and (c_t == c_r).all()
+
+
+# ---- round 2: the specs and scene shapes the reference ships that round 1 left out ------------------
+JAXON_BASE = ([-0.5, -1.0, 0.7, -0.3, -0.3, -1.0], [1.2, 1.0, 1.3, 0.3, 0.3, 1.0])
+PR2_BASE = ([-2.0, -2.5, -3.2], [2.5, 2.5, 3.2])
+
+
+def _moving_case(name):
+    if name == "jaxon":
+        spec, cst = workloads.make_jaxon()
+        return spec, cst, workloads.random_configs_moving_base(spec, 1500, 1, *JAXON_BASE)
+    if name == "jaxon_no_gripper":
+        spec, cst = workloads.make_jaxon(gripper_collision=False)
+        return spec, cst, workloads.random_configs_moving_base(spec, 1500, 2, *JAXON_BASE)
+    spec, cst = workloads.make_pr2_base_only()
+    return spec, cst, workloads.random_configs_moving_base(spec, 1500, 3, *PR2_BASE)
+
+
+@pytest.mark.parametrize("name", ["jaxon", "jaxon_no_gripper", "pr2_base_only"])
+def test_jaxon_and_base_only_specs_match_reference(name):
+    """JaxonSpec (robot_spec.py:841-933: FLOATING base, 37 entries, foot / gripper links filtered) and
+    PR2BaseOnlySpec (:720-732: no controlled joint, q = x, y, yaw)."""
+    spec, cst, Q = _moving_case(name)
+    Q = Q.astype(np.float64)
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    assert (o.q_dim, o.n_spheres) == (r.q_dim, r.n_spheres)
+    assert o.q_dim == {"jaxon": 37, "jaxon_no_gripper": 37, "pr2_base_only": 3}[name]
+    assert o.n_spheres == {"jaxon": 73, "jaxon_no_gripper": 41, "pr2_base_only": 161}[name]
+    v_o, v_r = o.is_valid_batch(Q), r.is_valid_batch(Q)
+    assert (v_o == v_r).all() and 0.05 < v_r.mean() < 0.95
+    vals_o, jac_o = o.evaluate_grad_batch(Q[:300])
+    vals_r, jac_r = r.evaluate_grad_batch(Q[:300])
+    assert (np.isnan(vals_o) == np.isnan(vals_r)).all()
+    np.testing.assert_allclose(vals_o, vals_r, atol=TOL, rtol=0)
+    np.testing.assert_allclose(jac_o, jac_r, atol=1e-7, rtol=0)
+    np.testing.assert_allclose(o.spheres_batch(Q[:32], True), r.spheres_batch(Q[:32], True), atol=TOL, rtol=0)
+
+
+def test_jaxon_spec_surface():
+    from plainmp_b200.robot_spec import JaxonSpec, PR2BaseOnlySpec
+
+    spec = JaxonSpec()
+    lb, ub = spec.angle_bounds()
+    assert lb.shape == ub.shape == (37,) and (lb < ub).all()
+    q = spec.reset_manip_pose_q
+    assert q.shape == (37,) and (q >= lb - 1e-9).all() and (q <= ub + 1e-9).all()
+    links = {s.parent_link_name for s in spec.parse_sphere_specs()}
+    assert "RLEG_LINK5" not in links and "RARM_LINK7" in links
+    assert "RARM_LINK7" not in {s.parent_link_name for s in JaxonSpec(gripper_collision=False).parse_sphere_specs()}
+    for name in ("rarm_end_coords", "lleg_end_coords"):  # conf/jaxon.yaml custom_links
+        spec.get_kin().get_link_ids([name])
+    base = PR2BaseOnlySpec()
+    assert base.base_type == BaseType.PLANAR and base.control_joint_names == []
+    assert base.q_default.shape == (0,)
+
+
+@pytest.mark.parametrize("n_grid", [6, 4])
+def test_attached_box_lattice_matches_reference(n_grid):
+    """create_attached_box_collision_const (robot_spec.py:561-595): one group of zero-radius spheres on
+    the surface shell of a grasped box (the r < 1e-6 shortcuts of every primitive)."""
+    spec = PandaSpec()
+    rot = rpy_matrix(0.7, 0.2, -0.4)
+    box = psdf.BoxSDF([0.1, 0.06, 0.2], psdf.Pose([0.3, 0.1, 0.5], rot))
+    rel = np.array([0.0, 0.0, 0.15])
+    cst = spec.create_attached_box_collision_const(box, "panda_hand", rel, n_grid=n_grid)
+    cst.set_sdf(workloads.panda_dual_bars_sdf())
+    # the lattice the reference builds, restated with its own formulas: meshgrid -> world -> keep sdf > -1e-2
+    ext = box.width
+    grid = np.meshgrid(*[np.linspace(-0.5 * e, 0.5 * e, n_grid) for e in ext])
+    pts = np.stack([g.flatten() for g in grid], axis=1) @ rot.T + box.pose.position
+    sd = bridge.OracleSDF.from_psdf(box).evaluate_batch(pts)
+    want = pts[sd > -1e-2] - box.pose.position + rel
+    got = cst._group_spheres[0][:, :3] if hasattr(cst, "_group_spheres") else None
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    assert o.n_spheres == r.n_spheres == len(want) and len(want) < n_grid ** 3
+    if got is not None:  # same point set (the constructor may reorder the spheres of a group)
+        key = lambda a: a[np.lexsort(np.round(a, 9).T)]
+        np.testing.assert_allclose(key(np.asarray(got, dtype=np.float64)), key(want), atol=1e-12)
+    Q = workloads.random_configs(spec, 3000, 2).astype(np.float64)
+    v_o, v_r = o.is_valid_batch(Q), r.is_valid_batch(Q)
+    assert (v_o == v_r).all() and 0.2 < v_r.mean() < 0.98
+    np.testing.assert_allclose(o.evaluate_batch(Q[:300]), r.evaluate_batch(Q[:300]), atol=TOL, rtol=0)
+
+
+def _pr2_several_clouds(radii=(0.002, 0.002, 0.002)):
+    spec = PR2DualarmSpec()
+    spec.reflect_default_joint_positions()
+    cst = spec.create_collision_const(use_cache=False)
+    pts = workloads.table_cloud(6000, 4)
+    shelf = np.random.default_rng(0).uniform([-0.2, -1.0, 0.2], [0.4, -0.5, 1.5], size=(2000, 3))
+    cst.set_sdf(
+        psdf.UnionSDF(
+            [
+                psdf.CloudSDF(pts[:3000], radii[0]),
+                psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.6, 0.6, 1.2])),
+                psdf.UnionSDF([psdf.CloudSDF(pts[3000:], radii[1]), psdf.CloudSDF(shelf, radii[2])]),
+            ]
+        )
+    )
+    return spec, cst
+
+
+def test_several_clouds_in_one_scene_match_reference():
+    """The reference keeps every CloudSDF leaf (primitive_sphere_collision.cpp:436-448); the host mirror
+    merges leaves of equal radius into one point set — same validity, same values."""
+    from plainmp_b200 import tables
+
+    spec, cst = _pr2_several_clouds()
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    Q = workloads.random_configs(spec, 1500, 1).astype(np.float64)
+    v_o, v_r = o.is_valid_batch(Q), r.is_valid_batch(Q)
+    assert (v_o == v_r).all() and 0.05 < v_r.mean() < 0.95
+    np.testing.assert_allclose(o.evaluate_batch(Q[:200]), r.evaluate_batch(Q[:200]), atol=TOL, rtol=0)
+    prims, cloud = tables.flatten_primitives(cst._leaves())
+    assert len(prims) == len(cst._leaves()) - 3 and cloud.points.shape == (8000, 3) and cloud.radius == 0.002
+    # a single merged CloudSDF gives the reference the same answers: the merge is exact
+    spec2 = PR2DualarmSpec()
+    spec2.reflect_default_joint_positions()
+    cst2 = spec2.create_collision_const(use_cache=False)
+    cst2.set_sdf(psdf.UnionSDF([psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.6, 0.6, 1.2])), psdf.CloudSDF(cloud.points, 0.002)]))
+    r2 = ref_bridge.RefCst(cst2)
+    assert (r2.is_valid_batch(Q) == v_r).all()
+    np.testing.assert_allclose(r2.evaluate_batch(Q[:200]), r.evaluate_batch(Q[:200]), atol=TOL, rtol=0)
+
+
+def test_position_only_link_with_spheres_at_its_origin_matches_reference():
+    from plainmp_b200 import tables
+
+    spec, cst = workloads.make_panda_position_only_link()
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    Q = workloads.random_configs(spec, 3000, 8).astype(np.float64)
+    v_o, v_r = o.is_valid_batch(Q), r.is_valid_batch(Q)
+    assert (v_o == v_r).all() and 0.1 < v_r.mean() < 0.95
+    np.testing.assert_allclose(o.evaluate_batch(Q[:300]), r.evaluate_batch(Q[:300]), atol=TOL, rtol=0)
+    np.testing.assert_allclose(o.spheres_batch(Q[:32], False), r.spheres_batch(Q[:32], False), atol=TOL, rtol=0)
+    # flattened for the device: the group sits on the parent link at the added link's local offset
+    a = tables.RobotTable.build_arrays(cst.get_kin(), cst._control_joint_ids, cst._base_type, cst._group_links, cst._group_spheres, cst._group_only_self, cst._pairs)
+    g = [i for i, l in enumerate(cst._group_links) if cst.get_kin().links[l].name == "tool_tip"][0]
+    hand = cst.get_kin().get_link_ids(["panda_hand"])[0]
+    assert a["groups"][g]["op"] == a["program"].op_of_link[hand]
+    b = a["groups"][g]["sphere_begin"]
+    np.testing.assert_allclose(a["spheres"][b : b + 2, :3], [[0.02, -0.01, 0.22]] * 2, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        _, bad = workloads.make_panda_position_only_link(offset_spheres=True)
+        tables.RobotTable.build_arrays(bad.get_kin(), bad._control_joint_ids, bad._base_type, bad._group_links, bad._group_spheres, bad._group_only_self, bad._pairs)

@@ -13,8 +13,9 @@ the GPU box).  Outputs are small, committed fixtures:
                                         <- /root/reference/src/plainmp/assets/openarm_v10.urdf
 
 The panda / fetch / pr2 URDFs are NOT in the reference tree (they are downloaded by
-scikit-robot at run time, conf/panda.yaml:1); plainmp_b200/data/urdf/{panda,fetch,pr2}.urdf are
-authored by this repo from the public robot descriptions ("robot tables").
+scikit-robot at run time, conf/panda.yaml:1), nor is jaxon_jvrc.urdf (robot_descriptions cache,
+conf/jaxon.yaml:1); plainmp_b200/data/urdf/{panda,fetch,pr2,jaxon}.urdf are authored by this repo
+("robot tables"; jaxon: tools/make_jaxon_skeleton.py).
 """
 import json
 import sys
@@ -32,6 +33,8 @@ CONFS = {
     "pr2_dualarm": "conf/pr2_dualarm.yaml",
     "pr2_rarm": "conf/pr2_rarm.yaml",
     "pr2_larm": "conf/pr2_larm.yaml",
+    "pr2_base_only": "conf/pr2_base_only.yaml",
+    "jaxon": "conf/jaxon.yaml",
     "openarm_v10_dual": "conf/openarm_v10/openarm_v10_dual.yaml",
     "openarm_v10_rarm": "conf/openarm_v10/openarm_v10_rarm.yaml",
     "openarm_v10_larm": "conf/openarm_v10/openarm_v10_larm.yaml",

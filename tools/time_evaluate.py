@@ -10,10 +10,10 @@ def timeit(fn, steps=5, warmup=2):
     for _ in range(steps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) * 1e-3 / steps
-for name, mk in (("panda", workloads.make_panda), ("fetch", workloads.make_fetch), ("pr2cloud100k", lambda: workloads.make_pr2_cloud(100000))):
+for name, mk in (("panda", workloads.make_panda), ("fetch", workloads.make_fetch), ("pr2cloud100k", lambda: workloads.make_pr2_cloud(100000)), ("pr2cloud1M", lambda: workloads.make_pr2_cloud(1000000))):
     spec, cst = mk()
     robot, scene = cst._robot(), cst._scene()
-    n = 1 << 20
+    n = (1 << 18) if name.startswith('pr2') else (1 << 20)
     q = torch.from_numpy(workloads.random_configs(spec, n, 1)).to(dev)
     out = torch.empty((n, 2), dtype=torch.float32, device=dev)
     jac = torch.empty((n, 2, q.shape[1]), dtype=torch.float32, device=dev)

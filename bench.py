@@ -68,6 +68,7 @@ def parse_args():
     p.add_argument("--extras", type=int, default=1, help="also measure edges/s, fetch and cloud side metrics (N=1)")
     p.add_argument("--cpu-sample", type=int, default=1 << 24, help="configurations per CPU-baseline pass (about 10 s of CPU work on 16 cores)")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --per-gpu configs on every rank; strong: --total configs split over the ranks")
+    p.add_argument("--host-mem", default="pinned", choices=["pinned", "wc"], help="e2e host input buffer: torch pinned memory, or write-combined pinned pages from pmp_host_alloc")
     p.add_argument("--total", type=int, default=1 << 24, help="global configurations per step with --scaling strong")
     p.add_argument("--sweep-out", default="", help="also run BASELINE config 5's sweep (strong scaling of 1M / 16M / 256M total, weak at the same per-GPU sizes) in this process and append one JSON line per point to this file")
     return p.parse_args()
@@ -458,7 +459,13 @@ def run_b200(args):
     lb, ub = spec.angle_bounds()
     dof = lb.shape[0]
     rng = np.random.default_rng(5 + rank)
-    q_host = torch.empty((n_local, dof), dtype=torch.float32, pin_memory=True)
+    if args.host_mem == "wc":
+        # write-combined pinned pages (pmp_host_alloc): written once, sequentially, by the generator below
+        wc_ptr = C.c_void_p()
+        _capi.check(lib.pmp_host_alloc(n_local * dof * 4, 1, C.byref(wc_ptr)))
+        q_host = torch.from_numpy(np.ctypeslib.as_array((C.c_float * (n_local * dof)).from_address(wc_ptr.value))).view(n_local, dof)
+    else:
+        q_host = torch.empty((n_local, dof), dtype=torch.float32, pin_memory=True)
     chunk = 1 << 20
     for i in range(0, n_local, chunk):
         m = min(chunk, n_local - i)
@@ -539,7 +546,7 @@ def run_b200(args):
     # what the reference's binding really holds: PAGEABLE FP64 numpy (bindings/constraint.cpp:82) — packed to
     # FP32 by host threads while staged (pmp_check_configs_host_f64)
     n64 = min(n_local, 1 << 22)
-    q64 = q_host[:n64].numpy().astype(np.float64)  # pageable
+    q64 = q_dev[:n64].cpu().numpy().astype(np.float64)  # pageable (read back from the device copy: the host buffer may be write-combined)
     w64 = np.zeros((n64 + 31) // 32, dtype=np.uint32)
     f64_step = lambda: _capi.check(lib.pmp_check_configs_host_f64(robot.handle, scene.handle, q64.ctypes.data, n64, w64.ctypes.data, C.byref(nv)))  # noqa: E731
     f64_step()
@@ -630,7 +637,7 @@ def run_b200(args):
             },
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * dof * 4 * world, "d2h_bytes_per_step": (((n_local + 31) // 32) * 4 + 8) * world, "steps": e2e_steps,
-                    "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs,
+                    "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs, "host_buffer": "torch pinned" if args.host_mem == "pinned" else "write-combined pinned (pmp_host_alloc)",
                     "frac_of_h2d_copy": (e2e_value / world) * dof * 4 / 1e9 / h2d_gbs,
                     "from_pageable_fp64": {"value": e2e_f64_value, "unit": UNIT, "configs_per_call": n64,
                                            "note": "pmp_check_configs_host_f64: pageable float64 numpy in (what the reference's binding holds), packed to FP32 by host threads into pinned staging"}},

@@ -41,6 +41,7 @@
 #ifndef PLAINMP_B200_H_
 #define PLAINMP_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -302,6 +303,13 @@ int pmp_set_device(int device);
 int pmp_measure_fp32_peak(double* tflops);
 /* Number of kernel launches issued by this library since load (all threads). */
 uint64_t pmp_launch_count(void);
+/* Page-locked host memory for the *_host entry points' inputs (any host pointer works there; pinned
+ * buffers let the H2D copies run asynchronously at the link rate).  write_combined != 0 asks for
+ * write-combined pages: the copy engine reads them without snooping the CPU caches, which raises the
+ * host-side ceiling when several GPUs pull from one socket; the CPU should only WRITE such memory
+ * sequentially (reads are uncached).  Free with pmp_host_free. */
+int pmp_host_alloc(size_t bytes, int write_combined, void** out);
+int pmp_host_free(void* p);
 
 #ifdef __cplusplus
 }

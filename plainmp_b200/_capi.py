@@ -120,6 +120,8 @@ SYMBOLS = {
     "pmp_abi_version": (_i32, []),
     "pmp_device_count": (_i32, []),
     "pmp_launch_count": (C.c_uint64, []),
+    "pmp_host_alloc": (_i32, [C.c_size_t, _i32, C.POINTER(C.c_void_p)]),
+    "pmp_host_free": (_i32, [_p]),
     "pmp_set_device": (_i32, [_i32]),
     "pmp_measure_fp32_peak": (_i32, [C.POINTER(C.c_double)]),
     "pmp_robot_create": (_i32, [C.POINTER(RobotDesc), C.POINTER(_p)]),

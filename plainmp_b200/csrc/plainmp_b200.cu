@@ -445,6 +445,20 @@ extern "C" {
 const char* pmp_last_error(void) { return g_err.c_str(); }
 int pmp_abi_version(void) { return PMP_ABI_VERSION; }
 uint64_t pmp_launch_count(void) { return g_launches.load(); }
+
+int pmp_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out) return fail(PMP_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (bytes == 0) return PMP_OK;
+  if (int rc = ensure_device()) return rc;
+  CUDA_OK(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+  return PMP_OK;
+}
+
+int pmp_host_free(void* p) {
+  if (p) CUDA_OK(cudaFreeHost(p));
+  return PMP_OK;
+}
 int pmp_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -1124,7 +1138,11 @@ struct WorkspaceLease {  // RAII check-out of a workspace of the current device
 constexpr int64_t kHostChunk = 1 << 19;  // items per pipelined chunk (multiple of 32): the tail that cannot overlap is one chunk's kernel
 // Edge batches: the first chunks are small so that the first kernel starts after a short copy, later ones
 // large so that per-chunk costs (prepare pass, launch, the persistent kernel's tail) stay small.
-inline int64_t edge_chunk_size(int k) { return (int64_t)1 << std::min(19, 16 + k); }
+inline int64_t edge_chunk_size(int k) {
+  static const int first = getenv("PMP_EDGE_CHUNK_FIRST") ? atoi(getenv("PMP_EDGE_CHUNK_FIRST")) : 16;  // log2; A/B experiments only
+  static const int last = getenv("PMP_EDGE_CHUNK_LAST") ? atoi(getenv("PMP_EDGE_CHUNK_LAST")) : 19;
+  return (int64_t)1 << std::min(last, first + k);
+}
 
 template <class T>
 int check_edges_host_any(const pmp_robot_t* robot, const pmp_scene_t* scene, const pmp_validator_t* validator, const T* q0_host,
@@ -1569,11 +1587,10 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
         ho[e + 1] = edge_n_test(r);  // n_test; turned into offsets below when the flat path is taken
       }
     };
-    const int n_thr = (int)std::min<int64_t>(8, m / 2048);
+    // (the persistent pool of the FP64 host entry points: spawning threads per call cost more than the pass itself)
+    const int n_thr = (int)std::min<int64_t>(PackPool::get().size(), m / 2048);
     if (n_thr > 1) {
-      std::vector<std::thread> th;
-      for (int t = 0; t < n_thr; t++) th.emplace_back(pack, m * t / n_thr, m * (t + 1) / n_thr);
-      for (auto& t : th) t.join();
+      PackPool::get().run(n_thr, [&](int t) { pack(m * t / n_thr, m * (t + 1) / n_thr); });
     } else {
       pack(0, m);
     }

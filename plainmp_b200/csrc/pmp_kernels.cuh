@@ -685,6 +685,7 @@ k_edge_prepare(const ValidatorDev V, const T* __restrict__ q0, const T* __restri
 // waypoint the reference would not have tested and the lanes stay full until the batch ends.
 // Valid edges set their bit with one atomicOr (k_edge_prepare zeroes the words first).
 // calls (optional): per edge, the number of is_valid calls = the reference's own count for that edge.
+constexpr int kCoopAfter = 12, kCoopMin = 20;  // see the cooperative round in k_check_edges_v3
 constexpr int kEdgeChunk = 32;  // one dispenser atomic per 32 edges: with 2960 resident warps, 256-edge chunks left a 1 M-edge batch with 1-2 chunks per warp (no balancing at all)
 
 struct EdgeArgs {
@@ -758,16 +759,41 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__
     }
     const bool work = e >= 0;
     if (!__any_sync(full, work)) break;
-    // ---- one waypoint per lane: s2 (w = 0), then the interior points 1 .. n_test-2 ----
-    const long long ge = work ? e : 0;
+    // ---- the round's mode (warp-uniform).  Normally every lane tests the next waypoint of ITS edge.  An edge
+    // that has survived kCoopAfter waypoints and still has kCoopMin or more to go is worked by the whole warp
+    // instead: 32 consecutive positions of the reference's visiting order in one round, the first failing
+    // position decides (and gives the reference's call count; the tests behind it are the only ones the
+    // reference would not have made, and an edge that got this far rarely fails).  A 116-waypoint valid
+    // edge then takes 12 + 4 rounds instead of 116 — it was the serial tail of every launch. ----
+    const unsigned coop = __ballot_sync(full, work && w >= kCoopAfter && n_test - 1 - w >= kCoopMin);
+    const int owner = coop ? __ffs(coop) - 1 : 0;
+    int ce = e, cn = n_test, ci = w;  // edge, its n_test, position in the visiting order (0 = s2)
+    bool act = work;
+    if (coop) {
+      ce = __shfl_sync(full, e, owner);
+      cn = __shfl_sync(full, n_test, owner);
+      ci = __shfl_sync(full, w, owner) + lane;
+      act = ci < cn - 1;
+    }
+    // ---- one waypoint per lane: s2 (position 0), then the interior points 1 .. n_test-2 ----
+    const long long ge = act ? ce : 0;
     float t = 1.f;
-    if (work && w > 0) {
-      const int idx = (n_test < 129) ? (int)seq[(n_test - 1) * 128 + (w + 1)] : w;  // sequence[i], i = w + 1
+    if (act && ci > 0) {
+      const int idx = (cn < 129) ? (int)seq[(cn - 1) * 128 + (ci + 1)] : ci;  // sequence[i], i = position + 1
       t = (float)((double)idx * __ldg(A.ratio + ge));
     }
-    QEdge acc{A.q0 + ge * R.q_dim, A.q1 + ge * R.q_dim, t, w == 0};
-    const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, work);
-    if (work) {
+    QEdge acc{A.q0 + ge * R.q_dim, A.q1 + ge * R.q_dim, t, ci == 0};
+    const bool ok = warp_check_v3<B, MODE, CLOUD>(R, S, T, acc, act);
+    if (coop) {
+      const unsigned fail = __ballot_sync(full, act && !ok);
+      if (lane == owner) {
+        const int consumed = fail ? __ffs(fail) : min(32, n_test - 1 - w);  // what the reference's walk would have called
+        cnt_checked += consumed;
+        w += consumed;
+        if (fail) decide(false);
+        else if (w >= n_test - 1) decide(true);
+      }
+    } else if (work) {
       cnt_checked++;
       w++;
       if (!ok) decide(false);  // first invalid waypoint decides the edge

@@ -907,3 +907,24 @@ def test_emulated_round2_specs_and_scenes(emu, name):
     np.testing.assert_allclose(vals, want_v, atol=1e-5, rtol=0, equal_nan=True, err_msg=name)
     assert_jacobian_parity(o, Q[:96], jac, want_j, name, max_fraction=0.05)
     np.testing.assert_allclose(t.fk_spheres(Q[:32], False), o.spheres_batch(Qd[:32], False), atol=2e-5, rtol=0)
+
+
+def test_emulated_long_edges_take_cooperative_rounds(emu):
+    """Edges of 30 - 200 waypoints, most of them valid or failing late: after kCoopAfter serial waypoints the
+    whole warp works such an edge 32 positions of the visiting order per round.  Validity AND the is_valid
+    call count must still be the serial walk's (first failing position in the reference's order)."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    rng = np.random.default_rng(41)
+    q0, _ = workloads.random_edges(spec, 96, 9, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    lb, ub = spec.angle_bounds()
+    # long moves of few joints: many stay valid for dozens of waypoints, some run into the bars late
+    step = rng.uniform(-1.2, 1.2, q0.shape) * (rng.random(q0.shape) < 0.4)
+    q1 = np.clip(q0.astype(np.float64) + step, lb, ub).astype(np.float32)
+    for widths in (np.full(7, 0.02), np.full(7, 0.006)):  # up to ~60 and ~200 waypoints (beyond 128: natural order)
+        ov = bridge.OracleValidator(0, 7, widths)
+        want, calls, _ = ov.check_motion_batch_ex(o, q0.astype(np.float64), q1.astype(np.float64), 4, with_margin=False)
+        assert (calls > 12 + 20).sum() >= 20 and 0.2 < want.mean() < 0.9, (calls.max(), want.mean())
+        got, n_checks = t.check_edges(0, widths, 0.0, q0, q1)
+        _edge_parity(got, n_checks, o, ov, q0.astype(np.float64), q1.astype(np.float64), f"long edges, width {widths[0]}")

@@ -1,0 +1,32 @@
+#!/bin/bash
+# r2m (multi-GPU box): bench at N = 8 / 4 / 2 (weak, the driver's command), the strong / weak sweep of
+# BASELINE config 5 at N = 8, e2e with write-combined host buffers, the 2-GPU NCCL correctness test.
+tag=${1:-r2m}
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/${tag}_topo.txt 2>&1
+run() { # N extra-args...
+  n=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n --steps 20 --warmup 3 "$@"
+}
+run 8 > gpurun_out/${tag}_bench_n8.json 2> gpurun_out/${tag}_bench_n8.err
+run 8 --host-mem wc > gpurun_out/${tag}_bench_n8_wc.json 2> gpurun_out/${tag}_bench_n8_wc.err
+run 8 --steps 5 --sweep-out gpurun_out/${tag}_sweep_n8.jsonl > /dev/null 2> gpurun_out/${tag}_sweep_n8.err
+run 4 --sweep-out gpurun_out/${tag}_sweep_n4.jsonl > gpurun_out/${tag}_bench_n4.json 2> gpurun_out/${tag}_bench_n4.err
+run 2 --sweep-out gpurun_out/${tag}_sweep_n2.jsonl > gpurun_out/${tag}_bench_n2.json 2> gpurun_out/${tag}_bench_n2.err
+timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --extras 0 --sweep-out gpurun_out/${tag}_sweep_n1.jsonl > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
+timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --extras 0 --host-mem wc > gpurun_out/${tag}_bench_n1_wc.json 2> gpurun_out/${tag}_bench_n1_wc.err
+timeout 300 python -m pytest tests/test_parallel_nccl.py -m gpu -q > gpurun_out/${tag}_nccl_test.log 2>&1
+python - <<'PY'
+import json, glob, os
+tag = os.environ.get("TAG", "r2m")
+for f in sorted(glob.glob(f"gpurun_out/{tag}_bench_n*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "value %.3e ms %.3f e2e %.3e h2d %.1f GB/s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["h2d_copy_gbs_measured"]), d.get("gather_check"))
+    except Exception as e:
+        print(f, "unreadable", e)
+for f in sorted(glob.glob(f"gpurun_out/{tag}_sweep_n*.jsonl")):
+    for l in open(f):
+        d = json.loads(l); print(d["scaling"], d["n_gpus"], d["global_configs"], "%.3e" % d["configs_per_s"], "%.3f ms" % d["ms_per_step"])
+PY
+tail -3 gpurun_out/${tag}_nccl_test.log

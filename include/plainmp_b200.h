@@ -146,6 +146,11 @@ typedef struct {
   const float* cloud_points; /* [n][3] host pointer */
   float cloud_radius;        /* CloudSDF::radius_ (primitive_sdf.hpp:597-603) */
   float cloud_cell;          /* grid cell edge in metres; <= 0 picks a default */
+  /* Several CloudSDF leaves in one scene (the reference keeps every leaf, primitive_sphere_collision.cpp:436-448)
+   * are passed as ONE point set.  Leaves of equal radius need nothing else; for leaves of different radii give
+   * the radius of the leaf every point came from here ([n] host pointer, at most 4 distinct values; cloud_radius
+   * is then ignored).  NULL = every point has cloud_radius. */
+  const float* cloud_point_radii;
 } pmp_scene_desc_t;
 
 typedef struct pmp_scene pmp_scene_t;
@@ -164,6 +169,9 @@ void pmp_scene_destroy(pmp_scene_t* scene);
 int pmp_scene_update_prims(pmp_scene_t* scene, const pmp_prim_t* prims, int32_t n_prims, void* stream);
 int pmp_scene_update_cloud(pmp_scene_t* scene, const float* cloud_points, int64_t n_cloud_points,
                            float cloud_radius, float cloud_cell);
+/* ... with per-point radii (see pmp_scene_desc_t.cloud_point_radii; NULL = cloud_radius for every point) */
+int pmp_scene_update_cloud_ex(pmp_scene_t* scene, const float* cloud_points, int64_t n_cloud_points,
+                              float cloud_radius, const float* cloud_point_radii, float cloud_cell);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 

@@ -34,6 +34,7 @@
 #ifndef PLAINMP_B200_PLAINMP_HPP_
 #define PLAINMP_B200_PLAINMP_HPP_
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -55,7 +56,8 @@ struct Flat {
   std::vector<float> spheres;  // [n][4]
   std::vector<int32_t> pairs;  // [n][2]
   std::vector<pmp_prim_t> prims;
-  std::vector<float> cloud_points;  // [n][3]
+  std::vector<float> cloud_points;  // [n][3]: the points of ALL CloudSDF leaves
+  std::vector<float> cloud_point_radii;  // [n]: filled only when the leaves have different radii
   float cloud_radius = 0.f;
   int32_t dof = 0, base_type = PMP_BASE_FIXED;
   float base_pose[7] = {0, 0, 0, 0, 0, 0, 1};
@@ -83,6 +85,7 @@ struct Flat {
     d.cloud_points = cloud_points.data();
     d.cloud_radius = cloud_radius;
     d.cloud_cell = 0.f;
+    d.cloud_point_radii = cloud_point_radii.empty() ? nullptr : cloud_point_radii.data();
     return d;
   }
   bool has_scene() const { return !prims.empty() || !cloud_points.empty(); }
@@ -210,17 +213,21 @@ struct Flatten {
     namespace col = plainmp::collision;
     out->prims.clear();
     out->cloud_points.clear();
+    out->cloud_point_radii.clear();
+    out->cloud_radius = 0.f;
+    std::vector<float> leaf_radii, per_point;
     for (const auto& s : cst.all_sdfs_cache_) {
       const col::SDFType t = s->get_type();
       if (t == col::SDFType::CLOUD) {
-        // CloudSDFs of equal radius are merged into one point set: min_k (sqrt(NN_k^2) - rho) =
-        // sqrt(min_k NN_k^2) - rho, and each leaf's AABB pre-test is implied by the distance test
+        // every CloudSDF leaf goes into ONE point set (one device index); leaves of different radii are kept
+        // apart by the per-point radius (radius classes, pmp_scene_desc_t.cloud_point_radii)
         const auto& c = static_cast<const col::CloudSDF&>(*s);
-        if (!out->cloud_points.empty() && out->cloud_radius != (float)c.radius_)
-          throw std::runtime_error("plainmp_b200: CloudSDFs of different radii in one scene are not supported");
-        for (const auto& node : c.kdtree_->nodes_)
+        leaf_radii.push_back((float)c.radius_);
+        for (const auto& node : c.kdtree_->nodes_) {
           for (int a = 0; a < 3; a++) out->cloud_points.push_back((float)node.point(a));
-        out->cloud_radius = (float)c.radius_;
+          per_point.push_back((float)c.radius_);
+        }
+        out->cloud_radius = std::max(out->cloud_radius, (float)c.radius_);
         continue;
       }
       pmp_prim_t P{};
@@ -267,6 +274,11 @@ struct Flatten {
       }
       out->prims.push_back(P);
     }
+    for (float r : leaf_radii)
+      if (r != leaf_radii.front()) {  // different radii: hand the per-point radii over
+        out->cloud_point_radii = per_point;
+        break;
+      }
   }
 };
 

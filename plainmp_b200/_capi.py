@@ -101,6 +101,7 @@ class SceneDesc(C.Structure):
         ("cloud_points", C.c_void_p),
         ("cloud_radius", C.c_float),
         ("cloud_cell", C.c_float),
+        ("cloud_point_radii", C.c_void_p),  # optional [n] float32: CloudSDF leaves of different radii in one scene
     ]
 
 
@@ -132,6 +133,7 @@ SYMBOLS = {
     "pmp_scene_create": (_i32, [C.POINTER(SceneDesc), C.POINTER(_p)]),
     "pmp_scene_destroy": (None, [_p]),
     "pmp_scene_update_prims": (_i32, [_p, _p, _i32, _p]),
+    "pmp_scene_update_cloud_ex": (_i32, [_p, _p, _i64, C.c_float, _p, C.c_float]),
     "pmp_scene_update_cloud": (_i32, [_p, _p, _i64, C.c_float, C.c_float]),
     "pmp_check_configs": (_i32, [_p, _p, _p, _i64, _p, _p, _p]),
     "pmp_eval_configs": (_i32, [_p, _p, _p, _i64, _p, _p]),

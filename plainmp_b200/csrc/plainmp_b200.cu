@@ -585,6 +585,12 @@ static void pack_prims(const pmp_prim_t* prims, int n, std::vector<float4>* out)
   }
 }
 
+static int cloud_build_status(const std::string& err) {
+  if (err.find("non-finite") != std::string::npos) return PMP_ERR_INVALID;
+  if (err.find("distinct cloud radii") != std::string::npos || err.find("too many cloud points") != std::string::npos) return PMP_ERR_LIMIT;
+  return PMP_ERR_CUDA;
+}
+
 int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
   if (!d || !out) return fail(PMP_ERR_INVALID, "null argument");
   if (d->n_prims < 0 || d->n_cloud_points < 0) return fail(PMP_ERR_INVALID, "negative table size");
@@ -617,10 +623,10 @@ int pmp_scene_create(const pmp_scene_desc_t* d, pmp_scene_t** out) {
     }
     std::string err;
     int launches = 0;
-    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_cell, num_sms(), &s->dev.cloud, &s->cloud[0], &s->cloud_scratch,
-                    &launches, &err)) {
+    if (cloud_build(d->cloud_points, d->n_cloud_points, d->cloud_radius, d->cloud_point_radii, d->cloud_cell, num_sms(), &s->dev.cloud,
+                    &s->cloud[0], &s->cloud_scratch, &launches, &err)) {
       pmp_scene_destroy(s);
-      return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
+      return fail(cloud_build_status(err), "cloud build: " + err);
     }
     g_launches += launches;
   }
@@ -655,6 +661,10 @@ int pmp_scene_update_prims(pmp_scene_t* s, const pmp_prim_t* prims, int32_t n_pr
 }
 
 int pmp_scene_update_cloud(pmp_scene_t* s, const float* points, int64_t n, float radius, float cell) {
+  return pmp_scene_update_cloud_ex(s, points, n, radius, nullptr, cell);
+}
+
+int pmp_scene_update_cloud_ex(pmp_scene_t* s, const float* points, int64_t n, float radius, const float* point_radii, float cell) {
   if (!s) return fail(PMP_ERR_INVALID, "scene handle is null");
   if (n < 0 || n >= (int64_t)1 << 31) return fail(PMP_ERR_INVALID, "bad cloud size");
   if (n > 0 && !points) return fail(PMP_ERR_INVALID, "cloud_points is null");
@@ -664,8 +674,8 @@ int pmp_scene_update_cloud(pmp_scene_t* s, const float* points, int64_t n, float
   if (n > 0) {
     std::string err;
     int launches = 0;
-    if (cloud_build(points, n, radius, cell, num_sms(), &fresh, &s->cloud[idle], &s->cloud_scratch, &launches, &err))
-      return fail(err.find("non-finite") != std::string::npos ? PMP_ERR_INVALID : PMP_ERR_CUDA, "cloud build: " + err);
+    if (cloud_build(points, n, radius, point_radii, cell, num_sms(), &fresh, &s->cloud[idle], &s->cloud_scratch, &launches, &err))
+      return fail(cloud_build_status(err), "cloud build: " + err);
     g_launches += launches;
   } else {
     fresh.enabled = 0;
@@ -1243,6 +1253,15 @@ namespace {
 // A few persistent host threads for the FP64 -> FP32 packing of large host batches (a pageable double
 // array cannot be DMA'd as it is: the bytes have to be touched once anyway, so they are converted while
 // being staged, which also halves what crosses PCIe).
+// FP64 -> FP32 over a contiguous range; cloned for AVX2 where the host compiler supports function
+// multi-versioning (the scalar loop converts ~1.3 GB/s per core, the vector one is memory-bound)
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+void pack_f64_f32(float* __restrict__ dst, const double* __restrict__ src, int64_t n) {
+  for (int64_t i = 0; i < n; i++) dst[i] = (float)src[i];
+}
+
 class PackPool {
  public:
   static PackPool& get() {
@@ -1364,7 +1383,7 @@ int pmp_check_configs_host_f64(const pmp_robot_t* robot, const pmp_scene_t* scen
     const int tasks = (int)std::min<int64_t>(pool.size(), std::max<int64_t>(1, total / 16384));
     pool.run(tasks, [&](int t) {
       const int64_t lo = total * t / tasks, hi = total * (t + 1) / tasks;
-      for (int64_t i = lo; i < hi; i++) dst[i] = (float)src[i];
+      pack_f64_f32(dst + lo, src + lo, hi - lo);
     });
     cudaStream_t st = W.stream[k];
     CUDA_OK(cudaMemcpyAsync(W.in[k][0], dst, bytes, cudaMemcpyHostToDevice, st));
@@ -1520,7 +1539,7 @@ int pmp_session_is_valid(pmp_session_t* s, const double* states, int64_t n, uint
     const size_t nq = (size_t)m * s->qd;
     const size_t o_bits = align256(std::max<size_t>(nq, 1) * 4);
     const size_t words = (size_t)((m + 31) / 32);
-    for (size_t i = 0; i < nq; i++) hq[i] = (float)states[off * s->qd + i];
+    pack_f64_f32(hq, states + off * s->qd, (int64_t)nq);
     const uint32_t* hbits = reinterpret_cast<const uint32_t*>(s->host + o_bits);
     if (m <= kZeroCopyStates) {
       if (int rc = pmp_check_configs(s->robot, s->scene, reinterpret_cast<const float*>(s->host_dev), m,
@@ -1578,10 +1597,8 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
       for (int64_t e = lo; e < hi; e++) {
         const double* a = s1 + (off + e) * s->qd;
         const double* b = s2 + (off + e) * s->qd;
-        for (int i = 0; i < s->qd; i++) {
-          h0[e * s->qd + i] = (float)a[i];
-          h1[e * s->qd + i] = (float)b[i];
-        }
+        pack_f64_f32(h0 + e * s->qd, a, s->qd);
+        pack_f64_f32(h1 + e * s->qd, b, s->qd);
         const double r = host_step_ratio(s, a, b);
         hr[e] = r;
         ho[e + 1] = edge_n_test(r);  // n_test; turned into offsets below when the flat path is taken

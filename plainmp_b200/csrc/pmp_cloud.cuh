@@ -25,6 +25,12 @@
 namespace pmp {
 
 constexpr int kCloudMaxLevels = 8;  // 8^8 * 8 points
+// Several CloudSDF leaves of one scene share ONE index.  Leaves of equal radius are simply one point set;
+// leaves of different radii become radius CLASSES: the class of a point rides in bits 28..30 of its w
+// (the original index keeps bits 0..27), the pruning tests use the largest radius (conservative for every
+// class), "certainly hit" decisions the smallest, and the exact per-point tests the point's own.
+constexpr int kCloudMaxClasses = 4;
+constexpr int kCloudClassShift = 28;
 
 struct CloudDev {
   const float4* pts;    // Morton-sorted, padded to a multiple of 8 with +inf; w = original index (int bits)
@@ -38,10 +44,21 @@ struct CloudDev {
   float h, inv_h;
   float e;           // half cell diagonal
   float dist_cap;
-  float rho;         // CloudSDF::radius_
+  float rho;         // CloudSDF::radius_ (the LARGEST one when the scene's clouds have different radii)
   float lbx, lby, lbz, ubx, uby, ubz;  // CloudSDF AABB = point bbox +- rho (primitive_sdf.hpp:573-582)
   int enabled;
+  int n_classes;     // 1 unless CloudSDFs of different radii were merged
+  float rho_min;     // smallest class radius (= rho for one class)
+  float rho_cls[kCloudMaxClasses];
 };
+
+__device__ __forceinline__ int cloud_point_class(const float w) { return (__float_as_int(w) >> kCloudClassShift) & 7; }
+// (r + rho of the point's class)^2: the exact per-point bound of an "any point within" query of radius r
+__device__ __forceinline__ float cloud_point_bound2(const CloudDev& C, const float w, const float r, const float bound2) {
+  if (C.n_classes == 1) return bound2;
+  const float d = r + C.rho_cls[cloud_point_class(w) & (kCloudMaxClasses - 1)];
+  return d * d;
+}
 
 __device__ __forceinline__ float box_dist2(const float4 lo, const float4 hi, const float3 p) {
   const float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
@@ -65,8 +82,9 @@ __device__ __forceinline__ unsigned cloud_children_mask(const CloudDev& C, const
   return m;
 }
 
-// any point with |x - p|^2 <= bound2 ?  (depth-first, early exit)
-__device__ inline bool cloud_any_within(const CloudDev& C, const float3 p, const float bound2) {
+// any point x with |x - p| <= r + rho(x) ?  (depth-first, early exit; boxes are pruned with the largest rho)
+__device__ inline bool cloud_any_within(const CloudDev& C, const float3 p, const float r) {
+  const float bound2 = (r + C.rho) * (r + C.rho);
   const int top = C.n_levels - 1;
   int l = top, n = 0;
   unsigned long long masks = 0;
@@ -94,7 +112,7 @@ __device__ inline bool cloud_any_within(const CloudDev& C, const float3 p, const
       for (int k = 0; k < 8; k++) {
         const float4 x = __ldg(q + k);
         const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
-        if (dx * dx + dy * dy + dz * dz <= bound2) return true;
+        if (dx * dx + dy * dy + dz * dz <= cloud_point_bound2(C, x.w, r, bound2)) return true;
       }
     } else {
       l--;
@@ -107,8 +125,9 @@ __device__ inline bool cloud_any_within(const CloudDev& C, const float3 p, const
 
 // exact: squared distance to the nearest cloud point if it is <= bound2, else a value > bound2
 // (+inf).  `idx` receives the original index of the best point (or -1).
+// `cls` >= 0 restricts the search to the points of one radius class (the boxes still cover all classes).
 __device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const float bound2, int* idx,
-                                        float3* nearest = nullptr) {
+                                        float3* nearest = nullptr, const int cls = -1) {
   const int top = C.n_levels - 1;
   // accept d2 <= bound2: search with a strict test against a bound nudged up by one ulp
   float best = __uint_as_float(__float_as_uint(fminf(fmaxf(bound2, 0.f), 3.0e38f)) + 1u);
@@ -142,7 +161,7 @@ __device__ inline float cloud_nn_within(const CloudDev& C, const float3 p, const
         const float4 x = __ldg(q + k);
         const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
         const float d2 = dx * dx + dy * dy + dz * dz;
-        if (d2 < best) {
+        if (d2 < best && (cls < 0 || cloud_point_class(x.w) == cls)) {
           best = d2;
           best_i = __float_as_int(x.w);
           best_p = make_float3(x.x, x.y, x.z);
@@ -190,13 +209,12 @@ __device__ inline bool cloud_is_outside(const CloudDev& C, const float3 p, const
   if (p.x < C.lbx - r || p.x > C.ubx + r || p.y < C.lby - r || p.y > C.uby + r || p.z < C.lbz - r ||
       p.z > C.ubz + r)
     return true;
-  const float d = r + C.rho;
   float lo, hi;
   cloud_bounds(C, p, lo, hi);
   // keep a small guard so that FP32 rounding of the field never decides a borderline query
-  if (lo > d + 1e-5f) return true;
-  if (hi < d - 1e-5f) return false;
-  return !cloud_any_within(C, p, d * d);
+  if (lo > r + C.rho + 1e-5f) return true;       // farther than the largest radius allows
+  if (hi < r + C.rho_min - 1e-5f) return false;  // some point closer than even the smallest radius needs
+  return !cloud_any_within(C, p, r);
 }
 
 // ---- 8-lane cooperative traversal ------------------------------------------------------------------
@@ -212,8 +230,9 @@ __device__ __forceinline__ unsigned cloud_children_mask8(const CloudDev& C, cons
   return (__ballot_sync(smask, d2 <= bound2) >> kshift) & 0xffu;
 }
 
-__device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, const float bound2, const unsigned smask,
+__device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, const float r, const unsigned smask,
                                          const int sub, const int kshift) {
+  const float bound2 = (r + C.rho) * (r + C.rho);
   const int top = C.n_levels - 1;
   int l = top, n = 0;
   unsigned long long masks = 0;
@@ -238,7 +257,7 @@ __device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, cons
     if (l == 1) {  // leaf box: one point per lane
       const float4 x = __ldg(C.pts + 8 * (size_t)child + sub);
       const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
-      if (__ballot_sync(smask, dx * dx + dy * dy + dz * dz <= bound2) & smask) return true;
+      if (__ballot_sync(smask, dx * dx + dy * dy + dz * dz <= cloud_point_bound2(C, x.w, r, bound2)) & smask) return true;
     } else {
       l--;
       n = child;
@@ -254,7 +273,7 @@ __device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, cons
 // uniform throughout.  Returns the squared NN distance (or the bound if nothing beat it) and the
 // original index of the nearest point through *idx (-1 if none).
 __device__ inline float cloud_nn8(const CloudDev& C, const float3 p, float best, const unsigned smask, const int sub,
-                                  const int kshift, int* idx, int* pos = nullptr) {
+                                  const int kshift, int* idx, int* pos = nullptr, const int cls = -1) {
   const int top = C.n_levels - 1;
   int best_i = -1, best_pos = -1;
   int l = top, n = 0;
@@ -286,6 +305,7 @@ __device__ inline float cloud_nn8(const CloudDev& C, const float3 p, float best,
       const float4 x = __ldg(C.pts + 8 * (size_t)child + sub);  // padding points are +inf
       const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
       float d2 = dx * dx + dy * dy + dz * dz;
+      if (cls >= 0 && cloud_point_class(x.w) != cls) d2 = INFINITY;  // another radius class
       int di = __float_as_int(x.w);
       int dp = 8 * child + sub;  // position in the Morton-sorted array
 #pragma unroll
@@ -348,11 +368,10 @@ __device__ __forceinline__ int cloud_classify(const CloudDev& C, const float3 p,
   if (p.x < C.lbx - r || p.x > C.ubx + r || p.y < C.lby - r || p.y > C.uby + r || p.z < C.lbz - r ||
       p.z > C.ubz + r)
     return 0;
-  const float d = r + C.rho;
   float lo, hi;
   cloud_bounds(C, p, lo, hi);
-  if (lo > d + 1e-5f) return 0;
-  if (hi < d - 1e-5f) return 1;
+  if (lo > r + C.rho + 1e-5f) return 0;
+  if (hi < r + C.rho_min - 1e-5f) return 1;
   return 2;
 }
 

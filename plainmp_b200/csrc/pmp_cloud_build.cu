@@ -36,11 +36,12 @@ __global__ void k_cloud_morton(const float* __restrict__ pts3, int64_t n, float3
 
 // sorted[i] = point vals[i] (w = its original index); the tail up to a multiple of 8 is +inf
 __global__ void k_cloud_gather(const float* __restrict__ pts3, int64_t n, int64_t n_pad, const unsigned* __restrict__ vals,
-                               float4* sorted) {
+                               const unsigned char* __restrict__ cls, float4* sorted) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
     if (i < n) {
       const unsigned s = vals[i];
-      sorted[i] = make_float4(pts3[3 * (int64_t)s], pts3[3 * (int64_t)s + 1], pts3[3 * (int64_t)s + 2], __int_as_float((int)s));
+      const unsigned w = s | (cls ? ((unsigned)cls[s] << kCloudClassShift) : 0u);  // radius class in bits 28..30
+      sorted[i] = make_float4(pts3[3 * (int64_t)s], pts3[3 * (int64_t)s + 1], pts3[3 * (int64_t)s + 2], __int_as_float((int)w));
     } else {
       sorted[i] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
     }
@@ -110,6 +111,7 @@ void cloud_free(CloudScratch* s) {
   if (s->vals) cudaFree(s->vals);
   if (s->vals2) cudaFree(s->vals2);
   if (s->tmp) cudaFree(s->tmp);
+  if (s->cls) cudaFree(s->cls);
   *s = CloudScratch{};
 }
 
@@ -127,8 +129,8 @@ cudaError_t reserve(T** p, size_t* cap, size_t bytes) {  // grow-only; 25 % head
 }
 }  // namespace
 
-int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num_sms, CloudDev* Cout, CloudBuffers* bufs,
-                CloudScratch* scr, int* n_launches, std::string* err) {
+int cloud_build(const float* host_pts, int64_t n, float rho, const float* point_radii, float cell, int num_sms, CloudDev* Cout,
+                CloudBuffers* bufs, CloudScratch* scr, int* n_launches, std::string* err) {
   auto bad = [&](const std::string& m, cudaError_t e) {
     *err = m + (e == cudaSuccess ? "" : std::string(": ") + cudaGetErrorString(e));
     return -1;
@@ -143,6 +145,34 @@ int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num
       lo[a] = std::min(lo[a], v);
       hi[a] = std::max(hi[a], v);
     }
+  // radius classes (clouds of different radii merged into this index): ascending distinct radii
+  std::vector<float> classes;
+  std::vector<unsigned char> cls_host;
+  if (point_radii) {
+    for (int64_t i = 0; i < n; i++) {
+      const float r = point_radii[i];
+      if (!std::isfinite(r)) return bad("non-finite cloud point radius", cudaSuccess);
+      if (std::find(classes.begin(), classes.end(), r) == classes.end()) {
+        if ((int)classes.size() == kCloudMaxClasses) return bad("more than 4 distinct cloud radii in one scene", cudaSuccess);
+        classes.push_back(r);
+      }
+    }
+    std::sort(classes.begin(), classes.end());
+  }
+  if (classes.size() > 1) {
+    if (n >= ((int64_t)1 << kCloudClassShift)) return bad("too many cloud points for radius classes", cudaSuccess);
+    cls_host.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++)
+      cls_host[(size_t)i] = (unsigned char)(std::find(classes.begin(), classes.end(), point_radii[i]) - classes.begin());
+    rho = classes.back();
+  } else if (classes.size() == 1) {
+    rho = classes[0];
+  }
+  C.n_classes = classes.size() > 1 ? (int)classes.size() : 1;
+  C.rho_min = classes.size() > 1 ? classes.front() : rho;
+  for (int k = 0; k < kCloudMaxClasses; k++) C.rho_cls[k] = k < (int)classes.size() ? classes[(size_t)k] : rho;
+  // (with several classes the AABB is the point box grown by the LARGEST radius: a superset of the union of
+  // the leaves' own AABBs — the AABB test is a conservative cull — and lb + rho is still the exact point box)
   C.rho = rho;
   C.lbx = lo[0] - rho; C.lby = lo[1] - rho; C.lbz = lo[2] - rho;
   C.ubx = hi[0] + rho; C.uby = hi[1] + rho; C.ubz = hi[2] + rho;
@@ -171,6 +201,8 @@ int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num
   if (e == cudaSuccess) e = reserve(&scr->keys2, &scr->cap_keys2, (size_t)n * 4);
   if (e == cudaSuccess) e = reserve(&scr->vals, &scr->cap_vals, (size_t)n * 4);
   if (e == cudaSuccess) e = reserve(&scr->vals2, &scr->cap_vals2, (size_t)n * 4);
+  if (e == cudaSuccess && !cls_host.empty()) e = reserve(&scr->cls, &scr->cap_cls, (size_t)n);
+  if (e == cudaSuccess && !cls_host.empty()) e = cudaMemcpy(scr->cls, cls_host.data(), (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = reserve(&bufs->pts, &bufs->cap_pts, (size_t)n_pad * sizeof(float4));
   if (e == cudaSuccess) e = reserve(&bufs->nodes, &bufs->cap_nodes, (size_t)total_nodes * 2 * sizeof(float4));
   if (e == cudaSuccess)
@@ -186,7 +218,7 @@ int cloud_build(const float* host_pts, int64_t n, float rho, float cell, int num
                                  1023.999f / std::max(hi[2] - lo[2], 1e-20f));
   k_cloud_morton<<<grid, 256>>>(raw, n, qlo, qsc, keys, vals);
   e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 30);
-  k_cloud_gather<<<grid, 256>>>(raw, n, n_pad, vals2, bufs->pts);
+  k_cloud_gather<<<grid, 256>>>(raw, n, n_pad, vals2, cls_host.empty() ? nullptr : scr->cls, bufs->pts);
   k_cloud_leaf_boxes<<<grid, 256>>>(bufs->pts, n, cnt[0], pad[0], bufs->nodes + 2 * (size_t)C.level_off[0]);
   *n_launches += 4;
   for (size_t l = 1; l < cnt.size(); l++) {

@@ -353,7 +353,9 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
               }
             }
           }
-          if (S.cloud.enabled && !cloud_surely_outside(S.cloud, gc, g.w + cutoff)) {
+          // the scene's cloud: eval_launch always takes the COOP form when there is one (the candidates go to
+          // k_eval_cloud_coop), so the primitives-only instantiation carries no tree traversal at all
+          if (COOP && !cloud_surely_outside(S.cloud, gc, g.w + cutoff)) {
             for (int s = 0; s < gw.z; s++) {
               const float4 sp = T.spheres[gw.y + s];
               const float3 c = xform(rm, f, sp.x, sp.y, sp.z);
@@ -361,29 +363,10 @@ k_eval_configs(const RobotDev R, const SceneDev S, const float* __restrict__ q, 
               if (c.x < S.cloud.lbx - rr || c.x > S.cloud.ubx + rr || c.y < S.cloud.lby - rr ||
                   c.y > S.cloud.uby + rr || c.z < S.cloud.lbz - rr || c.z > S.cloud.ubz + rr)
                 continue;
-              if (COOP) {
-                const long long slot = item * CC.stride + n_cand;
-                CC.sph[slot] = make_float4(c.x, c.y, c.z, sp.w);
-                if (GRAD) CC.op[slot] = op;
-                n_cand++;
-                continue;
-              }
-              float lo, hi;
-              cloud_bounds(S.cloud, c, lo, hi);
-              const float need = min_ext + sp.w + S.cloud.rho;  // only NN below this can lower the min
-              if (lo >= need) continue;
-              const float b = fminf(hi * (1.f + 1e-6f) + 1e-6f, need);
-              float3 nn;
-              const float d2 = cloud_nn_within(S.cloud, c, b * b, nullptr, GRAD ? &nn : nullptr);
-              if (d2 <= b * b) {
-                const float val = sqrtf(d2) - S.cloud.rho - sp.w;
-                if (val < min_ext) {
-                  min_ext = val;
-                  if (GRAD) {
-                    A.ext_op = op; A.ext_prim = -1; A.ext_c = c; A.ext_nn = nn;
-                  }
-                }
-              }
+              const long long slot = item * CC.stride + n_cand;
+              CC.sph[slot] = make_float4(c.x, c.y, c.z, sp.w);
+              if (GRAD) CC.op[slot] = op;
+              n_cand++;
             }
           }
         }
@@ -465,7 +448,7 @@ k_eval_cloud_coop(const SceneDev S, const CloudCand CC, const long long n, float
         cloud_bounds(C, make3(sp.x, sp.y, sp.z), lo, hi);
       }
       // the field's upper bounds: an upper bound of the answer (used only to prune, never reported)
-      float ub = (slot < m && hi < INFINITY) ? (hi * (1.f + 1e-6f) + 1e-6f) - C.rho - sp.w : INFINITY;
+      float ub = (slot < m && hi < INFINITY) ? (hi * (1.f + 1e-6f) + 1e-6f) - C.rho_min - sp.w : INFINITY;  // (a point that near has AT LEAST the smallest radius)
 #pragma unroll
       for (int off = 16; off; off >>= 1) ub = fminf(ub, __shfl_xor_sync(full, ub, off));
       const float prune = fminf(cur, ub + 2e-6f);
@@ -485,13 +468,21 @@ k_eval_cloud_coop(const SceneDev S, const CloudCand CC, const long long n, float
         const float qlo = __shfl_sync(full, lo, src);
         float val = INFINITY;
         int pos = -1;
-        const float need = fminf(cur, prune) + qs.w + C.rho;  // only a nearest point closer than this lowers the minimum
-        if (owner >= 0 && qlo < need && need > 0.f) {
-          // strict search against a bound nudged up by one ulp, so that a point AT the bound is found
-          const float b2 = __uint_as_float(__float_as_uint(need * need) + 1u);
-          int idx;
-          const float d2 = cloud_nn8(C, make3(qs.x, qs.y, qs.z), b2, smask, sub, 8 * k, &idx, &pos);
-          if (idx >= 0) val = sqrtf(d2) - C.rho - qs.w;
+        // one bounded search per radius class (one class, no filter, unless clouds of different radii were merged)
+        for (int kc = 0; kc < C.n_classes; kc++) {
+          const bool one = C.n_classes == 1;
+          const float rho = one ? C.rho : C.rho_cls[kc];
+          const float need = fminf(fminf(cur, prune), val) + qs.w + rho;  // only a nearest point closer than this lowers the minimum
+          if (owner >= 0 && qlo < need && need > 0.f) {
+            // strict search against a bound nudged up by one ulp, so that a point AT the bound is found
+            const float b2 = __uint_as_float(__float_as_uint(need * need) + 1u);
+            int idx, ps;
+            const float d2 = cloud_nn8(C, make3(qs.x, qs.y, qs.z), b2, smask, sub, 8 * k, &idx, &ps, one ? -1 : kc);
+            if (idx >= 0) {
+              val = sqrtf(d2) - rho - qs.w;
+              pos = ps;
+            }
+          }
         }
         // warp-wide minimum over the four answers (ties -> the lower sub-warp, deterministic)
         float bv = val;
@@ -875,7 +866,22 @@ __global__ void k_sdf_evaluate(const SceneDev S, const float* __restrict__ pts, 
     const float3 p = make3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
     float v = 3.402823466e+38f;  // UnionSDF::evaluate starts from numeric_limits::max()
     for (int k = 0; k < S.n_prims; k++) v = fminf(v, prim_evaluate(load_prim(S.prims, k), p));
-    if (S.cloud.enabled) v = fminf(v, sqrtf(cloud_nn_exact(S.cloud, p, nullptr)) - S.cloud.rho);
+    if (S.cloud.enabled) {
+      // min over the CloudSDF leaves of sqrt(NN_k^2) - rho_k: the nearest point of any class first, then
+      // every other class only within the distance at which it could still win
+      int bi;
+      const float d_any = sqrtf(cloud_nn_exact(S.cloud, p, &bi));
+      const int c0 = (S.cloud.n_classes == 1 || bi < 0) ? 0 : cloud_point_class(__int_as_float(bi));
+      float vc = d_any - (S.cloud.n_classes == 1 ? S.cloud.rho : S.cloud.rho_cls[c0]);
+      for (int kc = 0; kc < S.cloud.n_classes && S.cloud.n_classes > 1; kc++) {
+        if (kc == c0) continue;
+        const float b = vc + S.cloud.rho_cls[kc];
+        if (!(b > 0.f)) continue;
+        const float d2 = cloud_nn_within(S.cloud, p, b * b, nullptr, nullptr, kc);
+        if (d2 <= b * b) vc = fminf(vc, sqrtf(d2) - S.cloud.rho_cls[kc]);
+      }
+      v = fminf(v, vc);
+    }
     out[i] = v;
   }
 }
@@ -897,13 +903,12 @@ __global__ void k_sdf_is_outside(const SceneDev S, const float* __restrict__ pts
     }
     if (outside && S.cloud.enabled) {
       // CloudSDF::is_outside(p, r) = evaluate(p) > r, no AABB
-      const float d = r + S.cloud.rho;
       float lo, hi;
       cloud_bounds(S.cloud, p, lo, hi);
-      if (lo > d + 1e-5f) outside = true;
-      else if (hi < d - 1e-5f) outside = false;
-      else if (d < 0.f) outside = true;
-      else outside = !cloud_any_within(S.cloud, p, d * d);
+      if (lo > r + S.cloud.rho + 1e-5f) outside = true;
+      else if (hi < r + S.cloud.rho_min - 1e-5f) outside = false;
+      else if (r + S.cloud.rho < 0.f) outside = true;
+      else outside = !cloud_any_within(S.cloud, p, r);
     }
     out[i] = outside ? 1 : 0;
   }

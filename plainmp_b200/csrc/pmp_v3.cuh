@@ -187,7 +187,7 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
             if (s < gw.z) {
               const float4 sp = T.spheres[gw.y + s];
               c = place(f, sp.x, sp.y, sp.z);
-              d = sp.w + S.cloud.rho;
+              d = sp.w;
               st = cloud_classify(S.cloud, c, sp.w);
             }
             if (__ballot_sync(smask, st == 1)) {
@@ -200,7 +200,7 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
               mb &= mb - 1u;
               const float3 pq = make3(__shfl_sync(smask, c.x, owner), __shfl_sync(smask, c.y, owner), __shfl_sync(smask, c.z, owner));
               const float dq = __shfl_sync(smask, d, owner);
-              hit = cloud_any_within8(S.cloud, pq, dq * dq, smask, sub, k * 8);
+              hit = cloud_any_within8(S.cloud, pq, dq, smask, sub, k * 8);
             }
           }
         } else {

@@ -318,10 +318,11 @@ def flatten_primitives(leaves) -> Tuple[np.ndarray, Optional[object]]:
     """[anchor primitives..., user primitives...] -> pmp_prim_t array (+ the scene's cloud, if any).
 
     The reference keeps every CloudSDF leaf as its own entry (primitive_sphere_collision.cpp:436-448).
-    CloudSDFs of EQUAL radius are merged here into one point set: min over the leaves of
-    sqrt(NN_k^2) - rho equals sqrt(min_k NN_k^2) - rho, and a leaf's AABB pre-test
-    (primitive_sdf.hpp:573-582) is implied by the distance test, so validity and values are unchanged;
-    one device index then serves all of them."""
+    All CloudSDF leaves of a scene are merged here into ONE point set served by one device index.  For
+    leaves of equal radius min over the leaves of sqrt(NN_k^2) - rho equals sqrt(min_k NN_k^2) - rho; leaves
+    of different radii become radius classes of the index (per-point radius, csrc/pmp_cloud.cuh).  A leaf's
+    AABB pre-test (primitive_sdf.hpp:573-582) is implied by its distance test, so validity and values are
+    the reference's."""
     from . import psdf
 
     prims = []
@@ -374,25 +375,40 @@ def flatten_primitives(leaves) -> Tuple[np.ndarray, Optional[object]]:
     if len(clouds) == 1:
         cloud = clouds[0]
     elif clouds:
-        if len({c.radius for c in clouds}) > 1:
-            raise NotImplementedError("CloudSDFs of different radii in one scene are not supported on the CUDA path")
+        if len({c.radius for c in clouds}) > 4:
+            raise NotImplementedError("more than 4 distinct CloudSDF radii in one scene are not supported on the CUDA path")
         cloud = _MergedCloud(clouds)
     return arr, cloud
 
 
 class _MergedCloud:
-    """Several CloudSDF leaves of one radius as one point set (see flatten_primitives)."""
+    """Several CloudSDF leaves as one point set (see flatten_primitives); ``point_radii`` is None when all
+    leaves have the same radius, else the radius of the leaf each point came from (radius classes of the
+    device index, csrc/pmp_cloud.cuh)."""
 
     def __init__(self, clouds):
         self._members = list(clouds)  # keeps the leaves (and with them their uids) alive
-        self.radius = clouds[0].radius
+        radii = [c.radius for c in clouds]
+        self.radius = max(radii)
+        self._uniform = len(set(radii)) == 1
         self._points = None
+        self._point_radii = None
 
     @property
     def points(self) -> np.ndarray:
         if self._points is None:
             self._points = np.ascontiguousarray(np.vstack([c.points for c in self._members]))
         return self._points
+
+    @property
+    def point_radii(self) -> Optional[np.ndarray]:
+        if self._uniform:
+            return None
+        if self._point_radii is None:
+            self._point_radii = np.ascontiguousarray(
+                np.concatenate([np.full(c.points.shape[0], c.radius, dtype=np.float32) for c in self._members])
+            )
+        return self._point_radii
 
     def _state_key(self):
         return tuple(c._state_key() for c in self._members)
@@ -410,12 +426,16 @@ class SceneTable:
         desc.n_prims = self.n_prims
         desc.prims = self.prims.ctypes.data if self.n_prims else None
         self._cloud_pts = None
+        self._cloud_radii = None
         if cloud is not None:
             self._cloud_pts = np.ascontiguousarray(cloud.points, dtype=np.float32)
             desc.n_cloud_points = self._cloud_pts.shape[0]
             desc.cloud_points = self._cloud_pts.ctypes.data
             desc.cloud_radius = cloud.radius
             desc.cloud_cell = cloud_cell
+            self._cloud_radii = getattr(cloud, "point_radii", None)
+            if self._cloud_radii is not None:
+                desc.cloud_point_radii = self._cloud_radii.ctypes.data
         h = C.c_void_p()
         _device()
         _capi.check(lib.pmp_scene_create(C.byref(desc), C.byref(h)))
@@ -444,9 +464,11 @@ class SceneTable:
                 self._cloud_pts = None
             else:
                 self._cloud_pts = np.ascontiguousarray(cloud.points, dtype=np.float32)
+                self._cloud_radii = getattr(cloud, "point_radii", None)
                 _capi.check(
-                    self._lib.pmp_scene_update_cloud(
-                        self._h, self._cloud_pts.ctypes.data, self._cloud_pts.shape[0], cloud.radius, self._cloud_cell
+                    self._lib.pmp_scene_update_cloud_ex(
+                        self._h, self._cloud_pts.ctypes.data, self._cloud_pts.shape[0], cloud.radius,
+                        self._cloud_radii.ctypes.data if self._cloud_radii is not None else None, self._cloud_cell,
                     )
                 )
             self._cloud_id = new_id

@@ -960,12 +960,13 @@ def _round2_case(name, n):
     cst = spec.create_collision_const(use_cache=False)
     pts = workloads.table_cloud(30000, 4)
     shelf = np.random.default_rng(0).uniform([-0.2, -1.0, 0.2], [0.4, -0.5, 1.5], size=(8000, 3))
-    cst.set_sdf(psdf.UnionSDF([psdf.CloudSDF(pts[:15000], 0.002), psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.6, 0.6, 1.2])),
-                               psdf.UnionSDF([psdf.CloudSDF(pts[15000:], 0.002), psdf.CloudSDF(shelf, 0.002)])]))
+    r0, r1, r2 = (0.002, 0.03, 0.011) if name == "clouds_of_different_radii" else (0.002, 0.002, 0.002)
+    cst.set_sdf(psdf.UnionSDF([psdf.CloudSDF(pts[:15000], r0), psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.6, 0.6, 1.2])),
+                               psdf.UnionSDF([psdf.CloudSDF(pts[15000:], r1), psdf.CloudSDF(shelf, r2)])]))
     return spec, cst, workloads.random_configs(spec, n, 14)
 
 
-@pytest.mark.parametrize("name", ["jaxon", "jaxon_no_gripper", "pr2_base_only", "attached_box", "several_clouds", "position_only_link"])
+@pytest.mark.parametrize("name", ["jaxon", "jaxon_no_gripper", "pr2_base_only", "attached_box", "several_clouds", "clouds_of_different_radii", "position_only_link"])
 def test_round2_specs_and_scenes(cuda_lib, name):
     """JaxonSpec (FLOATING base, 37 entries), PR2BaseOnlySpec (no controlled joint, PLANAR base), the
     attached-box lattice of zero-radius spheres, several CloudSDF leaves in one scene: CUDA vs the compiled
@@ -1029,3 +1030,31 @@ def test_long_edges_take_cooperative_rounds(cuda_lib):
         got, n_checked, calls = mv.check_motion_batch(q0, q1, with_calls=True)
         want = assert_edge_parity(cst, 0, widths, 0.0, q0, q1, got, n_checked, calls, f"long edges, width {widths[0]}")
         assert (calls > 32).mean() > 0.2 and 0.2 < want.mean() < 0.9
+
+
+def test_union_of_clouds_with_different_radii_psdf_surface_and_edges(cuda_lib):
+    """CloudSDF leaves of different radii behind one device index (radius classes): UnionSDF.evaluate /
+    is_outside, and edges through the kernel with the cloud traversal."""
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-0.12, 0.12, (5000, 3)) + np.array([0.45, 0.0, 0.55])
+    b = rng.uniform(-0.10, 0.10, (3000, 3)) + np.array([0.25, 0.35, 0.35])
+    c = rng.uniform(-0.15, 0.15, (2000, 3)) + np.array([-0.3, -0.3, 0.6])
+    union = psdf.UnionSDF([psdf.CloudSDF(a, 0.004), psdf.BoxSDF([0.2, 0.2, 0.2], psdf.Pose([0.5, -0.4, 0.2])), psdf.CloudSDF(b, 0.05), psdf.CloudSDF(c, 0.02)])
+    o_sdf = bridge.OracleSDF.from_psdf(union)
+    pts = np.array([0.2, 0.0, 0.45]) + rng.uniform(-0.6, 0.6, (4000, 3))
+    pts = pts.astype(np.float32).astype(np.float64)
+    want = o_sdf.evaluate_batch(pts)
+    np.testing.assert_allclose(union.evaluate_batch(pts.T), want, atol=TOL, rtol=0)
+    radii = np.where(rng.random(4000) < 0.5, 0.0, rng.uniform(0, 0.1, 4000))
+    got = union.is_outside_batch(pts.T, radii)
+    clear = np.abs(want - radii) > EPS_BAND
+    assert (got == (want > radii))[clear].all()
+    spec, cst = workloads.make_panda()
+    cst.set_sdf(union)
+    o = bridge.OracleCst(cst, n_threads=4)
+    q0, q1 = workloads.random_edges(spec, 3000, 6, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    widths = [0.05] * 7
+    mv = MotionValidator(cst, ValidatorConfig(ValidatorType.BOX, 0.0, widths))
+    e_got, n_checked, calls = mv.check_motion_batch(q0, q1, with_calls=True)
+    e_want = assert_edge_parity(cst, 0, widths, 0.0, q0, q1, e_got, n_checked, calls, "edges vs clouds of different radii")
+    assert 0.05 < e_want.mean() < 0.95

@@ -570,3 +570,24 @@ def test_position_only_link_with_spheres_at_its_origin_matches_reference():
     with pytest.raises(NotImplementedError):
         _, bad = workloads.make_panda_position_only_link(offset_spheres=True)
         tables.RobotTable.build_arrays(bad.get_kin(), bad._control_joint_ids, bad._base_type, bad._group_links, bad._group_spheres, bad._group_only_self, bad._pairs)
+
+
+def test_clouds_of_different_radii_match_reference():
+    """CloudSDF leaves of different radii in one scene: the oracle and the reference keep them as separate leaves;
+    the host mirror hands them to the device as one point set with per-point radii (radius classes)."""
+    from plainmp_b200 import tables
+
+    spec, cst = _pr2_several_clouds(radii=(0.002, 0.03, 0.011))
+    o, r = bridge.OracleCst(cst), ref_bridge.RefCst(cst)
+    Q = workloads.random_configs(spec, 1500, 1).astype(np.float64)
+    v_o, v_r = o.is_valid_batch(Q), r.is_valid_batch(Q)
+    assert (v_o == v_r).all() and 0.03 < v_r.mean() < 0.95
+    np.testing.assert_allclose(o.evaluate_batch(Q[:200]), r.evaluate_batch(Q[:200]), atol=TOL, rtol=0)
+    prims, cloud = tables.flatten_primitives(cst._leaves())
+    assert cloud.points.shape == (8000, 3) and cloud.radius == 0.03
+    pr = cloud.point_radii
+    assert pr.shape == (8000,) and set(np.unique(pr)) == {np.float32(0.002), np.float32(0.03), np.float32(0.011)}
+    assert (pr[:3000] == np.float32(0.002)).all() and (pr[3000:6000] == np.float32(0.03)).all()
+    five = [psdf.CloudSDF(np.random.default_rng(i).uniform(0, 1, (10, 3)), 0.01 * (i + 1)) for i in range(5)]
+    with pytest.raises(NotImplementedError):
+        tables.flatten_primitives(five)

@@ -79,6 +79,9 @@ class EmuTables:
                 self._cloud = np.ascontiguousarray(cloud.points, dtype=np.float32)
                 sd.n_cloud_points, sd.cloud_points = len(self._cloud), self._cloud.ctypes.data
                 sd.cloud_radius, sd.cloud_cell = cloud.radius, 0.02  # coarse field: fewer cells to fill in emulation
+                self._cloud_radii = getattr(cloud, "point_radii", None)
+                if self._cloud_radii is not None:
+                    sd.cloud_point_radii = self._cloud_radii.ctypes.data
             self.scene = C.c_void_p()
             assert lib.pmp_scene_create(C.byref(sd), C.byref(self.scene)) == 0, lib.pmp_last_error()
 
@@ -888,12 +891,13 @@ def _round2_case(name):
     cst = spec.create_collision_const(use_cache=False)
     pts = workloads.table_cloud(3000, 4)
     shelf = np.random.default_rng(0).uniform([-0.2, -1.0, 0.2], [0.4, -0.5, 1.5], size=(800, 3))
-    cst.set_sdf(psdf.UnionSDF([psdf.CloudSDF(pts[:1500], 0.002), psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.6, 0.6, 1.2])),
-                               psdf.UnionSDF([psdf.CloudSDF(pts[1500:], 0.002), psdf.CloudSDF(shelf, 0.002)])]))
+    r0, r1, r2 = (0.002, 0.03, 0.011) if name == "clouds_of_different_radii" else (0.002, 0.002, 0.002)
+    cst.set_sdf(psdf.UnionSDF([psdf.CloudSDF(pts[:1500], r0), psdf.BoxSDF([0.3, 0.3, 0.3], psdf.Pose([0.6, 0.6, 1.2])),
+                               psdf.UnionSDF([psdf.CloudSDF(pts[1500:], r1), psdf.CloudSDF(shelf, r2)])]))
     return cst, workloads.random_configs(spec, 128, 14)
 
 
-@pytest.mark.parametrize("name", ["jaxon", "pr2_base_only", "attached_box", "several_clouds", "position_only_link"])
+@pytest.mark.parametrize("name", ["jaxon", "pr2_base_only", "attached_box", "several_clouds", "clouds_of_different_radii", "position_only_link"])
 def test_emulated_round2_specs_and_scenes(emu, name):
     cst, Q = _round2_case(name)
     t = EmuTables(emu, cst)
@@ -928,3 +932,45 @@ def test_emulated_long_edges_take_cooperative_rounds(emu):
         assert (calls > 12 + 20).sum() >= 20 and 0.2 < want.mean() < 0.9, (calls.max(), want.mean())
         got, n_checks = t.check_edges(0, widths, 0.0, q0, q1)
         _edge_parity(got, n_checks, o, ov, q0.astype(np.float64), q1.astype(np.float64), f"long edges, width {widths[0]}")
+
+
+def test_emulated_radius_classes_psdf_surface_edges_and_update(emu):
+    """CloudSDF leaves of different radii behind one device index (radius classes): the psdf surface
+    (evaluate / is_outside of the union), edges, and a cloud update that changes the class layout."""
+    spec, cst = workloads.make_panda()
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-0.12, 0.12, (500, 3)) + np.array([0.45, 0.0, 0.55])
+    b = rng.uniform(-0.10, 0.10, (300, 3)) + np.array([0.25, 0.35, 0.35])
+    c = rng.uniform(-0.15, 0.15, (200, 3)) + np.array([-0.3, -0.3, 0.6])
+    union = psdf.UnionSDF([psdf.CloudSDF(a, 0.004), psdf.BoxSDF([0.2, 0.2, 0.2], psdf.Pose([0.5, -0.4, 0.2])), psdf.CloudSDF(b, 0.05), psdf.CloudSDF(c, 0.02)])
+    cst.set_sdf(union)
+    t = EmuTables(emu, cst)
+    o = bridge.OracleCst(cst)
+    sdf = bridge.OracleSDF.from_psdf(union)
+    P = (np.array([0.2, 0.0, 0.45]) + rng.uniform(-0.6, 0.6, (300, 3))).astype(np.float32)
+    want_v = sdf.evaluate_batch(P.astype(np.float64))
+    got_v = np.zeros(300, dtype=np.float32)
+    assert emu.pmp_sdf_evaluate(t.scene, P.ctypes.data, 300, got_v.ctypes.data, None) == 0, emu.pmp_last_error()
+    np.testing.assert_allclose(got_v, want_v, atol=1e-5, rtol=0)
+    for r in (0.0, 0.03):
+        rad = np.full(300, r, dtype=np.float32)
+        flag = np.zeros(300, dtype=np.uint8)
+        assert emu.pmp_sdf_is_outside(t.scene, P.ctypes.data, rad.ctypes.data, 300, flag.ctypes.data, None) == 0
+        assert ((flag.astype(bool) == (want_v > r)) | (np.abs(want_v - r) < 1e-5)).all()
+    Q = workloads.random_configs(spec, 96, 21)
+    Qd = Q.astype(np.float64)
+    _parity(t.check(Q), o.is_valid_batch(Qd), o.margin_batch(Qd), "radius classes")
+    q0, q1 = workloads.random_edges(spec, 48, 6, True, lambda q: o.is_valid_batch(q.astype(np.float64)))
+    widths = np.full(7, 0.05)
+    got, n_checks = t.check_edges(0, widths, 0.0, q0, q1)
+    _edge_parity(got, n_checks, o, bridge.OracleValidator(0, 7, widths), q0.astype(np.float64), q1.astype(np.float64), "radius classes, edges")
+    # a new frame with another class layout (two radii, other order) through the update entry point
+    pts = np.ascontiguousarray(np.vstack([c, a]), dtype=np.float32)
+    radii = np.concatenate([np.full(len(c), 0.03, dtype=np.float32), np.full(len(a), 0.01, dtype=np.float32)])
+    assert emu.pmp_scene_update_cloud_ex(t.scene, pts.ctypes.data, len(pts), 0.0, radii.ctypes.data, 0.02) == 0, emu.pmp_last_error()
+    cst.set_sdf(psdf.UnionSDF([psdf.BoxSDF([0.2, 0.2, 0.2], psdf.Pose([0.5, -0.4, 0.2])), psdf.CloudSDF(c, 0.03), psdf.CloudSDF(a, 0.01)]))
+    o2 = bridge.OracleCst(cst)
+    _parity(t.check(Q), o2.is_valid_batch(Qd), o2.margin_batch(Qd), "radius classes after an update")
+    np.testing.assert_allclose(t.evaluate(Q[:48]), o2.evaluate_batch(Qd[:48]), atol=1e-5, rtol=0)
+    five = np.arange(len(pts), dtype=np.float32) % 5 * 0.01 + 0.01
+    assert emu.pmp_scene_update_cloud_ex(t.scene, pts.ctypes.data, len(pts), 0.0, five.ctypes.data, 0.02) == _capi.PMP_ERR_LIMIT

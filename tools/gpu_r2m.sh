@@ -8,13 +8,10 @@ run() { # N extra-args...
   n=$1; shift
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n --steps 20 --warmup 3 "$@"
 }
-run 8 > gpurun_out/${tag}_bench_n8.json 2> gpurun_out/${tag}_bench_n8.err
+run 8 --sweep-out gpurun_out/${tag}_sweep_n8.jsonl > gpurun_out/${tag}_bench_n8.json 2> gpurun_out/${tag}_bench_n8.err
 run 8 --host-mem wc > gpurun_out/${tag}_bench_n8_wc.json 2> gpurun_out/${tag}_bench_n8_wc.err
-run 8 --steps 5 --sweep-out gpurun_out/${tag}_sweep_n8.jsonl > /dev/null 2> gpurun_out/${tag}_sweep_n8.err
 run 4 --sweep-out gpurun_out/${tag}_sweep_n4.jsonl > gpurun_out/${tag}_bench_n4.json 2> gpurun_out/${tag}_bench_n4.err
 run 2 --sweep-out gpurun_out/${tag}_sweep_n2.jsonl > gpurun_out/${tag}_bench_n2.json 2> gpurun_out/${tag}_bench_n2.err
-timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --extras 0 --sweep-out gpurun_out/${tag}_sweep_n1.jsonl > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
-timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --extras 0 --host-mem wc > gpurun_out/${tag}_bench_n1_wc.json 2> gpurun_out/${tag}_bench_n1_wc.err
 timeout 300 python -m pytest tests/test_parallel_nccl.py -m gpu -q > gpurun_out/${tag}_nccl_test.log 2>&1
 python - <<'PY'
 import json, glob, os

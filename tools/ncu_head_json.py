@@ -53,30 +53,37 @@ for f in sorted((ROOT / "gpurun_out").glob(f"{tag}_prof_*_raw.csv")):
     rows = list(csv.reader(open(f)))
     if len(rows) < 3:
         continue
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    rec = {"kernel": vals[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")}
-    for k, m in KEYS.items():
-        if m not in hdr:
-            continue
-        i = hdr.index(m)
-        try:
-            v = float(vals[i].replace(",", ""))
-        except ValueError:
-            continue
-        u = units[i]
-        if k in ("dram_read", "dram_write"):
-            rec[k + "_bytes"] = v * SCALE.get(u, 1.0)
-        elif k == "duration_ms":
-            rec[k] = v * SCALE.get(u, 1.0)
-        else:
-            rec[k] = v
-    n = ITEMS.get(wl)
-    if n:
-        rec["items"] = n
-        rec["item"] = UNIT.get(wl, "config")
-        if "inst_executed" in rec:
-            rec["warp_inst_per_item"] = rec["inst_executed"] / n
-        if "dram_read_bytes" in rec:
-            rec["dram_bytes_per_item"] = (rec["dram_read_bytes"] + rec.get("dram_write_bytes", 0.0)) / n
+    hdr, units = rows[0], rows[1]
+
+    def record(vals):
+        rec = {"kernel": vals[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")}
+        for k, m in KEYS.items():
+            if m not in hdr:
+                continue
+            i = hdr.index(m)
+            try:
+                v = float(vals[i].replace(",", ""))
+            except ValueError:
+                continue
+            u = units[i]
+            if k in ("dram_read", "dram_write"):
+                rec[k + "_bytes"] = v * SCALE.get(u, 1.0)
+            elif k == "duration_ms":
+                rec[k] = v * SCALE.get(u, 1.0)
+            else:
+                rec[k] = v
+        n = ITEMS.get(wl)
+        if n:
+            rec["items"] = n
+            rec["item"] = UNIT.get(wl, "config")
+            if "inst_executed" in rec:
+                rec["warp_inst_per_item"] = rec["inst_executed"] / n
+            if "dram_read_bytes" in rec:
+                rec["dram_bytes_per_item"] = (rec["dram_read_bytes"] + rec.get("dram_write_bytes", 0.0)) / n
+        return rec
+
+    rec = record(rows[2])
+    if len(rows) > 3:  # a call that launches several kernels (evaluate against a cloud: pass 1 + the cooperative cloud stage)
+        rec["more_kernels"] = [record(r) for r in rows[3:] if len(r) == len(hdr)]
     out["workloads"][wl] = rec
 print(json.dumps(out, indent=1))

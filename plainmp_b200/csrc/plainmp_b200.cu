@@ -3,6 +3,7 @@
 // No torch, no CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -962,13 +963,18 @@ int validator_to_dev(const pmp_validator_t* v, int q_dim, ValidatorDev* out) {
 }
 
 // the persistent edge kernel on endpoints, ratios and n_test that are already on the device
+// Launch hint of the chunked host path (experiments): edges per lane the grid of the NEXT edge launch of this
+// thread is sized for (0 = fill the GPU, the default).
+thread_local int tl_edges_per_lane = 0;
+
 int launch_edges(const pmp_robot_t* robot, const SceneDev& S, const uint8_t* seq, const EdgeArgs& A, cudaStream_t st) {
   if (!mask_limit_ok(robot->fast, S)) return fail(PMP_ERR_LIMIT, "a robot with per-group scene masks needs a scene of at most 30 primitives");
   const int block = pick_block(robot->fast, S);
   const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
   const long long n_words = (A.n + 31) / 32;
-  const long long tiles = (n_words + (block / 32) - 1) / (block / 32);  // one warp per 32 edges at most
+  long long tiles = (n_words + (block / 32) - 1) / (block / 32);  // one warp per 32 edges at most
+  if (tl_edges_per_lane > 0) tiles = std::max<long long>(1, (A.n + (long long)block * tl_edges_per_lane - 1) / ((long long)block * tl_edges_per_lane));
   int grid = 0;
   const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
   const bool cloud = S.cloud.enabled != 0;
@@ -1102,6 +1108,26 @@ struct HostWorkspace {
   size_t out_cap[kWsStreams] = {};
   unsigned long long* counters = nullptr;       // device [2]: n_valid, n_checked
   unsigned long long* counters_host = nullptr;  // pinned [2]
+  // edge batches (check_edges_host_any): ONE copy stream that never waits for a kernel, and a ring of
+  // compute slots (stream + input buffers + "inputs arrived" / "slot free again" events)
+  static constexpr int kEdgeSlots = 6;
+  cudaStream_t ecopy = nullptr;
+  cudaStream_t ecomp[kEdgeSlots] = {};
+  cudaEvent_t e_in[kEdgeSlots] = {}, e_done[kEdgeSlots] = {};
+  void* ein[kEdgeSlots][2] = {};
+  size_t ein_cap[kEdgeSlots][2] = {};
+  void* eout[kEdgeSlots] = {};
+  size_t eout_cap[kEdgeSlots] = {};
+  int init_edges() {
+    if (ecopy) return PMP_OK;
+    CUDA_OK(cudaStreamCreateWithFlags(&ecopy, cudaStreamNonBlocking));
+    for (int i = 0; i < kEdgeSlots; i++) {
+      CUDA_OK(cudaStreamCreateWithFlags(&ecomp[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&e_done[i], cudaEventDisableTiming));
+    }
+    return PMP_OK;
+  }
   int init() {
     for (int i = 0; i < kWsStreams; i++) CUDA_OK(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
     CUDA_OK(cudaMalloc(&counters, 2 * sizeof(unsigned long long)));
@@ -1119,6 +1145,10 @@ struct HostWorkspace {
   }
   int sync_all() {
     for (int i = 0; i < kWsStreams; i++) CUDA_OK(cudaStreamSynchronize(stream[i]));
+    if (ecopy) {
+      CUDA_OK(cudaStreamSynchronize(ecopy));
+      for (int i = 0; i < kEdgeSlots; i++) CUDA_OK(cudaStreamSynchronize(ecomp[i]));
+    }
     return PMP_OK;
   }
 };
@@ -1147,9 +1177,11 @@ struct WorkspaceLease {  // RAII check-out of a workspace of the current device
 };
 constexpr int64_t kHostChunk = 1 << 19;  // items per pipelined chunk (multiple of 32): the tail that cannot overlap is one chunk's kernel
 // Edge batches: the first chunks are small so that the first kernel starts after a short copy, later ones
-// large so that per-chunk costs (prepare pass, launch, the persistent kernel's tail) stay small.
+// larger so that per-chunk costs (prepare pass, sort, launch) stay small — but not so large that the last
+// chunk, whose inputs arrive last, holds much of the work.
 inline int64_t edge_chunk_size(int k) {
-  static const int first = getenv("PMP_EDGE_CHUNK_FIRST") ? atoi(getenv("PMP_EDGE_CHUNK_FIRST")) : 16;  // log2; A/B experiments only
+  // log2 of the first / largest chunk; the environment overrides are for A/B runs (profiles/r02_s10_edges_e2e_pipeline.txt)
+  static const int first = getenv("PMP_EDGE_CHUNK_FIRST") ? atoi(getenv("PMP_EDGE_CHUNK_FIRST")) : 17;
   static const int last = getenv("PMP_EDGE_CHUNK_LAST") ? atoi(getenv("PMP_EDGE_CHUNK_LAST")) : 19;
   return (int64_t)1 << std::min(last, first + k);
 }
@@ -1171,23 +1203,68 @@ int check_edges_host_any(const pmp_robot_t* robot, const pmp_scene_t* scene, con
   const int qd = robot->full.dev.q_dim;
   CUDA_OK(cudaMemsetAsync(W.counters, 0, 2 * sizeof(unsigned long long), W.stream[0]));
   CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  if (int rc = W.init_edges()) return rc;
+  static const bool trace = getenv("PMP_TRACE_EDGES") != nullptr;
+  std::vector<cudaEvent_t> marks;
+  auto trace_mark = [&](cudaStream_t s) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks.push_back(e);
+  };
+  const auto t_host0 = std::chrono::steady_clock::now();
+  // The pipeline (device timelines: PMP_TRACE_EDGES=1).  Copies run back to back on their own stream at the
+  // link rate and never wait for a kernel (only for a ring slot, kEdgeSlots chunks back); every chunk's
+  // prepare pass / sort / persistent kernel / result copy run on the slot's stream behind the chunk's
+  // "inputs arrived" event; as a persistent CTA retires when its warps run dry, the tail of one chunk's kernel
+  // runs under the head of the next.  (Grids sized for a few edges per lane — PMP_EDGE_EPL, so that neighbouring
+  // chunks share the SMs from the start — were measured and lost: profiles/r02_s10_edges_e2e_pipeline.txt.)
+  static const int epl = getenv("PMP_EDGE_EPL") ? atoi(getenv("PMP_EDGE_EPL")) : 0;
+  constexpr int kSlots = HostWorkspace::kEdgeSlots;
+  const int64_t max_chunk = std::min<int64_t>(n, 3 * edge_chunk_size(64) / 2);
+  for (int b = 0; b < kSlots; b++) {  // all growth happens before anything is in flight (cudaMalloc synchronises)
+    for (int a = 0; a < 2; a++)
+      if (int rc = W.reserve(&W.ein[b][a], &W.ein_cap[b][a], (size_t)max_chunk * qd * sizeof(T))) return rc;
+    if (int rc = W.reserve(&W.eout[b], &W.eout_cap[b], (size_t)((max_chunk + 31) / 32) * 4)) return rc;
+  }
   int64_t off = 0;
   for (int k = 0; off < n; k++) {
-    const int64_t m = std::min<int64_t>(edge_chunk_size(k), n - off);
-    const int b = k % kWsStreams;
-    for (int a = 0; a < 2; a++)
-      if (int rc = W.reserve(&W.in[b][a], &W.in_cap[b][a], (size_t)m * qd * sizeof(T))) return rc;
-    if (int rc = W.reserve(&W.outb[b], &W.out_cap[b], (size_t)((m + 31) / 32) * 4)) return rc;
-    cudaStream_t st = W.stream[b];
-    CUDA_OK(cudaMemcpyAsync(W.in[b][0], q0_host + off * qd, (size_t)m * qd * sizeof(T), cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(W.in[b][1], q1_host + off * qd, (size_t)m * qd * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (int rc = check_edges_any<T>(robot, scene, validator, (const T*)W.in[b][0], (const T*)W.in[b][1], m, (uint32_t*)W.outb[b], nullptr,
-                                    W.counters, W.counters + 1, st))
-      return rc;
-    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, W.outb[b], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    int64_t m = std::min<int64_t>(edge_chunk_size(k), n - off);
+    if (n - off - m < m / 2) m = n - off;  // a short remainder rides with this chunk: a small last chunk would be all tail
+    const int b = k % kSlots;
+    cudaStream_t st = W.ecomp[b];
+    if (k >= kSlots) CUDA_OK(cudaStreamWaitEvent(W.ecopy, W.e_done[b], 0));  // the slot's previous chunk has been consumed
+    if (trace) trace_mark(W.ecopy);
+    CUDA_OK(cudaMemcpyAsync(W.ein[b][0], q0_host + off * qd, (size_t)m * qd * sizeof(T), cudaMemcpyHostToDevice, W.ecopy));
+    CUDA_OK(cudaMemcpyAsync(W.ein[b][1], q1_host + off * qd, (size_t)m * qd * sizeof(T), cudaMemcpyHostToDevice, W.ecopy));
+    CUDA_OK(cudaEventRecord(W.e_in[b], W.ecopy));
+    if (trace) trace_mark(W.ecopy);
+    CUDA_OK(cudaStreamWaitEvent(st, W.e_in[b], 0));
+    tl_edges_per_lane = epl;
+    const int rc = check_edges_any<T>(robot, scene, validator, (const T*)W.ein[b][0], (const T*)W.ein[b][1], m, (uint32_t*)W.eout[b], nullptr,
+                                      W.counters, W.counters + 1, st);
+    tl_edges_per_lane = 0;
+    if (rc) return rc;
+    if (trace) trace_mark(st);
+    CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, W.eout[b], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(W.e_done[b], st));
+    if (trace) trace_mark(st);
     off += m;
   }
   if (int rc = W.sync_all()) return rc;
+  if (trace) {  // PMP_TRACE_EDGES=1 (diagnostics): device timeline of the chunks, ms from the first mark
+    fprintf(stderr, "[pmp trace] check_edges_host n=%lld host enqueue %.3f ms\n", (long long)n,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+    for (size_t i = 0; i + 3 < marks.size(); i += 4) {
+      float a = 0, b2 = 0, c = 0, d = 0;
+      cudaEventElapsedTime(&a, marks[0], marks[i]);
+      cudaEventElapsedTime(&b2, marks[0], marks[i + 1]);
+      cudaEventElapsedTime(&c, marks[0], marks[i + 2]);
+      cudaEventElapsedTime(&d, marks[0], marks[i + 3]);
+      fprintf(stderr, "[pmp trace]   chunk %zu: h2d %.3f -> %.3f, kernels -> %.3f, d2h -> %.3f\n", i / 4, a, b2, c, d);
+    }
+    for (cudaEvent_t e : marks) cudaEventDestroy(e);
+  }
   CUDA_OK(cudaMemcpyAsync(W.counters_host, W.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, W.stream[0]));
   CUDA_OK(cudaStreamSynchronize(W.stream[0]));
   if (n_valid) *n_valid = W.counters_host[0];

@@ -315,6 +315,7 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (void*)1; return cudaS
 enum { cudaEventDisableTiming = 2 };
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)1; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }

@@ -559,6 +559,23 @@ def run_b200(args):
         dist.all_reduce(f64_s, op=dist.ReduceOp.MAX)
     e2e_f64_value = n64 * world * 3 / float(f64_s.item())
     assert (torch.from_numpy(w64.view(np.int32)).to(dev) == step.bits(last)[: (n64 + 31) // 32]).all()
+    # ... and the same FP64 values in a PAGE-LOCKED array (a caller that reuses its state buffer registers it once):
+    # the doubles cross PCIe as they are and are narrowed on the device
+    q64p = torch.empty((n64, dof), dtype=torch.float64, pin_memory=True)
+    q64p.copy_(torch.from_numpy(q64))
+    w64p = np.zeros((n64 + 31) // 32, dtype=np.uint32)
+    f64p_step = lambda: _capi.check(lib.pmp_check_configs_host_f64(robot.handle, scene.handle, q64p.data_ptr(), n64, w64p.ctypes.data, C.byref(nv)))  # noqa: E731
+    f64p_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        f64p_step()
+    f64p_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(f64p_s, op=dist.ReduceOp.MAX)
+    e2e_f64_pinned_value = n64 * world * 3 / float(f64p_s.item())
+    assert (w64p == w64).all()
+    del q64p
     clocks = sampler.stop() if rank == 0 else None
 
     extras = {}
@@ -640,7 +657,9 @@ def run_b200(args):
                     "bound": "pcie_h2d", "h2d_copy_gbs_measured": h2d_gbs, "host_buffer": "torch pinned" if args.host_mem == "pinned" else "write-combined pinned (pmp_host_alloc)",
                     "frac_of_h2d_copy": (e2e_value / world) * dof * 4 / 1e9 / h2d_gbs,
                     "from_pageable_fp64": {"value": e2e_f64_value, "unit": UNIT, "configs_per_call": n64,
-                                           "note": "pmp_check_configs_host_f64: pageable float64 numpy in (what the reference's binding holds), packed to FP32 by host threads into pinned staging"}},
+                                           "note": "pmp_check_configs_host_f64: pageable float64 numpy in (what the reference's binding holds), packed to FP32 by host threads into pinned staging; bound by the host's own memory bandwidth"},
+                    "from_pinned_fp64": {"value": e2e_f64_pinned_value, "unit": UNIT, "configs_per_call": n64,
+                                         "note": "the same entry point on a page-locked float64 array: the doubles are DMA'd as they are (56 B per configuration) and narrowed on the device"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -105,7 +105,7 @@ def lib() -> C.CDLL:
             "ref_cst_flatten": (vp, [vp]),
             "ref_flat_destroy": (None, [vp]),
             "ref_flat_sizes": (None, [vp, vp]),
-            "ref_flat_copy": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+            "ref_flat_copy": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
             "ref_check_motion_batch": (None, [vp, i, i, vp, d, vp, vp, i64, vp, C.POINTER(C.c_uint64)]),
             "ref_check_motion_batch_ex": (None, [vp, i, i, vp, d, vp, vp, i64, vp, vp, C.POINTER(C.c_uint64)]),
             "ref_composite_create": (vp, [vp, i]),
@@ -367,9 +367,12 @@ class RefCst:
                 "base_type": int(sz[7]),
             }
             cr = np.zeros(1, dtype=np.float32)
+            radii = np.zeros(max(int(sz[5]), 1), dtype=np.float32)
+            has = np.zeros(1, dtype=np.int32)
             lib().ref_flat_copy(f, _p(out["ops"]), _p(out["groups"]), _p(out["spheres"]), _p(out["pairs"]), _p(out["prims"]),
-                                _p(out["cloud_points"]), _p(out["base_pose"]), _p(cr))
+                                _p(out["cloud_points"]), _p(out["base_pose"]), _p(cr), _p(radii), _p(has))
             out["cloud_radius"] = float(cr[0])
+            out["cloud_point_radii"] = radii[: int(sz[5])] if has[0] else None  # CloudSDF leaves of different radii
             return out
         finally:
             lib().ref_flat_destroy(f)

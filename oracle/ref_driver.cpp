@@ -354,8 +354,9 @@ void ref_flat_sizes(void* f, int64_t* out) {
   out[6] = F->dof;
   out[7] = F->base_type;
 }
+// cloud_point_radii [n_cloud_points]: filled (and *has_point_radii set) only when the CloudSDF leaves have different radii
 void ref_flat_copy(void* f, void* ops, void* groups, float* spheres, int32_t* pairs, void* prims, float* cloud,
-                   float* base_pose7, float* cloud_radius) {
+                   float* base_pose7, float* cloud_radius, float* cloud_point_radii, int32_t* has_point_radii) {
   auto* F = static_cast<plainmp_b200::Flat*>(f);
   std::memcpy(ops, F->ops.data(), F->ops.size() * sizeof(pmp_link_op_t));
   std::memcpy(groups, F->groups.data(), F->groups.size() * sizeof(pmp_group_t));
@@ -365,6 +366,8 @@ void ref_flat_copy(void* f, void* ops, void* groups, float* spheres, int32_t* pa
   std::memcpy(cloud, F->cloud_points.data(), F->cloud_points.size() * sizeof(float));
   std::memcpy(base_pose7, F->base_pose, sizeof(F->base_pose));
   *cloud_radius = F->cloud_radius;
+  *has_point_radii = F->cloud_point_radii.empty() ? 0 : 1;
+  if (!F->cloud_point_radii.empty()) std::memcpy(cloud_point_radii, F->cloud_point_radii.data(), F->cloud_point_radii.size() * sizeof(float));
 }
 
 // ---- motion validators (ompl/motion_validator.cpp, installed as in ompl_thin_wrap.hpp:80-120) ----

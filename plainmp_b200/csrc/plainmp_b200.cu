@@ -1444,6 +1444,36 @@ int pmp_check_configs_host_f64(const pmp_robot_t* robot, const pmp_scene_t* scen
   const int qd = robot->full.dev.q_dim;
   CUDA_OK(cudaMemsetAsync(W.counters, 0, 2 * sizeof(unsigned long long), W.stream[0]));
   CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+  // Page-locked source (cudaHostAlloc / cudaHostRegister / pmp_host_alloc, e.g. a planner's reused state
+  // array): the doubles are DMA'd as they are and narrowed on the device — 56 B per panda configuration at the
+  // link rate instead of a host pack pass that the host's own memory bandwidth limits.
+  {
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, q_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // (an unregistered pointer sets the sticky-free "invalid value" on older drivers)
+    if (pinned) {
+      int k = 0;
+      for (int64_t off = 0; off < n; off += kHostChunk, k = (k + 1) % kWsStreams) {
+        const int64_t m = std::min<int64_t>(kHostChunk, n - off);
+        const size_t elems = (size_t)m * qd;
+        if (int rc = W.reserve(&W.in[k][0], &W.in_cap[k][0], elems * 4)) return rc;
+        if (int rc = W.reserve(&W.in[k][1], &W.in_cap[k][1], elems * 8)) return rc;
+        if (int rc = W.reserve(&W.outb[k], &W.out_cap[k], (size_t)((m + 31) / 32) * 4)) return rc;
+        cudaStream_t st = W.stream[k];
+        CUDA_OK(cudaMemcpyAsync(W.in[k][1], q_host + off * qd, elems * 8, cudaMemcpyHostToDevice, st));
+        k_f64_to_f32<<<(int)std::min<int64_t>(((int64_t)elems + 255) / 256, (int64_t)num_sms() * 8), 256, 0, st>>>(
+            (const double*)W.in[k][1], (float*)W.in[k][0], (long long)elems);
+        g_launches++;
+        if (int rc = pmp_check_configs(robot, scene, (const float*)W.in[k][0], m, (uint32_t*)W.outb[k], W.counters, st)) return rc;
+        CUDA_OK(cudaMemcpyAsync(valid_bits_host + off / 32, W.outb[k], (size_t)((m + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+      }
+      if (int rc = W.sync_all()) return rc;
+      CUDA_OK(cudaMemcpyAsync(W.counters_host, W.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, W.stream[0]));
+      CUDA_OK(cudaStreamSynchronize(W.stream[0]));
+      if (n_valid) *n_valid = W.counters_host[0];
+      return PMP_OK;
+    }
+  }
   constexpr int64_t kChunk = 1 << 18;  // small enough that packing chunk k + 1 overlaps the copy and kernel of chunk k
   PackPool& pool = PackPool::get();
   int k = 0;

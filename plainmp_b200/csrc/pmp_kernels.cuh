@@ -634,6 +634,14 @@ __host__ __device__ __forceinline__ int edge_n_test(const double ratio) {
   return nt > 2147483000.0 ? 2147483000 : (nt < 2.0 ? 2 : (int)nt);
 }
 
+// FP64 -> FP32 of a resident batch (the pinned-FP64 host path: the doubles cross PCIe as they are and are
+// narrowed here, instead of by host threads that the host's memory bandwidth limits)
+__global__ void __launch_bounds__(256)
+k_f64_to_f32(const double* __restrict__ src, float* __restrict__ dst, const long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (float)src[i];
+}
+
 // Pre-pass of the edge kernel: everything FP64 about an edge happens here, once, instead of inside
 // the persistent loop below (where it cost registers for the whole kernel): step ratio and n_test per
 // edge, the FP64 -> FP32 conversion of the endpoints when the caller holds doubles, and the zeroing

@@ -283,6 +283,9 @@ class RawTables:
             sd.cloud_points = flat["cloud_points"].ctypes.data if len(flat["cloud_points"]) else None
             sd.cloud_radius = flat["cloud_radius"]
             sd.cloud_cell = 0.0
+            self._cloud_radii = flat.get("cloud_point_radii")
+            if self._cloud_radii is not None:
+                sd.cloud_point_radii = self._cloud_radii.ctypes.data
             hs = C.c_void_p()
             _capi.check(lib.pmp_scene_create(C.byref(sd), C.byref(hs)))
             self.scene = RawTables._Handle(hs, lib, "pmp_scene_destroy")

@@ -296,6 +296,14 @@ inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc(p, n); }
 template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+// pointer attributes: every pointer is "pageable host" unless PMP_EMUL_PINNED is set (then every pointer counts as
+// page-locked, which sends the FP64 host entry point down its DMA-the-doubles path)
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) {
+  a->type = getenv("PMP_EMUL_PINNED") ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
+  return cudaSuccess;
+}
 template <class T, class U> inline cudaError_t cudaHostGetDevicePointer(T** d, U* h, unsigned) { *d = (T*)h; return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }

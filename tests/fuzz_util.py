@@ -62,7 +62,15 @@ def random_scene(rng: np.random.Generator, with_cloud: bool, big: bool = False):
     if with_cloud:
         n = int(rng.integers(1, 4000))
         c = rng.uniform(-0.8, 0.8, 3)
-        prims.append(psdf.CloudSDF(c + rng.uniform(-0.3, 0.3, (n, 3)) * rng.uniform(0.2, 1.0, 3), float(rng.uniform(0.0, 0.02))))
+        r0 = float(rng.uniform(0.0, 0.02))
+        prims.append(psdf.CloudSDF(c + rng.uniform(-0.3, 0.3, (n, 3)) * rng.uniform(0.2, 1.0, 3), r0))
+        # several CloudSDF leaves in one scene (round 2): of the same radius (one merged point set on the device)
+        # or of different radii (radius classes)
+        for _ in range(int(rng.integers(0, 3)) if rng.random() < 0.5 else 0):
+            m = int(rng.integers(1, 1500))
+            c2 = rng.uniform(-0.8, 0.8, 3)
+            r = r0 if rng.random() < 0.4 else float(rng.uniform(0.0, 0.06))
+            prims.insert(int(rng.integers(0, len(prims) + 1)), psdf.CloudSDF(c2 + rng.uniform(-0.25, 0.25, (m, 3)), r))
     return psdf.UnionSDF(prims) if len(prims) > 1 or rng.random() < 0.5 else prims[0]
 
 

@@ -1058,3 +1058,26 @@ def test_union_of_clouds_with_different_radii_psdf_surface_and_edges(cuda_lib):
     e_got, n_checked, calls = mv.check_motion_batch(q0, q1, with_calls=True)
     e_want = assert_edge_parity(cst, 0, widths, 0.0, q0, q1, e_got, n_checked, calls, "edges vs clouds of different radii")
     assert 0.05 < e_want.mean() < 0.95
+
+
+def test_fp64_host_entry_point_pageable_and_page_locked(cuda_lib):
+    """pmp_check_configs_host_f64: a pageable float64 array (packed by the host pool) and a page-locked one
+    (DMA'd as doubles, narrowed on the device) give the words of the FP32 device path."""
+    import ctypes as C
+
+    import torch
+
+    spec, cst = workloads.make_panda()
+    n = 200_001  # ragged last word, several chunks on neither path
+    Q = workloads.random_configs(spec, n, 17)
+    want = cst.is_valid_batch(Q)
+    robot, scene = cst._robot(), cst._scene()
+    Qd = np.ascontiguousarray(Q, dtype=np.float64)
+    pinned = torch.empty((n, 7), dtype=torch.float64, pin_memory=True)
+    pinned.copy_(torch.from_numpy(Qd))
+    for name, ptr in (("pageable", Qd.ctypes.data), ("page-locked", pinned.data_ptr())):
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        nv = C.c_uint64(0)
+        _capi.check(cuda_lib.pmp_check_configs_host_f64(robot.handle, scene.handle, ptr, n, words.ctypes.data, C.byref(nv)))
+        assert (tables.unpack_bits(words, n) == want).all(), name
+        assert nv.value == int(want.sum()), name

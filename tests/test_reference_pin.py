@@ -591,3 +591,25 @@ def test_clouds_of_different_radii_match_reference():
     five = [psdf.CloudSDF(np.random.default_rng(i).uniform(0, 1, (10, 3)), 0.01 * (i + 1)) for i in range(5)]
     with pytest.raises(NotImplementedError):
         tables.flatten_primitives(five)
+
+
+def test_reference_side_flatten_of_several_clouds():
+    """include/plainmp_b200_plainmp.hpp on the reference's own objects: every CloudSDF leaf of all_sdfs_cache_ goes
+    into one point set; per-point radii are handed over exactly when the leaves' radii differ."""
+    for radii, expect_classes in (((0.002, 0.002, 0.002), None), ((0.002, 0.03, 0.011), {0.002, 0.03, 0.011})):
+        spec, cst = _pr2_several_clouds(radii=radii)
+        flat = ref_bridge.RefCst(cst).flatten()
+        assert flat["cloud_points"].shape == (8000, 3) and abs(flat["cloud_radius"] - max(radii)) < 1e-9
+        if expect_classes is None:
+            assert flat["cloud_point_radii"] is None
+        else:
+            pr = flat["cloud_point_radii"]
+            assert pr.shape == (8000,) and {round(float(x), 6) for x in np.unique(pr)} == expect_classes
+            # the kd-tree permutes the points of a leaf, never across leaves: 3000 + 3000 + 2000, in leaf order
+            assert (pr[:3000] == np.float32(0.002)).all() and (pr[3000:6000] == np.float32(0.03)).all() and (pr[6000:] == np.float32(0.011)).all()
+        # same point set as the host mirror's merge (order inside a leaf differs: the reference stores kd-tree order)
+        from plainmp_b200 import tables
+
+        _, cloud = tables.flatten_primitives(cst._leaves())
+        key = lambda a: a[np.lexsort(a.T)]  # noqa: E731
+        np.testing.assert_array_equal(key(flat["cloud_points"]), key(cloud.points.astype(np.float32)))

@@ -857,6 +857,14 @@ def test_emulated_fp64_host_entry_points(emu):
     nv = C.c_uint64(0)
     assert emu.pmp_check_configs_host_f64(t.robot, t.scene, Qd.ctypes.data, 300, bits.ctypes.data, C.byref(nv)) == 0, emu.pmp_last_error()
     assert (tables.unpack_bits(bits, 300) == want).all() and nv.value == int(want.sum())
+    # a page-locked FP64 source takes the other path: the doubles are copied as they are and narrowed on the device
+    os.environ["PMP_EMUL_PINNED"] = "1"
+    try:
+        bits[:] = 0
+        assert emu.pmp_check_configs_host_f64(t.robot, t.scene, Qd.ctypes.data, 300, bits.ctypes.data, C.byref(nv)) == 0, emu.pmp_last_error()
+    finally:
+        del os.environ["PMP_EMUL_PINNED"]
+    assert (tables.unpack_bits(bits, 300) == want).all() and nv.value == int(want.sum())
     q0, q1 = workloads.random_edges(spec, 96, 4, True, lambda q: t.check(q))
     e32, nc32 = t.check_edges(0, np.full(7, 0.05), 0.0, q0, q1)
     v, keep = tables.make_validator(0, 7, np.full(7, 0.05), 0.0)

@@ -267,6 +267,72 @@ __device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, cons
   }
 }
 
+// Four such queries at once, one per 8-lane sub-warp, in LOCKSTEP: every collective is a full-warp ballot of
+// which each sub-warp reads its own byte, and every step of the loop is one node (or leaf) visit of every
+// sub-warp that is still walking.  cloud_any_within8 on four sub-warps with their own lane masks gives the same
+// answers but the four walks run one after the other (their collectives split the warp); here they overlap,
+// and the loads of the four visits are in flight together.  All 32 lanes must call; `valid` is sub-warp
+// uniform (false = this sub-warp has no query).  Returns, sub-warp uniform, "some point within r + rho(x)".
+__device__ inline bool cloud_any_within8x4(const CloudDev& C, const float3 p, const float r, const bool valid, const int sub,
+                                           const int kshift) {
+  constexpr unsigned full = 0xffffffffu;
+  const float bound2 = (r + C.rho) * (r + C.rho);
+  const int top = C.n_levels - 1;
+  int l = top, n = 0;
+  unsigned long long masks = 0;
+  bool done = !valid, hit = false;
+  if (top == 0) {
+    masks = 1ull << 8;
+    l = 1;
+  } else {
+    const float4* b = C.nodes + 2 * (size_t)(C.level_off[top - 1] + sub);
+    const float d2 = done ? INFINITY : box_dist2(__ldg(b), __ldg(b + 1), p);
+    masks = (unsigned long long)((__ballot_sync(full, d2 <= bound2) >> kshift) & 0xffu) << (8 * l);
+  }
+  const int vtop = l;
+  for (;;) {
+    unsigned m = 0;
+    if (!done) {
+      m = (unsigned)(masks >> (8 * l)) & 0xffu;
+      while (!m && l != vtop) {  // this level is exhausted: back to the parent's pending children
+        n >>= 3;
+        l++;
+        m = (unsigned)(masks >> (8 * l)) & 0xffu;
+      }
+      done = !m;
+    }
+    if (__all_sync(full, done)) break;
+    float d2 = INFINITY, thr = bound2;
+    int child = 0;
+    const bool leaf = l == 1;
+    if (!done) {
+      const int j = __ffs(m) - 1;
+      masks &= ~(1ull << (8 * l + j));
+      child = n * 8 + j;
+      if (leaf) {  // leaf box: one point per lane (padding points are +inf)
+        const float4 x = __ldg(C.pts + 8 * (size_t)child + sub);
+        const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+        d2 = dx * dx + dy * dy + dz * dz;
+        thr = cloud_point_bound2(C, x.w, r, bound2);
+      } else {  // inner node: one child box per lane (padding boxes are at +inf)
+        const float4* b = C.nodes + 2 * (size_t)(C.level_off[l - 2] + 8 * child + sub);
+        d2 = box_dist2(__ldg(b), __ldg(b + 1), p);
+      }
+    }
+    const unsigned within = (__ballot_sync(full, !done && d2 <= thr) >> kshift) & 0xffu;
+    if (!done) {
+      if (leaf) {
+        if (within) hit = done = true;
+      } else {
+        l--;
+        n = child;
+        masks = (masks & ~(0xffull << (8 * l))) | ((unsigned long long)within << (8 * l));
+      }
+    }
+  }
+  return hit;
+}
+
 // 8-lane cooperative exact nearest neighbour: the sub-warp shares one query p; lane j tests child box j
 // of the current node (strict test against the running best), a leaf is one point per lane followed by
 // a sub-warp arg-min.  `best` enters as an exclusive upper bound on the squared distance and is sub-warp

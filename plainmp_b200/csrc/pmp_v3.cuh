@@ -34,6 +34,13 @@ constexpr int kQS = 32;   // self items per warp: lane | pair << 5
 // item has been drained before the first self item is looked at, so the two are never live together.
 static_assert(kQE * 4 == 32 * 16, "the env queue and the scratch row share their bytes");
 constexpr int kV3WordsPerThread = (kQE + kQS) / 32;  // env queue (= scratch row) + self queue, per warp
+// CLOUD kernels: the cloud narrow phase does not go through the queue (v3_cloud_run below).  The upper half of
+// the env queue's bytes holds the spheres the distance field could not decide until enough of them have
+// gathered for tree walks four at a time, and — during phase 1 only — the bytes of the self queue hold two
+// small byte tables (rank -> lane of the run being worked, lane of each pending sphere).
+constexpr int kQEC = 64;    // env (primitive) items per warp in a CLOUD kernel
+constexpr int kPend = 16;   // pending spheres per warp: float4 (centre, radius) in the words kQEC .. kQE-1
+static_assert(kQEC * 4 + kPend * 16 == kQE * 4 && 32 + kPend <= kQS * 4, "the pending list lives in the queues' bytes");
 // (kSlotBase, pmp_kernels.cuh: the root frame of a FIXED-base robot is taken from the handle)
 //
 // Group centres in the stash.  They are read back only by the SELF broad phase (bounding spheres of a
@@ -151,8 +158,9 @@ __device__ __forceinline__ Frame apply_op_v3(const Frame& p, const float4 wB, co
 
 // ---- drains ---------------------------------------------------------------------------------------
 // env items: 8 lanes per (configuration, group, primitive) item, one sphere per lane per round.
-// Sub-warps are independent; they meet again at the REDUX that retires configurations.
-template <int B, bool CLOUD>
+// Sub-warps are independent; they meet again at the REDUX that retires configurations.  (The scene's point
+// cloud never appears here: see v3_cloud_run.)
+template <int B>
 __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const Frame& basef,
                                               const unsigned* qenv, const int n_env, unsigned bad, const int lane,
                                               const int wbase) {
@@ -174,34 +182,6 @@ __device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, 
           for (int s = sub; s < gw.z; s += 8) {
             const float4 sp = T.spheres[gw.y + s];
             hit |= !prim_is_outside(P, place(f, sp.x, sp.y, sp.z), sp.w);
-          }
-        } else if (CLOUD && kp == kItemCloud) {
-          // one sphere per lane through the O(1) distance-field test; the few spheres the field
-          // cannot decide go to the tree one at a time, the sub-warp's 8 lanes on one node per step
-          const unsigned smask = 0xffu << (k * 8);
-          for (int s0 = 0; s0 < gw.z && !hit; s0 += 8) {
-            const int s = s0 + sub;
-            int st = 0;
-            float3 c = make3(0.f, 0.f, 0.f);
-            float d = 0.f;
-            if (s < gw.z) {
-              const float4 sp = T.spheres[gw.y + s];
-              c = place(f, sp.x, sp.y, sp.z);
-              d = sp.w;
-              st = cloud_classify(S.cloud, c, sp.w);
-            }
-            if (__ballot_sync(smask, st == 1)) {
-              hit = true;
-              break;
-            }
-            unsigned mb = (__ballot_sync(smask, st == 2) >> (k * 8)) & 0xffu;
-            while (mb && !hit) {
-              const int owner = k * 8 + __ffs(mb) - 1;
-              mb &= mb - 1u;
-              const float3 pq = make3(__shfl_sync(smask, c.x, owner), __shfl_sync(smask, c.y, owner), __shfl_sync(smask, c.z, owner));
-              const float dq = __shfl_sync(smask, d, owner);
-              hit = cloud_any_within8(S.cloud, pq, dq, smask, sub, k * 8);
-            }
           }
         } else {
           for (int s = sub; s < gw.z; s += 8) {
@@ -300,6 +280,11 @@ struct V3Ctx {
   unsigned bad;       // warp-uniform: bit l set = lane l's configuration is known to be invalid
   int n_env, n_self;  // warp-uniform queue fills
   bool active;
+  // CLOUD kernels, phase 1 only (see kQEC / kPend)
+  float4* pend;             // [kPend] centre + radius of the spheres waiting for a tree walk
+  unsigned char* sel;       // [32] rank -> lane of the run being worked
+  unsigned char* pend_src;  // [kPend] lane (= configuration) of each pending sphere
+  int n_pend;               // warp-uniform
 };
 
 template <int B>
@@ -318,6 +303,10 @@ __device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, c
   X.n_env = 0;
   X.n_self = 0;
   X.active = active;
+  X.pend = reinterpret_cast<float4*>(X.qenv + kQEC);
+  X.sel = reinterpret_cast<unsigned char*>(X.qself);
+  X.pend_src = X.sel + 32;
+  X.n_pend = 0;
   return X;
 }
 
@@ -366,14 +355,14 @@ __device__ __forceinline__ unsigned v3_cull_mask(const SceneDev& S, const Smem& 
 // is still to be queued.  The caller drains and either restarts the group from its full mask (items
 // queued before are then only re-tested) or, for a group that cannot fit even into an empty queue,
 // calls again with the remaining bits.
-template <int B>
+template <int B, int CAP = kQE>
 __device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, unsigned& pm) {
   constexpr unsigned full = 0xffffffffu;
   if (!(X.active && !((X.bad >> X.lane) & 1u))) pm = 0u;
   unsigned ball = __ballot_sync(full, pm != 0u);
   while (ball) {
     const int cnt = __popc(ball);
-    if (X.n_env + cnt > kQE) return false;
+    if (X.n_env + cnt > CAP) return false;
     if (pm) {
       const unsigned b = __ffs(pm) - 1;
       pm &= pm - 1u;
@@ -384,6 +373,87 @@ __device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, unsigned&
     ball = __ballot_sync(full, pm != 0u);
   }
   return true;
+}
+
+// ---- cloud narrow phase (CLOUD kernels) ---------------------------------------------------------------
+// Tree walks of the pending spheres, four at a time (one per 8-lane sub-warp, in lockstep); a sphere whose
+// configuration has been retired in the meantime is dropped.
+template <int B>
+__device__ __forceinline__ void v3_cloud_flush(const SceneDev& S, V3Ctx<B>& X) {
+  constexpr unsigned full = 0xffffffffu;
+  const int sub = X.lane & 7, k = X.lane >> 3;
+  __syncwarp();
+  for (int i0 = 0; i0 < X.n_pend; i0 += 4) {
+    const int it = i0 + k;
+    int src = 0;
+    float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool valid = it < X.n_pend;
+    if (valid) {
+      src = X.pend_src[it];
+      pr = X.pend[it];
+      valid = !((X.bad >> src) & 1u);
+    }
+    const bool hit = cloud_any_within8x4(S.cloud, make3(pr.x, pr.y, pr.z), pr.w, valid, sub, k * 8);
+    X.bad |= __reduce_or_sync(full, hit ? (1u << src) : 0u);
+  }
+  X.n_pend = 0;
+  __syncwarp();
+}
+
+// The scene's point cloud against ONE sphere group of every configuration of the warp that passed the
+// group-level cull (`ball`, warp-uniform).  The group is the same for all of them, so the work is a dense
+// list of (configuration, member sphere) units: unit u belongs to the (u / count)-th set lane of `ball`
+// and member u % count, 32 units per round with one unit per lane whatever the size of the group (a
+// sub-warp per item would leave most of its 8 lanes idle on the 2-5 sphere groups of a PR2).  The group's
+// link frame is still in the registers of the lane that owns the configuration (phase 1 is at that link),
+// so a unit fetches it with seven shuffles — no stash read, no queue.  A unit places its sphere and asks the
+// distance field (cloud_classify): a certain hit retires the configuration, a sphere the field cannot
+// decide joins the pending list.
+template <int B>
+__device__ __forceinline__ void v3_cloud_run(const SceneDev& S, const Smem& T, V3Ctx<B>& X, const Frame& cur, unsigned ball,
+                                             const int sphere_begin, const int count) {
+  constexpr unsigned full = 0xffffffffu;
+  ball &= ~X.bad;
+  if (!ball || count <= 0) return;
+  if ((ball >> X.lane) & 1u) X.sel[__popc(ball & X.lt)] = (unsigned char)X.lane;
+  __syncwarp();
+  const int units = __popc(ball) * count;
+  const float inv_count = 1.f / (float)count;
+  for (int u0 = 0; u0 < units; u0 += 32) {
+    const int u = u0 + X.lane;
+    const bool have = u < units;
+    const int j = have ? (int)(((float)u + 0.5f) * inv_count) : 0;  // u / count (exact: u < 32 * count)
+    const int s = u - j * count;
+    const int src = have ? X.sel[j] : X.lane;
+    Frame f;
+    f.qx = __shfl_sync(full, cur.qx, src); f.qy = __shfl_sync(full, cur.qy, src);
+    f.qz = __shfl_sync(full, cur.qz, src); f.qw = __shfl_sync(full, cur.qw, src);
+    f.tx = __shfl_sync(full, cur.tx, src); f.ty = __shfl_sync(full, cur.ty, src);
+    f.tz = __shfl_sync(full, cur.tz, src);
+    int st = 0;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have && !((X.bad >> src) & 1u)) {
+      const float4 sp = T.spheres[sphere_begin + s];
+      const float3 w = place(f, sp.x, sp.y, sp.z);
+      c = make_float4(w.x, w.y, w.z, sp.w);
+      st = cloud_classify(S.cloud, w, sp.w);
+    }
+    X.bad |= __reduce_or_sync(full, st == 1 ? (1u << src) : 0u);
+    unsigned und = __ballot_sync(full, st == 2 && !((X.bad >> src) & 1u));
+    while (und) {  // (a round can leave more undecided spheres than the list has room for)
+      const int rank = __popc(und & X.lt);
+      const bool mine = ((und >> X.lane) & 1u) && X.n_pend + rank < kPend;
+      if (mine) {
+        X.pend[X.n_pend + rank] = c;
+        X.pend_src[X.n_pend + rank] = (unsigned char)src;
+      }
+      const unsigned took = __ballot_sync(full, mine);
+      und &= ~took;
+      X.n_pend += __popc(took);
+      if (X.n_pend == kPend) v3_cloud_flush<B>(S, X);
+    }
+  }
+  __syncwarp();  // the rank table is rewritten by the next run
 }
 
 // One listed group pair p; `near` = this lane's bounding spheres are within reach and the
@@ -416,6 +486,7 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
   bool far = false;
   unsigned pm = 0u;     // cull mask of the group being queued (what is left of it when resuming)
   int stall_gi = -1;    // group at which the queue last overflowed (warp-uniform)
+  int cloud_gi = -1;    // last group whose cloud narrow phase has run (warp-uniform)
   bool resume = false;  // warp-uniform: the group stalled twice in a row, keep pm across the drain
   Frame cur = base;
   int i = 0, gi = 0;
@@ -444,8 +515,14 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
           far |= v3_store_gc<B, GC16>(X, base, gi, gc);
           pm = (ext && !(gw.w & 1)) ? v3_cull_mask<CLOUD>(S, T, gc, g.w) : 0u;
           if (T.gmask) pm &= T.gmask[gi];  // composite constraints: a group sees its own member's scene entries only
+          if (CLOUD && cloud_gi != gi) {  // (a group restarted after a queue overflow has been through this already)
+            const bool alive = X.active && !((X.bad >> X.lane) & 1u);
+            v3_cloud_run<B>(S, T, X, cur, __ballot_sync(0xffffffffu, alive && (pm & kMaskCloud)), gw.y, gw.z);
+            cloud_gi = gi;
+          }
+          if (CLOUD) pm &= ~kMaskCloud;
         }
-        if (!v3_push_env(X, gi, pm)) {
+        if (!v3_push_env<B, CLOUD ? kQEC : kQE>(X, gi, pm)) {
           // After the drain the group is normally restarted from its full mask.  A group that yields
           // more items than the whole queue holds (e.g. 5+ primitives passing the cull on all 32
           // lanes) would stall again in exactly the same place for ever if no lane died in between:
@@ -462,11 +539,12 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
       ready = false;
     }
     __syncwarp();
-    X.bad = drain_env<B, CLOUD>(S, T, X.V, base, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
+    X.bad = drain_env<B>(S, T, X.V, base, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
     X.n_env = 0;
     if (!stalled) break;
     __syncwarp();
   }
+  if (CLOUD && X.n_pend) v3_cloud_flush<B>(S, X);  // the list's bytes become the self queue / scratch row now
   // listed group pairs: bounding-sphere test per lane, survivors queued
   for (int p = 0; R.n_pairs > 0;) {
     const bool alive = active && !((X.bad >> X.lane) & 1u);

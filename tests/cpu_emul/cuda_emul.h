@@ -9,7 +9,7 @@
 // anything but a few hundred items.  tests/cpu_emul/build.py builds it; tests/test_simt_emul.py uses it.
 //
 // Semantics implemented
-//   * __ballot_sync / __any_sync / __shfl_sync / __shfl_xor_sync / __shfl_down_sync / __reduce_or_sync /
+//   * __ballot_sync / __any_sync / __all_sync / __shfl_sync / __shfl_xor_sync / __shfl_down_sync / __reduce_or_sync /
 //     __syncwarp: every lane named in `mask` must arrive at a collective with the same mask; lanes of
 //     different (disjoint) masks proceed independently, like independent thread scheduling on sm_70+.
 //   * __syncthreads: barrier over the CTA.  One CTA runs at a time (grids are persistent / grid-stride
@@ -151,6 +151,7 @@ inline unsigned __ballot_sync(unsigned mask, bool pred) {
   return r;
 }
 inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
+inline bool __all_sync(unsigned mask, bool pred) { return __ballot_sync(mask, !pred) == 0u; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
   uint64_t all[32];
   emu::exchange(mask, 0, all);

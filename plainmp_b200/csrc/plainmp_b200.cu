@@ -422,13 +422,13 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   if (v3) {
     // FP16 group centres (MODE 2) cost a few instructions per pair; they are used only where the
     // bytes they save buy another resident CTA per SM (estimated with a 4-primitive scene and the
-    // register bound of these kernels: 5 CTAs of 128 threads, at most 96 registers; a 6-CTA variant at 80
-    // registers was measured in round 2 and lost, profiles/r02_s3_ab_flat_drain_6cta.txt)
+    // register bound of these kernels: the FIXED-base validity kernels need 76-80 registers since the environment
+    // narrow phase runs in place and the moving-base code is compiled out of them, i.e. up to 6 CTAs of 128 threads)
     const bool fixed = d->base_type == PMP_BASE_FIXED;
     auto ctas = [&](bool gc16) {
       const size_t stash = (size_t)n_slots * 7 + (size_t)v3_gc_floats(n_groups, gc16) + (size_t)kV3WordsPerThread;
       const size_t cta = (size_t)words * 16 + 4 * kPrimWords * 16 + stash * 4 * kBlock + 1024;
-      return std::min<size_t>(5, (size_t)233472 / cta);
+      return std::min<size_t>(6, (size_t)233472 / cta);
     };
     bool gc16 = fixed && ctas(true) > ctas(false);
     if (const char* e = getenv("PMP_V3_MODE")) gc16 = fixed && atoi(e) == 2;  // A/B experiments and tests only

@@ -30,7 +30,7 @@ struct RobotDev {
 };
 
 struct SceneDev {
-  const float4* prims;  // 6 words per primitive
+  const float4* prims;  // kPrimWords words per primitive
   int n_prims;
   CloudDev cloud;
 };
@@ -100,13 +100,15 @@ struct QLerp {  // s1 + (s2 - s1) * t  (OMPL RealVectorStateSpace::interpolate)
   }
 };
 
+// (bt = R.base_type; the validity kernels of a FIXED base pass the constant, which drops the other two cases
+// and their three sincosf from the kernel)
 template <class QAcc>
-__device__ __forceinline__ Frame base_frame(const RobotDev& R, const QAcc& q) {
+__device__ __forceinline__ Frame base_frame_bt(const RobotDev& R, const QAcc& q, const int bt) {
   Frame f;
-  if (R.base_type == PMP_BASE_FIXED) {
+  if (bt == PMP_BASE_FIXED) {
     f.tx = R.base_pose[0]; f.ty = R.base_pose[1]; f.tz = R.base_pose[2];
     f.qx = R.base_pose[3]; f.qy = R.base_pose[4]; f.qz = R.base_pose[5]; f.qw = R.base_pose[6];
-  } else if (R.base_type == PMP_BASE_PLANAR) {  // primitive.hpp:52-57
+  } else if (bt == PMP_BASE_PLANAR) {  // primitive.hpp:52-57
     f.tx = q(R.dof); f.ty = q(R.dof + 1); f.tz = 0.f;
     quat_from_rpy(0.f, 0.f, q(R.dof + 2), f.qx, f.qy, f.qz, f.qw);
   } else {  // primitive.hpp:44-51
@@ -114,6 +116,10 @@ __device__ __forceinline__ Frame base_frame(const RobotDev& R, const QAcc& q) {
     quat_from_rpy(q(R.dof + 3), q(R.dof + 4), q(R.dof + 5), f.qx, f.qy, f.qz, f.qw);
   }
   return f;
+}
+template <class QAcc>
+__device__ __forceinline__ Frame base_frame(const RobotDev& R, const QAcc& q) {
+  return base_frame_bt(R, q, R.base_type);
 }
 
 // Walk the link program; call visit(op_index, frame) after each frame is known.
@@ -155,7 +161,7 @@ struct QEdge {
 // ---- kernels ------------------------------------------------------------------------------------
 // Resident threads per SM the register allocation of the validity kernel is bounded for (A/B knob of the build).
 #ifndef PMP_CFG_MIN_THREADS
-#define PMP_CFG_MIN_THREADS 512  // 88 registers; bounding for 640 (85 registers) measured 4 % slower on every workload (profiles/r02_s5_ab_register_bound.txt)
+#define PMP_CFG_MIN_THREADS 512  // the FIXED-base, primitives-only kernels come out at 76 registers (6 CTAs/SM) on their own; bounding them for 768 threads (same register count!) measured 3 % slower, for 640 4 % (profiles/r02_s15_*, r02_s5_ab_register_bound.txt)
 #endif
 // v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  MODE: see warp_check_interp.  B = blockDim.x (compile-time so that the
 // stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
@@ -706,7 +712,7 @@ struct EdgeArgs {
 };
 
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 640 / B)  // 5 CTAs of 128 threads per SM: at most 96 registers
+__global__ void __launch_bounds__(B, 512 / B)  // (78-80 registers for a FIXED base: 6 CTAs of 128 threads per SM where the stash allows)
 k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__ seq, const EdgeArgs A) {
   extern __shared__ float4 sm[];
   const Smem T = stage_tables(R, S, sm);
@@ -828,7 +834,7 @@ k_check_edges_v3(const RobotDev R, const SceneDev S, const uint8_t* __restrict__
 constexpr int kFlatSmemEdges = 1024;
 
 template <int B, int MODE, bool CLOUD>
-__global__ void __launch_bounds__(B, 640 / B)
+__global__ void __launch_bounds__(B, 512 / B)
 k_check_waypoints_flat(const RobotDev R, const SceneDev S, const float* __restrict__ q0, const float* __restrict__ q1,
                        const double* __restrict__ ratio, const int* __restrict__ off, const int n_edges,
                        uint32_t* __restrict__ way_bits, uint8_t* __restrict__ way_ok) {

@@ -1,25 +1,26 @@
-// pmp_v3.cuh — v3 validity check: lean per-lane phase 1 + flat, warp-local work queues for the
-// narrow phases.
+// pmp_v3.cuh — validity check of one configuration per lane: lean phase 1, environment narrow phase in
+// place per sphere group, self narrow phase from a warp-local queue.
 //
-// ncu on v2 (profiles/r01_v2b_check_configs_ncu.md): 259 warp-instructions per configuration, of
-// which ~60 % sit in the narrow phases although only ~1.7 (configuration, group | pair) items per
-// configuration survive the broad phase.  v2 walks every group and every listed pair with a
-// ballot + publish + partially filled rounds; v3 instead
-//
-//   phase 1  (lane = configuration, uniform): FK with the joint quaternion taken from a
+//   phase 1  (lane = configuration, the warp converged): FK with the joint quaternion taken from a
 //            host-precomputed basis (local = s * A + c * B, A = origin (x) (axis, 0), B = origin:
 //            8 instructions instead of 19), points placed with q * v directly (no rotation
 //            matrices), group bounding spheres against the primitives' AABBs (branch-free
-//            centre / half-extent form) -> every surviving (configuration, group, primitive)
-//            triple is PUSHED into a warp-local queue in shared memory (the warp is converged, so
-//            the queue tail is a warp-uniform register: ballot + popc + one STS, no atomics);
-//   drain    one flat loop over the queue, four independent 8-lane sub-warps per round: an env
-//            item is one group against ONE primitive (one sphere per lane, the primitive's test
-//            variant resolved at scene build), a self item is one listed group pair.  A
-//            warp-uniform `bad` mask retires configurations (REDUX.OR); later items of a retired
-//            configuration are skipped.  If a push would overflow a queue, phase 1 stops, the
-//            queue is drained and phase 1 resumes where it stopped, so any table size works with
-//            fixed 512 + 128 byte queues.
+//            centre / half-extent form) and the cloud's distance field;
+//   env      right after a group's cull, while phase 1 is still at the group's link: the surviving
+//            (configuration, member sphere) units of that ONE group, densely packed 32 per round, the
+//            link frame fetched from the owning lane's registers by shuffles, the primitives visited in
+//            a warp-uniform loop (v3_group_run).  Round 1 / early round 2 pushed (configuration, group,
+//            primitive) items into a warp-local queue and drained them with four 8-lane sub-warps per
+//            round; ncu had that drain at 32 % of the panda kernel's and 68 % of the PR2-vs-cloud
+//            kernel's instructions at 16-19 of 32 lanes (sub-warps half empty on groups of 2-5 spheres,
+//            the four sub-warps on different primitives and trip counts);
+//   self     listed group pairs: bounding-sphere test per lane, survivors PUSHED into a warp-local queue
+//            in shared memory (the warp is converged, so the queue tail is a warp-uniform register:
+//            ballot + popc + one STS, no atomics), drained by four independent 8-lane sub-warps per
+//            round.  If a push would overflow the queue, the pair loop stops, the queue is drained and
+//            the loop resumes where it stopped.
+//   A warp-uniform `bad` mask retires configurations (REDUX.OR); work of a retired configuration is
+//   skipped from then on.
 //
 // The result is unchanged: validity depends neither on the broad-phase hierarchy nor on the order
 // of the tests (SURVEY finding 7, App. A.4; reference: check_ext_collision / check_self_collision,
@@ -28,19 +29,16 @@
 
 namespace pmp {
 
-constexpr int kQE = 128;  // env items per warp:  lane | group << 5 | primitive << 16
 constexpr int kQS = 32;   // self items per warp: lane | pair << 5
-// The self drain's scratch row (float4[32] per warp) lives in the bytes of the env queue: every env
-// item has been drained before the first self item is looked at, so the two are never live together.
-static_assert(kQE * 4 == 32 * 16, "the env queue and the scratch row share their bytes");
-constexpr int kV3WordsPerThread = (kQE + kQS) / 32;  // env queue (= scratch row) + self queue, per warp
-// CLOUD kernels: the cloud narrow phase does not go through the queue (v3_cloud_run below).  The upper half of
-// the env queue's bytes holds the spheres the distance field could not decide until enough of them have
-// gathered for tree walks four at a time, and — during phase 1 only — the bytes of the self queue hold two
-// small byte tables (rank -> lane of the run being worked, lane of each pending sphere).
-constexpr int kQEC = 64;    // env (primitive) items per warp in a CLOUD kernel
-constexpr int kPend = 16;   // pending spheres per warp: float4 (centre, radius) in the words kQEC .. kQE-1
-static_assert(kQEC * 4 + kPend * 16 == kQE * 4 && 32 + kPend <= kQS * 4, "the pending list lives in the queues' bytes");
+// Per-warp scratch, 512 + 128 bytes.  The 512-byte row is, during phase 1, the list of spheres the cloud's
+// distance field could not decide (float4 centre + radius, gathered for tree walks four at a time) and,
+// afterwards, the self drain's row of compacted spheres (float4[32]); the 128 bytes are, during phase 1,
+// two byte tables (rank -> lane of the group run being worked, lane of each pending sphere) and,
+// afterwards, the self queue.  The two uses of each are never live together.
+constexpr int kRowWords = 128;
+constexpr int kPend = 32;   // pending spheres per warp
+static_assert(kPend * 16 == kRowWords * 4 && 32 + kPend <= kQS * 4, "the pending list and its byte tables live in the row / the self queue");
+constexpr int kV3WordsPerThread = (kRowWords + kQS) / 32;  // row + self queue, per warp
 // (kSlotBase, pmp_kernels.cuh: the root frame of a FIXED-base robot is taken from the handle)
 //
 // Group centres in the stash.  They are read back only by the SELF broad phase (bounding spheres of a
@@ -56,9 +54,7 @@ constexpr float kGc16Range = 4.0f;
 constexpr float kGc16Pair = 4.0e-3f;    // added to Ra + Rb of a pair test (host: pairs4.w)
 constexpr float kGc16Sphere = 2.0e-3f;  // added to r + R of a sphere-vs-bounding-sphere cull
 constexpr unsigned kSelfItemFar = 1u << 31;
-constexpr unsigned kItemCloud = 0xffffu;     // primitive field: the scene's point cloud
-constexpr unsigned kItemOverflow = 0xfffeu;  // primitive field: every primitive with index >= 30
-constexpr int kMaxGroupsV3 = 2048;           // the group field of an env item has 11 bits
+constexpr int kMaxGroupsV3 = 2048;
 // bits of the per-(lane, group) cull mask: 0..29 primitive k, 30 cloud, 31 some primitive >= 30
 constexpr unsigned kMaskCloud = 1u << 30;
 constexpr unsigned kMaskOverflow = 1u << 31;
@@ -68,8 +64,7 @@ template <int B>
 struct V3View {
   float* frames;    // [slot][7][B]
   float* gc;        // [group][3][B] floats, or (GC16) the same shape in halves
-  float4* scratch;  // [warp][32]   (aliases qenv)
-  unsigned* qenv;   // [warp][kQE]
+  float4* scratch;  // [warp][32]   the 512-byte row
   unsigned* qself;  // [warp][kQS]
 };
 
@@ -82,8 +77,7 @@ __device__ __forceinline__ V3View<B> v3_view(const RobotDev& R, const Smem& T, c
   v.frames = T.stash;
   v.gc = T.stash + R.n_slots * 7 * B;
   v.scratch = reinterpret_cast<float4*>(v.gc + v3_gc_floats(R.n_groups, gc16) * B);
-  v.qenv = reinterpret_cast<unsigned*>(v.scratch);
-  v.qself = v.qenv + kQE * (B / 32);
+  v.qself = reinterpret_cast<unsigned*>(v.scratch) + kRowWords * (B / 32);
   return v;
 }
 
@@ -157,47 +151,6 @@ __device__ __forceinline__ Frame apply_op_v3(const Frame& p, const float4 wB, co
 }
 
 // ---- drains ---------------------------------------------------------------------------------------
-// env items: 8 lanes per (configuration, group, primitive) item, one sphere per lane per round.
-// Sub-warps are independent; they meet again at the REDUX that retires configurations.  (The scene's point
-// cloud never appears here: see v3_cloud_run.)
-template <int B>
-__device__ __forceinline__ unsigned drain_env(const SceneDev& S, const Smem& T, const V3View<B>& V, const Frame& basef,
-                                              const unsigned* qenv, const int n_env, unsigned bad, const int lane,
-                                              const int wbase) {
-  constexpr unsigned full = 0xffffffffu;
-  const int sub = lane & 7, k = lane >> 3;
-  for (int b0 = 0; b0 < n_env; b0 += 4) {
-    const int it = b0 + k;
-    unsigned hitbit = 0;
-    if (it < n_env) {
-      const unsigned h = qenv[it];
-      const int src = h & 31;
-      if (!((bad >> src) & 1u)) {
-        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * ((h >> 5) & (kMaxGroupsV3 - 1)) + 1]);
-        const Frame f = v3_group_frame(V, basef, gw.w >> 8, wbase + src);
-        const unsigned kp = h >> 16;
-        bool hit = false;
-        if (kp < 30u) {
-          const Prim P = load_prim(T.prims, kp);
-          for (int s = sub; s < gw.z; s += 8) {
-            const float4 sp = T.spheres[gw.y + s];
-            hit |= !prim_is_outside(P, place(f, sp.x, sp.y, sp.z), sp.w);
-          }
-        } else {
-          for (int s = sub; s < gw.z; s += 8) {
-            const float4 sp = T.spheres[gw.y + s];
-            const float3 c = place(f, sp.x, sp.y, sp.z);
-            for (int kk = 30; kk < S.n_prims; kk++) hit |= !prim_is_outside(load_prim(T.prims, kk), c, sp.w);
-          }
-        }
-        hitbit = hit ? (1u << src) : 0u;
-      }
-    }
-    bad |= __reduce_or_sync(full, hitbit);
-  }
-  return bad;
-}
-
 // self items: 8 lanes per (configuration, pair) item, four independent sub-warps per round (their
 // ballots / barriers use the sub-warp's own lane mask).  The lanes place 8 spheres of A at a time,
 // cull them against B's bounding sphere and compact the survivors into the sub-warp's scratch row;
@@ -272,15 +225,14 @@ __device__ __forceinline__ unsigned drain_self(const Smem& T, const V3View<B>& V
 template <int B>
 struct V3Ctx {
   V3View<B> V;
-  unsigned* qenv;
   unsigned* qself;
   float4* scratch;
   int tid, lane, wbase;
   unsigned lt;        // lanes below this one
   unsigned bad;       // warp-uniform: bit l set = lane l's configuration is known to be invalid
-  int n_env, n_self;  // warp-uniform queue fills
+  int n_self;  // warp-uniform fill of the self queue
   bool active;
-  // CLOUD kernels, phase 1 only (see kQEC / kPend)
+  // phase 1 only (see kPend)
   float4* pend;             // [kPend] centre + radius of the spheres waiting for a tree walk
   unsigned char* sel;       // [32] rank -> lane of the run being worked
   unsigned char* pend_src;  // [kPend] lane (= configuration) of each pending sphere
@@ -296,14 +248,12 @@ __device__ __forceinline__ V3Ctx<B> v3_begin(const RobotDev& R, const Smem& T, c
   X.lt = (1u << X.lane) - 1u;
   X.V = v3_view<B>(R, T, gc16);
   const int warp = X.tid >> 5;
-  X.qenv = X.V.qenv + warp * kQE;
   X.qself = X.V.qself + warp * kQS;
   X.scratch = X.V.scratch + warp * 32;
   X.bad = 0;
-  X.n_env = 0;
   X.n_self = 0;
   X.active = active;
-  X.pend = reinterpret_cast<float4*>(X.qenv + kQEC);
+  X.pend = X.scratch;
   X.sel = reinterpret_cast<unsigned char*>(X.qself);
   X.pend_src = X.sel + 32;
   X.n_pend = 0;
@@ -350,31 +300,6 @@ __device__ __forceinline__ unsigned v3_cull_mask(const SceneDev& S, const Smem& 
   return pm;
 }
 
-// Push one queue item per set bit of this lane's cull mask `pm` for group gi, consuming the bits as
-// they are queued.  Returns false when the items of the next round do not fit; `pm` then holds what
-// is still to be queued.  The caller drains and either restarts the group from its full mask (items
-// queued before are then only re-tested) or, for a group that cannot fit even into an empty queue,
-// calls again with the remaining bits.
-template <int B, int CAP = kQE>
-__device__ __forceinline__ bool v3_push_env(V3Ctx<B>& X, const int gi, unsigned& pm) {
-  constexpr unsigned full = 0xffffffffu;
-  if (!(X.active && !((X.bad >> X.lane) & 1u))) pm = 0u;
-  unsigned ball = __ballot_sync(full, pm != 0u);
-  while (ball) {
-    const int cnt = __popc(ball);
-    if (X.n_env + cnt > CAP) return false;
-    if (pm) {
-      const unsigned b = __ffs(pm) - 1;
-      pm &= pm - 1u;
-      const unsigned kp = (b < 30u) ? b : (b == 30u ? kItemCloud : kItemOverflow);
-      X.qenv[X.n_env + __popc(ball & X.lt)] = (unsigned)X.lane | ((unsigned)gi << 5) | (kp << 16);
-    }
-    X.n_env += cnt;
-    ball = __ballot_sync(full, pm != 0u);
-  }
-  return true;
-}
-
 // ---- cloud narrow phase (CLOUD kernels) ---------------------------------------------------------------
 // Tree walks of the pending spheres, four at a time (one per 8-lane sub-warp, in lockstep); a sphere whose
 // configuration has been retired in the meantime is dropped.
@@ -400,51 +325,42 @@ __device__ __forceinline__ void v3_cloud_flush(const SceneDev& S, V3Ctx<B>& X) {
   __syncwarp();
 }
 
-// The scene's point cloud against ONE sphere group of every configuration of the warp that passed the
-// group-level cull (`ball`, warp-uniform).  The group is the same for all of them, so the work is a dense
-// list of (configuration, member sphere) units: unit u belongs to the (u / count)-th set lane of `ball`
-// and member u % count, 32 units per round with one unit per lane whatever the size of the group (a
-// sub-warp per item would leave most of its 8 lanes idle on the 2-5 sphere groups of a PR2).  The group's
-// link frame is still in the registers of the lane that owns the configuration (phase 1 is at that link),
-// so a unit fetches it with seven shuffles — no stash read, no queue.  A unit places its sphere and asks the
-// distance field (cloud_classify): a certain hit retires the configuration, a sphere the field cannot
-// decide joins the pending list.
-template <int B>
-__device__ __forceinline__ void v3_cloud_run(const SceneDev& S, const Smem& T, V3Ctx<B>& X, const Frame& cur, unsigned ball,
-                                             const int sphere_begin, const int count) {
+// Scenes with more than 30 primitives: the sphere against every primitive from index 30 on (bit 31 of the cull
+// mask).  Out of line — a second inlined copy of the primitive tests made every validity kernel larger for a
+// case the stock scenes never reach, and these kernels are sensitive to their instruction footprint.
+__device__ __noinline__ bool v3_overflow_prims_hit(const float4* prims, const int n_prims, const bool have, const float cx,
+                                                   const float cy, const float cz, const float r) {
+  bool hit = false;
+  for (int kp = 30; kp < n_prims; kp++) {
+    const Prim P = load_prim(prims, kp);
+    if (have) hit |= !prim_is_outside(P, make3(cx, cy, cz), r);
+  }
+  return hit;
+}
+
+// One (configuration, member sphere) unit of v3_group_run: the sphere at world centre c against the scene
+// entries of the owner's mask spm.  The primitive loop is warp-uniform (um = union of the masks of the run).
+template <int B, bool CLOUD>
+__device__ __forceinline__ void v3_unit_test(const SceneDev& S, const Smem& T, V3Ctx<B>& X, const unsigned um, const bool have,
+                                             const unsigned spm, const int src, const float3 c, const float r) {
   constexpr unsigned full = 0xffffffffu;
-  ball &= ~X.bad;
-  if (!ball || count <= 0) return;
-  if ((ball >> X.lane) & 1u) X.sel[__popc(ball & X.lt)] = (unsigned char)X.lane;
-  __syncwarp();
-  const int units = __popc(ball) * count;
-  const float inv_count = 1.f / (float)count;
-  for (int u0 = 0; u0 < units; u0 += 32) {
-    const int u = u0 + X.lane;
-    const bool have = u < units;
-    const int j = have ? (int)(((float)u + 0.5f) * inv_count) : 0;  // u / count (exact: u < 32 * count)
-    const int s = u - j * count;
-    const int src = have ? X.sel[j] : X.lane;
-    Frame f;
-    f.qx = __shfl_sync(full, cur.qx, src); f.qy = __shfl_sync(full, cur.qy, src);
-    f.qz = __shfl_sync(full, cur.qz, src); f.qw = __shfl_sync(full, cur.qw, src);
-    f.tx = __shfl_sync(full, cur.tx, src); f.ty = __shfl_sync(full, cur.ty, src);
-    f.tz = __shfl_sync(full, cur.tz, src);
-    int st = 0;
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have && !((X.bad >> src) & 1u)) {
-      const float4 sp = T.spheres[sphere_begin + s];
-      const float3 w = place(f, sp.x, sp.y, sp.z);
-      c = make_float4(w.x, w.y, w.z, sp.w);
-      st = cloud_classify(S.cloud, w, sp.w);
-    }
-    X.bad |= __reduce_or_sync(full, st == 1 ? (1u << src) : 0u);
+  bool hit = false;
+  for (unsigned m = um & (kMaskCloud - 1u); m; m &= m - 1u) {
+    const int kp = __ffs(m) - 1;
+    const Prim P = load_prim(T.prims, kp);
+    if (have && ((spm >> kp) & 1u)) hit |= !prim_is_outside(P, c, r);
+  }
+  if (um & kMaskOverflow) hit |= v3_overflow_prims_hit(T.prims, S.n_prims, have && (spm & kMaskOverflow), c.x, c.y, c.z, r);
+  int st = 0;
+  if (CLOUD && have && !hit && (spm & kMaskCloud)) st = cloud_classify(S.cloud, c, r);
+  X.bad |= __reduce_or_sync(full, (hit || st == 1) ? (1u << src) : 0u);
+  if (CLOUD) {
     unsigned und = __ballot_sync(full, st == 2 && !((X.bad >> src) & 1u));
     while (und) {  // (a round can leave more undecided spheres than the list has room for)
       const int rank = __popc(und & X.lt);
       const bool mine = ((und >> X.lane) & 1u) && X.n_pend + rank < kPend;
       if (mine) {
-        X.pend[X.n_pend + rank] = c;
+        X.pend[X.n_pend + rank] = make_float4(c.x, c.y, c.z, r);
         X.pend_src[X.n_pend + rank] = (unsigned char)src;
       }
       const unsigned took = __ballot_sync(full, mine);
@@ -452,6 +368,55 @@ __device__ __forceinline__ void v3_cloud_run(const SceneDev& S, const Smem& T, V
       X.n_pend += __popc(took);
       if (X.n_pend == kPend) v3_cloud_flush<B>(S, X);
     }
+  }
+}
+
+// Narrow phase of ONE sphere group against the scene, for every configuration of the warp whose group
+// bounding sphere passed the cull (`pm` = this lane's cull mask: bits 0..29 primitive k, 30 the point cloud,
+// 31 some primitive >= 30; 0 for a lane that is retired or has no configuration).  It runs in place, right
+// after the group's cull, while phase 1 is at the group's link:
+//   * the group — member spheres, count — is the same for all those configurations, so the work is a dense
+//     list of (configuration, member sphere) units: unit u belongs to the (u / count)-th lane with a non-zero
+//     mask and member u % count; 32 units per round, one per lane, whatever the size of the group (an 8-lane
+//     sub-warp per item leaves most lanes idle on groups of 2-5 spheres);
+//   * the link frame is still in the registers of the lane that owns the configuration: a unit fetches it,
+//     and the owner's mask, with eight shuffles — no frame stash read, no queue, no queue overflow.  (Letting
+//     every lane place its OWN spheres when most lanes have work — no shuffles, no unit map — was measured and
+//     lost: the second copy of the unit test made the kernel larger, profiles/r02_s15_*);
+//   * primitives are visited in a warp-uniform loop over the UNION of the masks: the primitive's record and
+//     its test variant are the same for all 32 units (one broadcast load, no divergence on the variant); a
+//     unit whose owner's mask lacks the bit just sits the test out;
+//   * cloud: the unit asks the distance field (cloud_classify); a sphere the field cannot decide joins the
+//     pending list for a tree walk (v3_cloud_flush).
+// A hit retires the configuration (bit in X.bad): its remaining units, and its later groups, are skipped.
+// Same tests on the same spheres as check_ext_collision (constraints/primitive_sphere_collision.cpp:191-220);
+// the order does not matter for the result.
+template <int B, bool CLOUD>
+__device__ __forceinline__ void v3_group_run(const SceneDev& S, const Smem& T, V3Ctx<B>& X, const Frame& cur, const unsigned pm,
+                                             const int sphere_begin, const int count) {
+  constexpr unsigned full = 0xffffffffu;
+  const unsigned ball = __ballot_sync(full, pm != 0u);
+  if (!ball || count <= 0) return;
+  const unsigned um = __reduce_or_sync(full, pm);  // union of the masks
+  if ((ball >> X.lane) & 1u) X.sel[__popc(ball & X.lt)] = (unsigned char)X.lane;
+  __syncwarp();
+  const int units = __popc(ball) * count;
+  const float inv_count = 1.f / (float)count;
+  for (int u0 = 0; u0 < units; u0 += 32) {
+    const int u = u0 + X.lane;
+    const int j = u < units ? (int)(((float)u + 0.5f) * inv_count) : 0;  // u / count (exact: u < 32 * count)
+    const int s = u - j * count;
+    const int src = u < units ? X.sel[j] : X.lane;
+    Frame f;
+    f.qx = __shfl_sync(full, cur.qx, src); f.qy = __shfl_sync(full, cur.qy, src);
+    f.qz = __shfl_sync(full, cur.qz, src); f.qw = __shfl_sync(full, cur.qw, src);
+    f.tx = __shfl_sync(full, cur.tx, src); f.ty = __shfl_sync(full, cur.ty, src);
+    f.tz = __shfl_sync(full, cur.tz, src);
+    const unsigned spm = __shfl_sync(full, pm, src);  // the owner's mask
+    const bool have = u < units && !((X.bad >> src) & 1u);
+    const float4 sp = T.spheres[sphere_begin + (have ? s : 0)];
+    const float3 c = place(f, sp.x, sp.y, sp.z);
+    v3_unit_test<B, CLOUD>(S, T, X, um, have, spm, src, c, sp.w);
   }
   __syncwarp();  // the rank table is rewritten by the next run
 }
@@ -470,9 +435,10 @@ __device__ __forceinline__ bool v3_push_self(V3Ctx<B>& X, const int p, const boo
   return true;
 }
 
-// Table interpreter: FK over the link program, groups in op order, single drain site per queue
-// (phase 1 is resumable: when a push does not fit, the queue is drained and the group redone).
-// All 32 lanes of the warp must call this (lanes without a configuration pass active = false).
+// Table interpreter: FK over the link program, the sphere groups of a link right after its frame (cull + narrow
+// phase in place, v3_group_run), then the listed group pairs (bounding-sphere test per lane, survivors queued
+// for the sub-warp drain).  All 32 lanes of the warp must call this (lanes without a configuration pass
+// active = false).
 // MODE 0: exact sin/cos (moving base), FP32 group centres; 1: polynomial sin/cos (FIXED base), FP32
 // group centres; 2: FIXED base with FP16 group centres (chosen by the host when it buys a CTA per SM)
 template <int B, int MODE, bool CLOUD, class QAcc>
@@ -482,69 +448,37 @@ __device__ __forceinline__ bool warp_check_interp(const RobotDev& R, const Scene
   constexpr bool GC16 = MODE == 2;
   V3Ctx<B> X = v3_begin<B>(R, T, active, GC16);
   const bool ext = (S.n_prims > 0) || CLOUD;
-  const Frame base = base_frame(R, q);
+  const Frame base = base_frame_bt(R, q, APPROX ? (int)PMP_BASE_FIXED : R.base_type);  // MODE 1, 2: FIXED base by construction
   bool far = false;
-  unsigned pm = 0u;     // cull mask of the group being queued (what is left of it when resuming)
-  int stall_gi = -1;    // group at which the queue last overflowed (warp-uniform)
-  int cloud_gi = -1;    // last group whose cloud narrow phase has run (warp-uniform)
-  bool resume = false;  // warp-uniform: the group stalled twice in a row, keep pm across the drain
   Frame cur = base;
-  int i = 0, gi = 0;
-  bool ready = false;
-  for (;;) {
-    bool stalled = false;
-    for (; i < R.n_ops; i++) {
-      if (!ready) {
-        const float4* ow = T.ops + kOpWords * i;
-        const float4 wB = ow[0], w1 = ow[1], w2 = ow[2];
-        const int4 w3 = *reinterpret_cast<const int4*>(ow + 3);
-        const float4 wA = ow[4];
-        const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
-        if (w3.x != i - 1) cur = (w3.x < 0 || w3.w == kSlotBase) ? base : v3_frame_at(X.V, w3.w, X.tid);
-        const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
-        cur = apply_op_v3<APPROX>(cur, wB, w1, w2, wA, kind, w3.y, qv);
-        if (w3.z >= 0) v3_stash_frame(X, w3.z, cur);
-        ready = true;
+  int gi = 0;
+  for (int i = 0; i < R.n_ops; i++) {
+    const float4* ow = T.ops + kOpWords * i;
+    const float4 wB = ow[0], w1 = ow[1], w2 = ow[2];
+    const int4 w3 = *reinterpret_cast<const int4*>(ow + 3);
+    const float4 wA = ow[4];
+    const int kind = __float_as_int(w1.w), qi = __float_as_int(w2.w);
+    if (w3.x != i - 1) cur = (w3.x < 0 || w3.w == kSlotBase) ? base : v3_frame_at(X.V, w3.w, X.tid);
+    const float qv = (kind != PMP_OP_FIXED) ? q(qi) : 0.f;
+    cur = apply_op_v3<APPROX>(cur, wB, w1, w2, wA, kind, w3.y, qv);
+    if (w3.z >= 0) v3_stash_frame(X, w3.z, cur);
+    while (gi < R.n_groups) {
+      const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
+      if (gw.x != i) break;
+      const float4 g = T.groups[2 * gi];
+      const float3 gc = place(cur, g.x, g.y, g.z);
+      far |= v3_store_gc<B, GC16>(X, base, gi, gc);
+      if (ext && !(gw.w & 1)) {
+        unsigned pm = v3_cull_mask<CLOUD>(S, T, gc, g.w);
+        if (T.gmask) pm &= T.gmask[gi];  // composite constraints: a group sees its own member's scene entries only
+        if (!(X.active && !((X.bad >> X.lane) & 1u))) pm = 0u;
+        v3_group_run<B, CLOUD>(S, T, X, cur, pm, gw.y, gw.z);
       }
-      while (gi < R.n_groups) {
-        const int4 gw = *reinterpret_cast<const int4*>(&T.groups[2 * gi + 1]);
-        if (gw.x != i) break;
-        if (!resume) {
-          const float4 g = T.groups[2 * gi];
-          const float3 gc = place(cur, g.x, g.y, g.z);
-          far |= v3_store_gc<B, GC16>(X, base, gi, gc);
-          pm = (ext && !(gw.w & 1)) ? v3_cull_mask<CLOUD>(S, T, gc, g.w) : 0u;
-          if (T.gmask) pm &= T.gmask[gi];  // composite constraints: a group sees its own member's scene entries only
-          if (CLOUD && cloud_gi != gi) {  // (a group restarted after a queue overflow has been through this already)
-            const bool alive = X.active && !((X.bad >> X.lane) & 1u);
-            v3_cloud_run<B>(S, T, X, cur, __ballot_sync(0xffffffffu, alive && (pm & kMaskCloud)), gw.y, gw.z);
-            cloud_gi = gi;
-          }
-          if (CLOUD) pm &= ~kMaskCloud;
-        }
-        if (!v3_push_env<B, CLOUD ? kQEC : kQE>(X, gi, pm)) {
-          // After the drain the group is normally restarted from its full mask.  A group that yields
-          // more items than the whole queue holds (e.g. 5+ primitives passing the cull on all 32
-          // lanes) would stall again in exactly the same place for ever if no lane died in between:
-          // from its second consecutive stall on, continue with the bits that are still to be queued.
-          resume = (stall_gi == gi);
-          stall_gi = gi;
-          stalled = true;
-          break;
-        }
-        resume = false;
-        gi++;
-      }
-      if (stalled) break;
-      ready = false;
+      gi++;
     }
-    __syncwarp();
-    X.bad = drain_env<B>(S, T, X.V, base, X.qenv, X.n_env, X.bad, X.lane, X.wbase);
-    X.n_env = 0;
-    if (!stalled) break;
-    __syncwarp();
   }
   if (CLOUD && X.n_pend) v3_cloud_flush<B>(S, X);  // the list's bytes become the self queue / scratch row now
+  __syncwarp();
   // listed group pairs: bounding-sphere test per lane, survivors queued
   for (int p = 0; R.n_pairs > 0;) {
     const bool alive = active && !((X.bad >> X.lane) & 1u);

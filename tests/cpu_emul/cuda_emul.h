@@ -40,6 +40,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
 

@@ -7,7 +7,7 @@ tag=${1:-r2a}; shift
 wls=${@:-panda edgesA edgesB pr2cloud fetch eval_panda eval_pr2cloud}
 for wl in $wls; do
   n=4194304; kr='k_check_(configs|edges)'; sk=1; cn=1
-  case $wl in pr2cloud*) n=1048576;; edges*) n=1048576;; eval_pr2cloud*) n=65536; kr='k_eval'; sk=2; cn=2;; eval_*) n=1048576; kr='k_eval';; esac
+  case $wl in pr2*) n=1048576;; edges*) n=1048576;; eval_pr2cloud*) n=65536; kr='k_eval'; sk=2; cn=2;; eval_*) n=1048576; kr='k_eval';; esac
   rep=gpurun_out/${tag}_prof_$wl
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$kr" -s $sk -c $cn -f -o $rep python tools/prof_configs.py $wl $n 3 > $rep.log 2>&1
   ncu -i $rep.ncu-rep --page raw --csv > ${rep}_raw.csv 2>> $rep.log

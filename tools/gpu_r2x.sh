@@ -1,0 +1,15 @@
+#!/bin/bash
+# r2x: environment narrow phase in place per sphere group (v3_group_run: dense units, frames by shuffle, warp-uniform
+# primitive loop) instead of the warp-local queue + sub-warp drain: A/B against the previous build, then the GPU suite
+tag=${1:-r2x}
+mkdir -p gpurun_out
+rm -f gpurun_out/${tag}_ab.txt
+for rep in 1 2; do
+  for lib in libplainmp_b200_prev.so libplainmp_b200.so; do
+    echo "== $lib (pass $rep)" >> gpurun_out/${tag}_ab.txt
+    PMP_B200_LIB=$PWD/plainmp_b200/$lib timeout 600 python tools/time_workloads.py >> gpurun_out/${tag}_ab.txt 2>&1
+  done
+done
+cat gpurun_out/${tag}_ab.txt
+timeout 2400 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_pytest.log
+tail -5 gpurun_out/${tag}_pytest.log

@@ -45,7 +45,7 @@ elif wl.startswith("eval_"):
     torch.cuda.synchronize()
     print(wl, n, "mean ext", float(dist[:, 0].mean()))
 else:
-    spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch,
+    spec, cst = {"panda": workloads.make_panda, "panda_ceiled": lambda: workloads.make_panda(ceiled=True), "fetch": workloads.make_fetch, "pr2": workloads.make_pr2_table,
                  "pr2cloud": lambda: workloads.make_pr2_cloud(1_000_000), "pr2cloud100k": lambda: workloads.make_pr2_cloud(100_000)}[wl]()
     robot, scene = cst._robot(), cst._scene()
     q = torch.from_numpy(workloads.random_configs(spec, n, 5)).to(dev)

@@ -218,61 +218,19 @@ __device__ inline bool cloud_is_outside(const CloudDev& C, const float3 p, const
 }
 
 // ---- 8-lane cooperative traversal ------------------------------------------------------------------
-// The tree is 8-ary and a narrow-phase item is worked by 8 lanes, so one sub-warp visits one node per
-// step: lane j tests child j (two LDG.128 + ~12 instructions per lane instead of 8 x that in one
-// lane), the ballot over the sub-warp is the child mask, and a leaf is one point per lane.  All
-// 8 lanes of `smask` (lanes 8k .. 8k+7) must call with identical p / bound2; the traversal state
-// (level, node, pending masks) is sub-warp uniform, so there is no divergence inside a sub-warp.
-__device__ __forceinline__ unsigned cloud_children_mask8(const CloudDev& C, const int level, const int first, const float3 p,
-                                                         const float bound2, const unsigned smask, const int sub, const int kshift) {
-  const float4* b = C.nodes + 2 * (size_t)(C.level_off[level] + first + sub);
-  const float d2 = box_dist2(__ldg(b), __ldg(b + 1), p);
-  return (__ballot_sync(smask, d2 <= bound2) >> kshift) & 0xffu;
-}
-
-__device__ inline bool cloud_any_within8(const CloudDev& C, const float3 p, const float r, const unsigned smask,
-                                         const int sub, const int kshift) {
-  const float bound2 = (r + C.rho) * (r + C.rho);
-  const int top = C.n_levels - 1;
-  int l = top, n = 0;
-  unsigned long long masks = 0;
-  if (top == 0) {
-    masks = 1ull << 8;
-    l = 1;
-  } else {
-    masks = (unsigned long long)cloud_children_mask8(C, l - 1, 0, p, bound2, smask, sub, kshift) << (8 * l);
-  }
-  const int vtop = l;
-  for (;;) {
-    const unsigned m = (unsigned)(masks >> (8 * l)) & 0xffu;
-    if (!m) {
-      if (l == vtop) return false;
-      n >>= 3;
-      l++;
-      continue;
-    }
-    const int j = __ffs(m) - 1;
-    masks &= ~(1ull << (8 * l + j));
-    const int child = n * 8 + j;
-    if (l == 1) {  // leaf box: one point per lane
-      const float4 x = __ldg(C.pts + 8 * (size_t)child + sub);
-      const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
-      if (__ballot_sync(smask, dx * dx + dy * dy + dz * dz <= cloud_point_bound2(C, x.w, r, bound2)) & smask) return true;
-    } else {
-      l--;
-      n = child;
-      masks = (masks & ~(0xffull << (8 * l))) |
-              ((unsigned long long)cloud_children_mask8(C, l - 1, n * 8, p, bound2, smask, sub, kshift) << (8 * l));
-    }
-  }
-}
-
-// Four such queries at once, one per 8-lane sub-warp, in LOCKSTEP: every collective is a full-warp ballot of
-// which each sub-warp reads its own byte, and every step of the loop is one node (or leaf) visit of every
-// sub-warp that is still walking.  cloud_any_within8 on four sub-warps with their own lane masks gives the same
-// answers but the four walks run one after the other (their collectives split the warp); here they overlap,
-// and the loads of the four visits are in flight together.  All 32 lanes must call; `valid` is sub-warp
-// uniform (false = this sub-warp has no query).  Returns, sub-warp uniform, "some point within r + rho(x)".
+// The tree is 8-ary and a query is worked by 8 lanes, so one sub-warp visits one node per step: lane j tests
+// child j (two LDG.128 + ~12 instructions per lane instead of 8 x that in one lane), a ballot gives the child
+// mask, and a leaf is one point per lane.  The 8 lanes of a sub-warp (lanes 8k .. 8k+7) share p and the bound;
+// the traversal state (level, node, pending masks) is sub-warp uniform, so there is no divergence inside a
+// sub-warp.
+//
+// "Any point within r + rho(x) of p", four queries at once, one per 8-lane sub-warp, in lockstep: every
+// collective is a full-warp ballot of which each sub-warp reads its own byte, and every step of the loop is one
+// node (or leaf) visit of every sub-warp that is still walking.  All 32 lanes must call; `valid` is sub-warp
+// uniform (false = this sub-warp has no query); the result is sub-warp uniform.  (Letting each sub-warp walk on
+// its own with collectives on its 8-lane mask measured the same in the validity kernels, 8.0e8 vs 8.0e8 PR2
+// configurations/s; for the exact nearest-point search below, where walks are long and of very different
+// lengths, lockstep measured 8-9 % SLOWER, so cloud_nn8 keeps independent sub-warps.)
 __device__ inline bool cloud_any_within8x4(const CloudDev& C, const float3 p, const float r, const bool valid, const int sub,
                                            const int kshift) {
   constexpr unsigned full = 0xffffffffu;

@@ -14,7 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 tag, commit = sys.argv[1], sys.argv[2]
 # items per captured launch (tools/gpu_r2a.sh / tools/prof_configs.py)
-ITEMS = {"panda": 4194304, "panda_ceiled": 4194304, "fetch": 4194304, "pr2cloud": 1048576, "pr2cloud100k": 1048576, "edgesA": 1048576,
+ITEMS = {"panda": 4194304, "panda_ceiled": 4194304, "fetch": 4194304, "pr2": 1048576, "pr2cloud": 1048576, "pr2cloud100k": 1048576, "edgesA": 1048576,
          "edgesB": 1048576, "eval_panda": 1048576, "eval_fetch": 1048576, "eval_pr2cloud": 65536, "eval_pr2cloud100k": 65536}
 UNIT = {"edgesA": "edge", "edgesB": "edge"}
 KEYS = {

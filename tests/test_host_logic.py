@@ -388,3 +388,14 @@ def test_ompl_adaptor_header_compiles_against_the_ompl_stand_in(tmp_path):
     )
     _capi.load()
     assert C.CDLL(str(so)).probe_validators is not None
+
+
+def test_group_run_unit_index_formula_is_exact():
+    """pmp_v3.cuh, v3_group_run: unit u of a group run belongs to the (u / count)-th surviving lane; the kernel
+    computes the quotient as (int)((float(u) + 0.5f) * (1.f / count)) for u < 32 * count.  FP32 arithmetic restated
+    here: exact for every group size the shared-memory tables can hold (<= 12 800 spheres)."""
+    for count in list(range(1, 1200)) + [2047, 2048, 4095, 4096, 5000, 8191, 12800]:
+        u = np.arange(32 * count, dtype=np.int64)
+        inv = np.float32(1.0) / np.float32(count)
+        j = ((u.astype(np.float32) + np.float32(0.5)) * inv).astype(np.int32)
+        assert (j == u // count).all(), count

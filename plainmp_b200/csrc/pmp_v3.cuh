@@ -381,8 +381,9 @@ __device__ __forceinline__ void v3_unit_test(const SceneDev& S, const Smem& T, V
 //     sub-warp per item leaves most lanes idle on groups of 2-5 spheres);
 //   * the link frame is still in the registers of the lane that owns the configuration: a unit fetches it,
 //     and the owner's mask, with eight shuffles — no frame stash read, no queue, no queue overflow.  (Letting
-//     every lane place its OWN spheres when most lanes have work — no shuffles, no unit map — was measured and
-//     lost: the second copy of the unit test made the kernel larger, profiles/r02_s15_*);
+//     every lane place its OWN spheres when most lanes have work — no shuffles, no unit map — was measured
+//     twice and lost both times: as a second copy of the unit test, which made the kernel larger, and folded
+//     into this loop body, where a round per member at 60 - 80 % fill loses to dense rounds, profiles/r02_s15_*);
 //   * primitives are visited in a warp-uniform loop over the UNION of the masks: the primitive's record and
 //     its test variant are the same for all 32 units (one broadcast load, no divergence on the variant); a
 //     unit whose owner's mask lacks the bit just sits the test out;

@@ -415,7 +415,7 @@ int build_tables(const ProgramD& P, const pmp_robot_desc_t* d, int q_dim, bool v
   D.base_type = d->base_type;
   D.n_slots = n_slots;
   memcpy(D.base_pose, d->base_pose, sizeof(D.base_pose));
-  // per thread: frames [slot][7], group centres [group][3], + the per-warp scratch row and queues
+  // per thread: frames [slot][7], group centres [group][3], + the per-warp scratch row and self queue
   // (the evaluate kernel keeps one word per group instead)
   out->stash_floats_per_thread_eval = (size_t)n_slots * 7 + (size_t)n_groups * 3 + (size_t)n_groups + 1;
   out->stash_floats_per_thread = out->stash_floats_per_thread_eval;

@@ -163,7 +163,7 @@ struct QEdge {
 #ifndef PMP_CFG_MIN_THREADS
 #define PMP_CFG_MIN_THREADS 512  // the FIXED-base, primitives-only kernels come out at 76 registers (6 CTAs/SM) on their own; bounding them for 768 threads (same register count!) measured 3 % slower, for 640 4 % (profiles/r02_s15_*, r02_s5_ab_register_bound.txt)
 #endif
-// v3: lean phase 1 + warp-local work queues (pmp_v3.cuh).  MODE: see warp_check_interp.  B = blockDim.x (compile-time so that the
+// v3: lean phase 1, environment narrow phase in place per sphere group, self queue (pmp_v3.cuh).  MODE: see warp_check_interp.  B = blockDim.x (compile-time so that the
 // stash offsets fold into immediates); CLOUD = the scene has a CloudSDF (keeps the tree traversal
 // out of the primitives-only kernel).
 template <int B, int MODE, bool CLOUD>

@@ -1546,6 +1546,56 @@ namespace {
 constexpr long long kFlatMaxWaypoints = 1 << 17;  // beyond this the early-exit kernel wins
 constexpr long long kZeroCopyWaypoints = 4096;    // flat path: results come back as bytes in mapped memory
 constexpr int64_t kZeroCopyStates = 2048;
+// Completion of a small session call without cudaStreamSynchronize: the flat kernel writes one byte (0 / 1) per
+// waypoint into mapped host memory, the host presets those bytes to 0xff and spins until none is left.  One kernel
+// round trip costs 11.4 us with a stream synchronise and 7.2 us this way (profiles/r02_s21_latency_floor.txt).
+// Returns false when the bytes did not all arrive within the limit (the caller then synchronises, which also
+// surfaces a failed launch).
+bool spin_until_written(const uint8_t* bytes, long long n) {
+  const volatile uint8_t* p = bytes;
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned polls = 0;
+  for (long long i = 0; i < n; i++) {
+    while (p[i] == 0xffu) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((++polls & 0x3ffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(2000)) return false;
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return true;
+}
+
+// every waypoint of every edge in one wave (k_check_waypoints_flat); results as bits (way_bits) or bytes (way_ok)
+int launch_waypoints_flat(const pmp_robot_t* robot, const SceneDev& S, const float* d0, const float* d1, const double* dr, const int* dof,
+                          int m, long long total, uint32_t* dwb, uint8_t* dway, cudaStream_t st) {
+  const int block = pick_block(robot->fast, S);
+  const size_t smem = smem_bytes(robot->fast, S, block);  // the static offset table is accounted for by the occupancy query
+  if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
+  const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
+  const bool cloud = S.cloud.enabled != 0;
+  const long long tiles = (total + block - 1) / block;
+  int grid = 0;
+#define PMP_F3(BB, AP, CL)                                                                                      \
+  do {                                                                                                          \
+    if (int rc = grid_for(k_check_waypoints_flat<BB, AP, CL>, smem, tiles, &grid, block)) return rc;            \
+    k_check_waypoints_flat<BB, AP, CL><<<grid, block, smem, st>>>(robot->fast.dev, S, d0, d1, dr, dof, m, dwb, dway); \
+  } while (0)
+#define PMP_F3_B(BB)                                                                      \
+  do {                                                                                    \
+    if (mode == 2) { if (cloud) PMP_F3(BB, 2, true); else PMP_F3(BB, 2, false); }         \
+    else if (mode == 1) { if (cloud) PMP_F3(BB, 1, true); else PMP_F3(BB, 1, false); }    \
+    else { if (cloud) PMP_F3(BB, 0, true); else PMP_F3(BB, 0, false); }                   \
+  } while (0)
+  if (block == 128) PMP_F3_B(128); else PMP_F3_B(64);
+#undef PMP_F3_B
+#undef PMP_F3
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return PMP_OK;
+}
+
 // BoxMotionValidator / EuclideanMotionValidator::determine_step_ratio in FP64 on the caller's
 // doubles (ompl/motion_validator.cpp:89-126)
 double host_step_ratio(const pmp_session* s, const double* a, const double* b) {
@@ -1641,12 +1691,31 @@ int pmp_session_is_valid(pmp_session_t* s, const double* states, int64_t n, uint
   std::lock_guard<std::mutex> lk(s->mu);
   if (int rc = ensure_device()) return rc;
   float* hq = reinterpret_cast<float*>(s->host);
+  const SceneDev S = s->scene ? s->scene->dev : empty_scene();
+  if (!mask_limit_ok(s->robot->fast, S)) return fail(PMP_ERR_LIMIT, "a robot with per-group scene masks needs a scene of at most 30 primitives");
   for (int64_t off = 0; off < n; off += s->cap) {
     const int64_t m = std::min<int64_t>(s->cap, n - off);
     const size_t nq = (size_t)m * s->qd;
     const size_t o_bits = align256(std::max<size_t>(nq, 1) * 4);
     const size_t words = (size_t)((m + 31) / 32);
     pack_f64_f32(hq, states + off * s->qd, (int64_t)nq);
+    if (m <= kFlatSmemEdges) {
+      // latency path: the states go through the flat waypoint kernel as m "edges" of one waypoint (s2 itself, the
+      // ratio is never read), read from the mapped staging; one result byte per state comes back the same way and
+      // the host sees the call complete by spinning on those bytes instead of synchronising the stream
+      const size_t o_off = o_bits, o_way = o_off + align256((size_t)(m + 1) * 4);
+      int* ho = reinterpret_cast<int*>(s->host + o_off);
+      for (int64_t i = 0; i <= m; i++) ho[i] = (int)i;
+      uint8_t* hway = reinterpret_cast<uint8_t*>(s->host + o_way);
+      std::memset(hway, 0xff, (size_t)m);
+      const float* dq = reinterpret_cast<const float*>(s->host_dev);
+      if (int rc = launch_waypoints_flat(s->robot, S, dq, dq, reinterpret_cast<const double*>(s->host_dev), reinterpret_cast<const int*>(s->host_dev + o_off),
+                                         (int)m, m, nullptr, reinterpret_cast<uint8_t*>(s->host_dev + o_way), s->stream))
+        return rc;
+      if (!spin_until_written(hway, m)) CUDA_OK(cudaStreamSynchronize(s->stream));
+      for (int64_t i = 0; i < m; i++) valid[off + i] = hway[i] != 0;
+      continue;
+    }
     const uint32_t* hbits = reinterpret_cast<const uint32_t*>(s->host + o_bits);
     if (m <= kZeroCopyStates) {
       if (int rc = pmp_check_configs(s->robot, s->scene, reinterpret_cast<const float*>(s->host_dev), m,
@@ -1683,8 +1752,6 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
   const int block = pick_block(robot->fast, S);
   const size_t smem = smem_bytes(robot->fast, S, block);
   if (smem > (size_t)kMaxSmem) return fail(PMP_ERR_LIMIT, "robot + scene tables exceed the shared-memory budget");
-  const int mode = robot->fast.v3_mode;  // 0 moving base (exact sin/cos), 1 FIXED base, 2 FIXED base + FP16 group centres
-  const bool cloud = S.cloud.enabled != 0;
   const uint8_t* seq = sequence_table_host().data();
   uint64_t checked = 0;
   for (int64_t off = 0; off < n; off += s->cap) {
@@ -1728,34 +1795,17 @@ int pmp_session_check_motion(pmp_session_t* s, const double* s1, const double* s
       const size_t way_words = (size_t)((total + 31) / 32);
       char* base = zero_copy ? s->host_dev : s->dev;
       if (total > 0) {
-        if (!zero_copy) CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_bits, cudaMemcpyHostToDevice, s->stream));
-        const long long tiles = (total + block - 1) / block;
-        int grid = 0;
+        if (zero_copy) std::memset(hbits, 0xff, (size_t)total);  // completion is seen byte by byte (spin_until_written)
+        else CUDA_OK(cudaMemcpyAsync(s->dev, s->host, o_bits, cudaMemcpyHostToDevice, s->stream));
         const float* d0 = reinterpret_cast<const float*>(base);
         const float* d1 = reinterpret_cast<const float*>(base + o_q1);
         const double* dr = reinterpret_cast<const double*>(base + o_ratio);
         const int* dof = reinterpret_cast<const int*>(base + o_off);
         uint32_t* dwb = zero_copy ? nullptr : reinterpret_cast<uint32_t*>(base + o_bits);
         uint8_t* dway = zero_copy ? reinterpret_cast<uint8_t*>(base + o_bits) : nullptr;
-        const size_t smem_flat = smem;  // the static offset table is accounted for by the occupancy query
-#define PMP_F3(BB, AP, CL)                                                                                      \
-  do {                                                                                                          \
-    if (int rc = grid_for(k_check_waypoints_flat<BB, AP, CL>, smem_flat, tiles, &grid, block)) return rc;       \
-    k_check_waypoints_flat<BB, AP, CL><<<grid, block, smem_flat, s->stream>>>(robot->fast.dev, S, d0, d1, dr, dof, (int)m, dwb, dway); \
-  } while (0)
-#define PMP_F3_B(BB)                                                                      \
-  do {                                                                                    \
-    if (mode == 2) { if (cloud) PMP_F3(BB, 2, true); else PMP_F3(BB, 2, false); }         \
-    else if (mode == 1) { if (cloud) PMP_F3(BB, 1, true); else PMP_F3(BB, 1, false); }    \
-    else { if (cloud) PMP_F3(BB, 0, true); else PMP_F3(BB, 0, false); }                   \
-  } while (0)
-        if (block == 128) PMP_F3_B(128); else PMP_F3_B(64);
-#undef PMP_F3_B
-#undef PMP_F3
-        g_launches++;
-        CUDA_OK(cudaGetLastError());
+        if (int rc = launch_waypoints_flat(robot, S, d0, d1, dr, dof, (int)m, total, dwb, dway, s->stream)) return rc;
         if (!zero_copy) CUDA_OK(cudaMemcpyAsync(hbits, s->dev + o_bits, way_words * 4, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_OK(cudaStreamSynchronize(s->stream));
+        if (!zero_copy || !spin_until_written(reinterpret_cast<const uint8_t*>(hbits), total)) CUDA_OK(cudaStreamSynchronize(s->stream));
       }
       // per edge: AND over its waypoints, and the reference's call count = position of the first failing
       // waypoint in ITS visiting order (s2, then sequence[2..] of the farthest-first table; natural order

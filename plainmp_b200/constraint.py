@@ -184,9 +184,9 @@ class SphereCollisionCst(IneqConstraintBase):
 
     def is_valid(self, q: Sequence[float]) -> bool:
         """One configuration, same call as the binding (constraint.cpp:82).  Goes through a cached
-        validator session (pinned, mapped staging; one kernel launch and a stream synchronise, no
-        torch tensors) so that callers that loop over single states pay ~20 us, not a tensor round
-        trip; the session is rebuilt when the robot or scene tables it points at are replaced."""
+        validator session (pinned, mapped staging; one kernel launch whose completion the host sees by
+        spinning on the result byte, no torch tensors) so that callers that loop over single states pay
+        ~20 us, not a tensor round trip; the session is rebuilt when the robot or scene tables it points at are replaced."""
         from .ompl import ValidatorSession  # late import: ompl imports tables
 
         robot, scene = self._robot(), self._scene()

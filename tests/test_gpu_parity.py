@@ -1081,3 +1081,29 @@ def test_fp64_host_entry_point_pageable_and_page_locked(cuda_lib):
         _capi.check(cuda_lib.pmp_check_configs_host_f64(robot.handle, scene.handle, ptr, n, words.ctypes.data, C.byref(nv)))
         assert (tables.unpack_bits(words, n) == want).all(), name
         assert nv.value == int(want.sum()), name
+
+
+def test_session_is_valid_batch_size_boundaries(cuda_lib):
+    """pmp_session_is_valid: batches up to 1024 states ride the flat waypoint kernel (one result byte per state in
+    mapped memory, completion by spinning on those bytes), up to 2048 the validity kernel with mapped words, larger
+    ones the staged path; a session of small capacity chunks.  Every size gives the words of the device path."""
+    spec, cst = workloads.make_panda(ceiled=True)
+    Q = workloads.random_configs(spec, 5000, 29)
+    want = cst.is_valid_batch(Q)
+    Qd = Q.astype(np.float64)
+    ses = ValidatorSession(cst, None, capacity=4096)
+    for n in (1, 2, 31, 32, 33, 1023, 1024, 1025, 2047, 2048, 2049, 4096, 5000):
+        got = ses.is_valid(Qd[:n])
+        assert (np.atleast_1d(got) == want[:n]).all(), n
+    ses.close()
+    small = ValidatorSession(cst, None, capacity=64)  # rounded up to a multiple of 32: chunks of 64 states
+    assert (small.is_valid(Qd[:1000]) == want[:1000]).all()
+    small.close()
+    # ... and with a point cloud in the scene (the CLOUD instantiation of the flat kernel)
+    spec2, cst2 = workloads.make_pr2_cloud(20_000)
+    Q2 = workloads.random_configs(spec2, 600, 31)
+    want2 = cst2.is_valid_batch(Q2)
+    ses2 = ValidatorSession(cst2, None, capacity=1024)
+    assert (ses2.is_valid(Q2.astype(np.float64)) == want2).all()
+    assert [ses2.is_valid(q) for q in Q2[:20].astype(np.float64)] == list(want2[:20])
+    ses2.close()

@@ -193,7 +193,7 @@ __device__ __forceinline__ void cloud_bounds(const CloudDev& C, const float3 p, 
     return;
   }
   const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-  const int64_t cell = ((int64_t)iz * C.ny + iy) * C.nx + ix;
+  const int cell = (iz * C.ny + iy) * C.nx + ix;  // (the build keeps the field below 64 M cells)
   const float d = __ldg(C.dist + cell);
   // NN is 1-Lipschitz: |NN(p) - NN(centre)| <= |p - centre| (<= e, the half diagonal); the guard
   // covers the FP32 rounding of the offset

@@ -1,7 +1,7 @@
 #!/bin/bash
-# r3p: the round's final evidence pass on one GPU — ncu --set full of every workload's dominant kernel (CSV
+# r4p: the round's final evidence pass on one GPU — ncu --set full of every workload's dominant kernel (CSV
 # exports), the ncu launch list of the bench command, the bench itself and the reference arm, GPU tests, smoke.
-tag=${1:-r3p}
+tag=${1:-r4p}
 mkdir -p gpurun_out
 SKIP_TIMES=1 timeout 2400 bash tools/gpu_r2a.sh $tag panda panda_ceiled fetch pr2 pr2cloud pr2cloud100k edgesA edgesB eval_panda eval_pr2cloud > gpurun_out/${tag}_prof.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --extras 0 > gpurun_out/${tag}_launches.log 2>&1

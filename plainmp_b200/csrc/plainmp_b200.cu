@@ -1008,7 +1008,8 @@ int check_edges_batch(const pmp_robot_t* robot, const SceneDev& S, const Validat
                       uint32_t* bits, uint32_t* calls, unsigned long long* n_valid, unsigned long long* n_checked, cudaStream_t st) {
   constexpr bool f64 = sizeof(T) == 8;
   const int qd = robot->fast.dev.q_dim;
-  const bool sorted = n >= kSortEdgesFrom;
+  static const int64_t sort_from = getenv("PMP_EDGE_SORT_FROM") ? atoll(getenv("PMP_EDGE_SORT_FROM")) : kSortEdgesFrom;  // (A/B runs)
+  const bool sorted = n >= sort_from;
   size_t sort_tmp = 0;
   if (sorted)
     CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint8_t*)nullptr, (uint8_t*)nullptr, (const uint32_t*)nullptr,
